@@ -1,0 +1,71 @@
+"""ctypes binding of libgpp_b200.so (include/gpp_b200.h).  There is no fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpp_b200.so")
+
+GPP_OK = 0
+STATUS_NAMES = {0: "GPP_OK", -1: "GPP_ERR_BAD_SHAPE", -2: "GPP_ERR_UNSUPPORTED", -3: "GPP_ERR_NOT_PD",
+                -4: "GPP_ERR_CUDA", -5: "GPP_ERR_WORKSPACE", -6: "GPP_ERR_NULL"}
+
+# symbol -> (restype, argtypes); mirrors include/gpp_b200.h one for one (tests check every declared symbol resolves)
+_P = c_void_p
+SIGNATURES = {
+    "gpp_version": (c_int, []),
+    "gpp_last_error": (c_char_p, []),
+    "gpp_launch_count": (c_ulonglong, []),
+    "gpp_ekxz": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, c_double, _P, _P, _P]),
+    "gpp_ekzxkxz": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P, c_double, _P, c_int, _P, c_double, _P, _P, _P]),
+    "gpp_gp_model_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, c_int,
+                                    POINTER(c_double), c_int, _P]),
+    "gpp_gp_model_destroy": (c_int, [_P]),
+    "gpp_gp_model_weights": (c_int, [_P, _P, _P, _P]),
+    "gpp_profile_enable": (c_int, [c_int]),
+    "gpp_profile_last_ms": (c_int, [POINTER(ctypes.c_float)]),
+    "gpp_microbench_fp64": (c_int, [c_int, c_int, c_int, _P, _P]),
+    "gpp_mm_gp_predict_workspace_bytes": (c_size_t, [_P, c_int]),
+    "gpp_mm_gp_predict_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_double, _P, c_size_t, _P, _P]),
+}
+
+_lib = None
+
+
+class GppError(RuntimeError):
+  def __init__(self, code: int, message: str):
+    super().__init__(f"{STATUS_NAMES.get(code, code)}: {message}")
+    self.code = code
+
+
+def load() -> ctypes.CDLL:
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise RuntimeError(
+        f"{LIB_PATH} is missing. The CUDA library is the only implementation of this path (no CPU fallback): "
+        "build it with `python -m gpflowpilco_b200.build` (needs nvcc, targets sm_100a).")
+  lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+  for name, (res, args) in SIGNATURES.items():
+    fn = getattr(lib, name)            # AttributeError here == header/library mismatch
+    fn.restype = res
+    fn.argtypes = args
+  _lib = lib
+  return lib
+
+
+def check(code: int):
+  if code == GPP_OK:
+    return
+  msg = load().gpp_last_error()
+  text = msg.decode() if msg else ""
+  if code == -3:
+    raise GppError(code, text)        # façade maps this to the same failure class the reference shows (Cholesky)
+  if code in (-1, -6):
+    raise ValueError(f"{STATUS_NAMES[code]}: {text}")
+  if code == -2:
+    raise NotImplementedError(f"{STATUS_NAMES[code]}: {text}")
+  raise GppError(code, text)

@@ -1,0 +1,148 @@
+// Internal helpers shared by the translation units of libgpp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/gpp_b200.h"
+#include "gpp_math.h"
+
+namespace gpp {
+
+// ---- host-side error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(unsigned long long n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define GPP_CUDA_OK(expr)                                                                        \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      gpp::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return GPP_ERR_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+
+#define GPP_REQUIRE(cond, code, ...)      \
+  do {                                    \
+    if (!(cond)) {                        \
+      gpp::set_error(__VA_ARGS__);        \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+// profiling hooks (api_common.cu)
+void profile_begin(cudaStream_t stream);
+void profile_end(cudaStream_t stream);
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- device-side helpers ------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void flag_not_pd(int* info, int index) {
+  if (info) atomicCAS(info, 0, index + 1);   // first writer wins; 0 means "all fine"
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+#endif
+
+// ---- per-(input, kernel pair) coefficients of  log Q_ij = r_i + s_j + z1'_i^T R z2'_j  ------------------
+//  (re-derived in coordinates centred at mu_n so that both quadratic forms are negative
+//   semi-definite and nothing cancels:  with V = V1 V2/(V1+V2), A1 = V/V1, A2 = V/V2 (A1 + A2 = I), G = (Sigma+V)^-1
+//     log Q_ij = c0 - 1/2 (z1-z2)^T (V1+V2)^-1 (z1-z2) - 1/2 (A1 z1' + A2 z2')^T G (A1 z1' + A2 z2'),  z' = z - mu
+//   which equals kernel_expectation.py:125-187 term by term.)
+template <int D>
+struct PairPack {
+  static constexpr int TRI = D * (D + 1) / 2;
+  static constexpr int R = 0;            // [D][D]   cross matrix
+  static constexpr int P1 = D * D;       // packed upper triangle, off-diagonals doubled, -1/2 folded in
+  static constexpr int P2 = P1 + TRI;
+  static constexpr int C0 = P2 + TRI;    // log(var1 var2) + 1/2 sum log V - sum log diag chol(Sigma+V)
+  static constexpr int MU = C0 + 1;      // [D]
+  static constexpr int SIZE = ((MU + D + 1) / 2) * 2;   // doubles, even => 16-byte multiple
+};
+
+template <int D>
+GPP_HD bool make_pair_pack(const double* mu, const double* Sigma, const double* V1, const double* V2,
+                           double log_amp, double* out) {
+  using PP = PairPack<D>;
+  Mat<D> S, Li, G;
+  double A1[D], A2[D], dg[D];
+  double half_log_v = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double s12 = V1[d] + V2[d];
+    dg[d] = 1.0 / s12;
+    A1[d] = V2[d] * dg[d];
+    A2[d] = V1[d] * dg[d];
+    double V = V1[d] * A1[d];
+    half_log_v += log(V);
+#pragma unroll
+    for (int e = 0; e < D; ++e) S(d, e) = Sigma[d * D + e] + (d == e ? V : 0.0);
+  }
+  bool ok = cholesky<D>(S);
+  double log_det = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) log_det += log(S(d, d));
+  tri_inverse<D>(S, Li);
+  gram_inverse<D>(Li, G);
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int e = 0; e < D; ++e)
+      out[PP::R + d * D + e] = (d == e ? dg[d] : 0.0) - A1[d] * G(d, e) * A2[e];
+  int t = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int e = d; e < D; ++e, ++t) {
+      double g1 = A1[d] * G(d, e) * A1[e], g2 = A2[d] * G(d, e) * A2[e];
+      out[PP::P1 + t] = (d == e) ? -0.5 * (dg[d] + g1) : -g1;
+      out[PP::P2 + t] = (d == e) ? -0.5 * (dg[d] + g2) : -g2;
+    }
+  out[PP::C0] = log_amp + 0.5 * half_log_v - log_det;
+#pragma unroll
+  for (int d = 0; d < D; ++d) out[PP::MU + d] = mu[d];
+  if (PP::MU + D < PP::SIZE) out[PP::MU + D] = 0.0;
+  return ok;
+}
+
+// quadratic form with packed upper-triangular coefficients (off-diagonals pre-doubled)
+template <int D>
+GPP_HD double packed_quad(const double* P, const double* z) {
+  double acc = 0.0;
+  int t = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double row = 0.0;
+#pragma unroll
+    for (int e = d; e < D; ++e, ++t) row = fma_(P[t], z[e], row);
+    acc = fma_(row, z[d], acc);
+  }
+  return acc;
+}
+
+}  // namespace gpp

@@ -1,0 +1,147 @@
+// Scalar FP64 building blocks shared by every kernel (host+device so they can be unit-tested with gcc).
+//
+//  * fast_exp   : branch-free double exp, <= 1 ulp-class error on [-745, 709]; 15 FP64-pipe ops
+//                 (1 FMA magic-round, 1 ADD, 2 FMA Cody-Waite, 11 FMA Horner) + integer exponent insert.
+//                 MUFU is FP32-only, so the FP64 exp is software on every path; this one drops libdevice's
+//                 slow-path branch and special cases (inputs here are log-kernel-expectations: finite, <= log var^2).
+//  * small dense linear algebra on D x D matrices held in registers (D is a template parameter).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define GPP_HD __host__ __device__ __forceinline__
+#else
+#define GPP_HD inline
+#endif
+
+namespace gpp {
+
+GPP_HD int32_t lo_int(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(x);
+#else
+  int64_t b; std::memcpy(&b, &x, 8); return (int32_t)(b & 0xffffffff);
+#endif
+}
+GPP_HD int32_t hi_int(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  int64_t b; std::memcpy(&b, &x, 8); return (int32_t)(b >> 32);
+#endif
+}
+GPP_HD double make_double(int32_t hi, int32_t lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, lo);
+#else
+  int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; std::memcpy(&x, &b, 8); return x;
+#endif
+}
+GPP_HD double fma_(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return std::fma(a, b, c);
+#endif
+}
+
+// exp(x) for x <= ~709.  x < -744 (incl. -inf) returns 0.
+GPP_HD double fast_exp(double x) {
+  const double LOG2E = 1.4426950408889634074;
+  const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: low word of (t) holds rint(x*log2e)
+  const double LN2_HI = 6.93147180369123816490e-01;    // fdlibm split of ln 2
+  const double LN2_LO = 1.90821492927058770002e-10;
+  double t = fma_(x, LOG2E, MAGIC);
+  int32_t k = lo_int(t);
+  double kd = t - MAGIC;
+  double r = fma_(kd, -LN2_HI, x);
+  r = fma_(kd, -LN2_LO, r);
+  // degree-11 polynomial: 1 + r + r^2 Q(r), Q interpolated at Chebyshev nodes on [-ln2/2, ln2/2] in 60-digit
+  // arithmetic (max relative error 1.6e-17 before rounding).
+  double p = 0x1.af38a9b0ec855p-26;
+  p = fma_(p, r, 0x1.289185613a3d6p-22);
+  p = fma_(p, r, 0x1.71de0dae63bb3p-19);
+  p = fma_(p, r, 0x1.a019b90d2ae7ap-16);
+  p = fma_(p, r, 0x1.a01a01a7c41d5p-13);
+  p = fma_(p, r, 0x1.6c16c1788bd90p-10);
+  p = fma_(p, r, 0x1.11111111109b3p-7);
+  p = fma_(p, r, 0x1.5555555553d63p-5);
+  p = fma_(p, r, 0x1.5555555555556p-3);
+  p = fma_(p, r, 0x1.0000000000001p-1);
+  p = fma_(p, r, 1.0);
+  p = fma_(p, r, 1.0);
+  // scale by 2^k through the exponent field (integer pipe); clamp keeps the result a normal number
+  int32_t kc = k < -1021 ? -1021 : (k > 1023 ? 1023 : k);
+  double res = make_double(hi_int(p) + (kc << 20), lo_int(p));
+  // hi word of -744.0 is 0xC0874000; anything more negative (as unsigned compare) underflows to zero
+  return ((uint32_t)hi_int(x) > 0xC0874000u) ? 0.0 : res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// D x D helpers, row-major in registers.  All loops fully unrolled (D is compile-time).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct Mat {
+  double a[D * D];
+  GPP_HD double& operator()(int i, int j) { return a[i * D + j]; }
+  GPP_HD const double& operator()(int i, int j) const { return a[i * D + j]; }
+};
+
+// In-place lower Cholesky A = L L^T (upper triangle left untouched/garbage). Returns false if not PD.
+template <int D>
+GPP_HD bool cholesky(Mat<D>& A) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double d = A(j, j);
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fma_(-A(j, k), A(j, k), d);
+    ok = ok && (d > 0.0);
+    double s = sqrt(d);
+    A(j, j) = s;
+    double inv = 1.0 / s;
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+      double v = A(i, j);
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma_(-A(i, k), A(j, k), v);
+      A(i, j) = v * inv;
+    }
+  }
+  return ok;
+}
+
+// Li = L^{-1} (lower), from lower-triangular L.
+template <int D>
+GPP_HD void tri_inverse(const Mat<D>& L, Mat<D>& Li) {
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (i < j) { Li(i, j) = 0.0; continue; }
+      double v = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = j; k < i; ++k) v = fma_(-L(i, k), Li(k, j), v);
+      Li(i, j) = v / L(i, i);
+    }
+  }
+}
+
+// G = Li^T Li  (= (L L^T)^{-1}), full symmetric.
+template <int D>
+GPP_HD void gram_inverse(const Mat<D>& Li, Mat<D>& G) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = j; k < D; ++k) v = fma_(Li(k, i), Li(k, j), v);
+      G(i, j) = v;
+      G(j, i) = v;
+    }
+}
+
+}  // namespace gpp

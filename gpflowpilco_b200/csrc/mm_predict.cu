@@ -1,0 +1,502 @@
+// Fused exact moment matching through a (multi-output) sparse / exact GP  —  the hot kernel of the path.
+//
+// Replaces gpflow_pilco/moment_matching/models.py:200-299 (and :44-197 as special cases).  The reference
+// materialises eKuffu [N,L,M,L,M] (gpflow_pilco/utils/kernel_expectation.py:217-247) and runs two batched
+// triangular solves over it (models.py:224-226, O(N L^2 M^3)); here Psi2 is never written:
+//
+//   k_pack     one thread per (input n, kernel pair ab): D x D Cholesky, coefficients of
+//              log Q_ij = r_i + s_j + z1'_i^T R z2'_j  (common.cuh, PairPack)
+//   k_psi1     one warp per (n, latent): Psi1 contracted with beta -> latent mean and pre-inverted cross term
+//   k_contract persistent CTAs pull (pair, tile, input-chunk) items; a CTA keeps one T x T tile of C_a
+//              (= beta beta^T - B, diagonal pairs) or the beta vectors (off-diagonal pairs) on chip and streams
+//              inputs through it: per entry 1 DADD + D DFMA (bilinear form) + 15 FP64 ops (exp) + 1 DFMA
+//              (contraction).  Diagonal pairs use the symmetry Q_aa = Q_aa^T (upper tiles only, weight 2).
+//   k_finalize per input: deterministic fixed-order sum of the tile partials, Sff = f2 - f1 f1^T + diag(var),
+//              optional W mixing (LinearCoregionalization, models.py:279-286), mean constant, jitter.
+//
+// FP64 throughout (the reference is float64; 1e-6 relative parity target).  The tensor cores are not used:
+// the contraction is a Hadamard-weighted reduction of an elementwise exp, not a GEMM.
+#include <algorithm>
+
+#include "model.cuh"
+
+namespace gpp {
+
+// ---------------------------------------------------------------------------------------------------------
+// k_pack
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(64) k_pack(const double* __restrict__ m, const double* __restrict__ S, int N,
+                                             const double* __restrict__ ell, const double* __restrict__ var,
+                                             const int* __restrict__ pair_ab, int npairs,
+                                             double* __restrict__ packs, int* info) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * npairs) return;
+  int n = idx / npairs, p = idx % npairs;
+  int a = pair_ab[2 * p], b = pair_ab[2 * p + 1];
+  double V1[D], V2[D], mu[D], Sg[D * D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double e1 = ell[a * D + d], e2 = ell[b * D + d];
+    V1[d] = e1 * e1;
+    V2[d] = e2 * e2;
+    mu[d] = m[(size_t)n * D + d];
+  }
+#pragma unroll
+  for (int d = 0; d < D * D; ++d) Sg[d] = S[(size_t)n * D * D + d];
+  double out[PairPack<D>::SIZE];
+  bool ok = make_pair_pack<D>(mu, Sg, V1, V2, log(var[a] * var[b]), out);
+  if (!ok) flag_not_pd(info, n);
+  double* dst = packs + (size_t)idx * PairPack<D>::SIZE;
+#pragma unroll
+  for (int t = 0; t < PairPack<D>::SIZE; ++t) dst[t] = out[t];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_psi1: latent mean  f1[n,l] = sum_m beta_l[m] Psi1[n,m,l]  and  cross[n,:,l] = (S_n+Lambda_l)^-1 sum_m beta Psi1 (z_m - mu)
+//         (models.py:236 and :264-277; Psi1 is GPflow's eKxz)
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) k_psi1(const double* __restrict__ m, const double* __restrict__ S, int N, int L, int M,
+                                              const double* __restrict__ Z, const double* __restrict__ ell,
+                                              const double* __restrict__ var, const double* __restrict__ beta,
+                                              double* __restrict__ f1lat /*[N,L]*/, double* __restrict__ crosslat /*[N,D,L]*/,
+                                              int* info) {
+  int n = blockIdx.x;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  double mu[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) mu[d] = m[(size_t)n * D + d];
+  for (int l = warp; l < L; l += nwarps) {
+    Mat<D> A, Li;
+    double half_log_v = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double e = ell[l * D + d];
+      half_log_v += log(e);
+#pragma unroll
+      for (int e2 = 0; e2 < D; ++e2) A(d, e2) = S[(size_t)n * D * D + d * D + e2] + (d == e2 ? e * e : 0.0);
+    }
+    bool ok = cholesky<D>(A);
+    if (!ok && lane == 0) flag_not_pd(info, n);
+    double log_det = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) log_det += log(A(d, d));
+    tri_inverse<D>(A, Li);
+    double c0 = log(var[l]) + half_log_v - log_det;
+    double acc = 0.0, vec[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) vec[d] = 0.0;
+    const double* Zl = Z + (size_t)l * M * D;
+    for (int j = lane; j < M; j += 32) {
+      double dz[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) dz[d] = Zl[(size_t)j * D + d] - mu[d];
+      double maha = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double y = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) y = fma(Li(i, k), dz[k], y);
+        maha = fma(y, y, maha);
+      }
+      double w = beta[(size_t)l * M + j] * fast_exp(c0 - 0.5 * maha);
+      acc += w;
+#pragma unroll
+      for (int d = 0; d < D; ++d) vec[d] = fma(w, dz[d], vec[d]);
+    }
+    acc = warp_sum(acc);
+#pragma unroll
+    for (int d = 0; d < D; ++d) vec[d] = warp_sum(vec[d]);
+    if (lane == 0) {
+      f1lat[(size_t)n * L + l] = acc;
+      // G vec with G = Li^T Li
+      double y[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) t = fma(Li(i, k), vec[k], t);
+        y[i] = t;
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = d; i < D; ++i) t = fma(Li(i, d), y[i], t);
+        crosslat[((size_t)n * D + d) * L + l] = t;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_contract
+// ---------------------------------------------------------------------------------------------------------
+struct ContractParams {
+  const double* Z;
+  const double* beta;
+  const double* C;
+  const double* packs;
+  double* part;            // [N, nslots]
+  const gpp_slot* slots;
+  unsigned* counter;
+  int N, M, L, npairs, nslots, nchunks, chunk;
+};
+
+template <int D>
+struct ColLayout {
+  static constexpr int STRIDE = (D + 2 + 1) & ~1;   // z'[D], s, w  (even => 16-byte rows)
+};
+
+template <int D, int T, int H>
+__global__ void __launch_bounds__(T* H) k_contract(ContractParams p) {
+  using PP = PairPack<D>;
+  constexpr int NT = T * H;          // threads
+  constexpr int NW = NT / 32;
+  constexpr int CS = ColLayout<D>::STRIDE;
+  constexpr int COLS = T / H;        // columns per thread
+
+  extern __shared__ __align__(16) double smem[];
+  double* Ct = smem;                         // [T][T]  Ct[j*T + i]
+  double* colbuf = Ct + T * T;               // [T][CS]
+  double* packbuf = colbuf + T * CS;         // [2][PP::SIZE]
+  double* red = packbuf + 2 * PP::SIZE;      // [2][NW]
+  __shared__ int s_item;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row_in_tile = tid % T, half = tid / T;
+  const int nitems = p.nslots * p.nchunks;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = (int)atomicAdd(p.counter, 1u);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= nitems) break;
+    const int slot_id = item / p.nchunks, chunk_id = item % p.nchunks;
+    const gpp_slot sl = p.slots[slot_id];
+    const int n0 = chunk_id * p.chunk, n1 = min(p.N, n0 + p.chunk);
+    const bool diag = (sl.a == sl.b);
+    const int i_glob = sl.ti * T + row_in_tile;
+
+    // static per-item operands
+    double z1[D], beta_i = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) z1[d] = (i_glob < p.M) ? p.Z[((size_t)sl.a * p.M + i_glob) * D + d] : 0.0;
+    if (!diag && i_glob < p.M) beta_i = p.beta[(size_t)sl.a * p.M + i_glob];
+    double z2[D], w_col = 0.0;
+    if (tid < T) {
+      int j_glob = sl.tj * T + tid;
+#pragma unroll
+      for (int d = 0; d < D; ++d) z2[d] = (j_glob < p.M) ? p.Z[((size_t)sl.b * p.M + j_glob) * D + d] : 0.0;
+      if (!diag && j_glob < p.M) w_col = p.beta[(size_t)sl.b * p.M + j_glob];
+    }
+    if (diag) {   // C tile, transposed so that lanes (rows i) read consecutive words; C is symmetric => read C[j][i]
+      const double* Ca = p.C + (size_t)sl.a * p.M * p.M;
+      for (int idx = tid; idx < T * T; idx += NT) {
+        int jj = idx / T, ii = idx % T;
+        int jg = sl.tj * T + jj, ig = sl.ti * T + ii;
+        Ct[idx] = (jg < p.M && ig < p.M) ? Ca[(size_t)jg * p.M + ig] : 0.0;
+      }
+    }
+    // prefetch first pack
+    {
+      const double* src = p.packs + ((size_t)n0 * p.npairs + sl.pair) * PP::SIZE;
+      for (int t = tid; t < PP::SIZE / 2; t += NT) cp_async16(packbuf + 2 * t, src + 2 * t);
+      cp_async_commit();
+    }
+
+    for (int n = n0; n < n1; ++n) {
+      const int buf = (n - n0) & 1;
+      cp_async_wait<0>();
+      __syncthreads();                                     // pack(n) visible, colbuf + red[buf^1] free to reuse
+      if (n + 1 < n1) {
+        const double* src = p.packs + ((size_t)(n + 1) * p.npairs + sl.pair) * PP::SIZE;
+        for (int t = tid; t < PP::SIZE / 2; t += NT) cp_async16(packbuf + (buf ^ 1) * PP::SIZE + 2 * t, src + 2 * t);
+      }
+      cp_async_commit();
+      if (tid == 0 && n > n0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += red[(buf ^ 1) * NW + w];
+        p.part[(size_t)(n - 1) * p.nslots + slot_id] = s;
+      }
+      const double* pk = packbuf + buf * PP::SIZE;
+      if (tid < T) {                                        // column staging: z2' = z2 - mu, s_j
+        double zc[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) zc[d] = z2[d] - pk[PP::MU + d];
+        double s = packed_quad<D>(pk + PP::P2, zc);
+        double* dst = colbuf + tid * CS;
+#pragma unroll
+        for (int d = 0; d < D; ++d) dst[d] = zc[d];
+        dst[D] = s;
+        dst[D + 1] = w_col;
+      }
+      // row prologue
+      double zr[D], g[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) zr[d] = z1[d] - pk[PP::MU + d];
+#pragma unroll
+      for (int e = 0; e < D; ++e) {
+        double t = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) t = fma(zr[d], pk[PP::R + d * D + e], t);
+        g[e] = t;
+      }
+      const double r = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zr);
+      __syncthreads();
+
+      double acc = 0.0;
+      const double* cb = colbuf + half * COLS * CS;
+      if (diag) {
+        const double* ct = Ct + (half * COLS) * T + row_in_tile;
+#pragma unroll 4
+        for (int jj = 0; jj < COLS; ++jj) {
+          const double* c = cb + jj * CS;
+          double t = r + c[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) t = fma(g[d], c[d], t);
+          acc = fma(fast_exp(t), ct[jj * T], acc);
+        }
+      } else {
+#pragma unroll 4
+        for (int jj = 0; jj < COLS; ++jj) {
+          const double* c = cb + jj * CS;
+          double t = r + c[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) t = fma(g[d], c[d], t);
+          acc = fma(fast_exp(t), c[D + 1], acc);
+        }
+        acc *= beta_i;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) red[buf * NW + warp] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int buf = (n1 - 1 - n0) & 1;
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += red[buf * NW + w];
+      p.part[(size_t)(n1 - 1) * p.nslots + slot_id] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_finalize
+// ---------------------------------------------------------------------------------------------------------
+struct FinalizeParams {
+  const double* part;
+  const gpp_slot* slots;
+  const int* pair_start;
+  const int* pair_ab;
+  const double* f1lat;      // [N,L]
+  const double* crosslat;   // [N,D,L]
+  const double* var;        // [L]
+  const double* mean;       // [P]
+  const double* W;          // [P,L] or null
+  double* f1;               // [N,P]
+  double* Sff;              // [N,P,P]
+  double* cross;            // [N,D,P]
+  int N, L, P, D, npairs, nslots, full_cov, model_uncertainty;
+  double jitter;
+};
+
+__global__ void __launch_bounds__(128) k_finalize(FinalizeParams p) {
+  __shared__ double f2[GPP_MAX_L * GPP_MAX_L];
+  __shared__ double SffL[GPP_MAX_L * GPP_MAX_L];
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L, P = p.P;
+  for (int t = threadIdx.x; t < L * L; t += blockDim.x) f2[t] = 0.0;
+  __syncthreads();
+  for (int pr = warp; pr < p.npairs; pr += 4) {
+    double s = 0.0;
+    for (int k = p.pair_start[pr] + lane; k < p.pair_start[pr + 1]; k += 32)
+      s = fma(p.slots[k].weight, p.part[(size_t)n * p.nslots + k], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      int a = p.pair_ab[2 * pr], b = p.pair_ab[2 * pr + 1];
+      f2[a * L + b] = s;
+      f2[b * L + a] = s;
+    }
+  }
+  __syncthreads();
+  const double* f1l = p.f1lat + (size_t)n * L;
+  for (int t = threadIdx.x; t < L * L; t += blockDim.x) {
+    int a = t / L, b = t % L;
+    double v = f2[t] - f1l[a] * f1l[b];
+    if (a == b && p.model_uncertainty) v += p.var[a];
+    SffL[t] = v;
+  }
+  __syncthreads();
+  // outputs (optionally mixed by W)
+  for (int t = threadIdx.x; t < P; t += blockDim.x) {
+    double v = p.mean[t];
+    if (p.W) {
+      for (int l = 0; l < L; ++l) v = fma(p.W[t * L + l], f1l[l], v);
+    } else {
+      v += f1l[t];
+    }
+    p.f1[(size_t)n * P + t] = v;
+  }
+  for (int t = threadIdx.x; t < P * P; t += blockDim.x) {
+    int a = t / P, b = t % P;
+    double v;
+    if (p.W) {
+      v = 0.0;
+      for (int l = 0; l < L; ++l)
+        for (int k = 0; k < L; ++k) v = fma(p.W[a * L + l] * p.W[b * L + k], SffL[l * L + k], v);
+    } else {
+      v = SffL[t];
+    }
+    if (a == b) v += p.jitter;
+    if (!p.full_cov && a != b) v = 0.0;
+    p.Sff[(size_t)n * P * P + t] = v;
+  }
+  for (int t = threadIdx.x; t < p.D * P; t += blockDim.x) {
+    int d = t / P, o = t % P;
+    const double* cl = p.crosslat + ((size_t)n * p.D + d) * L;
+    double v;
+    if (p.W) {
+      v = 0.0;
+      for (int l = 0; l < L; ++l) v = fma(p.W[o * L + l], cl[l], v);
+    } else {
+      v = cl[o];
+    }
+    p.cross[((size_t)n * p.D + d) * P + o] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct Plan {
+  int tile_idx;      // 0: T=64, 1: T=128
+  int diag_only;
+  int nchunks, chunk;
+  size_t off_packs, off_part, off_f1lat, off_crosslat, off_counter, total;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Plan make_plan(const gpp_gp_model* m, int N, int full_output_cov) {
+  Plan pl{};
+  pl.diag_only = (!full_output_cov && !m->coreg) ? 1 : 0;
+  const int sms = num_sms();
+  // big tiles once there is enough work to fill the machine with them, small tiles otherwise
+  const gpp_gp_model::SlotTable& big = m->tables[1][pl.diag_only];
+  pl.tile_idx = ((long long)big.nslots * N >= 8LL * sms && m->M >= 128) ? 1 : 0;
+  const gpp_gp_model::SlotTable& tab = m->tables[pl.tile_idx][pl.diag_only];
+  // aim for ~64 items per SM (dynamic scheduling tail <= ~1.5%), but keep chunks >= 8 inputs to amortise the tile load
+  long long want_items = 64LL * sms;
+  int nchunks = (int)std::max(1LL, std::min<long long>((want_items + tab.nslots - 1) / tab.nslots, (N + 7) / 8));
+  pl.chunk = (N + nchunks - 1) / nchunks;
+  pl.nchunks = (N + pl.chunk - 1) / pl.chunk;
+  const int D = m->D;
+  size_t pack_doubles = 0;
+  switch (D) {
+#define GPP_CASE(d) case d: pack_doubles = PairPack<d>::SIZE; break;
+    GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+  }
+  size_t off = 0;
+  pl.off_packs = off;    off = align_up(off + sizeof(double) * pack_doubles * tab.npairs * N, 256);
+  pl.off_part = off;     off = align_up(off + sizeof(double) * (size_t)tab.nslots * N, 256);
+  pl.off_f1lat = off;    off = align_up(off + sizeof(double) * (size_t)m->L * N, 256);
+  pl.off_crosslat = off; off = align_up(off + sizeof(double) * (size_t)m->L * D * N, 256);
+  pl.off_counter = off;  off = align_up(off + 256, 256);
+  pl.total = off;
+  return pl;
+}
+
+template <int D, int T, int H>
+static int launch_contract(const ContractParams& cp, cudaStream_t stream) {
+  using PP = PairPack<D>;
+  constexpr int NT = T * H;
+  size_t smem = sizeof(double) * (T * T + T * ColLayout<D>::STRIDE + 2 * PP::SIZE + 2 * (NT / 32));
+  static bool configured = false;
+  if (!configured) {
+    GPP_CUDA_OK(cudaFuncSetAttribute(k_contract<D, T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int per_sm = 1;
+  GPP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<D, T, H>, NT, smem));
+  per_sm = std::max(per_sm, 1);
+  int grid = std::min(num_sms() * per_sm, cp.nslots * cp.nchunks);
+  profile_begin(stream);
+  k_contract<D, T, H><<<grid, NT, smem, stream>>>(cp);
+  profile_end(stream);
+  count_launch();
+  return GPP_OK;
+}
+
+template <int D>
+static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S, int N, double* f1, double* Sff,
+                       double* cross, int full_output_cov, double jitter, char* ws, const Plan& pl, int* info,
+                       cudaStream_t stream) {
+  using PP = PairPack<D>;
+  const gpp_gp_model::SlotTable& tab = m->tables[pl.tile_idx][pl.diag_only];
+  double* packs = (double*)(ws + pl.off_packs);
+  double* part = (double*)(ws + pl.off_part);
+  double* f1lat = (double*)(ws + pl.off_f1lat);
+  double* crosslat = (double*)(ws + pl.off_crosslat);
+  unsigned* counter = (unsigned*)(ws + pl.off_counter);
+  GPP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+  int total = N * tab.npairs;
+  k_pack<D><<<(total + 63) / 64, 64, 0, stream>>>(mu, S, N, m->ell, m->var, tab.d_pair_ab, tab.npairs, packs, info);
+  k_psi1<D><<<N, 128, 0, stream>>>(mu, S, N, m->L, m->M, m->Z, m->ell, m->var, m->beta, f1lat, crosslat, info);
+  count_launch(2);
+  ContractParams cp;
+  cp.Z = m->Z; cp.beta = m->beta; cp.C = m->C; cp.packs = packs; cp.part = part; cp.slots = tab.d_slots;
+  cp.counter = counter; cp.N = N; cp.M = m->M; cp.L = m->L; cp.npairs = tab.npairs; cp.nslots = tab.nslots;
+  cp.nchunks = pl.nchunks; cp.chunk = pl.chunk;
+  int rc = pl.tile_idx ? launch_contract<D, 128, 2>(cp, stream) : launch_contract<D, 64, 2>(cp, stream);
+  if (rc != GPP_OK) return rc;
+  FinalizeParams fp;
+  fp.part = part; fp.slots = tab.d_slots; fp.pair_start = tab.d_pair_start; fp.pair_ab = tab.d_pair_ab;
+  fp.f1lat = f1lat; fp.crosslat = crosslat; fp.var = m->var; fp.mean = m->mean; fp.W = m->W;
+  fp.f1 = f1; fp.Sff = Sff; fp.cross = cross; fp.N = N; fp.L = m->L; fp.P = m->P; fp.D = D;
+  fp.npairs = tab.npairs; fp.nslots = tab.nslots; fp.full_cov = full_output_cov;
+  fp.model_uncertainty = m->model_uncertainty; fp.jitter = jitter;
+  k_finalize<<<N, 128, 0, stream>>>(fp);
+  count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  (void)sizeof(PP);
+  return GPP_OK;
+}
+
+}  // namespace gpp
+
+extern "C" {
+
+size_t gpp_mm_gp_predict_workspace_bytes(const gpp_gp_model* model, int N) {
+  if (!model || N <= 0) return 0;
+  // worst case over the two covariance modes so one workspace serves both
+  return std::max(gpp::make_plan(model, N, 1).total, gpp::make_plan(model, N, 0).total);
+}
+
+int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
+                          double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
+                          int* info, void* stream_) {
+  GPP_REQUIRE(model && m && S && f1 && Sff && cross && workspace, GPP_ERR_NULL, "gpp_mm_gp_predict_fwd: null argument");
+  GPP_REQUIRE(N >= 1, GPP_ERR_BAD_SHAPE, "gpp_mm_gp_predict_fwd: N=%d", N);
+  gpp::Plan pl = gpp::make_plan(model, N, full_output_cov);
+  GPP_REQUIRE(workspace_bytes >= pl.total, GPP_ERR_WORKSPACE, "gpp_mm_gp_predict_fwd: workspace %zu < required %zu",
+              workspace_bytes, pl.total);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  switch (model->D) {
+#define GPP_CASE(d) \
+  case d: return gpp::predict_fwd<d>(model, m, S, N, f1, Sff, cross, full_output_cov, jitter, ws, pl, info, stream);
+    GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+    default:
+      gpp::set_error("gpp_mm_gp_predict_fwd: unsupported D=%d", model->D);
+      return GPP_ERR_UNSUPPORTED;
+  }
+}
+
+}  // extern "C"

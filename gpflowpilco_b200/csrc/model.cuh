@@ -1,0 +1,37 @@
+// Internal definition of the opaque GP model handle.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct gpp_slot {        // one (kernel pair, tile) work unit of the Psi2 contraction
+  int pair;              // index into the pair list
+  int a, b;              // latent indices (a <= b)
+  int ti, tj;            // tile coordinates
+  double weight;         // 2 for strictly-upper tiles of a diagonal pair (symmetry), else 1
+};
+
+struct gpp_gp_model {
+  int L = 0, M = 0, D = 0, P = 0;
+  int whiten = 0, model_uncertainty = 1, coreg = 0;
+  // device arrays owned by the handle
+  double* Z = nullptr;        // [L,M,D]
+  double* ell = nullptr;      // [L,D]
+  double* var = nullptr;      // [L]
+  double* beta = nullptr;     // [L,M]
+  double* C = nullptr;        // [L,M,M]   beta beta^T - B
+  double* mean = nullptr;     // [P] (zeros if none)
+  double* W = nullptr;        // [P,L] or null
+  double* Luu = nullptr;      // [L,M,M]   row-major lower Cholesky of Kuu (kept for the pathwise update)
+  // host copies of small parameters
+  std::vector<double> h_ell, h_var;
+  // slot tables (device) for the two tile sizes x {all pairs, diagonal pairs only}
+  struct SlotTable {
+    int tile = 0, npairs = 0, nslots = 0;
+    gpp_slot* d_slots = nullptr;
+    int* d_pair_start = nullptr;   // [npairs+1] slot range per pair
+    int* d_pair_ab = nullptr;      // [npairs,2]
+    std::vector<gpp_slot> h_slots;
+  };
+  SlotTable tables[2][2];     // [tile 64|128][full|diag-only]
+};

@@ -1,0 +1,103 @@
+/* gpp_b200.h — C ABI of libgpp_b200.so: the B200-native (sm_100a) moment-matching / pathwise rollout path.
+ *
+ * Drop-in boundary for the hot path of j-wilson/GPflowPILCO.  Every entry point names the upstream
+ * interface (file:line, relative to the upstream repo root) whose arithmetic it replaces; the Python
+ * host side (gpflowpilco_b200/) re-registers the same dispatch keys and marshals tensors to these calls.
+ *
+ * Conventions
+ *   - all array arguments are DEVICE pointers to float64, row-major, batch-leading ([N,...]) unless a
+ *     parameter is documented as host; sizes are explicit; nothing is retained past the call except by
+ *     gpp_gp_model_* handles; caller owns every buffer (inputs, outputs, workspace).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no implicit synchronisation.
+ *   - return value: GPP_OK or a negative gpp_status; gpp_last_error() gives a thread-local message.
+ *   - `info` (device int32[1], may be NULL): set to 1+index of the first batch element whose D x D
+ *     Cholesky failed (0 = all positive definite).  It is written asynchronously; read it after syncing.
+ */
+#ifndef GPP_B200_H
+#define GPP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gpp_status {
+  GPP_OK = 0,
+  GPP_ERR_BAD_SHAPE = -1,      /* inconsistent / non-positive sizes */
+  GPP_ERR_UNSUPPORTED = -2,    /* e.g. D > GPP_MAX_D */
+  GPP_ERR_NOT_PD = -3,         /* Kuu / Kyy Cholesky failed while building a model handle */
+  GPP_ERR_CUDA = -4,
+  GPP_ERR_WORKSPACE = -5,      /* workspace too small */
+  GPP_ERR_NULL = -6
+} gpp_status;
+
+#define GPP_MAX_D 8            /* GP input dimension supported by the compiled kernels (1..8) */
+#define GPP_MAX_L 8            /* latent GPs per model */
+
+int gpp_version(void);
+const char* gpp_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long gpp_launch_count(void);
+
+/* ---- Psi1: eKxz[n,m] = E_{x~N(mu_n,cov_n)} k(x, z_m) ------------------------------------------------
+ * replaces GPflow expectation(p, (kernel, Z)) as called at
+ * gpflow_pilco/moment_matching/models.py:62,141,212 and gpflow_pilco/utils/kernel_expectation.py:87-88. */
+int gpp_ekxz(const double* mu, const double* cov, int N, int D,
+             const double* Z, int M, const double* lengthscales /*[D]*/, double variance,
+             double* out /*[N,M]*/, int* info, void* stream);
+
+/* ---- Psi2: eKzxKxz[n,i,j] = E[k1(z1_i,x) k2(x,z2_j)], materialised -------------------------------------
+ * replaces `_E`, gpflow_pilco/utils/kernel_expectation.py:72-187.  Pass Z2 = NULL (and lengthscales2 = NULL)
+ * for the same-kernel/same-feature case (:96-97). */
+int gpp_ekzxkxz(const double* mu, const double* cov, int N, int D,
+                const double* Z1, int M1, const double* lengthscales1, double variance1,
+                const double* Z2, int M2, const double* lengthscales2, double variance2,
+                double* out /*[N,M1,M2]*/, int* info, void* stream);
+
+/* ---- sparse / exact GP model handle --------------------------------------------------------------------
+ * Caches the step-invariant solves the reference redoes in every call
+ * (gpflow_pilco/moment_matching/models.py:216-235: Kuu, its Cholesky, Luu^-1 q_mu, Luu^-1 q_sqrt):
+ *   beta_l = Kuu_l^-1 m_l,   C_l = beta_l beta_l^T - [model_uncertainty](Kuu_l^-1 - Kuu_l^-1 S_l Kuu_l^-1).
+ * Covers gpflow.models.SVGP with SeparateIndependent / LinearCoregionalization kernels (models.py:200-299),
+ * single-output SVGP (L = 1, :129-197) and exact GPR (:44-111: pass Z = X, q_mu = Y - c, q_sqrt = NULL,
+ * whiten = 0, kuu_jitter = noise variance).
+ *   Z [L,M,D], lengthscales [L,D], variance [L], q_mu [M,L], q_sqrt [L,M,M] lower (NULL = zero),
+ *   mean_const [P] (NULL = Zero mean), W [P,L] (NULL = no coregionalisation, then P = L). */
+typedef struct gpp_gp_model gpp_gp_model;
+
+int gpp_gp_model_create(gpp_gp_model** out, int L, int M, int D,
+                        const double* Z, const double* lengthscales, const double* variance,
+                        const double* q_mu, const double* q_sqrt, int whiten,
+                        const double* mean_const, const double* W, int P,
+                        const double* kuu_jitter /*host [L]*/, int model_uncertainty, void* stream);
+int gpp_gp_model_destroy(gpp_gp_model* model);
+/* Copies the cached weights into caller buffers (either may be NULL): beta [L,M], C [L,M,M]. */
+int gpp_gp_model_weights(const gpp_gp_model* model, double* beta, double* C, void* stream);
+
+/* ---- fused exact moment matching through the GP ---------------------------------------------------------
+ * replaces _mm_gauss_svgp_mo / _so / _gpr, gpflow_pilco/moment_matching/models.py:44-299:
+ *   f1 [N,P] mean, Sff [N,P,P] covariance (diagonal only filled when full_output_cov = 0),
+ *   cross [N,D,P] = Cov(x,x)^-1 Cov(x,f)  (the reference's pre-inverted cross term, :264-277),
+ *   `jitter` added to diag(Sff) (:293-296).  Psi2 is never materialised. */
+size_t gpp_mm_gp_predict_workspace_bytes(const gpp_gp_model* model, int N);
+int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m /*[N,D]*/, const double* S /*[N,D,D]*/, int N,
+                          double* f1, double* Sff, double* cross,
+                          int full_output_cov, double jitter,
+                          void* workspace, size_t workspace_bytes, int* info, void* stream);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------------
+ * gpp_profile_enable(1): every entry point records CUDA events on its stream around its dominant kernel
+ * (k_contract for gpp_mm_gp_predict_fwd, k_ekzxkxz for gpp_ekzxkxz, the rollout kernels for the rollouts).
+ * gpp_profile_last_ms synchronises on the last recorded pair and returns its duration.
+ * gpp_microbench_fp64 launches `blocks` x `threads` threads, each running 8 independent DFMA chains of `iters`
+ * steps (2*8*iters flop per thread): the measured FP64-pipe roofline denominator. */
+int gpp_profile_enable(int on);
+int gpp_profile_last_ms(float* ms);
+int gpp_microbench_fp64(int blocks, int threads, int iters, double* sink /*device [blocks*threads]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPP_B200_H */

@@ -42,3 +42,34 @@ def mc_close(a, b, num_samples):
 
 def log_uniform(shape, lo, hi, gen=None):
   return torch.exp(math.log(lo) + (math.log(hi) - math.log(lo)) * torch.rand(shape, dtype=DTYPE, generator=gen))
+
+
+def oracle_svgp(params, model_uncertainty=True):
+  """dict from gpflowpilco_b200.synthetic -> oracle.gp_models.SVGPModel."""
+  from oracle import gp_models as gm
+  from oracle import psi_stats as ps
+  L = params["Z"].shape[0]
+  ks = [ps.SEKernel(float(params["variance"][l]), torch.as_tensor(params["lengthscales"][l])) for l in range(L)]
+  Zs = [torch.as_tensor(params["Z"][l]) for l in range(L)]
+  W = params.get("W")
+  return gm.SVGPModel(ks, Zs, torch.as_tensor(params["q_mu"]), torch.as_tensor(params["q_sqrt"]),
+                      whiten=bool(params["whiten"]), mean_const=torch.as_tensor(params["mean_const"]),
+                      W=None if W is None else torch.as_tensor(W))
+
+
+def cuda_handle(params, model_uncertainty=True, kuu_jitter=1e-6):
+  from gpflowpilco_b200 import ops
+  dev = torch.device("cuda")
+  t = lambda k: None if params.get(k) is None else torch.as_tensor(params[k], dtype=DTYPE, device=dev)
+  return ops.GPModelHandle(t("Z"), t("lengthscales"), t("variance"), t("q_mu"), t("q_sqrt"), whiten=bool(params["whiten"]),
+                           mean_const=t("mean_const"), W=t("W"), kuu_jitter=kuu_jitter, model_uncertainty=model_uncertainty)
+
+
+def scaled_close(actual, expected, rel=1e-6, what=""):
+  """max |a-e| <= rel * max|e|  — the north-star tolerance (1e-6 relative, FP64 path)."""
+  actual = actual.detach().cpu() if hasattr(actual, "cpu") else torch.as_tensor(actual)
+  expected = expected.detach().cpu()
+  scale = float(expected.abs().max())
+  err = float((actual - expected).abs().max())
+  assert err <= rel * max(scale, 1e-300), f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rel {err / max(scale, 1e-300):.3e} > {rel:.1e})"
+  return err / max(scale, 1e-300)
