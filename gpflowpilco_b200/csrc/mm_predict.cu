@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "model.cuh"
+#include "contract_kernel.cuh"
 
 namespace gpp {
 
@@ -126,161 +127,6 @@ __global__ void __launch_bounds__(128) k_psi1(const double* __restrict__ m, cons
         for (int i = d; i < D; ++i) t = fma(Li(i, d), y[i], t);
         crosslat[((size_t)n * D + d) * L + l] = t;
       }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_contract
-// ---------------------------------------------------------------------------------------------------------
-struct ContractParams {
-  const double* Z;
-  const double* beta;
-  const double* C;
-  const double* packs;
-  double* part;            // [N, nslots]
-  const gpp_slot* slots;
-  unsigned* counter;
-  int N, M, L, npairs, nslots, nchunks, chunk;
-};
-
-template <int D>
-struct ColLayout {
-  static constexpr int STRIDE = (D + 2 + 1) & ~1;   // z'[D], s, w  (even => 16-byte rows)
-};
-
-template <int D, int T, int H>
-__global__ void __launch_bounds__(T* H) k_contract(ContractParams p) {
-  using PP = PairPack<D>;
-  constexpr int NT = T * H;          // threads
-  constexpr int NW = NT / 32;
-  constexpr int CS = ColLayout<D>::STRIDE;
-  constexpr int COLS = T / H;        // columns per thread
-
-  extern __shared__ __align__(16) double smem[];
-  double* Ct = smem;                         // [T][T]  Ct[j*T + i]
-  double* colbuf = Ct + T * T;               // [T][CS]
-  double* packbuf = colbuf + T * CS;         // [2][PP::SIZE]
-  double* red = packbuf + 2 * PP::SIZE;      // [2][NW]
-  __shared__ int s_item;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row_in_tile = tid % T, half = tid / T;
-  const int nitems = p.nslots * p.nchunks;
-
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = (int)atomicAdd(p.counter, 1u);
-    __syncthreads();
-    const int item = s_item;
-    if (item >= nitems) break;
-    const int slot_id = item / p.nchunks, chunk_id = item % p.nchunks;
-    const gpp_slot sl = p.slots[slot_id];
-    const int n0 = chunk_id * p.chunk, n1 = min(p.N, n0 + p.chunk);
-    const bool diag = (sl.a == sl.b);
-    const int i_glob = sl.ti * T + row_in_tile;
-
-    // static per-item operands
-    double z1[D], beta_i = 0.0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) z1[d] = (i_glob < p.M) ? p.Z[((size_t)sl.a * p.M + i_glob) * D + d] : 0.0;
-    if (!diag && i_glob < p.M) beta_i = p.beta[(size_t)sl.a * p.M + i_glob];
-    double z2[D], w_col = 0.0;
-    if (tid < T) {
-      int j_glob = sl.tj * T + tid;
-#pragma unroll
-      for (int d = 0; d < D; ++d) z2[d] = (j_glob < p.M) ? p.Z[((size_t)sl.b * p.M + j_glob) * D + d] : 0.0;
-      if (!diag && j_glob < p.M) w_col = p.beta[(size_t)sl.b * p.M + j_glob];
-    }
-    if (diag) {   // C tile, transposed so that lanes (rows i) read consecutive words; C is symmetric => read C[j][i]
-      const double* Ca = p.C + (size_t)sl.a * p.M * p.M;
-      for (int idx = tid; idx < T * T; idx += NT) {
-        int jj = idx / T, ii = idx % T;
-        int jg = sl.tj * T + jj, ig = sl.ti * T + ii;
-        Ct[idx] = (jg < p.M && ig < p.M) ? Ca[(size_t)jg * p.M + ig] : 0.0;
-      }
-    }
-    // prefetch first pack
-    {
-      const double* src = p.packs + ((size_t)n0 * p.npairs + sl.pair) * PP::SIZE;
-      for (int t = tid; t < PP::SIZE / 2; t += NT) cp_async16(packbuf + 2 * t, src + 2 * t);
-      cp_async_commit();
-    }
-
-    for (int n = n0; n < n1; ++n) {
-      const int buf = (n - n0) & 1;
-      cp_async_wait<0>();
-      __syncthreads();                                     // pack(n) visible, colbuf + red[buf^1] free to reuse
-      if (n + 1 < n1) {
-        const double* src = p.packs + ((size_t)(n + 1) * p.npairs + sl.pair) * PP::SIZE;
-        for (int t = tid; t < PP::SIZE / 2; t += NT) cp_async16(packbuf + (buf ^ 1) * PP::SIZE + 2 * t, src + 2 * t);
-      }
-      cp_async_commit();
-      if (tid == 0 && n > n0) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) s += red[(buf ^ 1) * NW + w];
-        p.part[(size_t)(n - 1) * p.nslots + slot_id] = s;
-      }
-      const double* pk = packbuf + buf * PP::SIZE;
-      if (tid < T) {                                        // column staging: z2' = z2 - mu, s_j
-        double zc[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) zc[d] = z2[d] - pk[PP::MU + d];
-        double s = packed_quad<D>(pk + PP::P2, zc);
-        double* dst = colbuf + tid * CS;
-#pragma unroll
-        for (int d = 0; d < D; ++d) dst[d] = zc[d];
-        dst[D] = s;
-        dst[D + 1] = w_col;
-      }
-      // row prologue
-      double zr[D], g[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) zr[d] = z1[d] - pk[PP::MU + d];
-#pragma unroll
-      for (int e = 0; e < D; ++e) {
-        double t = 0.0;
-#pragma unroll
-        for (int d = 0; d < D; ++d) t = fma(zr[d], pk[PP::R + d * D + e], t);
-        g[e] = t;
-      }
-      const double r = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zr);
-      __syncthreads();
-
-      double acc = 0.0;
-      const double* cb = colbuf + half * COLS * CS;
-      if (diag) {
-        const double* ct = Ct + (half * COLS) * T + row_in_tile;
-#pragma unroll 4
-        for (int jj = 0; jj < COLS; ++jj) {
-          const double* c = cb + jj * CS;
-          double t = r + c[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d) t = fma(g[d], c[d], t);
-          acc = fma(fast_exp(t), ct[jj * T], acc);
-        }
-      } else {
-#pragma unroll 4
-        for (int jj = 0; jj < COLS; ++jj) {
-          const double* c = cb + jj * CS;
-          double t = r + c[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d) t = fma(g[d], c[d], t);
-          acc = fma(fast_exp(t), c[D + 1], acc);
-        }
-        acc *= beta_i;
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) red[buf * NW + warp] = acc;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const int buf = (n1 - 1 - n0) & 1;
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) s += red[buf * NW + w];
-      p.part[(size_t)(n1 - 1) * p.nslots + slot_id] = s;
     }
   }
 }
@@ -412,22 +258,21 @@ static Plan make_plan(const gpp_gp_model* m, int N, int full_output_cov) {
   return pl;
 }
 
-template <int D, int T, int H>
+template <int D, int T>
 static int launch_contract(const ContractParams& cp, cudaStream_t stream) {
-  using PP = PairPack<D>;
-  constexpr int NT = T * H;
-  size_t smem = sizeof(double) * (T * T + T * ColLayout<D>::STRIDE + 2 * PP::SIZE + 2 * (NT / 32));
+  constexpr int NT = ContractSmem<D, T>::NT;
+  size_t smem = sizeof(double) * ContractSmem<D, T>::TOTAL;
   static bool configured = false;
   if (!configured) {
-    GPP_CUDA_OK(cudaFuncSetAttribute(k_contract<D, T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPP_CUDA_OK(cudaFuncSetAttribute(k_contract<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int per_sm = 1;
-  GPP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<D, T, H>, NT, smem));
+  GPP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<D, T>, NT, smem));
   per_sm = std::max(per_sm, 1);
   int grid = std::min(num_sms() * per_sm, cp.nslots * cp.nchunks);
   profile_begin(stream);
-  k_contract<D, T, H><<<grid, NT, smem, stream>>>(cp);
+  k_contract<D, T><<<grid, NT, smem, stream>>>(cp);
   profile_end(stream);
   count_launch();
   return GPP_OK;
@@ -453,7 +298,7 @@ static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S,
   cp.Z = m->Z; cp.beta = m->beta; cp.C = m->C; cp.packs = packs; cp.part = part; cp.slots = tab.d_slots;
   cp.counter = counter; cp.N = N; cp.M = m->M; cp.L = m->L; cp.npairs = tab.npairs; cp.nslots = tab.nslots;
   cp.nchunks = pl.nchunks; cp.chunk = pl.chunk;
-  int rc = pl.tile_idx ? launch_contract<D, 128, 2>(cp, stream) : launch_contract<D, 64, 2>(cp, stream);
+  int rc = pl.tile_idx ? launch_contract<D, 128>(cp, stream) : launch_contract<D, 64>(cp, stream);
   if (rc != GPP_OK) return rc;
   FinalizeParams fp;
   fp.part = part; fp.slots = tab.d_slots; fp.pair_start = tab.d_pair_start; fp.pair_ab = tab.d_pair_ab;

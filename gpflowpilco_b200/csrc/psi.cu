@@ -113,22 +113,30 @@ __global__ void __launch_bounds__(128) k_ekzxkxz(const double* __restrict__ pack
     __syncthreads();
     const int rows = min(RT, M1 - i0);
     if (j0 >= M2) continue;
-#pragma unroll 2
-    for (int ii = 0; ii < rows; ++ii) {
-      const double* rb = rowbuf + ii * RS;
-      double t0 = rb[D] + s[0], t1 = rb[D] + s[1];
+    // 2 rows x 2 columns in lock-step (4 independent FP64 chains per thread); rowbuf is zero-padded past M1
+#pragma unroll 1
+    for (int ii = 0; ii < rows; ii += 2) {
+      const double* rb0 = rowbuf + ii * RS;
+      const double* rb1 = rb0 + RS;
+      double t[4] = {rb0[D] + s[0], rb0[D] + s[1], rb1[D] + s[0], rb1[D] + s[1]};
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        t0 = fma(rb[d], g[0][d], t0);
-        t1 = fma(rb[d], g[1][d], t1);
+        t[0] = fma(rb0[d], g[0][d], t[0]);
+        t[1] = fma(rb0[d], g[1][d], t[1]);
+        t[2] = fma(rb1[d], g[0][d], t[2]);
+        t[3] = fma(rb1[d], g[1][d], t[3]);
       }
-      double q0 = fast_exp(t0), q1 = fast_exp(t1);
-      double* dst = outn + (size_t)(i0 + ii) * M2 + j0;
-      if (pair_ok) {
-        __stcs(reinterpret_cast<double2*>(dst), make_double2(q0, q1));   // streaming store: written once, never re-read
-      } else {
-        __stcs(dst, q0);
-        if (j0 + 1 < M2) __stcs(dst + 1, q1);
+      fast_exp_n<4>(t);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (ii + rr >= rows) break;
+        double* dst = outn + (size_t)(i0 + ii + rr) * M2 + j0;
+        if (pair_ok) {
+          __stcs(reinterpret_cast<double2*>(dst), make_double2(t[2 * rr], t[2 * rr + 1]));   // streaming: never re-read
+        } else {
+          __stcs(dst, t[2 * rr]);
+          if (j0 + 1 < M2) __stcs(dst + 1, t[2 * rr + 1]);
+        }
       }
     }
   }
