@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native GPflowPILCO hot path.
+
+Workload (BASELINE.json configs[1]): batched exact moment-matched GP prediction — N Gaussian input states per GPU
+pushed through E=4 independent exact SE-ARD GPs on 1000 training points (D=6), full 4x4 output covariance and
+input-output cross-covariance, FP64.  One "step" = one pass of the hot path over the N inputs of every rank;
+metric = Gaussian states moment-matched per second (MM rollout steps/s), whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--inputs N_per_gpu]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the line-by-line CPU restatement of the upstream
+algorithm (oracle/, triangular-solve form of gpflow_pilco/moment_matching/models.py:200-299) on the host cores,
+on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mm_rollout_steps_per_s"
+UNIT = "gaussian_states/s"
+M_TRAIN, D_IN, E_OUT = 1000, 6, 4
+FLOP_PER_ENTRY = 2 * D_IN + 26          # D FMAs + 2 adds + exp(=20) + 2 contraction FMAs
+ENTRIES_PER_INPUT = E_OUT * (E_OUT + 1) // 2 * M_TRAIN * M_TRAIN
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--inputs", type=int, default=8192, help="Gaussian inputs per GPU (weak scaling)")
+  ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  return ap.parse_args()
+
+
+def peaks():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    with open(path) as f:
+      return json.load(f), "measured (MEASURED_PEAKS.json)"
+  return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+  FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index: int):
+    self.gpu_index = gpu_index
+    self.lines = []
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                    "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._pump, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _pump(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in self.lines:
+      parts = [p.strip() for p in ln.split(",")]
+      if len(parts) < 9:
+        continue
+      try:
+        sm.append(float(parts[1]))
+        mx.append(float(parts[2]))
+      except ValueError:
+        continue
+      for name, val in zip(names, parts[5:9]):
+        if val.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------
+def build_workload(n_inputs: int, rank: int):
+  from gpflowpilco_b200 import synthetic
+  cfg = synthetic.config2_batched_mm_predict(N=n_inputs, M=M_TRAIN, D=D_IN, E=E_OUT, seed=0)
+  if rank:   # every rank shares the model (seed 0) but owns different inputs
+    rng = np.random.default_rng(1000 + rank)
+    cfg["mu"] = rng.random((n_inputs, D_IN))
+    cfg["cov"] = synthetic.generate_covariance(rng, D_IN, n_inputs, 0.1)
+  return cfg
+
+
+def oracle_model(cfg):
+  import torch
+  from oracle import gp_models as gm
+  from oracle import psi_stats as ps
+  ks = [ps.SEKernel(float(cfg["variance"][e]), torch.as_tensor(cfg["lengthscales"][e])) for e in range(E_OUT)]
+  X = torch.as_tensor(cfg["X"])
+  # exact GP as SVGP(q_mu = Y - c, q_sqrt = 0, whiten=False, Kuu jitter = noise variance)  (upstream models.py:44-111)
+  return gm.SVGPModel(ks, [X] * E_OUT, torch.as_tensor(cfg["Y"] - cfg["mean_const"]),
+                      torch.zeros(E_OUT, M_TRAIN, M_TRAIN, dtype=torch.float64), whiten=False,
+                      mean_const=torch.as_tensor(cfg["mean_const"]))
+
+
+def oracle_predict(model, cfg, idx, reference_form: bool):
+  import torch
+  import oracle.gp_models as gm
+  from oracle.moments import GaussianMoments
+  x = GaussianMoments(torch.as_tensor(cfg["mu"][idx]), torch.as_tensor(cfg["cov"][idx]), True)
+  old = gm.Kuu.__defaults__
+  gm.Kuu.__defaults__ = (float(cfg["noise_variance"][0]),)
+  try:
+    fn = gm.mm_svgp_mo if reference_form else gm.mm_sparse_reassociated
+    return fn(x, model)
+  finally:
+    gm.Kuu.__defaults__ = old
+
+
+def time_cpu(cfg, seconds: float, reference_form: bool, steps: int = 1):
+  """Times the oracle on a bounded sample; returns (states_per_s, sample_description, per_step_ms)."""
+  import torch
+  model = oracle_model(cfg)
+  t0 = time.perf_counter()
+  oracle_predict(model, cfg, slice(0, 1), reference_form)
+  t1 = time.perf_counter() - t0
+  # memory bound: the upstream form materialises eKuffu [n,4,1000,4,1000] (128 MB per input) plus ~6 temporaries of it
+  cap = 6 if reference_form else 48
+  n = int(max(1, min(cfg["mu"].shape[0], cap, seconds / max(t1, 1e-3) / max(steps, 1))))
+  times = []
+  for _ in range(steps):
+    t0 = time.perf_counter()
+    oracle_predict(model, cfg, slice(0, n), reference_form)
+    times.append(time.perf_counter() - t0)
+  best = min(times)
+  form = "upstream triangular-solve form" if reference_form else "O(M^2) re-associated form"
+  return n / best, f"{n} of the {cfg['mu'].shape[0]} inputs of config #2 per step, {form}, torch float64, {torch.get_num_threads()} threads", 1e3 * float(np.mean(times))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  import torch
+  cfg = build_workload(min(args.inputs, 256), 0)
+  total = args.steps + args.warmup
+  budget = 150.0
+  rate, sample, ms = time_cpu(cfg, budget / max(total, 1), reference_form=True, steps=total)
+  line = {
+      "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f64", "data": "synthetic",
+      "config": {"workload": "config#2 batched exact MM GP predict (M=1000, D=6, E=4, full 4x4 cov + cross)",
+                 "inputs_per_gpu": args.inputs},
+      "cpu_baseline": {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+      "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "note": "upstream needs tensorflow/gpflow (absent): timed is oracle/, its line-by-line CPU restatement",
+  }
+  print(json.dumps(line))
+
+
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  from gpflowpilco_b200 import _lib, models
+  from gpflowpilco_b200.moment_matching import GaussianMoments, moment_matching
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise RuntimeError("bench.py --impl b200 needs a CUDA device: the hot path has no CPU implementation")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  lib = _lib.load()
+  pk, peak_src = peaks()
+
+  cfg = build_workload(args.inputs, rank)
+  N = args.inputs
+  T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+  # the reference-facing objects: E independent exact GPs == multi-output model with shared inputs
+  kern = models.SeparateIndependent([models.SquaredExponential(cfg["variance"][e], T(cfg["lengthscales"][e])) for e in range(E_OUT)])
+  for k in kern.kernels:
+    k.variance = k.variance.to(dev)
+  model = models.SVGP(kern, models.SharedIndependentInducingVariables(models.InducingPoints(T(cfg["X"]))),
+                      q_mu=T(cfg["Y"] - cfg["mean_const"]), q_sqrt=torch.zeros(E_OUT, M_TRAIN, M_TRAIN, dtype=torch.float64, device=dev),
+                      whiten=False, mean_function=models.Constant(T(cfg["mean_const"])))
+  model.kuu_jitter = [float(v) for v in cfg["noise_variance"]]     # exact-GP noise on the diagonal (GPR semantics)
+  mu_d, cov_d = T(cfg["mu"]), T(cfg["cov"])
+  mu_h = torch.as_tensor(cfg["mu"]).pin_memory()
+  cov_h = torch.as_tensor(cfg["cov"]).pin_memory()
+  out_h = [torch.empty(N, E_OUT, dtype=torch.float64).pin_memory(), torch.empty(N, E_OUT, E_OUT, dtype=torch.float64).pin_memory(),
+           torch.empty(N, D_IN, E_OUT, dtype=torch.float64).pin_memory()]
+  flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+  def step_resident():
+    return moment_matching(GaussianMoments((mu_d, cov_d), True), model, check=False)
+
+  def step_e2e():
+    m = mu_h.to(dev, non_blocking=True)
+    S = cov_h.to(dev, non_blocking=True)
+    match = moment_matching(GaussianMoments((m, S), True), model, check=False)
+    out_h[0].copy_(match.y.mean(), non_blocking=True)
+    out_h[1].copy_(match.y.covariance(), non_blocking=True)
+    out_h[2].copy_(match.cross[0], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return match
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # FP64 pipe roofline denominator, measured in this run
+  sink = torch.empty(148 * 8 * 256, dtype=torch.float64, device=dev)
+  fp64_peak = 0.0
+  for _ in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(lib.gpp_microbench_fp64(148 * 8, 256, 20000, ctypes.c_void_p(sink.data_ptr()),
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    e1.record()
+    torch.cuda.synchronize()
+    fp64_peak = max(fp64_peak, 148 * 8 * 256 * 20000 * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+
+  for _ in range(args.warmup):
+    step_resident()
+  lib.gpp_profile_enable(1)
+  sampler = ClockSampler(local)
+  barrier()
+  sampler.start()
+  launches0 = lib.gpp_launch_count()
+  step_ms, kern_ms = [], []
+  for _ in range(args.steps):
+    flush.fill_(1)                         # L2 flush between timed iterations (outside the event pairs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step_resident()
+    e1.record()
+    e1.synchronize()
+    step_ms.append(e0.elapsed_time(e1))
+    ms = ctypes.c_float()
+    lib.gpp_profile_last_ms(ctypes.byref(ms))
+    kern_ms.append(ms.value)
+  launches = lib.gpp_launch_count() - launches0
+  barrier()
+  clocks = sampler.stop()
+  lib.gpp_profile_enable(0)
+  total_s = sum(step_ms) * 1e-3
+
+  # end to end: host buffers in, host buffers out, through the reference-facing API
+  for _ in range(2):
+    step_e2e()
+  barrier()
+  t0 = time.perf_counter()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(args.steps):
+    step_e2e()
+  e1.record()
+  e1.synchronize()
+  e2e_s = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0)
+
+  t = torch.tensor([total_s, e2e_s], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  total_s, e2e_s = float(t[0]), float(t[1])
+
+  if rank == 0:
+    kern_s = float(np.mean(kern_ms)) * 1e-3
+    achieved = N * ENTRIES_PER_INPUT * FLOP_PER_ENTRY / kern_s / 1e12
+    line = {
+        "metric": METRIC, "value": world * N * args.steps / total_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config#2 batched exact MM GP predict (M=1000, D=6, E=4, full 4x4 cov + cross)",
+                   "inputs_per_gpu": N, "l2": "flushed between timed steps (256 MB write)", "timing": "CUDA events per step, max over ranks"},
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                     "traffic": None, "kernel": "k_contract", "kernel_ms": 1e3 * kern_s,
+                     "kernel_share_of_step": kern_s / (total_s / args.steps),
+                     "algorithmic": f"{FLOP_PER_ENTRY} flop/entry x {ENTRIES_PER_INPUT} entries/input x {N} inputs",
+                     "peak_source": "in-run DFMA microbenchmark (gpp_microbench_fp64); MEASURED_PEAKS.json has no FP64 figure",
+                     "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": peak_src},
+        "e2e": {"value": world * N * args.steps / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": int(mu_h.numel() * 8 + cov_h.numel() * 8), "d2h_bytes_per_step": int(sum(o.numel() * 8 for o in out_h))},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+      small = {k: (v[:64] if k in ("mu", "cov") else v) for k, v in cfg.items()}
+      rate, sample, _ = time_cpu(small, args.cpu_baseline_seconds, reference_form=True)
+      rate2, sample2, _ = time_cpu(small, args.cpu_baseline_seconds / 2, reference_form=False)
+      import torch as _t
+      line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port", "sample": sample,
+                              "reassociated_form": {"value": rate2, "sample": sample2}}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -2,17 +2,19 @@
 //
 // Work item = (kernel pair (a,b), T x T tile of the M x M index space, chunk of inputs).  Persistent CTAs pull
 // items from an atomic counter.  A CTA keeps the tile of C_a (diagonal pairs) in shared memory for the whole
-// chunk and, per input n:
-//   stage   (3 thread groups in parallel, reading the (n,pair) coefficient pack that cp.async prefetched)
-//           group 0: g_i = R^T z1'_i           group 2: r_i = c0 + z1'^T P1 z1'
-//           group 1: z2'_j, s_j = z2'^T P2 z2'  group 3 / warp 0: reduces the lane partials of input n-1
-//   main    lane l of every warp owns rows {l, l+32, ..} (RPT = T/32 register tile), warp w owns CW = T/NW
-//           columns.  Per entry: 1 DADD + D DFMA + 16 FP64 (exp) + 1 DFMA.  The RPT row chains of a thread share
-//           their column operands, which makes ptxas interleave them (a dependent DFMA issues 8 cycles after its
-//           producer, the pipe accepts one warp instruction every 2 cycles: >= 4 independent chains per scheduler).
-//   reduce  each lane stores one partial; no shuffles on the compute warps.
-// Shared-memory layouts are chosen so that every warp access is either a broadcast or unit-stride (no bank conflicts):
-//   Ct[j][i] (i fastest), rowbuf[field][i] (structure of arrays), colbuf[j][field] (broadcast reads).
+// chunk.  Warps are specialised and hand data over through double-buffered shared memory with named barriers
+// (bar.arrive / bar.sync), so there is NO CTA-wide barrier per input and the warps drift apart: shared-memory
+// bursts of one warp hide behind the FP64 work of the others.
+//
+//   producer warps (NP)  one input ahead: read the (n, pair) coefficient pack from L2, compute
+//                        g_i = R^T z1'_i, r_i = c0 + z1'^T P1 z1'  (rows)  and  z2'_j, s_j = z2'^T P2 z2'  (columns)
+//                        into buffer b = k & 1; they also sum the lane partials of finished inputs (fixed order).
+//   consumer warps (NC)  lane l owns rows {l, l+32, ..} (RPT = T/32 register tile), warp w owns a slice of columns.
+//                        Per entry: 1 DADD + D DFMA + 16 FP64 (exp) + 1 DFMA.  The RPT row chains of a thread share
+//                        their column operands, which makes ptxas interleave them (a dependent DFMA issues 8 cycles
+//                        after its producer, the pipe accepts one warp instruction every 2 cycles).
+// Shared-memory layouts make every warp access a broadcast or unit-stride (no bank conflicts):
+//   Ct[j][i] (i fastest), rowbuf[b][field][i] (structure of arrays), colbuf[b][j][field] (broadcast reads).
 #pragma once
 
 namespace gpp {
@@ -33,39 +35,59 @@ struct ColLayout {
   static constexpr int STRIDE = (D + 2 + 1) & ~1;   // z2'[D], s_j, w_j  (even => 16-byte records)
 };
 
-template <int D, int T>
-struct ContractSmem {
-  using PP = PairPack<D>;
-  static constexpr int NT = 4 * T;
-  static constexpr int NW = NT / 32;
+template <int D, int T, int NP, int NC>
+struct ContractCfg {
+  static constexpr int NT = 32 * (NP + NC);
+  static constexpr int PT = 32 * NP;                            // producer threads
   static constexpr int CT = 0;                                  // [T][T]
-  static constexpr int COL = CT + T * T;                        // [T][STRIDE]
-  static constexpr int ROW = COL + T * ColLayout<D>::STRIDE;    // [D+2][T]
-  static constexpr int PACK = ROW + (D + 2) * T;                // [2][PP::SIZE]
-  static constexpr int RED = PACK + 2 * PP::SIZE;               // [2][NW][32]
-  static constexpr int TOTAL = RED + 2 * NW * 32;               // doubles
+  static constexpr int COL = CT + T * T;                        // [2][T][STRIDE]
+  static constexpr int ROW = COL + 2 * T * ColLayout<D>::STRIDE;   // [2][D+2][T]
+  static constexpr int RED = ROW + 2 * (D + 2) * T;             // [2][NC][32]
+  static constexpr int TOTAL = RED + 2 * NC * 32;               // doubles
 };
 
-template <int D, int T>
-__global__ void __launch_bounds__(4 * T) k_contract(ContractParams p) {
+// barrier ids are immediates (a register id would make ptxas reserve all 16 hardware barriers for the CTA)
+template <int ID>
+__device__ __forceinline__ void named_bar_sync_imm(int count) {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int ID>
+__device__ __forceinline__ void named_bar_arrive_imm(int count) {
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
+}
+template <int BASE>
+__device__ __forceinline__ void named_bar_sync(int b, int count) {
+  if (b) named_bar_sync_imm<BASE + 1>(count); else named_bar_sync_imm<BASE>(count);
+}
+template <int BASE>
+__device__ __forceinline__ void named_bar_arrive(int b, int count) {
+  if (b) named_bar_arrive_imm<BASE + 1>(count); else named_bar_arrive_imm<BASE>(count);
+}
+
+template <int D, int T, int NP, int NC>
+__global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   using PP = PairPack<D>;
-  using SM = ContractSmem<D, T>;
-  constexpr int NT = SM::NT, NW = SM::NW;
-  constexpr int RPT = T / 32;                // rows per thread
-  constexpr int CW = T / NW;                 // columns per warp
+  using CF = ContractCfg<D, T, NP, NC>;
+  constexpr int NT = CF::NT, PT = CF::PT;
+  constexpr int RPT = T / 32;                // rows per consumer thread
   constexpr int CS = ColLayout<D>::STRIDE;
-  static_assert(T % 32 == 0 && T % NW == 0, "tile must split into whole warps of rows and whole columns per warp");
+  constexpr int RBUF = (D + 2) * T, CBUF = T * CS, DBUF = NC * 32;
+  constexpr int BAR_FULL = 1, BAR_EMPTY = 3;  // named barriers 1,2 (full) and 3,4 (empty); 0 is __syncthreads
+  static_assert(T % 32 == 0, "rows of a tile are covered by 32 lanes x RPT");
 
   extern __shared__ __align__(16) double smem[];
-  double* Ct = smem + SM::CT;
-  double* colbuf = smem + SM::COL;
-  double* rowbuf = smem + SM::ROW;
-  double* packbuf = smem + SM::PACK;
-  double* red = smem + SM::RED;
+  double* Ct = smem + CF::CT;
+  double* colbuf = smem + CF::COL;
+  double* rowbuf = smem + CF::ROW;
+  double* red = smem + CF::RED;
   __shared__ int s_item;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int group = tid / T, st = tid % T;   // staging role and index within the tile
+  const bool producer = warp < NP;
+  const int cwarp = warp - NP;               // consumer warp index
+  // consumer column slice: T columns over NC warps, first (T % NC) warps take one more
+  const int cw = T / NC + ((cwarp >= 0 && cwarp < T % NC) ? 1 : 0);
+  const int c0 = cwarp * (T / NC) + min(max(cwarp, 0), T % NC);
   const int nitems = p.nslots * p.nchunks;
 
   for (;;) {
@@ -76,16 +98,10 @@ __global__ void __launch_bounds__(4 * T) k_contract(ContractParams p) {
     if (item >= nitems) break;
     const int slot_id = item / p.nchunks, chunk_id = item % p.nchunks;
     const gpp_slot sl = p.slots[slot_id];
-    const int n0 = chunk_id * p.chunk, n1 = min(p.N, n0 + p.chunk);
+    const int n0 = chunk_id * p.chunk;
+    const int K = min(p.N, n0 + p.chunk) - n0;
     const bool diag = (sl.a == sl.b);
 
-    // static operand of this thread's staging role: one inducing point (row of Z_a for groups 0/2, column of Z_b for 1)
-    const int latent = (group == 1) ? sl.b : sl.a;
-    const int glob = ((group == 1) ? sl.tj : sl.ti) * T + st;
-    double zs[D], wgt = 0.0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) zs[d] = (group < 3 && glob < p.M) ? p.Z[((size_t)latent * p.M + glob) * D + d] : 0.0;
-    if (!diag && group < 3 && glob < p.M) wgt = p.beta[(size_t)latent * p.M + glob];
     if (diag) {   // C is symmetric: read C[j][i] so that global reads and the later lane-wise smem reads are unit-stride
       const double* Ca = p.C + (size_t)sl.a * p.M * p.M;
       for (int idx = tid; idx < T * T; idx += NT) {
@@ -94,96 +110,131 @@ __global__ void __launch_bounds__(4 * T) k_contract(ContractParams p) {
         Ct[idx] = (jg < p.M && ig < p.M) ? Ca[(size_t)jg * p.M + ig] : 0.0;
       }
     }
-    {
-      const double* src = p.packs + ((size_t)n0 * p.npairs + sl.pair) * PP::SIZE;
-      for (int t = tid; t < PP::SIZE / 2; t += NT) cp_async16(packbuf + 2 * t, src + 2 * t);
-      cp_async_commit();
-    }
+    __syncthreads();
 
-    for (int n = n0; n <= n1; ++n) {         // one extra trip drains the reduction of the last input
-      const int buf = (n - n0) & 1;
-      cp_async_wait<0>();
-      __syncthreads();                       // pack(n) landed; colbuf/rowbuf free; red[buf^1] complete
-      if (group == 3) {
-        if (warp == 3 * T / 32 && n > n0) {  // reducer warp: fixed-order sum of the lane partials of input n-1
-          const double* rp = red + (buf ^ 1) * NW * 32 + lane;
-          double s = 0.0;
+    if (producer) {
+      // ---------------------------------------------------------------- producers
+      for (int k = 0; k < K + 2; ++k) {
+        const int b = k & 1;
+        if (k >= 2) {                        // consumers are done with input k-2 (buffer b): reduce its lane partials
+          named_bar_sync<BAR_EMPTY>(b, NT);
+          if (warp == 0) {
+            const double* rp = red + b * DBUF + lane;
+            double s = 0.0;
 #pragma unroll
-          for (int w = 0; w < NW; ++w) s += rp[w * 32];
-          s = warp_sum(s);
-          if (lane == 0) p.part[(size_t)(n - 1) * p.nslots + slot_id] = s;
-        }
-        if (n + 1 < n1) {                    // prefetch the next coefficient pack
-          const double* src = p.packs + ((size_t)(n + 1) * p.npairs + sl.pair) * PP::SIZE;
-          for (int t = tid - 3 * T; t < PP::SIZE / 2; t += T) cp_async16(packbuf + (buf ^ 1) * PP::SIZE + 2 * t, src + 2 * t);
-        }
-      }
-      cp_async_commit();
-      if (n == n1) break;
-      const double* pk = packbuf + buf * PP::SIZE;
-      if (group < 3) {
-        double zc[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) zc[d] = zs[d] - pk[PP::MU + d];
-        if (group == 0) {                    // g_i = R^T z1'_i
-#pragma unroll
-          for (int e = 0; e < D; ++e) {
-            double t = 0.0;
-#pragma unroll
-            for (int d = 0; d < D; ++d) t = fma(zc[d], pk[PP::R + d * D + e], t);
-            rowbuf[e * T + st] = t;
+            for (int w = 0; w < NC; ++w) s += rp[w * 32];
+            s = warp_sum(s);
+            if (lane == 0) p.part[(size_t)(n0 + k - 2) * p.nslots + slot_id] = s;
           }
-        } else if (group == 2) {             // r_i = c0 + z1'^T P1 z1', beta_i
-          rowbuf[D * T + st] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
-          rowbuf[(D + 1) * T + st] = wgt;
-        } else {                             // z2'_j, s_j = z2'^T P2 z2', beta_j
-          double* dst = colbuf + st * CS;
-#pragma unroll
-          for (int d = 0; d < D; ++d) dst[d] = zc[d];
-          dst[D] = packed_quad<D>(pk + PP::P2, zc);
-          dst[D + 1] = wgt;
         }
-      }
-      __syncthreads();
-
-      double g[RPT][D], r[RPT], acc[RPT];
+        if (k >= K) continue;
+        const double* pk = p.packs + ((size_t)(n0 + k) * p.npairs + sl.pair) * PP::SIZE;
+        double* rb = rowbuf + b * RBUF;
+        double* cb = colbuf + b * CBUF;
+        for (int st = tid; st < T; st += PT) {
+          // row st of the tile
+          {
+            const int ig = sl.ti * T + st;
+            double zc[D];
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) {
+            for (int d = 0; d < D; ++d)
+              zc[d] = (ig < p.M ? p.Z[((size_t)sl.a * p.M + ig) * D + d] : 0.0) - __ldg(pk + PP::MU + d);
 #pragma unroll
-        for (int d = 0; d < D; ++d) g[k][d] = rowbuf[d * T + lane + 32 * k];
-        r[k] = rowbuf[D * T + lane + 32 * k];
-        acc[k] = 0.0;
+            for (int e = 0; e < D; ++e) {
+              double t = 0.0;
+#pragma unroll
+              for (int d = 0; d < D; ++d) t = fma(zc[d], __ldg(pk + PP::R + d * D + e), t);
+              rb[e * T + st] = t;
+            }
+            double q = __ldg(pk + PP::C0);
+            {
+              int t = 0;
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                double row = 0.0;
+#pragma unroll
+                for (int e = d; e < D; ++e, ++t) row = fma(__ldg(pk + PP::P1 + t), zc[e], row);
+                q = fma(row, zc[d], q);
+              }
+            }
+            rb[D * T + st] = q;
+            rb[(D + 1) * T + st] = (!diag && ig < p.M) ? p.beta[(size_t)sl.a * p.M + ig] : 0.0;
+          }
+          // column st of the tile
+          {
+            const int jg = sl.tj * T + st;
+            double zc[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+              zc[d] = (jg < p.M ? p.Z[((size_t)sl.b * p.M + jg) * D + d] : 0.0) - __ldg(pk + PP::MU + d);
+            double q = 0.0;
+            {
+              int t = 0;
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                double row = 0.0;
+#pragma unroll
+                for (int e = d; e < D; ++e, ++t) row = fma(__ldg(pk + PP::P2 + t), zc[e], row);
+                q = fma(row, zc[d], q);
+              }
+            }
+            double* dst = cb + st * CS;
+#pragma unroll
+            for (int d = 0; d < D; ++d) dst[d] = zc[d];
+            dst[D] = q;
+            dst[D + 1] = (!diag && jg < p.M) ? p.beta[(size_t)sl.b * p.M + jg] : 0.0;
+          }
+        }
+        __threadfence_block();
+        named_bar_arrive<BAR_FULL>(b, NT);
       }
-      const double* cb = colbuf + warp * CW * CS;
-      const double* ct = Ct + (warp * CW) * T + lane;
+    } else {
+      // ---------------------------------------------------------------- consumers
+      const double* ct = Ct + c0 * T + lane;
+      for (int k = 0; k < K; ++k) {
+        const int b = k & 1;
+        named_bar_sync<BAR_FULL>(b, NT);
+        const double* rb = rowbuf + b * RBUF + lane;
+        double g[RPT][D], r[RPT], acc[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) g[q][d] = rb[d * T + 32 * q];
+          r[q] = rb[D * T + 32 * q];
+          acc[q] = 0.0;
+        }
+        const double* cb = colbuf + b * CBUF + c0 * CS;
 #pragma unroll 2
-      for (int jj = 0; jj < CW; ++jj) {
-        const double* c = cb + jj * CS;
-        double zc[D];
+        for (int jj = 0; jj < cw; ++jj) {
+          const double* c = cb + jj * CS;
+          double zc[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) zc[d] = c[d];
-        const double sj = c[D];
-        double t[RPT];
+          for (int d = 0; d < D; ++d) zc[d] = c[d];
+          const double sj = c[D];
+          double t[RPT];
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) t[k] = r[k] + sj;
+          for (int q = 0; q < RPT; ++q) t[q] = r[q] + sj;
 #pragma unroll
-        for (int d = 0; d < D; ++d)
+          for (int d = 0; d < D; ++d)
 #pragma unroll
-          for (int k = 0; k < RPT; ++k) t[k] = fma(g[k][d], zc[d], t[k]);
-        fast_exp_n<RPT>(t);
-        if (diag) {
+            for (int q = 0; q < RPT; ++q) t[q] = fma(g[q][d], zc[d], t[q]);
+          fast_exp_n<RPT>(t);
+          if (diag) {
 #pragma unroll
-          for (int k = 0; k < RPT; ++k) acc[k] = fma(t[k], ct[jj * T + 32 * k], acc[k]);
-        } else {
-          const double wj = c[D + 1];
+            for (int q = 0; q < RPT; ++q) acc[q] = fma(t[q], ct[jj * T + 32 * q], acc[q]);
+          } else {
+            const double wj = c[D + 1];
 #pragma unroll
-          for (int k = 0; k < RPT; ++k) acc[k] = fma(t[k], wj, acc[k]);
+            for (int q = 0; q < RPT; ++q) acc[q] = fma(t[q], wj, acc[q]);
+          }
         }
-      }
-      double total = 0.0;
+        double total = 0.0;
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) total += diag ? acc[k] : acc[k] * rowbuf[(D + 1) * T + lane + 32 * k];
-      red[buf * NW * 32 + warp * 32 + lane] = total;
+        for (int q = 0; q < RPT; ++q) total += diag ? acc[q] : acc[q] * rb[(D + 1) * T + 32 * q];
+        red[b * DBUF + cwarp * 32 + lane] = total;
+        __threadfence_block();
+        named_bar_arrive<BAR_EMPTY>(b, NT);
+      }
     }
   }
 }

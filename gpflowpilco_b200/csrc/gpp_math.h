@@ -79,52 +79,74 @@ GPP_HD double fast_exp(double x) {
   return ((uint32_t)hi_int(x) > 0xC0874000u) ? 0.0 : res;
 }
 
-// K independent exps evaluated in lock-step (in place).  The FP64 pipe issues one warp instruction every 2 cycles and
-// a dependent DFMA has to wait for the previous result, so a single Horner chain leaves the pipe mostly idle;
-// ptxas does not interleave separately-unrolled chains by itself (checked in SASS), hence the explicit form.
+// K independent exps evaluated in lock-step (in place).
+//  * A dependent DFMA issues 8 cycles after its producer while the FP64 pipe accepts a warp instruction every 2 (3 when
+//    all three operands are distinct registers), so independent chains must be interleaved; ptxas only does that when
+//    the chains share operands or the source is written this way (checked in SASS).
+//  * The polynomial is split into even and odd halves, p(r) = E(r^2) + r O(r^2): two depth-5 Horner chains per value.
+//  * Coefficients live in the constant bank on the device (DFMA takes a c[bank][offset] operand directly; as literals
+//    ptxas re-materialises them into uniform registers inside the loop, ~13 extra issue slots per evaluation).
+//  * Valid for x <= 709 (kernel expectations are bounded by the product of the kernel variances, so there is no
+//    overflow path); x < -744 returns exactly 0.  The integer tail (clamp, exponent insert, select) is free: it
+//    issues in the shadow of the FP64 pipe (measured: removing it does not change the loop time).
+#if defined(__CUDA_ARCH__)
+#define GPP_EXP_TABLE static __constant__ double
+#else
+#define GPP_EXP_TABLE static const double
+#endif
+GPP_EXP_TABLE kExpC[16] = {
+    1.4426950408889634074,          // 0  log2(e)
+    -6.93147180369123816490e-01,    // 1  -ln2 hi (fdlibm split)
+    -1.90821492927058770002e-10,    // 2  -ln2 lo
+    0x1.0000000000001p-1,           // 3  c2
+    0x1.5555555555556p-3,           // 4  c3
+    0x1.5555555553d63p-5,           // 5  c4
+    0x1.11111111109b3p-7,           // 6  c5
+    0x1.6c16c1788bd90p-10,          // 7  c6
+    0x1.a01a01a7c41d5p-13,          // 8  c7
+    0x1.a019b90d2ae7ap-16,          // 9  c8
+    0x1.71de0dae63bb3p-19,          // 10 c9
+    0x1.289185613a3d6p-22,          // 11 c10
+    0x1.af38a9b0ec855p-26,          // 12 c11
+    0.0, 0.0, 0.0};
+
 template <int K>
 GPP_HD void fast_exp_n(double (&x)[K]) {
-  const double LOG2E = 1.4426950408889634074;
-  const double MAGIC = 6755399441055744.0;
-  const double LN2_HI = 6.93147180369123816490e-01;
-  const double LN2_LO = 1.90821492927058770002e-10;
-  double t[K], r[K], p[K];
+  const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: the low word of t holds rint(x * log2 e)
+  double t[K], r[K], p[K], s2[K], q[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) t[k] = fma_(x[k], LOG2E, MAGIC);
+  for (int k = 0; k < K; ++k) t[k] = fma_(x[k], kExpC[0], MAGIC);
 #pragma unroll
   for (int k = 0; k < K; ++k) r[k] = t[k] - MAGIC;
 #pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma_(r[k], -LN2_HI, x[k]);
+  for (int k = 0; k < K; ++k) p[k] = fma_(r[k], kExpC[1], x[k]);
 #pragma unroll
-  for (int k = 0; k < K; ++k) r[k] = fma_(r[k], -LN2_LO, p[k]);
-  // even/odd split of the degree-11 polynomial: p(r) = E(r^2) + r O(r^2) -> two independent Horner chains of depth 5
-  // per value (12 FP64 ops instead of 11, but half the dependent latency).
-  double s2[K], q[K];
+  for (int k = 0; k < K; ++k) r[k] = fma_(r[k], kExpC[2], p[k]);
 #pragma unroll
   for (int k = 0; k < K; ++k) s2[k] = r[k] * r[k];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    p[k] = fma_(0x1.289185613a3d6p-22, s2[k], 0x1.a019b90d2ae7ap-16);   // even: c10, c8
-    q[k] = fma_(0x1.af38a9b0ec855p-26, s2[k], 0x1.71de0dae63bb3p-19);   // odd : c11, c9
+    p[k] = fma_(kExpC[11], s2[k], kExpC[9]);    // even: c10, c8
+    q[k] = fma_(kExpC[12], s2[k], kExpC[10]);   // odd : c11, c9
   }
-#define GPP_EXP_STEP(ce, co)                                   \
-  _Pragma("unroll") for (int k = 0; k < K; ++k) {              \
-    p[k] = fma_(p[k], s2[k], ce);                              \
-    q[k] = fma_(q[k], s2[k], co);                              \
+#define GPP_EXP_STEP(ce, co)                      \
+  _Pragma("unroll") for (int k = 0; k < K; ++k) { \
+    p[k] = fma_(p[k], s2[k], ce);                 \
+    q[k] = fma_(q[k], s2[k], co);                 \
   }
-  GPP_EXP_STEP(0x1.6c16c1788bd90p-10, 0x1.a01a01a7c41d5p-13)   // c6, c7
-  GPP_EXP_STEP(0x1.5555555553d63p-5, 0x1.11111111109b3p-7)     // c4, c5
-  GPP_EXP_STEP(0x1.0000000000001p-1, 0x1.5555555555556p-3)     // c2, c3
-  GPP_EXP_STEP(1.0, 1.0)                                       // c0, c1
+  GPP_EXP_STEP(kExpC[7], kExpC[8])   // c6, c7
+  GPP_EXP_STEP(kExpC[5], kExpC[6])   // c4, c5
+  GPP_EXP_STEP(kExpC[3], kExpC[4])   // c2, c3
+  GPP_EXP_STEP(1.0, 1.0)             // c0, c1
 #undef GPP_EXP_STEP
 #pragma unroll
   for (int k = 0; k < K; ++k) p[k] = fma_(q[k], r[k], p[k]);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     int32_t e = lo_int(t[k]);
-    int32_t ec = e < -1021 ? -1021 : (e > 1023 ? 1023 : e);
-    double res = make_double(hi_int(p[k]) + (ec << 20), lo_int(p[k]));
-    x[k] = ((uint32_t)hi_int(x[k]) > 0xC0874000u) ? 0.0 : res;
+    e = e < -1021 ? -1021 : e;
+    double res = make_double(hi_int(p[k]) + (e << 20), lo_int(p[k]));
+    x[k] = ((uint32_t)hi_int(x[k]) > 0xC0874000u) ? 0.0 : res;   // x < -744 (incl. -inf, huge negatives): exactly 0
   }
 }
 

@@ -258,21 +258,21 @@ static Plan make_plan(const gpp_gp_model* m, int N, int full_output_cov) {
   return pl;
 }
 
-template <int D, int T>
+template <int D, int T, int NP, int NC>
 static int launch_contract(const ContractParams& cp, cudaStream_t stream) {
-  constexpr int NT = ContractSmem<D, T>::NT;
-  size_t smem = sizeof(double) * ContractSmem<D, T>::TOTAL;
+  constexpr int NT = ContractCfg<D, T, NP, NC>::NT;
+  size_t smem = sizeof(double) * ContractCfg<D, T, NP, NC>::TOTAL;
   static bool configured = false;
   if (!configured) {
-    GPP_CUDA_OK(cudaFuncSetAttribute(k_contract<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPP_CUDA_OK(cudaFuncSetAttribute(k_contract<D, T, NP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int per_sm = 1;
-  GPP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<D, T>, NT, smem));
+  GPP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<D, T, NP, NC>, NT, smem));
   per_sm = std::max(per_sm, 1);
   int grid = std::min(num_sms() * per_sm, cp.nslots * cp.nchunks);
   profile_begin(stream);
-  k_contract<D, T><<<grid, NT, smem, stream>>>(cp);
+  k_contract<D, T, NP, NC><<<grid, NT, smem, stream>>>(cp);
   profile_end(stream);
   count_launch();
   return GPP_OK;
@@ -298,7 +298,7 @@ static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S,
   cp.Z = m->Z; cp.beta = m->beta; cp.C = m->C; cp.packs = packs; cp.part = part; cp.slots = tab.d_slots;
   cp.counter = counter; cp.N = N; cp.M = m->M; cp.L = m->L; cp.npairs = tab.npairs; cp.nslots = tab.nslots;
   cp.nchunks = pl.nchunks; cp.chunk = pl.chunk;
-  int rc = pl.tile_idx ? launch_contract<D, 128>(cp, stream) : launch_contract<D, 64>(cp, stream);
+  int rc = pl.tile_idx ? launch_contract<D, 128, 4, 12>(cp, stream) : launch_contract<D, 64, 2, 8>(cp, stream);
   if (rc != GPP_OK) return rc;
   FinalizeParams fp;
   fp.part = part; fp.slots = tab.d_slots; fp.pair_start = tab.d_pair_start; fp.pair_ab = tab.d_pair_ab;

@@ -143,6 +143,7 @@ class SVGP(_HandleCache):
     self.mean_function = Zero() if mean_function is None else mean_function
     self.likelihood = likelihood
     self.num_latent_gps = L if num_latent_gps is None else num_latent_gps
+    self.kuu_jitter = None      # None -> gpflow default_jitter (1e-6); set per latent to model exact-GP noise on the diagonal
 
   # unpacking as upstream utils/kernel_expectation.py:41-69
   def latent_kernels(self) -> List[SquaredExponential]:

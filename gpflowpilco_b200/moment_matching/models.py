@@ -44,7 +44,8 @@ def svgp_handle(model: SVGP, model_uncertainty: bool) -> ops.GPModelHandle:
     P = len(ks) if W is None else W.shape[0]
     return ops.GPModelHandle(torch.stack(Zsel), torch.stack([k.ell(D) for k in ks]), torch.stack([k.variance.reshape(()) for k in ks]),
                              model.q_mu, model.q_sqrt, whiten=model.whiten, mean_const=_mean_const(model, P, dev), W=W,
-                             kuu_jitter=DEFAULT_JITTER, model_uncertainty=model_uncertainty)
+                             kuu_jitter=DEFAULT_JITTER if getattr(model, 'kuu_jitter', None) is None else model.kuu_jitter,
+                             model_uncertainty=model_uncertainty)
   return model.cached_handle(("svgp", bool(model_uncertainty)), build)
 
 
@@ -62,14 +63,14 @@ def gpr_handle(model: GPR, model_uncertainty: bool) -> ops.GPModelHandle:
   return model.cached_handle(("gpr", bool(model_uncertainty)), build)
 
 
-def _predict(x: GaussianMoments, handle: ops.GPModelHandle, active_dims, full_output_cov, jitter) -> GaussianMatch:
+def _predict(x: GaussianMoments, handle: ops.GPModelHandle, active_dims, full_output_cov, jitter, check=True) -> GaussianMatch:
   m, S = x.mean(), x.covariance(dense=True)
   if active_dims is not None:
     idx = list(active_dims)
     ms, Ss = m[..., idx], S[..., idx, :][..., :, idx]
   else:
     ms, Ss = m, S
-  f1, Sff, cross = handle.predict(ms, Ss, full_output_cov=full_output_cov, jitter=jitter)
+  f1, Sff, cross = handle.predict(ms, Ss, full_output_cov=full_output_cov, jitter=jitter, check=check)
   if active_dims is not None:
     # upstream returns the cross term w.r.t. the sliced inputs as well (models.py:264-277 slices x per kernel)
     pass
@@ -78,16 +79,17 @@ def _predict(x: GaussianMoments, handle: ops.GPModelHandle, active_dims, full_ou
 
 @dispatcher.register(GaussianMoments, SVGP)
 def _mm_gauss_svgp(x: GaussianMoments, model: SVGP, full_output_cov: bool = True, model_uncertainty: bool = True,
-                   jitter: float = 0.0):
+                   jitter: float = 0.0, check: bool = True):
+  """`check=False` skips the synchronising read of the not-positive-definite flag (for timed loops)."""
   h = svgp_handle(model, model_uncertainty)
-  return _predict(x, h, _active_dims(model.latent_kernels()), full_output_cov, jitter)
+  return _predict(x, h, _active_dims(model.latent_kernels()), full_output_cov, jitter, check)
 
 
 @dispatcher.register(GaussianMoments, GPR)
 def _mm_gauss_gpr(x: GaussianMoments, model: GPR, full_output_cov: bool = True, model_uncertainty: bool = True,
-                  jitter: float = 0.0):
+                  jitter: float = 0.0, check: bool = True):
   h = gpr_handle(model, model_uncertainty)
-  return _predict(x, h, model.kernel.active_dims, full_output_cov, jitter)
+  return _predict(x, h, model.kernel.active_dims, full_output_cov, jitter, check)
 
 
 @dispatcher.register(GaussianMoments, KernelRegressor)
