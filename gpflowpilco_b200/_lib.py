@@ -24,6 +24,10 @@ SIGNATURES = {
                                     POINTER(c_double), c_int, _P]),
     "gpp_gp_model_destroy": (c_int, [_P]),
     "gpp_gp_model_weights": (c_int, [_P, _P, _P, _P]),
+    "gpp_policy_prepare": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_double, _P, _P, _P]),
+    "gpp_rollout_mm_workspace_bytes": (c_size_t, [_P, c_int, c_int]),
+    "gpp_rollout_mm_fwd": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_double, c_double,
+                                   _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "gpp_profile_enable": (c_int, [c_int]),
     "gpp_profile_last_ms": (c_int, [POINTER(ctypes.c_float)]),
     "gpp_microbench_fp64": (c_int, [c_int, c_int, c_int, _P, _P]),

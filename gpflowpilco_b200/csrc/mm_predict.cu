@@ -345,3 +345,13 @@ int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m, const doub
 }
 
 }  // extern "C"
+
+namespace gpp {
+// internal alias used by the rollout (same checks, typed stream)
+int mm_predict_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
+                       double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
+                       int* info, cudaStream_t stream) {
+  return gpp_mm_gp_predict_fwd(model, m, S, N, f1, Sff, cross, full_output_cov, jitter, workspace, workspace_bytes, info,
+                               (void*)stream);
+}
+}  // namespace gpp

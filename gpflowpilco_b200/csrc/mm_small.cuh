@@ -1,0 +1,220 @@
+// Small-dimension moment-matching rules evaluated by one thread per Gaussian state (dims <= GPP_SMALL_MAX):
+// the glue between the heavy GP predict kernels inside a rollout step.  Generic in a scalar type S so that the
+// same code runs on doubles (forward) and on forward-mode dual numbers (backward, dual.cuh).
+//
+//   sincos / encoder rule   upstream gpflow_pilco/moment_matching/maths.py:143-176, moment_matching/components.py:19-57
+//   NormalCDF rule (1-D)    upstream gpflow_pilco/moment_matching/bijectors.py:37-69  (Owen's T by 32-pt Gauss-Legendre)
+//   Shift / Scale           upstream gpflow_pilco/moment_matching/maths.py:47-78
+//   GaussianObjective       upstream gpflow_pilco/components.py:30-37
+//   Euler moment update     upstream gpflow_pilco/dynamics/solvers.py:121-129
+#pragma once
+#include "common.cuh"
+
+#define GPP_SMALL_MAX 8
+
+namespace gpp {
+
+struct EncoderSpec {
+  int Dx;                 // state dimension
+  int na;                 // number of sincos-encoded (active) dims
+  int active[4];          // their indices
+  __host__ __device__ int De() const { return Dx + na; }
+  __host__ __device__ int nb() const { return Dx - na; }
+  __host__ __device__ bool is_active(int i) const {
+    for (int k = 0; k < na; ++k) if (active[k] == i) return true;
+    return false;
+  }
+  // j-th inactive dim in increasing order (upstream components.py:58-67 builds tuple(set(...)), i.e. sorted)
+  __host__ __device__ int inactive(int j) const {
+    int c = 0;
+    for (int i = 0; i < Dx; ++i) if (!is_active(i)) { if (c == j) return i; ++c; }
+    return -1;
+  }
+};
+
+// 32-point Gauss-Legendre on [-1,1], positive half (nodes symmetric)
+__device__ const double kGL32_X[16] = {0.048307665687738324, 0.14447196158279649, 0.23928736225213706, 0.33186860228212767,
+                                       0.42135127613063533, 0.50689990893222936, 0.5877157572407623, 0.66304426693021523,
+                                       0.73218211874028971, 0.79448379596794239, 0.84936761373256997, 0.89632115576605209,
+                                       0.93490607593773967, 0.96476225558750639, 0.98561151154526838, 0.99726386184948157};
+__device__ const double kGL32_W[16] = {0.096540088514727659, 0.095638720079274708, 0.093844399080804511, 0.09117387869576378,
+                                       0.087652093004403783, 0.083311924226946707, 0.078193895787070228, 0.072345794108848338,
+                                       0.065822222776361683, 0.058684093478535565, 0.050998059262376091, 0.042835898022226836,
+                                       0.034273862913021765, 0.025392065309262024, 0.016274394730905743, 0.0070186100094705058};
+
+// scalar helpers overloaded for double (dual.cuh adds the dual-number overloads)
+__device__ __forceinline__ double s_exp(double x) { return exp(x); }
+__device__ __forceinline__ double s_sin(double x) { return sin(x); }
+__device__ __forceinline__ double s_cos(double x) { return cos(x); }
+__device__ __forceinline__ double s_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double s_erfc(double x) { return erfc(x); }
+__device__ __forceinline__ double s_value(double x) { return x; }
+
+// Owen's T(h, a), 0 < a <= 1:  (1/2pi) int_0^a exp(-h^2 (1+x^2)/2) / (1+x^2) dx   (abs. error < 1e-16 for |h| <= 12)
+template <typename S>
+__device__ S owens_t(S h, S a) {
+  S acc = S(0.0);
+  S half = a * 0.5;
+  S mh2 = h * h * (-0.5);
+  for (int k = 0; k < 16; ++k) {
+#pragma unroll
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+      S x = half * (1.0 + sgn * kGL32_X[k]);
+      S d = x * x + 1.0;
+      acc = acc + s_exp(mh2 * d) / d * kGL32_W[k];
+    }
+  }
+  return acc * half * 0.15915494309189535;   // 1/(2 pi)
+}
+
+template <typename S>
+__device__ S ndtr(S x) { return s_erfc(x * (-0.70710678118654752440)) * 0.5; }
+
+// ---- encoder: e = [sin(a), cos(a), b]; returns mean me[De], covariance See[De][De], Cxe = Cov(x, e) [Dx][De] -------------
+template <typename S>
+__device__ void mm_encoder(const EncoderSpec& es, const S* m, const S* Sx /*[Dx][Dx]*/, S* me, S* See, S* Cxe) {
+  const int Dx = es.Dx, na = es.na, De = es.De(), nb = es.nb();
+  S s1[4], c1[4];
+  for (int k = 0; k < na; ++k) {
+    int i = es.active[k];
+    S ev = s_exp(Sx[i * Dx + i] * (-0.5));
+    s1[k] = ev * s_sin(m[i]);
+    c1[k] = ev * s_cos(m[i]);
+    me[k] = s1[k];
+    me[na + k] = c1[k];
+  }
+  for (int j = 0; j < nb; ++j) me[2 * na + j] = m[es.inactive(j)];
+  // covariance of [sin, cos] block: uncentred moments (maths.py:147-170) minus outer product of the means
+  for (int k = 0; k < na; ++k)
+    for (int l = 0; l < na; ++l) {
+      int i = es.active[k], j = es.active[l];
+      S vsum = Sx[i * Dx + i] + Sx[j * Dx + j];
+      S ssum = Sx[i * Dx + j] + Sx[j * Dx + i];
+      S A = s_exp((vsum + ssum) * (-0.5)), B = s_exp((vsum - ssum) * (-0.5));
+      S ca = A * s_cos(m[i] + m[j]), cs = B * s_cos(m[i] - m[j]);
+      S sx_cx = s_sin(m[i]) * s_cos(m[j]), cx_sx = s_cos(m[i]) * s_sin(m[j]);
+      S ss = (cs - ca) * 0.5, cc = (cs + ca) * 0.5;
+      S sc = (sx_cx * (B + A) - cx_sx * (B - A)) * 0.5;      // E[sin x_k cos x_l]
+      See[k * De + l] = ss - s1[k] * s1[l];
+      See[(na + k) * De + na + l] = cc - c1[k] * c1[l];
+      See[k * De + na + l] = sc - s1[k] * c1[l];
+      See[(na + l) * De + k] = sc - s1[k] * c1[l];
+    }
+  // Cov(x, y) = Sxa diag-pre-inverted cross (maths.py:173: [diag(c1), diag(-s1)])
+  for (int i = 0; i < Dx; ++i) {
+    for (int k = 0; k < na; ++k) {
+      S sxa = Sx[i * Dx + es.active[k]];
+      Cxe[i * De + k] = sxa * c1[k];
+      Cxe[i * De + na + k] = sxa * s1[k] * (-1.0);
+    }
+    for (int j = 0; j < nb; ++j) Cxe[i * De + 2 * na + j] = Sx[i * Dx + es.inactive(j)];
+  }
+  // blocks involving the inactive dims (components.py:44-52)
+  for (int j = 0; j < nb; ++j) {
+    int bj = es.inactive(j);
+    for (int k = 0; k < 2 * na; ++k) {
+      See[(2 * na + j) * De + k] = Cxe[bj * De + k];
+      See[k * De + 2 * na + j] = Cxe[bj * De + k];
+    }
+    for (int l = 0; l < nb; ++l) See[(2 * na + j) * De + 2 * na + l] = Sx[bj * Dx + es.inactive(l)];
+  }
+}
+
+// ---- squashing link  u = scale * (Phi(f) + shift)  applied to a 1-D Gaussian f ~ N(mf, vf) -----------------------------------
+// returns mean, variance of u and d = Cov(f,f)^-1 Cov(f,u)  (chain of bijectors.py:37-69, maths.py:47-78)
+template <typename S>
+__device__ void mm_squash_1d(S mf, S vf, double scale, double shift, S& mu, S& vu, S& gain) {
+  S vw = vf + 1.0;
+  S isq = S(1.0) / s_sqrt(vw);
+  S h = isq * mf;
+  S y1 = ndtr(h);
+  S y2 = y1 - owens_t(h, S(1.0) / s_sqrt(vf * 2.0 + 1.0)) * 2.0;       // E[Phi^2]   (bijectors.py:57-58)
+  S phi = s_exp(h * h * (-0.5)) * 0.39894228040143267794;
+  mu = (y1 + shift) * scale;
+  vu = (y2 - y1 * y1) * (scale * scale);
+  gain = isq * phi * scale;
+}
+
+// ---- general small linear algebra (runtime n <= GPP_SMALL_MAX) ----------------------------------------------------------------
+// LU with partial pivoting (pivot chosen on values); A overwritten; returns det.  inv may be null.
+template <typename S>
+__device__ S lu_inverse(int n, S* A, S* inv) {
+  int perm[GPP_SMALL_MAX];
+  S det = S(1.0);
+  for (int i = 0; i < n; ++i) perm[i] = i;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    double best = fabs(s_value(A[c * n + c]));
+    for (int r = c + 1; r < n; ++r) {
+      double v = fabs(s_value(A[r * n + c]));
+      if (v > best) { best = v; piv = r; }
+    }
+    if (piv != c) {
+      for (int k = 0; k < n; ++k) { S t = A[c * n + k]; A[c * n + k] = A[piv * n + k]; A[piv * n + k] = t; }
+      int t = perm[c]; perm[c] = perm[piv]; perm[piv] = t;
+      det = det * (-1.0);
+    }
+    det = det * A[c * n + c];
+    S ip = S(1.0) / A[c * n + c];
+    for (int r = c + 1; r < n; ++r) {
+      A[r * n + c] = A[r * n + c] * ip;
+      for (int k = c + 1; k < n; ++k) A[r * n + k] = A[r * n + k] - A[r * n + c] * A[c * n + k];
+    }
+  }
+  if (inv) {
+    for (int col = 0; col < n; ++col) {
+      S y[GPP_SMALL_MAX];
+      for (int i = 0; i < n; ++i) {
+        S v = S(perm[i] == col ? 1.0 : 0.0);
+        for (int k = 0; k < i; ++k) v = v - A[i * n + k] * y[k];
+        y[i] = v;
+      }
+      for (int i = n - 1; i >= 0; --i) {
+        S v = y[i];
+        for (int k = i + 1; k < n; ++k) v = v - A[i * n + k] * inv[k * n + col];
+        inv[i * n + col] = v / A[i * n + i];
+      }
+    }
+  }
+  return det;
+}
+
+// ---- expected saturating cost  E[-exp(-1/2 (e-t)^T W (e-t))]  for e ~ N(me, See)   (components.py:30-37) ------------------------
+template <typename S>
+__device__ S expected_cost(int n, const S* me, const S* See, const double* target, const double* W) {
+  S IpSW[GPP_SMALL_MAX * GPP_SMALL_MAX], inv[GPP_SMALL_MAX * GPP_SMALL_MAX], err[GPP_SMALL_MAX];
+  for (int i = 0; i < n; ++i) {
+    err[i] = me[i] - target[i];
+    for (int j = 0; j < n; ++j) {
+      S v = S(i == j ? 1.0 : 0.0);
+      for (int k = 0; k < n; ++k) v = v + See[i * n + k] * W[k * n + j];
+      IpSW[i * n + j] = v;
+    }
+  }
+  S det = lu_inverse<S>(n, IpSW, inv);
+  // dist2 = err^T W inv(I + S W) err
+  S d2 = S(0.0);
+  for (int i = 0; i < n; ++i) {
+    S row = S(0.0);
+    for (int j = 0; j < n; ++j) {
+      S wij = S(0.0);
+      for (int k = 0; k < n; ++k) wij = wij + inv[k * n + j] * W[i * n + k];
+      row = row + wij * err[j];
+    }
+    d2 = d2 + row * err[i];
+  }
+  return s_exp(d2 * (-0.5)) / s_sqrt(det) * (-1.0);
+}
+
+// sample-path cost  -exp(-1/2 (e-t)^T W (e-t))   (components.py:39-41)
+__device__ __forceinline__ double sample_cost(int n, const double* e, const double* target, const double* W) {
+  double d2 = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double row = 0.0;
+    for (int j = 0; j < n; ++j) row = fma(W[i * n + j], e[j] - target[j], row);
+    d2 = fma(row, e[i] - target[i], d2);
+  }
+  return -exp(-0.5 * d2);
+}
+
+}  // namespace gpp

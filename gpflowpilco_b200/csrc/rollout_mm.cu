@@ -1,0 +1,415 @@
+// Moment-matched rollout: H sequential steps of  encoder -> RBF policy -> squash -> joint (e,u) -> GP dynamics ->
+// cross-covariance re-assembly -> Euler moment update -> expected cost, for N independent Gaussian initial states
+// (and R = 1 or N policy parameter sets), entirely on the device.
+//
+// Replaces, per step, upstream gpflow_pilco/dynamics/forward_sde.py:95-137 (+ the rules it dispatches to),
+// gpflow_pilco/dynamics/solvers.py:110-135 and the loss callback gpflow_pilco/loops/pilco.py:199-205; the H-loop
+// is upstream's tf.foldl (solvers.py:84-105).  Launch structure per step (all on the caller's stream, capturable in
+// a CUDA graph — no allocation, no synchronisation):
+//   k_step_pre   one CTA per rollout: encoder rule, policy moment matching (Psi1/Psi2 of the small policy GP done by the
+//                CTA's threads), squashing link, joint moments of d = (e,u), and Sxd = Cov(x, d) rows (forward_sde.py:105-124)
+//   GP predict   the fused kernels of mm_predict.cu on the N joint states
+//   k_step_post  one thread per rollout: Sxf = Sxd cross, Euler update (solvers.py:128-129), encoder rule on the new state,
+//                expected cost (components.py:30-37), loss accumulation.
+#include "mm_small.cuh"
+#include "model.cuh"
+
+namespace gpp {
+
+int mm_predict_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
+                       double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
+                       int* info, cudaStream_t stream);   // mm_predict.cu
+
+// ---------------------------------------------------------------------------------------------------------
+// policy weights: beta_r = Kuu_r^-1 m_r  for R small kernel regressors (one CTA each; Cholesky in shared memory)
+//   whitened: beta = Luu^-T q_mu     else: beta = Kuu^-1 q_mu        (upstream moment_matching/models.py:228-235)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_policy_prepare(int Mp, int Dp, const double* __restrict__ Z, const double* __restrict__ ell,
+                                                        const double* __restrict__ var, const double* __restrict__ q_mu,
+                                                        int whiten, double jitter, double* __restrict__ beta, int* info) {
+  extern __shared__ double sm[];
+  double* K = sm;            // [Mp][Mp+1]
+  double* v = K + Mp * (Mp + 1);
+  const int r = blockIdx.x, tid = threadIdx.x, ld = Mp + 1;
+  const double* Zr = Z + (size_t)r * Mp * Dp;
+  const double* er = ell + (size_t)r * Dp;
+  for (int idx = tid; idx < Mp * Mp; idx += blockDim.x) {
+    int i = idx / Mp, j = idx % Mp;
+    double acc = 0.0;
+    for (int d = 0; d < Dp; ++d) {
+      double t = (Zr[i * Dp + d] - Zr[j * Dp + d]) / er[d];
+      acc = fma(t, t, acc);
+    }
+    K[i * ld + j] = var[r] * exp(-0.5 * acc) + (i == j ? jitter : 0.0);
+  }
+  for (int i = tid; i < Mp; i += blockDim.x) v[i] = q_mu[(size_t)r * Mp + i];
+  __syncthreads();
+  // right-looking Cholesky, column by column
+  for (int j = 0; j < Mp; ++j) {
+    if (tid == 0) {
+      double d = K[j * ld + j];
+      if (!(d > 0.0)) flag_not_pd(info, r);
+      K[j * ld + j] = sqrt(d);
+    }
+    __syncthreads();
+    double djj = K[j * ld + j];
+    for (int i = j + 1 + tid; i < Mp; i += blockDim.x) K[i * ld + j] /= djj;
+    __syncthreads();
+    for (int idx = tid; idx < (Mp - j - 1) * (Mp - j - 1); idx += blockDim.x) {
+      int a = j + 1 + idx / (Mp - j - 1), b = j + 1 + idx % (Mp - j - 1);
+      if (b <= a) K[a * ld + b] -= K[a * ld + j] * K[b * ld + j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (!whiten)   // w = L^-1 q
+      for (int i = 0; i < Mp; ++i) {
+        double t = v[i];
+        for (int k = 0; k < i; ++k) t -= K[i * ld + k] * v[k];
+        v[i] = t / K[i * ld + i];
+      }
+    for (int i = Mp - 1; i >= 0; --i) {   // beta = L^-T w
+      double t = v[i];
+      for (int k = i + 1; k < Mp; ++k) t -= K[k * ld + i] * v[k];
+      v[i] = t / K[i * ld + i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < Mp; i += blockDim.x) beta[(size_t)r * Mp + i] = v[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct RolloutMMParams {
+  EncoderSpec enc;
+  int N, Dx, De, D, L;       // D = De + 1 (scalar action), L = Dx outputs of the dynamics
+  int R, Mp;                 // policy sets (1 = shared, or N) and centres per policy
+  const double *pZ, *pEll, *pVar, *pBeta;   // [R,Mp,De], [R,De], [R], [R,Mp]
+  double scale, shift;
+  const double *target, *W;  // [De], [De,De]
+  double *m, *S, *loss;      // [N,Dx], [N,Dx,Dx], [N]   current state / accumulated loss
+  double *md, *Sd, *Sxd;     // [N,D], [N,D,D], [N,Dx,D]
+  double *f1, *Sff, *cross;  // [N,L], [N,L,L], [N,D,L]
+  double *traj_m, *traj_S;   // optional [H+1,N,Dx], [H+1,N,Dx,Dx]
+  int* info;
+};
+
+// k_step_pre: one CTA per rollout
+template <int DP>
+__global__ void __launch_bounds__(128) k_step_pre(RolloutMMParams p) {
+  using PP = PairPack<DP>;
+  __shared__ double me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  __shared__ double pack[PP::SIZE], Li1[DP * DP], c01;
+  __shared__ double red[4][DP + 2];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Dx = p.Dx, De = p.De, D = p.D;
+  const int r = (p.R == 1) ? 0 : n;
+  const double* ell = p.pEll + (size_t)r * De;
+  const double var = p.pVar[r];
+  if (tid == 0) {
+    double m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
+    for (int i = 0; i < Dx; ++i) m[i] = p.m[(size_t)n * Dx + i];
+    for (int i = 0; i < Dx * Dx; ++i) S[i] = p.S[(size_t)n * Dx * Dx + i];
+    mm_encoder<double>(p.enc, m, S, me, See, Cxe);
+    // coefficient pack of the (policy kernel, policy kernel) pair and the Psi1 factorisation
+    double V[DP], mu[DP], Sg[DP * DP];
+    Mat<DP> A, Li;
+    double half_log_v = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      V[d] = ell[d] * ell[d];
+      mu[d] = me[d];
+      half_log_v += log(ell[d]);
+#pragma unroll
+      for (int e = 0; e < DP; ++e) {
+        Sg[d * DP + e] = See[d * DP + e];
+        A(d, e) = See[d * DP + e] + (d == e ? V[d] : 0.0);
+      }
+    }
+    bool ok = make_pair_pack<DP>(mu, Sg, V, V, 2.0 * log(var), pack);
+    ok = cholesky<DP>(A) && ok;
+    if (!ok) flag_not_pd(p.info, n);
+    double log_det = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) log_det += log(A(d, d));
+    tri_inverse<DP>(A, Li);
+#pragma unroll
+    for (int d = 0; d < DP * DP; ++d) Li1[d] = Li.a[d];
+    c01 = log(var) + half_log_v - log_det;
+  }
+  __syncthreads();
+  // ---- policy Psi1 terms: f1 = sum_i beta_i psi1_i, vec = sum_i beta_i psi1_i (z_i - me)
+  const double* Zp = p.pZ + (size_t)r * p.Mp * DP;
+  const double* beta = p.pBeta + (size_t)r * p.Mp;
+  double acc = 0.0, vec[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) vec[d] = 0.0;
+  for (int i = tid; i < p.Mp; i += blockDim.x) {
+    double dz[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) dz[d] = Zp[i * DP + d] - me[d];
+    double maha = 0.0;
+#pragma unroll
+    for (int a = 0; a < DP; ++a) {
+      double y = 0.0;
+#pragma unroll
+      for (int k = 0; k <= a; ++k) y = fma(Li1[a * DP + k], dz[k], y);
+      maha = fma(y, y, maha);
+    }
+    double w = beta[i] * fast_exp(c01 - 0.5 * maha);
+    acc += w;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) vec[d] = fma(w, dz[d], vec[d]);
+  }
+  // ---- policy Psi2 contraction: f2 = sum_ij beta_i beta_j Q_ij  (KernelRegressor: no model uncertainty, models.py:34-41)
+  double f2 = 0.0;
+  for (int i = tid; i < p.Mp; i += blockDim.x) {
+    double zr[DP], g[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) zr[d] = Zp[i * DP + d] - pack[PP::MU + d];
+#pragma unroll
+    for (int e = 0; e < DP; ++e) {
+      double t = 0.0;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) t = fma(zr[d], pack[PP::R + d * DP + e], t);
+      g[e] = t;
+    }
+    double ri = pack[PP::C0] + packed_quad<DP>(pack + PP::P1, zr);
+    double row = 0.0;
+    for (int j = 0; j < p.Mp; ++j) {
+      double zc[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) zc[d] = Zp[j * DP + d] - pack[PP::MU + d];
+      double t = ri + packed_quad<DP>(pack + PP::P2, zc);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) t = fma(g[d], zc[d], t);
+      row = fma(beta[j], fast_exp(t), row);
+    }
+    f2 = fma(beta[i], row, f2);
+  }
+  acc = warp_sum(acc);
+  f2 = warp_sum(f2);
+#pragma unroll
+  for (int d = 0; d < DP; ++d) vec[d] = warp_sum(vec[d]);
+  if (lane == 0) {
+    red[warp][0] = acc;
+    red[warp][1] = f2;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) red[warp][2 + d] = vec[d];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double f1 = 0.0, f2s = 0.0, v[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) v[d] = 0.0;
+    for (int w = 0; w < 4; ++w) {
+      f1 += red[w][0];
+      f2s += red[w][1];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) v[d] += red[w][2 + d];
+    }
+    // pre-inverted cross term of the regressor: (See + Lambda)^-1 vec  with (See+Lambda)^-1 = Li^T Li
+    double y[DP], cpre[DP];
+#pragma unroll
+    for (int a = 0; a < DP; ++a) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k <= a; ++k) t = fma(Li1[a * DP + k], v[k], t);
+      y[a] = t;
+    }
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      double t = 0.0;
+#pragma unroll
+      for (int a = d; a < DP; ++a) t = fma(Li1[a * DP + d], y[a], t);
+      cpre[d] = t;
+    }
+    double vf = f2s - f1 * f1;
+    double mu_u, vu, gain;
+    mm_squash_1d<double>(f1, vf, p.scale, p.shift, mu_u, vu, gain);
+    // joint moments of d = (e, u)  (gaussian.py:53-63): Seu = See cpre gain
+    double seu[DP];
+#pragma unroll
+    for (int a = 0; a < DP; ++a) {
+      double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < DP; ++b) t = fma(See[a * DP + b], cpre[b], t);
+      seu[a] = t * gain;
+    }
+    double* md = p.md + (size_t)n * D;
+    double* Sd = p.Sd + (size_t)n * D * D;
+    for (int a = 0; a < De; ++a) {
+      md[a] = me[a];
+      for (int b = 0; b < De; ++b) Sd[a * D + b] = See[a * De + b];
+      Sd[a * D + De] = seu[a];
+      Sd[De * D + a] = seu[a];
+    }
+    md[De] = mu_u;
+    Sd[De * D + De] = vu;
+    // Sxd = Cov(x, d): active rows through the encoder linearisation, inactive rows copied from S_d (forward_sde.py:112-124)
+    double* Sxd = p.Sxd + (size_t)n * Dx * D;
+    const int na = p.enc.na, nb = p.enc.nb();
+    for (int k = 0; k < na; ++k) {
+      int i = p.enc.active[k];
+      double sau = 0.0;
+      for (int b = 0; b < De; ++b) {
+        Sxd[i * D + b] = Cxe[i * De + b];
+        sau = fma(Cxe[i * De + b], cpre[b], sau);
+      }
+      Sxd[i * D + De] = sau * gain;
+    }
+    for (int j = 0; j < nb; ++j) {
+      int i = p.enc.inactive(j);
+      for (int b = 0; b < D; ++b) Sxd[i * D + b] = Sd[(2 * na + j) * D + b];
+    }
+  }
+}
+
+__global__ void k_step_post(RolloutMMParams p, int step) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int Dx = p.Dx, De = p.De, D = p.D, L = p.L;
+  double m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX], Sxf[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  const double* Sxd = p.Sxd + (size_t)n * Dx * D;
+  const double* cr = p.cross + (size_t)n * D * L;
+  for (int i = 0; i < Dx; ++i)
+    for (int l = 0; l < L; ++l) {
+      double t = 0.0;
+      for (int b = 0; b < D; ++b) t = fma(Sxd[i * D + b], cr[b * L + l], t);
+      Sxf[i * L + l] = t;
+    }
+  for (int i = 0; i < Dx; ++i) m[i] = p.m[(size_t)n * Dx + i] + p.f1[(size_t)n * L + i];          // dt = 1 (pilco.py:186)
+  for (int i = 0; i < Dx; ++i)
+    for (int j = 0; j < Dx; ++j)
+      S[i * Dx + j] = p.S[(size_t)n * Dx * Dx + i * Dx + j] + Sxf[i * L + j] + Sxf[j * L + i] + p.Sff[(size_t)n * L * L + i * L + j];
+  for (int i = 0; i < Dx; ++i) p.m[(size_t)n * Dx + i] = m[i];
+  for (int i = 0; i < Dx * Dx; ++i) p.S[(size_t)n * Dx * Dx + i] = S[i];
+  if (p.traj_m) {
+    for (int i = 0; i < Dx; ++i) p.traj_m[((size_t)(step + 1) * p.N + n) * Dx + i] = m[i];
+    for (int i = 0; i < Dx * Dx; ++i) p.traj_S[((size_t)(step + 1) * p.N + n) * Dx * Dx + i] = S[i];
+  }
+  double me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  mm_encoder<double>(p.enc, m, S, me, See, Cxe);
+  p.loss[n] += expected_cost<double>(De, me, See, p.target, p.W);
+}
+
+__global__ void k_rollout_init(RolloutMMParams p, const double* m0, const double* S0) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int Dx = p.Dx;
+  for (int i = 0; i < Dx; ++i) {
+    double v = m0[(size_t)n * Dx + i];
+    p.m[(size_t)n * Dx + i] = v;
+    if (p.traj_m) p.traj_m[(size_t)n * Dx + i] = v;
+  }
+  for (int i = 0; i < Dx * Dx; ++i) {
+    double v = S0[(size_t)n * Dx * Dx + i];
+    p.S[(size_t)n * Dx * Dx + i] = v;
+    if (p.traj_S) p.traj_S[(size_t)n * Dx * Dx + i] = v;
+  }
+  p.loss[n] = 0.0;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct RolloutLayout {
+  size_t m, S, md, Sd, Sxd, f1, Sff, cross, predict, total, predict_bytes;
+};
+
+static RolloutLayout rollout_layout(const gpp_gp_model* dyn, int N, int Dx) {
+  RolloutLayout lo{};
+  const int D = dyn->D, L = dyn->P;
+  size_t off = 0;
+  auto take = [&](size_t doubles) { size_t o = off; off = align_up(off + doubles * sizeof(double), 256); return o; };
+  lo.m = take((size_t)N * Dx);
+  lo.S = take((size_t)N * Dx * Dx);
+  lo.md = take((size_t)N * D);
+  lo.Sd = take((size_t)N * D * D);
+  lo.Sxd = take((size_t)N * Dx * D);
+  lo.f1 = take((size_t)N * L);
+  lo.Sff = take((size_t)N * L * L);
+  lo.cross = take((size_t)N * D * L);
+  lo.predict = off;
+  lo.predict_bytes = gpp_mm_gp_predict_workspace_bytes(dyn, N);
+  lo.total = off + align_up(lo.predict_bytes, 256);
+  return lo;
+}
+
+}  // namespace gpp
+
+extern "C" {
+
+int gpp_policy_prepare(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance,
+                       const double* q_mu, int whiten, double jitter, double* beta, int* info, void* stream) {
+  GPP_REQUIRE(Z && lengthscales && variance && q_mu && beta, GPP_ERR_NULL, "gpp_policy_prepare: null argument");
+  GPP_REQUIRE(R >= 1 && Mp >= 1 && Dp >= 1, GPP_ERR_BAD_SHAPE, "gpp_policy_prepare: bad sizes R=%d Mp=%d Dp=%d", R, Mp, Dp);
+  size_t smem = sizeof(double) * ((size_t)Mp * (Mp + 1) + Mp);
+  GPP_REQUIRE(smem <= 200 * 1024, GPP_ERR_UNSUPPORTED, "gpp_policy_prepare: Mp=%d too large for the in-CTA Cholesky (use gpp_gp_model_create)", Mp);
+  if (smem > 48 * 1024) GPP_CUDA_OK(cudaFuncSetAttribute(gpp::k_policy_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gpp::k_policy_prepare<<<R, 128, smem, (cudaStream_t)stream>>>(Mp, Dp, Z, lengthscales, variance, q_mu, whiten, jitter, beta, info);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+size_t gpp_rollout_mm_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx) {
+  if (!dynamics || N <= 0) return 0;
+  return gpp::rollout_layout(dynamics, N, Dx).total;
+}
+
+int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims /*host*/,
+                       int R, int Mp, const double* policy_Z, const double* policy_lengthscales, const double* policy_variance,
+                       const double* policy_beta, double squash_scale, double squash_shift,
+                       const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
+                       double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final,
+                       void* workspace, size_t workspace_bytes, int* info, void* stream_) {
+  using namespace gpp;
+  GPP_REQUIRE(dynamics && policy_Z && policy_lengthscales && policy_variance && policy_beta && cost_target && cost_W && m0 && S0 &&
+                  loss && workspace, GPP_ERR_NULL, "gpp_rollout_mm_fwd: null argument");
+  GPP_REQUIRE(N >= 1 && H >= 0 && Dx >= 1 && Dx <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_fwd: bad sizes N=%d H=%d Dx=%d", N, H, Dx);
+  GPP_REQUIRE(num_active >= 0 && num_active <= 4 && num_active <= Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_fwd: bad number of encoded dims %d", num_active);
+  GPP_REQUIRE(R == 1 || R == N, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_fwd: R=%d must be 1 (shared policy) or N=%d", R, N);
+  RolloutMMParams p{};
+  p.enc.Dx = Dx; p.enc.na = num_active;
+  for (int k = 0; k < num_active; ++k) {
+    GPP_REQUIRE(active_dims[k] >= 0 && active_dims[k] < Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_fwd: active dim %d out of range", active_dims[k]);
+    p.enc.active[k] = active_dims[k];
+  }
+  p.N = N; p.Dx = Dx; p.De = Dx + num_active; p.D = p.De + 1; p.L = dynamics->P;
+  GPP_REQUIRE(p.De <= GPP_SMALL_MAX - 1, GPP_ERR_UNSUPPORTED, "gpp_rollout_mm_fwd: encoded dimension %d too large", p.De);
+  GPP_REQUIRE(dynamics->D == p.D, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_fwd: dynamics input dim %d != encoded state + action = %d", dynamics->D, p.D);
+  GPP_REQUIRE(dynamics->P == Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_fwd: dynamics output dim %d != state dim %d", dynamics->P, Dx);
+  RolloutLayout lo = rollout_layout(dynamics, N, Dx);
+  GPP_REQUIRE(workspace_bytes >= lo.total, GPP_ERR_WORKSPACE, "gpp_rollout_mm_fwd: workspace %zu < required %zu", workspace_bytes, lo.total);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  p.R = R; p.Mp = Mp; p.pZ = policy_Z; p.pEll = policy_lengthscales; p.pVar = policy_variance; p.pBeta = policy_beta;
+  p.scale = squash_scale; p.shift = squash_shift; p.target = cost_target; p.W = cost_W;
+  p.m = (double*)(ws + lo.m); p.S = (double*)(ws + lo.S); p.loss = loss;
+  p.md = (double*)(ws + lo.md); p.Sd = (double*)(ws + lo.Sd); p.Sxd = (double*)(ws + lo.Sxd);
+  p.f1 = (double*)(ws + lo.f1); p.Sff = (double*)(ws + lo.Sff); p.cross = (double*)(ws + lo.cross);
+  p.traj_m = traj_m; p.traj_S = traj_S; p.info = info;
+  GPP_REQUIRE((traj_m == nullptr) == (traj_S == nullptr), GPP_ERR_NULL, "gpp_rollout_mm_fwd: traj_m and traj_S go together");
+
+  const int tb = 64, gb = (N + tb - 1) / tb;
+  k_rollout_init<<<gb, tb, 0, stream>>>(p, m0, S0);
+  count_launch();
+  for (int t = 0; t < H; ++t) {
+    switch (p.De) {
+#define GPP_CASE(d) case d: k_step_pre<d><<<N, 128, 0, stream>>>(p); break;
+      GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7)
+#undef GPP_CASE
+      default: set_error("gpp_rollout_mm_fwd: unsupported encoded dimension %d", p.De); return GPP_ERR_UNSUPPORTED;
+    }
+    count_launch();
+    int rc = mm_predict_enqueue(dynamics, p.md, p.Sd, N, p.f1, p.Sff, p.cross, 1, 0.0, ws + lo.predict, lo.predict_bytes, info, stream);
+    if (rc != GPP_OK) return rc;
+    k_step_post<<<gb, tb, 0, stream>>>(p, t);
+    count_launch();
+  }
+  if (m_final) GPP_CUDA_OK(cudaMemcpyAsync(m_final, p.m, sizeof(double) * N * Dx, cudaMemcpyDeviceToDevice, stream));
+  if (S_final) GPP_CUDA_OK(cudaMemcpyAsync(S_final, p.S, sizeof(double) * N * Dx * Dx, cudaMemcpyDeviceToDevice, stream));
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""Tensor-level wrappers of the fused rollout entry points (gpp_policy_prepare, gpp_rollout_mm_fwd, ...)."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from gpflowpilco_b200 import _lib
+from gpflowpilco_b200.ops import F64, GPModelHandle, _c, _dev_check, _new_info, _ptr, _stream, raise_if_not_pd
+
+
+@dataclass
+class PolicyParams:
+  """R sets of SE-ARD kernel-regressor parameters with a scalar output (the upstream RBF policy):
+  Z [R,Mp,Dp], lengthscales [R,Dp], variance [R], q_mu [R,Mp]; squashing link scale*(Phi(f)+shift)."""
+  Z: torch.Tensor
+  lengthscales: torch.Tensor
+  variance: torch.Tensor
+  q_mu: torch.Tensor
+  whiten: bool = True
+  jitter: float = 1e-6
+  squash_scale: float = 1.0
+  squash_shift: float = -0.5
+
+  def __post_init__(self):
+    self.Z, self.lengthscales, self.variance, self.q_mu = map(_c, (self.Z, self.lengthscales, self.variance, self.q_mu))
+    _dev_check(self.Z, self.lengthscales, self.variance, self.q_mu)
+    R, Mp, Dp = self.Z.shape
+    if self.lengthscales.shape != (R, Dp) or self.variance.shape != (R,) or self.q_mu.shape != (R, Mp):
+      raise ValueError("PolicyParams: expected Z [R,Mp,Dp], lengthscales [R,Dp], variance [R], q_mu [R,Mp]")
+
+  @property
+  def shape(self):
+    return tuple(self.Z.shape)
+
+  def beta(self, check: bool = True) -> torch.Tensor:
+    """beta_r = Kuu_r^-1 m_r (device kernel, one CTA per parameter set)."""
+    R, Mp, Dp = self.Z.shape
+    out = torch.empty(R, Mp, dtype=F64, device=self.Z.device)
+    info = _new_info(self.Z.device)
+    _lib.check(_lib.load().gpp_policy_prepare(R, Mp, Dp, _ptr(self.Z), _ptr(self.lengthscales), _ptr(self.variance), _ptr(self.q_mu),
+                                              int(self.whiten), float(self.jitter), _ptr(out), _ptr(info), _stream()))
+    if check and int(info.item()):
+      raise _lib.GppError(-3, f"policy Kuu of parameter set {int(info.item()) - 1} is not positive definite")
+    return out
+
+
+@dataclass
+class MMRolloutResult:
+  loss: torch.Tensor                      # [N]
+  m_final: torch.Tensor                   # [N,Dx]
+  S_final: torch.Tensor                   # [N,Dx,Dx]
+  traj_m: Optional[torch.Tensor] = None   # [H+1,N,Dx]
+  traj_S: Optional[torch.Tensor] = None   # [H+1,N,Dx,Dx]
+
+
+def rollout_mm(dynamics: GPModelHandle, policy: PolicyParams, m0: torch.Tensor, S0: torch.Tensor, horizon: int,
+               active_dims: Sequence[int], cost_target: torch.Tensor, cost_W: torch.Tensor, return_trajectory: bool = False,
+               beta: Optional[torch.Tensor] = None, check: bool = True) -> MMRolloutResult:
+  """Moment-matched rollout + expected cost for N initial Gaussian states (upstream loops/pilco.py:192-220)."""
+  m0, S0, cost_target, cost_W = map(_c, (m0, S0, cost_target, cost_W))
+  _dev_check(m0, S0, cost_target, cost_W)
+  N, Dx = m0.shape
+  na = len(active_dims)
+  De = Dx + na
+  R, Mp, Dp = policy.shape
+  if S0.shape != (N, Dx, Dx):
+    raise ValueError("rollout_mm: S0 must be [N,Dx,Dx]")
+  if Dp != De:
+    raise ValueError(f"rollout_mm: policy input dim {Dp} != encoded state dim {De}")
+  if cost_target.shape != (De,) or cost_W.shape != (De, De):
+    raise ValueError("rollout_mm: cost target/precision must live in the encoded space")
+  if R not in (1, N):
+    raise ValueError("rollout_mm: policy must have 1 or N parameter sets")
+  dev = m0.device
+  if beta is None:
+    beta = policy.beta(check=check)
+  lib = _lib.load()
+  need = lib.gpp_rollout_mm_workspace_bytes(dynamics._h, N, Dx)
+  ws = torch.empty(need, dtype=torch.uint8, device=dev)
+  loss = torch.empty(N, dtype=F64, device=dev)
+  mf = torch.empty(N, Dx, dtype=F64, device=dev)
+  Sf = torch.empty(N, Dx, Dx, dtype=F64, device=dev)
+  tm = torch.empty(horizon + 1, N, Dx, dtype=F64, device=dev) if return_trajectory else None
+  tS = torch.empty(horizon + 1, N, Dx, Dx, dtype=F64, device=dev) if return_trajectory else None
+  info = _new_info(dev)
+  act = (ctypes.c_int * max(na, 1))(*active_dims)
+  _lib.check(lib.gpp_rollout_mm_fwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
+                                    _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
+                                    _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
+                                    _ptr(mf), _ptr(Sf), _ptr(ws), ws.numel(), _ptr(info), _stream()))
+  if check:
+    raise_if_not_pd(info, "rollout_mm")
+  return MMRolloutResult(loss, mf, Sf, tm, tS)

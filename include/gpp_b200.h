@@ -87,6 +87,32 @@ int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m /*[N,D]*/, 
                           int full_output_cov, double jitter,
                           void* workspace, size_t workspace_bytes, int* info, void* stream);
 
+/* ---- policy weights ---------------------------------------------------------------------------------------
+ * beta_r = Kuu_r^-1 m_r for R small SE-ARD kernel regressors (KernelRegressor(SVGP), upstream models/core.py:61-63,
+ * moment_matching/models.py:228-235): whitened beta = Luu^-T q_mu, else Kuu^-1 q_mu; Kuu includes `jitter`.
+ *   Z [R,Mp,Dp], lengthscales [R,Dp], variance [R], q_mu [R,Mp] -> beta [R,Mp]. */
+int gpp_policy_prepare(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance,
+                       const double* q_mu, int whiten, double jitter, double* beta, int* info, void* stream);
+
+/* ---- moment-matched rollout ------------------------------------------------------------------------------
+ * replaces the closure body of MomentMatchingPILCO._policy_loss_closure (upstream loops/pilco.py:192-220): H steps of
+ * forward_sde (dynamics/forward_sde.py:95-137: TrigonometricEncoder -> InverseLinkWrapper(KernelRegressor) with the
+ * Chain[Scale,Shift,NormalCDF] link -> GP dynamics) + MomentMatchingEuler.step (dynamics/solvers.py:110-135, dt = 1)
+ * + the GaussianObjective callback (components.py:30-37), for N independent initial states.
+ *   dynamics      handle with D = Dx + num_active + 1 inputs and Dx outputs
+ *   active_dims   HOST array: state dims encoded as (sin, cos)  (TrigonometricEncoder.active_dims)
+ *   policy_*      R = 1 (shared) or R = N parameter sets; action dimension 1; beta from gpp_policy_prepare
+ *   cost_target [De], cost_W [De,De] with De = Dx + num_active
+ *   m0 [N,Dx], S0 [N,Dx,Dx] -> loss [N]; optional traj_m [H+1,N,Dx], traj_S [H+1,N,Dx,Dx], m_final, S_final.
+ * All launches go to `stream` without synchronisation (capturable in a CUDA graph). */
+size_t gpp_rollout_mm_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx);
+int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims,
+                       int R, int Mp, const double* policy_Z, const double* policy_lengthscales,
+                       const double* policy_variance, const double* policy_beta, double squash_scale, double squash_shift,
+                       const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
+                       double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final,
+                       void* workspace, size_t workspace_bytes, int* info, void* stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------------
  * gpp_profile_enable(1): every entry point records CUDA events on its stream around its dominant kernel
  * (k_contract for gpp_mm_gp_predict_fwd, k_ekzxkxz for gpp_ekzxkxz, the rollout kernels for the rollouts).

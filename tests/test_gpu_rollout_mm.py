@@ -1,0 +1,103 @@
+"""GPU parity: fused moment-matched rollout vs the oracle's step-by-step restatement of
+forward_sde + MomentMatchingEuler + GaussianObjective (upstream dynamics/forward_sde.py:95-137, dynamics/solvers.py:110-135,
+loops/pilco.py:199-217).  Tolerance 1e-6 relative (north star); observed errors are reported in the assertion text."""
+import numpy as np
+import pytest
+import torch
+
+from gpflowpilco_b200 import synthetic
+from oracle import gp_models as gm
+from oracle import moments as mo
+from oracle import rollout as ro
+from tests.helpers import DTYPE, cuda_handle, generate_covariance, oracle_svgp, scaled_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x):
+  return torch.as_tensor(x, dtype=DTYPE, device="cuda")
+
+
+def _policy_params(pol, scale, shift=-0.5):
+  from gpflowpilco_b200.rollouts import PolicyParams
+  return PolicyParams(_dev(pol["Z"]), _dev(pol["lengthscales"]), _dev(pol["variance"]), _dev(pol["q_mu"][:, 0][None]),
+                      whiten=bool(pol["whiten"]), squash_scale=scale, squash_shift=shift)
+
+
+def _oracle_rollout(cfg, dyn, pol, m0, S0, H, reference_form=True):
+  enc = mo.TrigonometricEncoder(cfg["active_dims"])
+  obj = mo.GaussianObjective(cfg["target"], cfg["W"])
+  drift = (lambda s: gm.mm_svgp(s, dyn)) if reference_form else (lambda s: gm.mm_sparse_reassociated(s, dyn))
+  return ro.mm_rollout(m0, S0, H, drift, lambda s: gm.mm_policy(s, pol, cfg["squash_scale"], cfg["squash_shift"]), enc, obj, True)
+
+
+def test_policy_beta():
+  cfg = synthetic.config1_cartpole(M=64)
+  pol = oracle_svgp(cfg["policy"])
+  beta_ref, _ = gm.sparse_weights(pol, model_uncertainty=False)
+  beta = _policy_params(cfg["policy"], 1.0).beta()
+  scaled_close(beta[0], beta_ref[0], 1e-9, "policy beta")
+
+
+def test_cartpole_rollout_config1():
+  """BASELINE config #1: cart-pole MM rollout, M=256 dynamics, 30 policy centres, H=30, N=1."""
+  from gpflowpilco_b200.rollouts import rollout_mm
+  cfg = synthetic.config1_cartpole()
+  dyn, pol = oracle_svgp(cfg["dynamics"]), oracle_svgp(cfg["policy"])
+  H = cfg["horizon"]
+  m0, S0 = torch.as_tensor(cfg["m0"]), torch.as_tensor(cfg["S0"])
+  loss_ref, traj = _oracle_rollout(cfg, dyn, pol, m0, S0, H)
+  res = rollout_mm(cuda_handle(cfg["dynamics"]), _policy_params(cfg["policy"], cfg["squash_scale"], cfg["squash_shift"]),
+                   _dev(m0), _dev(S0), H, cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]), return_trajectory=True)
+  tm_ref = torch.stack([t[0] for t in traj])
+  tS_ref = torch.stack([t[1] for t in traj])
+  scaled_close(res.traj_m, tm_ref, 1e-6, "trajectory means")
+  scaled_close(res.traj_S, tS_ref, 1e-6, "trajectory covariances")
+  scaled_close(res.loss, loss_ref, 1e-6, "loss")
+  scaled_close(res.m_final, tm_ref[-1], 1e-6, "final mean")
+
+
+@pytest.mark.parametrize("shared_policy", [True, False])
+def test_batched_rollout_random_models(shared_policy):
+  """N = 5 initial states, well-conditioned random dynamics; one shared policy or one policy per rollout (restarts)."""
+  from gpflowpilco_b200.rollouts import PolicyParams, rollout_mm
+  N, H = 5, 6
+  g = torch.Generator().manual_seed(5)
+  dynp = synthetic.random_svgp(L=4, M=48, D=6, seed=21, whiten=True, z_scale=1.5)
+  dynp["q_mu"] = 0.2 * dynp["q_mu"]
+  dynp["mean_const"] = np.zeros(4)
+  dyn = oracle_svgp(dynp)
+  R = 1 if shared_policy else N
+  pols = []
+  for r in range(R):
+    pp = synthetic.random_svgp(L=1, M=12, D=5, seed=40 + r, whiten=(r % 2 == 0))
+    pp["mean_const"] = np.zeros(1)
+    pols.append(pp)
+  m0 = torch.tensor([0.0, 2.5, 0.0, 0.0], dtype=DTYPE) + 0.3 * torch.randn(N, 4, dtype=DTYPE, generator=g)
+  S0 = generate_covariance(4, [N], 0.15, g)
+  cfg = dict(active_dims=(1,), target=np.array([0.0, 1.0, 0.0, 0.0, 0.0]), W=synthetic.config1_cartpole(M=8, Mp=4)["W"],
+             squash_scale=3.0, squash_shift=-0.5)
+  losses, finals = [], []
+  for n in range(N):
+    pol = oracle_svgp(pols[0 if shared_policy else n])
+    l, traj = _oracle_rollout(cfg, dyn, pol, m0[n:n + 1], S0[n:n + 1], H)
+    losses.append(l)
+    finals.append(traj[-1])
+  # whiten differs per restart in the non-shared case: the C ABI takes one flag, so prepare beta per set on the host side
+  if shared_policy:
+    P = PolicyParams(_dev(pols[0]["Z"]), _dev(pols[0]["lengthscales"]), _dev(pols[0]["variance"]), _dev(pols[0]["q_mu"][:, 0][None]),
+                     whiten=bool(pols[0]["whiten"]), squash_scale=3.0)
+    beta = None
+  else:
+    P = PolicyParams(_dev(np.concatenate([p["Z"] for p in pols])), _dev(np.concatenate([p["lengthscales"] for p in pols])),
+                     _dev(np.concatenate([p["variance"] for p in pols])), _dev(np.stack([p["q_mu"][:, 0] for p in pols])),
+                     whiten=True, squash_scale=3.0)
+    betas = []
+    for p in pols:
+      one = PolicyParams(_dev(p["Z"]), _dev(p["lengthscales"]), _dev(p["variance"]), _dev(p["q_mu"][:, 0][None]), whiten=bool(p["whiten"]))
+      betas.append(one.beta())
+    beta = torch.cat(betas)
+  res = rollout_mm(cuda_handle(dynp), P, _dev(m0), _dev(S0), H, (1,), _dev(cfg["target"]), _dev(cfg["W"]), beta=beta)
+  scaled_close(res.loss, torch.cat(losses), 1e-7, "loss")
+  scaled_close(res.m_final, torch.cat([f[0] for f in finals]), 1e-7, "final means")
+  scaled_close(res.S_final, torch.cat([f[1] for f in finals]), 1e-6, "final covariances")
