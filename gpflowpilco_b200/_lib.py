@@ -28,6 +28,12 @@ SIGNATURES = {
     "gpp_rollout_mm_workspace_bytes": (c_size_t, [_P, c_int, c_int]),
     "gpp_rollout_mm_fwd": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_double, c_double,
                                    _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
+    "gpp_pathwise_tile": (c_int, []),
+    "gpp_pathwise_particles_per_cta": (c_int, []),
+    "gpp_pathwise_pack_basis": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gpp_rollout_pathwise_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
+                                         _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
+                                         _P, _P, _P, _P, _P]),
     "gpp_profile_enable": (c_int, [c_int]),
     "gpp_profile_last_ms": (c_int, [POINTER(ctypes.c_float)]),
     "gpp_microbench_fp64": (c_int, [c_int, c_int, c_int, _P, _P]),

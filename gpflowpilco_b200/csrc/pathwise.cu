@@ -1,0 +1,391 @@
+// Pathwise (function-space sample) rollout: S particles, each pushed H steps through its own posterior function draw
+//   f_{s,l}(x) = c_l + sum_i w[l,i,s] phi_{l,i}(x) + sum_j v[l,j,s] k_l(x, z_{l,j})          (decoupled sampling,
+//   random-Fourier prior + canonical-basis update; gpflow_sampling, called at upstream loops/pilco.py:282-288 and
+//   models/svgp.py:129-130), with the deterministic RBF policy (models/core.py:61-71) and the sample cost
+//   (components.py:39-41) accumulated on the way (loops/pilco.py:272-275).  Replaces the closure body of
+//   PathwisePILCO._policy_loss_closure (loops/pilco.py:277-295) — the H-loop is upstream's tf.foldl.
+//
+// One thread per particle, the whole rollout in one launch.  Per particle-step the kernel streams that particle's
+// weights (8 B per feature: L (F + M) doubles ~ 139 KB at L=4, F=4096, M=256) — the HBM roofline term — and evaluates
+// L F cosines + L M exps in FP64 — the FP64-pipe term; the two are within 20% of each other on B200.
+//   * weights are stored particle-minor ([L,F,S]) so that a warp reads 256 contiguous bytes per feature;
+//   * a producer warp moves [TF features x P particles] weight tiles and the matching [TF x 8] basis tile into a ring
+//     of shared-memory stages with cp.async.bulk (TMA, SASS UBLKCP) + mbarrier complete_tx; consumer warps never wait
+//     on a global load;
+//   * cos is evaluated in quarter turns: the basis is pre-scaled by 4/(2 pi ell) so the reduction is an exact
+//     round-to-nearest (no Cody-Waite), then a degree-6 polynomial in r^2 with sin/cos coefficients selected by quadrant.
+#include <cublas_v2.h>
+
+#include "mm_small.cuh"
+#include "model.cuh"
+#include "philox.cuh"
+
+namespace gpp {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// cos(pi/2 * q) for K values in lock-step; q in quarter turns.
+static __constant__ double kCosC[7] = {0x1.0000000000000p+0, -0x1.3bd3cc9be458bp+0, 0x1.03c1f081b076ap-2, -0x1.55d3c7dbfb7afp-6,
+                                       0x1.e1f4fb5e72646p-11, -0x1.a6c9c0e8a7a20p-16, 0x1.f3db80db0de94p-22};
+static __constant__ double kSinC[7] = {0x1.921fb54442d18p+0, -0x1.4abbce625be41p-1, 0x1.466bc677587efp-4, -0x1.32d2cce2e5063p-8,
+                                       0x1.50782fd95b428p-13, -0x1.e30070fc48deap-19, 0x1.e3f34257daf3bp-25};
+
+template <int K>
+__device__ __forceinline__ void cos_quarter_turns(double (&q)[K]) {
+  const double MAGIC = 6755399441055744.0;
+  double t[K], r[K], z[K], p[K];
+  bool odd[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = q[k] + MAGIC;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r[k] = q[k] - (t[k] - MAGIC);        // exact: r in [-1/2, 1/2]
+#pragma unroll
+  for (int k = 0; k < K; ++k) { z[k] = r[k] * r[k]; odd[k] = lo_int(t[k]) & 1; }
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = odd[k] ? kSinC[6] : kCosC[6];
+#pragma unroll
+  for (int j = 5; j >= 0; --j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = fma(p[k], z[k], odd[k] ? kSinC[j] : kCosC[j]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    // cos(x + n pi/2): n=0 -> C, 1 -> -r S, 2 -> -C, 3 -> r S
+    int n = lo_int(t[k]) & 3;
+    double val = odd[k] ? p[k] * r[k] : p[k];
+    q[k] = (n == 1 || n == 2) ? -val : val;
+  }
+}
+
+struct PathwiseParams {
+  EncoderSpec enc;
+  int S, ldS, H, L, F, Mpad, Dx, De, Mp;
+  const double* basis;    // [L][F][BS]     4 omega/(2 pi ell) [D], 4 b/(2 pi)
+  const double* zbasis;   // [L][Mpad][BS]  z/ell [D]
+  const double* w;        // [L][F][ldS]
+  const double* v;        // [L][Mpad][ldS]
+  const double* amp;      // [L] sqrt(2 var/F)
+  const double* var;      // [L]
+  const double* inv_ell;  // [L][D]
+  const double* mean;     // [L]
+  const double* pZs;      // [Mp][De]  policy centres / ell_pi
+  const double* pInvEll;  // [De]
+  const double* pAlpha;   // [Mp]      var_pi * Kuu^-1 m
+  double scale, shift;
+  const double *target, *W;
+  const double* x0;       // [S][Dx]
+  double* loss;           // [S]
+  double* x_final;        // [S][Dx]
+  double* traj;           // optional [H+1][S][Dx]
+};
+
+template <int D, int P, int TF, int NS>
+struct PathwiseCfg {
+  static constexpr int BS = (D + 1 + 1) & ~1;
+  static constexpr int STAGE_DOUBLES = TF * BS + TF * P;
+  static constexpr int NWARPS = P / 32 + 1;
+  static constexpr size_t SMEM = sizeof(double) * NS * STAGE_DOUBLES + 2 * NS * sizeof(uint64_t) +
+                                 sizeof(double) * (64 * (GPP_SMALL_MAX + 1) + 8 * GPP_SMALL_MAX * GPP_SMALL_MAX);
+};
+
+template <int D, int P, int TF, int NS>
+__global__ void __launch_bounds__(P + 32) k_pathwise_rollout(PathwiseParams p) {
+  using CF = PathwiseCfg<D, P, TF, NS>;
+  constexpr int BS = CF::BS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + NS * CF::STAGE_DOUBLES);
+  uint64_t* empty = full + NS;
+  double* pol = reinterpret_cast<double*>(empty + NS);          // policy centres [Mp][De] + alpha [Mp]  (Mp <= 64)
+  double* cst = pol + 64 * (GPP_SMALL_MAX + 1);                  // target, W, inv_ell, amp, var, mean
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s0 = blockIdx.x * P;
+  const int tiles_f = p.F / TF, tiles_m = p.Mpad / TF;
+  const int tiles_per_step = p.L * (tiles_f + tiles_m);
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], P / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < p.Mp * p.De; i += blockDim.x) pol[i] = p.pZs[i];
+  for (int i = tid; i < p.Mp; i += blockDim.x) pol[64 * GPP_SMALL_MAX + i] = p.pAlpha[i];
+  {
+    const int De = p.De;
+    for (int i = tid; i < De; i += blockDim.x) { cst[i] = p.target[i]; cst[8 + 64 + i] = p.pInvEll[i]; }
+    for (int i = tid; i < De * De; i += blockDim.x) cst[8 + i] = p.W[i];
+    for (int i = tid; i < p.L * D; i += blockDim.x) cst[8 + 64 + 8 + i] = p.inv_ell[i];
+    for (int i = tid; i < p.L; i += blockDim.x) {
+      cst[8 + 64 + 8 + 64 + i] = p.amp[i];
+      cst[8 + 64 + 8 + 64 + 8 + i] = p.var[i];
+      cst[8 + 64 + 8 + 64 + 16 + i] = p.mean[i];
+    }
+  }
+  __syncthreads();
+  const double* c_target = cst;
+  const double* c_W = cst + 8;
+  const double* c_pinv = cst + 8 + 64;
+  const double* c_inv_ell = cst + 8 + 64 + 8;
+  const double* c_amp = cst + 8 + 64 + 8 + 64;
+  const double* c_var = c_amp + 8;
+  const double* c_mean = c_amp + 16;
+
+  if (warp == P / 32) {
+    // ------------------------------------------------------------------ producer warp (one elected lane)
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)(sizeof(double) * CF::STAGE_DOUBLES);
+      long it = 0;
+      for (int t = 0; t < p.H; ++t)
+        for (int l = 0; l < p.L; ++l)
+          for (int tile = 0; tile < tiles_f + tiles_m; ++tile, ++it) {
+            const int st = (int)(it % NS);
+            const unsigned ph = (unsigned)((it / NS) & 1);
+            mbar_wait(&empty[st], ph ^ 1u);
+            double* sb = stages + st * CF::STAGE_DOUBLES;
+            mbar_expect_tx(&full[st], bytes);
+            const bool rff = tile < tiles_f;
+            const int row0 = (rff ? tile : tile - tiles_f) * TF;
+            const double* bsrc = rff ? p.basis + ((size_t)l * p.F + row0) * BS : p.zbasis + ((size_t)l * p.Mpad + row0) * BS;
+            const double* wsrc = rff ? p.w + ((size_t)l * p.F + row0) * p.ldS + s0 : p.v + ((size_t)l * p.Mpad + row0) * p.ldS + s0;
+            bulk_g2s(sb, bsrc, (unsigned)(sizeof(double) * TF * BS), &full[st]);
+#pragma unroll 1
+            for (int f = 0; f < TF; ++f)
+              bulk_g2s(sb + TF * BS + f * P, wsrc + (size_t)f * p.ldS, (unsigned)(sizeof(double) * P), &full[st]);
+          }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers: one particle per thread
+  const int s = s0 + tid;
+  const bool valid = s < p.S;
+  const int Dx = p.Dx, De = p.De;
+  double x[GPP_SMALL_MAX], loss = 0.0;
+  for (int i = 0; i < Dx; ++i) x[i] = valid ? p.x0[(size_t)s * Dx + i] : 0.0;
+  if (p.traj && valid)
+    for (int i = 0; i < Dx; ++i) p.traj[(size_t)s * Dx + i] = x[i];
+  long it = 0;
+  for (int t = 0; t < p.H; ++t) {
+    // e = [sin, cos, inactive]; u = scale (Phi(policy mean) + shift); d = (e, u)
+    double dd[D];
+    {
+      const int na = p.enc.na;
+      for (int k = 0; k < na; ++k) {
+        double sv, cv;
+        sincos(x[p.enc.active[k]], &sv, &cv);
+        dd[k] = sv;
+        dd[na + k] = cv;
+      }
+      for (int j = 0; j < p.enc.nb(); ++j) dd[2 * na + j] = x[p.enc.inactive(j)];
+      double es[GPP_SMALL_MAX], f = 0.0;
+      for (int a = 0; a < De; ++a) es[a] = dd[a] * c_pinv[a];
+      for (int i = 0; i < p.Mp; ++i) {
+        double d2 = 0.0;
+        for (int a = 0; a < De; ++a) {
+          double df = es[a] - pol[i * De + a];
+          d2 = fma(df, df, d2);
+        }
+        f = fma(pol[64 * GPP_SMALL_MAX + i], fast_exp(-0.5 * d2), f);
+      }
+      dd[De] = p.scale * (0.5 * erfc(-f * 0.70710678118654752440) + p.shift);
+    }
+    double fx[GPP_SMALL_MAX];
+    for (int l = 0; l < p.L; ++l) {
+      double accw[4] = {0.0, 0.0, 0.0, 0.0}, accv[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int tile = 0; tile < tiles_f; ++tile, ++it) {
+        const int st = (int)(it % NS);
+        mbar_wait(&full[st], (unsigned)((it / NS) & 1));
+        const double* bs = stages + st * CF::STAGE_DOUBLES;
+        const double* ws = bs + TF * BS + tid;
+#pragma unroll
+        for (int f0 = 0; f0 < TF; f0 += 4) {
+          double q[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) q[k] = bs[(f0 + k) * BS + D];
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = fma(bs[(f0 + k) * BS + d], dd[d], q[k]);
+          cos_quarter_turns<4>(q);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) accw[k] = fma(ws[(f0 + k) * P], q[k], accw[k]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+      }
+      double ds[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) ds[d] = dd[d] * c_inv_ell[l * D + d];
+      for (int tile = 0; tile < tiles_m; ++tile, ++it) {
+        const int st = (int)(it % NS);
+        mbar_wait(&full[st], (unsigned)((it / NS) & 1));
+        const double* bs = stages + st * CF::STAGE_DOUBLES;
+        const double* ws = bs + TF * BS + tid;
+#pragma unroll
+        for (int f0 = 0; f0 < TF; f0 += 4) {
+          double q[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              double df = ds[d] - bs[(f0 + k) * BS + d];
+              q[k] = fma(df, df, q[k]);
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) q[k] *= -0.5;
+          fast_exp_n<4>(q);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) accv[k] = fma(ws[(f0 + k) * P], q[k], accv[k]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+      }
+      fx[l] = c_mean[l] + c_amp[l] * ((accw[0] + accw[1]) + (accw[2] + accw[3])) + c_var[l] * ((accv[0] + accv[1]) + (accv[2] + accv[3]));
+    }
+    for (int i = 0; i < Dx; ++i) x[i] += fx[i];                       // Euler, dt = 1, no diffusion (solvers.py:49-65)
+    {
+      double e[GPP_SMALL_MAX];
+      const int na = p.enc.na;
+      for (int k = 0; k < na; ++k) {
+        double sv, cv;
+        sincos(x[p.enc.active[k]], &sv, &cv);
+        e[k] = sv;
+        e[na + k] = cv;
+      }
+      for (int j = 0; j < p.enc.nb(); ++j) e[2 * na + j] = x[p.enc.inactive(j)];
+      loss += sample_cost(De, e, c_target, c_W);
+    }
+    if (p.traj && valid)
+      for (int i = 0; i < Dx; ++i) p.traj[((size_t)(t + 1) * p.S + s) * Dx + i] = x[i];
+  }
+  if (valid) {
+    p.loss[s] = loss;
+    if (p.x_final)
+      for (int i = 0; i < Dx; ++i) p.x_final[(size_t)s * Dx + i] = x[i];
+  }
+}
+
+// ---- basis packing ---------------------------------------------------------------------------------------
+// basis[l][i][:] = 4 omega[l,i,:] / (2 pi ell_l), 4 phase/(2 pi);   zbasis[l][j][:] = z_{l,j} / ell_l  (zero rows pad to Mpad)
+__global__ void k_pack_basis(int L, int F, int M, int Mpad, int D, int BS, const double* __restrict__ omega,
+                             const double* __restrict__ phase, const double* __restrict__ Z, const double* __restrict__ ell,
+                             double* __restrict__ basis, double* __restrict__ zbasis) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const double inv2pi = 0.15915494309189533577;
+  if (idx < L * F) {
+    int l = idx / F;
+    for (int d = 0; d < BS; ++d) {
+      double v = 0.0;
+      if (d < D) v = 4.0 * inv2pi * omega[(size_t)idx * D + d] / ell[l * D + d];
+      else if (d == D) v = 4.0 * inv2pi * phase[idx];
+      basis[(size_t)idx * BS + d] = v;
+    }
+  }
+  if (idx < L * Mpad) {
+    int l = idx / Mpad, j = idx % Mpad;
+    for (int d = 0; d < BS; ++d) {
+      double v = 0.0;
+      if (d < D && j < M) v = Z[((size_t)l * M + j) * D + d] / ell[l * D + d];
+      zbasis[(size_t)idx * BS + d] = v;
+    }
+  }
+}
+
+template <int D>
+static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
+  constexpr int P = 256, TF = 16, NS = 4;
+  using CF = PathwiseCfg<D, P, TF, NS>;
+  static bool configured = false;
+  if (!configured) {
+    GPP_CUDA_OK(cudaFuncSetAttribute(k_pathwise_rollout<D, P, TF, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+    configured = true;
+  }
+  int grid = (p.S + P - 1) / P;
+  profile_begin(stream);
+  k_pathwise_rollout<D, P, TF, NS><<<grid, P + 32, CF::SMEM, stream>>>(p);
+  profile_end(stream);
+  count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+}  // namespace gpp
+
+extern "C" {
+
+int gpp_pathwise_tile(void) { return 16; }
+int gpp_pathwise_particles_per_cta(void) { return 256; }
+
+int gpp_pathwise_pack_basis(int L, int F, int M, int Mpad, int D, const double* omega, const double* phase, const double* Z,
+                            const double* lengthscales, double* basis, double* zbasis, void* stream) {
+  GPP_REQUIRE(omega && phase && Z && lengthscales && basis && zbasis, GPP_ERR_NULL, "gpp_pathwise_pack_basis: null argument");
+  GPP_REQUIRE(D >= 1 && D <= GPP_MAX_D && Mpad >= M, GPP_ERR_BAD_SHAPE, "gpp_pathwise_pack_basis: bad sizes");
+  int BS = (D + 2) & ~1;
+  int n = L * (F > Mpad ? F : Mpad);
+  gpp::k_pack_basis<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(L, F, M, Mpad, D, BS, omega, phase, Z, lengthscales, basis, zbasis);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
+                             const double* basis, const double* zbasis, const double* w, const double* v, const double* amp,
+                             const double* variance, const double* inv_lengthscales, const double* mean_const,
+                             int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                             double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                             const double* x0, double* loss, double* x_final, double* traj, void* stream) {
+  using namespace gpp;
+  GPP_REQUIRE(basis && zbasis && w && v && amp && variance && inv_lengthscales && mean_const && policy_Zs && policy_inv_lengthscales &&
+                  policy_alpha && cost_target && cost_W && x0 && loss, GPP_ERR_NULL, "gpp_rollout_pathwise_fwd: null argument");
+  GPP_REQUIRE(S >= 1 && H >= 0 && L >= 1 && L <= GPP_SMALL_MAX && Dx >= 1 && Dx <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE,
+              "gpp_rollout_pathwise_fwd: bad sizes S=%d H=%d L=%d Dx=%d", S, H, L, Dx);
+  GPP_REQUIRE(L == Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: the drift must have one output per state dim (L=%d, Dx=%d)", L, Dx);
+  GPP_REQUIRE(F % 16 == 0 && Mpad % 16 == 0, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: F=%d and Mpad=%d must be multiples of 16", F, Mpad);
+  GPP_REQUIRE(ldS % 256 == 0 && ldS >= S, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: ldS=%d must be a multiple of 256 and >= S=%d", ldS, S);
+  GPP_REQUIRE(Mp >= 1 && Mp <= 64, GPP_ERR_UNSUPPORTED, "gpp_rollout_pathwise_fwd: Mp=%d policy centres (max 64)", Mp);
+  GPP_REQUIRE(num_active >= 0 && num_active <= 4 && D == Dx + num_active + 1, GPP_ERR_BAD_SHAPE,
+              "gpp_rollout_pathwise_fwd: D=%d must be Dx + num_active + 1", D);
+  PathwiseParams p{};
+  p.enc.Dx = Dx; p.enc.na = num_active;
+  for (int k = 0; k < num_active; ++k) p.enc.active[k] = active_dims[k];
+  p.S = S; p.ldS = ldS; p.H = H; p.L = L; p.F = F; p.Mpad = Mpad; p.Dx = Dx; p.De = Dx + num_active; p.Mp = Mp;
+  p.basis = basis; p.zbasis = zbasis; p.w = w; p.v = v; p.amp = amp; p.var = variance; p.inv_ell = inv_lengthscales; p.mean = mean_const;
+  p.pZs = policy_Zs; p.pInvEll = policy_inv_lengthscales; p.pAlpha = policy_alpha; p.scale = squash_scale; p.shift = squash_shift;
+  p.target = cost_target; p.W = cost_W; p.x0 = x0; p.loss = loss; p.x_final = x_final; p.traj = traj;
+  switch (D) {
+#define GPP_CASE(d) case d: return launch_pathwise<d>(p, (cudaStream_t)stream);
+    GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+    default: set_error("gpp_rollout_pathwise_fwd: unsupported D=%d", D); return GPP_ERR_UNSUPPORTED;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+"""Pathwise sample paths on the device: packed layouts + the fused particle rollout.
+
+`PackedPaths` holds function draws of a multi-output SVGP in the layout the kernel streams (particle-minor weights);
+`rollout_pathwise` runs S particles x H steps + sample cost in one launch (upstream loops/pilco.py:263-303).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from gpflowpilco_b200 import _lib
+from gpflowpilco_b200.ops import F64, _c, _dev_check, _ptr, _stream
+from gpflowpilco_b200.rollouts import PolicyParams
+
+
+def _round_up(x: int, m: int) -> int:
+  return (x + m - 1) // m * m
+
+
+@dataclass
+class PackedPaths:
+  """Function draws  f_{s,l}(x) = mean_l + sum_i w[l,i,s] phi_{l,i}(x) + sum_j v[l,j,s] k_l(x, z_{l,j})."""
+  basis: torch.Tensor       # [L,F,BS]
+  zbasis: torch.Tensor      # [L,Mpad,BS]
+  w: torch.Tensor           # [L,F,ldS]
+  v: torch.Tensor           # [L,Mpad,ldS]
+  amp: torch.Tensor         # [L]
+  variance: torch.Tensor    # [L]
+  inv_lengthscales: torch.Tensor   # [L,D]
+  mean_const: torch.Tensor  # [L]
+  num_particles: int
+  D: int
+
+  @staticmethod
+  def layout(S: int, F: int, M: int):
+    lib = _lib.load()
+    tile, ppc = lib.gpp_pathwise_tile(), lib.gpp_pathwise_particles_per_cta()
+    return _round_up(S, ppc), _round_up(M, tile), tile
+
+  @classmethod
+  def from_sample_major(cls, Z, lengthscales, variance, mean_const, omega, phase, w, v) -> "PackedPaths":
+    """Pack draws given in the sampler's natural layout: omega [L,F,D], phase [L,F], w [S,L,F], v [S,L,M] (all CUDA f64)."""
+    Z, lengthscales, variance, omega, phase, w, v = map(_c, (Z, lengthscales, variance, omega, phase, w, v))
+    _dev_check(Z, lengthscales, variance, omega, phase, w, v)
+    L, M, D = Z.shape
+    S, _, F = w.shape
+    ldS, Mpad, tile = cls.layout(S, F, M)
+    if F % tile:
+      raise ValueError(f"number of Fourier bases must be a multiple of {tile}")
+    dev = Z.device
+    BS = (D + 2) & ~1
+    basis = torch.empty(L, F, BS, dtype=F64, device=dev)
+    zbasis = torch.empty(L, Mpad, BS, dtype=F64, device=dev)
+    _lib.check(_lib.load().gpp_pathwise_pack_basis(L, F, M, Mpad, D, _ptr(omega), _ptr(phase), _ptr(Z), _ptr(lengthscales),
+                                                   _ptr(basis), _ptr(zbasis), _stream()))
+    wp = torch.zeros(L, F, ldS, dtype=F64, device=dev)
+    wp[:, :, :S] = w.permute(1, 2, 0)
+    vp = torch.zeros(L, Mpad, ldS, dtype=F64, device=dev)
+    vp[:, :M, :S] = v.permute(1, 2, 0)
+    mean = torch.zeros(L, dtype=F64, device=dev) if mean_const is None else _c(mean_const)
+    return cls(basis, zbasis, wp, vp, torch.sqrt(2.0 * variance / F), variance, (1.0 / lengthscales).contiguous(), mean, S, D)
+
+
+def rollout_pathwise(paths: PackedPaths, policy: PolicyParams, x0: torch.Tensor, horizon: int, active_dims: Sequence[int],
+                     cost_target: torch.Tensor, cost_W: torch.Tensor, return_trajectory: bool = False,
+                     beta: Optional[torch.Tensor] = None):
+  """loss [S] (and final states / trajectory) of S particles, particle s evaluated on function draw s."""
+  x0, cost_target, cost_W = map(_c, (x0, cost_target, cost_W))
+  _dev_check(x0, cost_target, cost_W)
+  S, Dx = x0.shape
+  if S != paths.num_particles:
+    raise ValueError("one initial state per function draw (upstream loops/pilco.py:300-303)")
+  L, F, _ = paths.basis.shape
+  Mpad = paths.zbasis.shape[1]
+  ldS = paths.w.shape[2]
+  na = len(active_dims)
+  De = Dx + na
+  R, Mp, Dp = policy.shape
+  if R != 1 or Dp != De:
+    raise ValueError("rollout_pathwise: one shared policy with input dim = encoded state dim")
+  if beta is None:
+    beta = policy.beta()
+  alpha = (policy.variance[0] * beta[0]).contiguous()
+  pZs = (policy.Z[0] / policy.lengthscales[0]).contiguous()
+  pinv = (1.0 / policy.lengthscales[0]).contiguous()
+  dev = x0.device
+  loss = torch.empty(S, dtype=F64, device=dev)
+  xf = torch.empty(S, Dx, dtype=F64, device=dev)
+  traj = torch.empty(horizon + 1, S, Dx, dtype=F64, device=dev) if return_trajectory else None
+  act = (ctypes.c_int * max(na, 1))(*active_dims)
+  _lib.check(_lib.load().gpp_rollout_pathwise_fwd(
+      S, ldS, int(horizon), L, F, Mpad, paths.D, Dx, na, act, _ptr(paths.basis), _ptr(paths.zbasis), _ptr(paths.w), _ptr(paths.v),
+      _ptr(paths.amp), _ptr(paths.variance), _ptr(paths.inv_lengthscales), _ptr(paths.mean_const), Mp, _ptr(pZs), _ptr(pinv),
+      _ptr(alpha), float(policy.squash_scale), float(policy.squash_shift), _ptr(cost_target), _ptr(cost_W), _ptr(x0), _ptr(loss),
+      _ptr(xf), _ptr(traj), _stream()))
+  return loss, xf, traj

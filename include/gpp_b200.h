@@ -113,6 +113,28 @@ int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
                        double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final,
                        void* workspace, size_t workspace_bytes, int* info, void* stream);
 
+/* ---- pathwise (sample-path) rollout ----------------------------------------------------------------------
+ * replaces the closure body of PathwisePILCO._policy_loss_closure (upstream loops/pilco.py:263-303) for paths drawn by
+ * gpflow_sampling's decoupled sampler (random-Fourier prior + canonical-basis update; contract in oracle/pathwise.py):
+ *   f_{s,l}(d) = mean_l + amp_l sum_i w[l,i,s] cos(omega_{l,i}.(d/ell_l) + b_{l,i}) + var_l sum_j v[l,j,s] exp(-|d/ell_l - z_{l,j}/ell_l|^2/2)
+ * Layouts (particle-minor so that a warp streams 256 contiguous bytes per feature):
+ *   basis  [L,F,BS]     BS = (D+2)&~1:  4 omega/(2 pi ell) [D], 4 b/(2 pi)      (gpp_pathwise_pack_basis)
+ *   zbasis [L,Mpad,BS]  z/ell [D]; rows >= M are zero and must carry zero weights
+ *   w [L,F,ldS], v [L,Mpad,ldS]  with ldS a multiple of gpp_pathwise_particles_per_cta(), F and Mpad multiples of gpp_pathwise_tile()
+ *   policy: centres / ell_pi [Mp,De], 1/ell_pi [De], alpha = var_pi Kuu^-1 m [Mp] (deterministic mean, models/core.py:61-71)
+ *   x0 [S,Dx] -> loss [S], optional x_final [S,Dx], traj [H+1,S,Dx]. */
+int gpp_pathwise_tile(void);
+int gpp_pathwise_particles_per_cta(void);
+int gpp_pathwise_pack_basis(int L, int F, int M, int Mpad, int D, const double* omega /*[L,F,D]*/, const double* phase /*[L,F]*/,
+                            const double* Z /*[L,M,D]*/, const double* lengthscales /*[L,D]*/, double* basis, double* zbasis,
+                            void* stream);
+int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
+                             const double* basis, const double* zbasis, const double* w, const double* v, const double* amp,
+                             const double* variance, const double* inv_lengthscales, const double* mean_const,
+                             int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                             double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                             const double* x0, double* loss, double* x_final, double* traj, void* stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------------
  * gpp_profile_enable(1): every entry point records CUDA events on its stream around its dominant kernel
  * (k_contract for gpp_mm_gp_predict_fwd, k_ekzxkxz for gpp_ekzxkxz, the rollout kernels for the rollouts).
