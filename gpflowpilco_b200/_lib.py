@@ -34,6 +34,11 @@ SIGNATURES = {
     "gpp_rollout_pathwise_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
                                          _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
                                          _P, _P, _P, _P, _P]),
+    "gpp_philox_raw": (c_int, [c_ulonglong, c_int, ctypes.c_uint, c_ulonglong, _P, _P]),
+    "gpp_pathwise_draw_basis": (c_int, [c_int, c_int, c_int, c_ulonglong, _P, _P, _P]),
+    "gpp_pathwise_draw_x0": (c_int, [c_int, c_ulonglong, c_int, _P, _P, c_ulonglong, _P, _P]),
+    "gpp_pathwise_generate_workspace_bytes": (c_size_t, [_P, c_int, c_int]),
+    "gpp_pathwise_generate": (c_int, [_P, c_int, c_int, c_ulonglong, c_int, c_int, c_ulonglong, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gpp_profile_enable": (c_int, [c_int]),
     "gpp_profile_last_ms": (c_int, [POINTER(ctypes.c_float)]),
     "gpp_microbench_fp64": (c_int, [c_int, c_int, c_int, _P, _P]),

@@ -144,6 +144,16 @@ int gpp_gp_model_create(gpp_gp_model** out, int L, int M, int D, const double* Z
     status = GPP_ERR_CUDA;
     goto done;
   }
+  if (cudaMalloc(&m->q_mu, sizeof(double) * M * L) != cudaSuccess || cudaMalloc(&m->q_sqrt, sizeof(double) * L * mm) != cudaSuccess) {
+    gpp::set_error("gpp_gp_model_create: device allocation failed (q_mu/q_sqrt copies)");
+    status = GPP_ERR_CUDA;
+    goto done;
+  }
+  cudaMemcpyAsync(m->q_mu, q_mu, sizeof(double) * M * L, cudaMemcpyDeviceToDevice, stream);
+  for (int l = 0; l < L; ++l) {
+    tril_kernel<<<grd, blk, 0, stream>>>(q_sqrt ? q_sqrt + (size_t)l * mm : nullptr, M, m->q_sqrt + (size_t)l * mm);
+    m->h_jitter.push_back(kuu_jitter[l]);
+  }
   if (W) {
     if (cudaMalloc(&m->W, sizeof(double) * P * L) != cudaSuccess) { status = GPP_ERR_CUDA; goto done; }
     cudaMemcpyAsync(m->W, W, sizeof(double) * P * L, cudaMemcpyDeviceToDevice, stream);
@@ -225,7 +235,8 @@ done:
 int gpp_gp_model_destroy(gpp_gp_model* m) {
   if (!m) return GPP_OK;
   cudaFree(m->Z); cudaFree(m->ell); cudaFree(m->var); cudaFree(m->beta); cudaFree(m->C);
-  cudaFree(m->mean); cudaFree(m->W); cudaFree(m->Luu);
+  cudaFree(m->mean); cudaFree(m->W); cudaFree(m->Luu); cudaFree(m->q_mu); cudaFree(m->q_sqrt);
+  if (m->blas) cublasDestroy((cublasHandle_t)m->blas);
   for (int t = 0; t < 2; ++t)
     for (int d = 0; d < 2; ++d) {
       cudaFree(m->tables[t][d].d_slots);

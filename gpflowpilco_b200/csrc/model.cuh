@@ -23,6 +23,10 @@ struct gpp_gp_model {
   double* mean = nullptr;     // [P] (zeros if none)
   double* W = nullptr;        // [P,L] or null
   double* Luu = nullptr;      // [L,M,M]   row-major lower Cholesky of Kuu (kept for the pathwise update)
+  double* q_mu = nullptr;     // [M,L]     copies of the variational parameters (pathwise u-samples)
+  double* q_sqrt = nullptr;   // [L,M,M]   lower triangle only (zeros if none)
+  std::vector<double> h_jitter;   // [L] diagonal added to Kuu
+  void* blas = nullptr;       // lazily created cublasHandle_t used by gpp_pathwise_generate
   // host copies of small parameters
   std::vector<double> h_ell, h_var;
   // slot tables (device) for the two tile sizes x {all pairs, diagonal pairs only}

@@ -113,6 +113,11 @@ class GPModelHandle:
                                                  _ptr(q_mu), _ptr(q_sqrt), int(bool(whiten)), _ptr(mean_const), _ptr(W), P,
                                                  arr, int(bool(model_uncertainty)), _stream()))
     self._ws = None
+    self._params = (lengthscales, variance, Z, torch.zeros(P, dtype=F64, device=self.device) if mean_const is None else mean_const)
+
+  def parameters(self):
+    """(lengthscales [L,D], variance [L], Z [L,M,D], mean_const [P]) as passed at construction."""
+    return self._params
 
   def __del__(self):
     h = getattr(self, "_h", None)

@@ -65,6 +65,58 @@ class PackedPaths:
     return cls(basis, zbasis, wp, vp, torch.sqrt(2.0 * variance / F), variance, (1.0 / lengthscales).contiguous(), mean, S, D)
 
 
+def philox_raw(first_index: int, count: int, stream_id: int, seed: int, device="cuda") -> torch.Tensor:
+  """Raw Philox4x32-10 words [count,4] (int64 holding uint32) — bit-exactness hook against oracle/philox.py."""
+  out = torch.empty(count, 4, dtype=torch.int32, device=device)
+  _lib.check(_lib.load().gpp_philox_raw(int(first_index), int(count), int(stream_id), int(seed), _ptr(out), _stream()))
+  return out.to(torch.int64) & 0xFFFFFFFF
+
+
+def draw_basis(L: int, F: int, D: int, seed: int, device="cuda"):
+  omega = torch.empty(L, F, D, dtype=F64, device=device)
+  phase = torch.empty(L, F, dtype=F64, device=device)
+  _lib.check(_lib.load().gpp_pathwise_draw_basis(L, F, D, int(seed), _ptr(omega), _ptr(phase), _stream()))
+  return omega, phase
+
+
+def draw_initial_states(m0: torch.Tensor, S0: torch.Tensor, seed: int, first_particle: int, count: int) -> torch.Tensor:
+  """x0_s = m0 + chol(S0) n_s for global particles first_particle.. (upstream loops/pilco.py:300-303: p.sample([batch]))."""
+  m0, chol = _c(m0.reshape(-1)), _c(torch.linalg.cholesky(S0.reshape(m0.numel(), m0.numel())))
+  _dev_check(m0, chol)
+  x0 = torch.empty(count, m0.numel(), dtype=F64, device=m0.device)
+  _lib.check(_lib.load().gpp_pathwise_draw_x0(count, int(first_particle), m0.numel(), _ptr(m0), _ptr(chol), int(seed), _ptr(x0), _stream()))
+  return x0
+
+
+def generate_paths(handle, num_samples: int, num_bases: int, seed: int, first_particle: int = 0, basis=None,
+                   out: Optional[PackedPaths] = None) -> PackedPaths:
+  """Draw `num_samples` function samples of the GP behind `handle` (ops.GPModelHandle) for global particles
+  first_particle.. ; the basis (omega, phase) is shared by all particles and depends on the seed only.
+  Mirrors drift.generate_paths(num_samples, num_bases, sample_axis=0) (upstream loops/pilco.py:282-284)."""
+  lib = _lib.load()
+  L, M, D = handle.L, handle.M, handle.D
+  ldS, Mpad, tile = PackedPaths.layout(num_samples, num_bases, M)
+  if num_bases % tile:
+    raise ValueError(f"num_bases must be a multiple of {tile}")
+  dev = handle.device
+  omega, phase = draw_basis(L, num_bases, D, seed, dev) if basis is None else basis
+  if out is None:
+    BS = (D + 2) & ~1
+    ell, var, Z, mean = handle.parameters()
+    pb = torch.empty(L, num_bases, BS, dtype=F64, device=dev)
+    zb = torch.empty(L, Mpad, BS, dtype=F64, device=dev)
+    _lib.check(lib.gpp_pathwise_pack_basis(L, num_bases, M, Mpad, D, _ptr(omega), _ptr(phase), _ptr(Z), _ptr(ell), _ptr(pb), _ptr(zb), _stream()))
+    out = PackedPaths(pb, zb, torch.empty(L, num_bases, ldS, dtype=F64, device=dev), torch.empty(L, Mpad, ldS, dtype=F64, device=dev),
+                      torch.sqrt(2.0 * var / num_bases), var, (1.0 / ell).contiguous(), mean, num_samples, D)
+  need = lib.gpp_pathwise_generate_workspace_bytes(handle._h, ldS, num_bases)
+  ws = torch.empty(need, dtype=torch.uint8, device=dev)
+  _lib.check(lib.gpp_pathwise_generate(handle._h, num_samples, ldS, int(first_particle), num_bases, Mpad, int(seed), _ptr(omega), _ptr(phase),
+                                       _ptr(out.w), _ptr(out.v), _ptr(ws), ws.numel(), _stream()))
+  out.num_particles = num_samples
+  out.omega, out.phase = omega, phase
+  return out
+
+
 def rollout_pathwise(paths: PackedPaths, policy: PolicyParams, x0: torch.Tensor, horizon: int, active_dims: Sequence[int],
                      cost_target: torch.Tensor, cost_W: torch.Tensor, return_trajectory: bool = False,
                      beta: Optional[torch.Tensor] = None):

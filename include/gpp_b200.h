@@ -135,6 +135,24 @@ int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int 
                              double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
                              const double* x0, double* loss, double* x_final, double* traj, void* stream);
 
+/* ---- pathwise draws on the device (counter-based, sharding-invariant) --------------------------------------
+ * Random streams: Philox4x32-10 keyed by (seed, stream, logical element index) with the GLOBAL particle index in the
+ * element index (oracle/philox.py is the contract; raw words are bit-identical).  Replaces the set-up half of
+ * gpflow_sampling's generate_paths (upstream call site loops/pilco.py:281-284) and p.sample (loops/pilco.py:300-303).
+ *   gpp_philox_raw          raw 4x32-bit words of counters first_index.. (test hook for bit-exactness)
+ *   gpp_pathwise_draw_basis omega [L,F,D] ~ N(0,1), phase [L,F] ~ U(0, 2 pi)
+ *   gpp_pathwise_draw_x0    x0[s] = m0 + chol0 n_s for global particles first_particle .. first_particle+S-1
+ *   gpp_pathwise_generate   w [L,F,ldS] and v [L,Mpad,ldS] for those particles, from the model handle's q(u). */
+int gpp_philox_raw(unsigned long long first_index, int count, unsigned stream_id, unsigned long long seed,
+                   unsigned* out /*[count,4]*/, void* stream);
+int gpp_pathwise_draw_basis(int L, int F, int D, unsigned long long seed, double* omega, double* phase, void* stream);
+int gpp_pathwise_draw_x0(int S, unsigned long long first_particle, int Dx, const double* m0, const double* chol0 /*[Dx,Dx] lower*/,
+                         unsigned long long seed, double* x0 /*[S,Dx]*/, void* stream);
+size_t gpp_pathwise_generate_workspace_bytes(const gpp_gp_model* model, int ldS, int F);
+int gpp_pathwise_generate(gpp_gp_model* model, int S, int ldS, unsigned long long first_particle, int F, int Mpad,
+                          unsigned long long seed, const double* omega, const double* phase, double* w, double* v,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------------
  * gpp_profile_enable(1): every entry point records CUDA events on its stream around its dominant kernel
  * (k_contract for gpp_mm_gp_predict_fwd, k_ekzxkxz for gpp_ekzxkxz, the rollout kernels for the rollouts).
