@@ -44,6 +44,10 @@ def parse_args():
   ap.add_argument("--inputs", type=int, default=8192, help="Gaussian inputs per GPU (weak scaling)")
   ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-pathwise", action="store_true")
+  ap.add_argument("--pathwise-particles", type=int, default=148 * 256, help="particles per GPU per launch (one wave of CTAs)")
+  ap.add_argument("--pathwise-horizon", type=int, default=100)
+  ap.add_argument("--pathwise-bases", type=int, default=4096)
   return ap.parse_args()
 
 
@@ -161,6 +165,68 @@ def time_cpu(cfg, seconds: float, reference_form: bool, steps: int = 1):
   best = min(times)
   form = "upstream triangular-solve form" if reference_form else "O(M^2) re-associated form"
   return n / best, f"{n} of the {cfg['mu'].shape[0]} inputs of config #2 per step, {form}, torch float64, {torch.get_num_threads()} threads", 1e3 * float(np.mean(times))
+
+
+ARGS = None
+
+
+def pathwise_section(dev, lib, pk, world):
+  """Second half of BASELINE's metric: pathwise trajectory-steps/s (config #4 shapes: L=4, M=256, D=6, F=4096, H=100).
+  Particles are sharded over ranks by global index (no data-path collective); value is the whole-job aggregate."""
+  import ctypes
+  import torch
+  import torch.distributed as dist
+  from gpflowpilco_b200 import ops, synthetic
+  from gpflowpilco_b200.pathwise import draw_initial_states, generate_paths, rollout_pathwise
+  from gpflowpilco_b200.rollouts import PolicyParams
+  args = ARGS
+  rank = int(os.environ.get("RANK", "0"))
+  S, H, F = args.pathwise_particles, args.pathwise_horizon, args.pathwise_bases
+  cfg = synthetic.config1_cartpole()
+  T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+  d, p = cfg["dynamics"], cfg["policy"]
+  handle = ops.GPModelHandle(T(d["Z"]), T(d["lengthscales"]), T(d["variance"]), T(d["q_mu"]), T(d["q_sqrt"]), whiten=True,
+                             mean_const=T(d["mean_const"]))
+  policy = PolicyParams(T(p["Z"]), T(p["lengthscales"]), T(p["variance"]), T(p["q_mu"][:, 0][None]), whiten=True,
+                        squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  t0 = time.perf_counter()
+  paths = generate_paths(handle, S, F, seed=0, first_particle=rank * S)
+  x0 = draw_initial_states(T(cfg["m0"][0]), T(cfg["S0"][0]), 0, rank * S, S)
+  torch.cuda.synchronize()
+  gen_s = time.perf_counter() - t0
+  beta = policy.beta()
+  target, W = T(cfg["target"]), T(cfg["W"])
+  lib.gpp_profile_enable(1)
+  times = []
+  for it in range(3):
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    loss, _, _ = rollout_pathwise(paths, policy, x0, H, cfg["active_dims"], target, W, beta=beta)
+    ms = ctypes.c_float()
+    lib.gpp_profile_last_ms(ctypes.byref(ms))
+    if it:
+      times.append(ms.value)
+  lib.gpp_profile_enable(0)
+  t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  sec = float(t[0]) * 1e-3
+  L, M, D = 4, d["Z"].shape[1], 6
+  bytes_per_pstep = 8 * L * (F + M) + 2 * 8 * 4
+  flop_per_pstep = L * F * (2 * D + 2 + 20) + L * M * (2 * D + 2 + 20) + 30 * (2 * 5 + 22)
+  psteps = S * H
+  return {
+      "metric": "pathwise_particle_steps_per_s", "value": world * psteps / sec, "unit": "particle_steps/s",
+      "config": {"workload": "config#4 pathwise cart-pole rollouts", "particles_per_gpu_per_launch": S, "bases": F, "horizon": H,
+                 "latents": L, "inducing": M, "weights": "streamed from HBM (generated on device beforehand, Philox by global particle index)",
+                 "note": "1M particles = ceil(2^20 / particles_per_launch) identical launches per GPU"},
+      "ms_per_launch": 1e3 * sec, "generation_s": gen_s, "mean_loss": float(loss.mean()),
+      "roofline": {"bound": "hbm", "achieved": bytes_per_pstep * psteps / sec / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                   "frac": bytes_per_pstep * psteps / sec / 1e9 / pk.get("hbm_gbs"), "traffic": None, "kernel": "k_pathwise_rollout",
+                   "algorithmic": f"{bytes_per_pstep} B and {flop_per_pstep} flop per particle-step",
+                   "fp64_achieved_tflops": flop_per_pstep * psteps / sec / 1e12},
+  }
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -315,6 +381,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if not args.no_pathwise:
+      line["pathwise"] = pathwise_section(dev, lib, pk, world)
     if not args.no_cpu_baseline:
       small = {k: (v[:64] if k in ("mu", "cov") else v) for k, v in cfg.items()}
       rate, sample, _ = time_cpu(small, args.cpu_baseline_seconds, reference_form=True)
@@ -328,7 +396,9 @@ def run_b200(args):
 
 
 def main():
+  global ARGS
   args = parse_args()
+  ARGS = args
   if args.impl == "reference":
     run_reference(args)
   else:

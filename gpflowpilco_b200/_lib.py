@@ -24,6 +24,11 @@ SIGNATURES = {
                                     POINTER(c_double), c_int, _P]),
     "gpp_gp_model_destroy": (c_int, [_P]),
     "gpp_gp_model_weights": (c_int, [_P, _P, _P, _P]),
+    "gpp_mm_encoder": (c_int, [c_int, c_int, c_int, POINTER(c_int), _P, _P, _P, _P, _P, _P]),
+    "gpp_mm_squash": (c_int, [c_int, _P, _P, c_double, c_double, _P, _P, _P, _P]),
+    "gpp_cost_gaussian": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "gpp_cost_samples": (c_int, [c_int, c_int, _P, _P, _P, _P, _P]),
+    "gpp_owens_t": (c_int, [c_int, _P, _P, _P, _P]),
     "gpp_policy_prepare": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_double, _P, _P, _P]),
     "gpp_rollout_mm_workspace_bytes": (c_size_t, [_P, c_int, c_int]),
     "gpp_rollout_mm_fwd": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_double, c_double,

@@ -82,6 +82,9 @@ __device__ __forceinline__ void cos_quarter_turns(double (&q)[K]) {
   }
 }
 
+constexpr int kPathP = 512;    // particles per CTA (one consumer thread each) -> 16 consumer warps + 1 producer warp
+constexpr int kPathTF = 8;    // feature rows per pipeline stage
+
 struct PathwiseParams {
   EncoderSpec enc;
   int S, ldS, H, L, F, Mpad, Dx, De, Mp;
@@ -321,7 +324,7 @@ __global__ void k_pack_basis(int L, int F, int M, int Mpad, int D, int BS, const
 
 template <int D>
 static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
-  constexpr int P = 256, TF = 16, NS = 4;
+  constexpr int P = kPathP, TF = kPathTF, NS = 4;
   using CF = PathwiseCfg<D, P, TF, NS>;
   static bool configured = false;
   if (!configured) {
@@ -341,8 +344,8 @@ static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
 
 extern "C" {
 
-int gpp_pathwise_tile(void) { return 16; }
-int gpp_pathwise_particles_per_cta(void) { return 256; }
+int gpp_pathwise_tile(void) { return gpp::kPathTF; }
+int gpp_pathwise_particles_per_cta(void) { return gpp::kPathP; }
 
 int gpp_pathwise_pack_basis(int L, int F, int M, int Mpad, int D, const double* omega, const double* phase, const double* Z,
                             const double* lengthscales, double* basis, double* zbasis, void* stream) {
@@ -368,8 +371,8 @@ int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int 
   GPP_REQUIRE(S >= 1 && H >= 0 && L >= 1 && L <= GPP_SMALL_MAX && Dx >= 1 && Dx <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE,
               "gpp_rollout_pathwise_fwd: bad sizes S=%d H=%d L=%d Dx=%d", S, H, L, Dx);
   GPP_REQUIRE(L == Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: the drift must have one output per state dim (L=%d, Dx=%d)", L, Dx);
-  GPP_REQUIRE(F % 16 == 0 && Mpad % 16 == 0, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: F=%d and Mpad=%d must be multiples of 16", F, Mpad);
-  GPP_REQUIRE(ldS % 256 == 0 && ldS >= S, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: ldS=%d must be a multiple of 256 and >= S=%d", ldS, S);
+  GPP_REQUIRE(F % kPathTF == 0 && Mpad % kPathTF == 0, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: F=%d and Mpad=%d must be multiples of %d", F, Mpad, kPathTF);
+  GPP_REQUIRE(ldS % kPathP == 0 && ldS >= S, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: ldS=%d must be a multiple of %d and >= S=%d", ldS, kPathP, S);
   GPP_REQUIRE(Mp >= 1 && Mp <= 64, GPP_ERR_UNSUPPORTED, "gpp_rollout_pathwise_fwd: Mp=%d policy centres (max 64)", Mp);
   GPP_REQUIRE(num_active >= 0 && num_active <= 4 && D == Dx + num_active + 1, GPP_ERR_BAD_SHAPE,
               "gpp_rollout_pathwise_fwd: D=%d must be Dx + num_active + 1", D);

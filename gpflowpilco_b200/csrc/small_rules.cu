@@ -1,0 +1,112 @@
+// Batched entry points for the small moment-matching rules (one thread per Gaussian state), used by the Python
+// façade when the rules are applied one at a time (moment_matching(x, encoder), moment_matching(x, bijector), objective(x))
+// instead of through the fused rollout.  Same device code as the rollout kernels (mm_small.cuh).
+#include "mm_small.cuh"
+
+namespace gpp {
+
+__global__ void k_mm_encoder(EncoderSpec es, int N, const double* m, const double* S, double* me, double* See, double* Cxe) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int Dx = es.Dx, De = es.De();
+  double lm[GPP_SMALL_MAX], lS[GPP_SMALL_MAX * GPP_SMALL_MAX], ome[GPP_SMALL_MAX], oS[GPP_SMALL_MAX * GPP_SMALL_MAX],
+      oC[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  for (int i = 0; i < Dx; ++i) lm[i] = m[(size_t)n * Dx + i];
+  for (int i = 0; i < Dx * Dx; ++i) lS[i] = S[(size_t)n * Dx * Dx + i];
+  mm_encoder<double>(es, lm, lS, ome, oS, oC);
+  for (int i = 0; i < De; ++i) me[(size_t)n * De + i] = ome[i];
+  for (int i = 0; i < De * De; ++i) See[(size_t)n * De * De + i] = oS[i];
+  for (int i = 0; i < Dx * De; ++i) Cxe[(size_t)n * Dx * De + i] = oC[i];
+}
+
+__global__ void k_mm_squash(int N, const double* mf, const double* vf, double scale, double shift, double* mu, double* vu, double* gain) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double a, b, c;
+  mm_squash_1d<double>(mf[n], vf[n], scale, shift, a, b, c);
+  mu[n] = a; vu[n] = b; gain[n] = c;
+}
+
+__global__ void k_cost_gaussian(int N, int De, const double* me, const double* See, const double* target, const double* W, double* out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double lm[GPP_SMALL_MAX], lS[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  for (int i = 0; i < De; ++i) lm[i] = me[(size_t)n * De + i];
+  for (int i = 0; i < De * De; ++i) lS[i] = See[(size_t)n * De * De + i];
+  out[n] = expected_cost<double>(De, lm, lS, target, W);
+}
+
+__global__ void k_cost_samples(int N, int De, const double* e, const double* target, const double* W, double* out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double le[GPP_SMALL_MAX];
+  for (int i = 0; i < De; ++i) le[i] = e[(size_t)n * De + i];
+  out[n] = sample_cost(De, le, target, W);
+}
+
+__global__ void k_owens_t(int N, const double* h, const double* a, double* out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) out[n] = owens_t<double>(h[n], a[n]);
+}
+
+}  // namespace gpp
+
+extern "C" {
+
+int gpp_mm_encoder(int N, int Dx, int num_active, const int* active_dims, const double* m, const double* S, double* me, double* See,
+                   double* Cxe, void* stream) {
+  GPP_REQUIRE(m && S && me && See && Cxe, GPP_ERR_NULL, "gpp_mm_encoder: null argument");
+  GPP_REQUIRE(N >= 0 && Dx >= 1 && num_active >= 0 && num_active <= 4 && num_active <= Dx && Dx + num_active <= GPP_SMALL_MAX,
+              GPP_ERR_BAD_SHAPE, "gpp_mm_encoder: bad sizes Dx=%d active=%d", Dx, num_active);
+  if (N == 0) return GPP_OK;
+  gpp::EncoderSpec es{};
+  es.Dx = Dx; es.na = num_active;
+  for (int k = 0; k < num_active; ++k) {
+    GPP_REQUIRE(active_dims[k] >= 0 && active_dims[k] < Dx, GPP_ERR_BAD_SHAPE, "gpp_mm_encoder: active dim out of range");
+    es.active[k] = active_dims[k];
+  }
+  gpp::k_mm_encoder<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(es, N, m, S, me, See, Cxe);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+int gpp_mm_squash(int N, const double* mf, const double* vf, double scale, double shift, double* mu, double* vu, double* gain, void* stream) {
+  GPP_REQUIRE(mf && vf && mu && vu && gain, GPP_ERR_NULL, "gpp_mm_squash: null argument");
+  if (N <= 0) return GPP_OK;
+  gpp::k_mm_squash<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(N, mf, vf, scale, shift, mu, vu, gain);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+int gpp_cost_gaussian(int N, int De, const double* me, const double* See, const double* target, const double* W, double* out, void* stream) {
+  GPP_REQUIRE(me && See && target && W && out, GPP_ERR_NULL, "gpp_cost_gaussian: null argument");
+  GPP_REQUIRE(De >= 1 && De <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE, "gpp_cost_gaussian: De=%d", De);
+  if (N <= 0) return GPP_OK;
+  gpp::k_cost_gaussian<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(N, De, me, See, target, W, out);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+int gpp_cost_samples(int N, int De, const double* e, const double* target, const double* W, double* out, void* stream) {
+  GPP_REQUIRE(e && target && W && out, GPP_ERR_NULL, "gpp_cost_samples: null argument");
+  GPP_REQUIRE(De >= 1 && De <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE, "gpp_cost_samples: De=%d", De);
+  if (N <= 0) return GPP_OK;
+  gpp::k_cost_samples<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, De, e, target, W, out);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+int gpp_owens_t(int N, const double* h, const double* a, double* out, void* stream) {
+  GPP_REQUIRE(h && a && out, GPP_ERR_NULL, "gpp_owens_t: null argument");
+  if (N <= 0) return GPP_OK;
+  gpp::k_owens_t<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, h, a, out);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+}  // extern "C"

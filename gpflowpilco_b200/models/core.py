@@ -231,14 +231,21 @@ class Scale(Bijector):
   def __init__(self, scale):
     self.scale = float(scale)
 
+  def __call__(self, x):
+    return self.scale * x
+
 
 class Shift(Bijector):
   def __init__(self, shift):
     self.shift = float(shift)
 
+  def __call__(self, x):
+    return x + self.shift
+
 
 class NormalCDF(Bijector):
-  pass
+  def __call__(self, x):
+    return 0.5 * torch.erfc(-x * 0.7071067811865476)     # ndtr, upstream utils/bvn.py:38-42
 
 
 class BijectorChain(Bijector):
@@ -246,6 +253,11 @@ class BijectorChain(Bijector):
 
   def __init__(self, bijectors: Sequence[Bijector]):
     self.bijectors = list(bijectors)
+
+  def __call__(self, x):
+    for b in reversed(self.bijectors):
+      x = b(x)
+    return x
 
   def squash_parameters(self) -> Tuple[float, float]:
     """(scale, shift) if the chain is Scale o Shift o NormalCDF (the upstream policy link), else raises."""

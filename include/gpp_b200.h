@@ -87,6 +87,23 @@ int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m /*[N,D]*/, 
                           int full_output_cov, double jitter,
                           void* workspace, size_t workspace_bytes, int* info, void* stream);
 
+/* ---- small moment-matching rules, batched (one thread per Gaussian state) -----------------------------------
+ *   gpp_mm_encoder    e = [sin x_a, cos x_a, x_b]: mean me [N,De], covariance See [N,De,De], Cxe = Cov(x,e) [N,Dx,De]
+ *                     (upstream moment_matching/components.py:19-57 with maths.py:143-176; De = Dx + num_active)
+ *   gpp_mm_squash     u = scale (Phi(f) + shift), f ~ N(mf, vf): mean, variance and gain = Cov(f,f)^-1 Cov(f,u)
+ *                     (upstream moment_matching/bijectors.py:21-69 chained with maths.py:47-78; Owen's T on device)
+ *   gpp_cost_gaussian E[-exp(-1/2 (e-t)^T W (e-t))] for e ~ N(me, See)   (upstream components.py:30-37)
+ *   gpp_cost_samples  -exp(-1/2 (e-t)^T W (e-t))                           (upstream components.py:39-41)
+ *   gpp_owens_t       Owen's T(h, a), 0 < a <= 1 (stands in for tfp.math.owens_t, upstream bijectors.py:15,58) */
+int gpp_mm_encoder(int N, int Dx, int num_active, const int* active_dims /*host*/, const double* m, const double* S,
+                   double* me, double* See, double* Cxe, void* stream);
+int gpp_mm_squash(int N, const double* mf, const double* vf, double scale, double shift, double* mu, double* vu, double* gain,
+                  void* stream);
+int gpp_cost_gaussian(int N, int De, const double* me, const double* See, const double* target, const double* W, double* out,
+                      void* stream);
+int gpp_cost_samples(int N, int De, const double* e, const double* target, const double* W, double* out, void* stream);
+int gpp_owens_t(int N, const double* h, const double* a, double* out, void* stream);
+
 /* ---- policy weights ---------------------------------------------------------------------------------------
  * beta_r = Kuu_r^-1 m_r for R small SE-ARD kernel regressors (KernelRegressor(SVGP), upstream models/core.py:61-63,
  * moment_matching/models.py:228-235): whitened beta = Luu^-T q_mu, else Kuu^-1 q_mu; Kuu includes `jitter`.

@@ -1,0 +1,144 @@
+"""GPU tests of the reference-facing Python surface (same names / call structure as upstream gpflow_pilco):
+moment_matching rules one at a time, kernel_expectation, forward_sde + MomentMatchingEuler (rule-by-rule path) against
+the fused rollout and against the oracle, and the two PILCO policy-loss closures."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from gpflowpilco_b200 import synthetic
+from oracle import gp_models as gm
+from oracle import moments as mo
+from oracle import psi_stats as ps
+from oracle import rollout as ro
+from tests.helpers import DTYPE, generate_covariance, log_uniform, oracle_svgp, scaled_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x):
+  return torch.as_tensor(x, dtype=DTYPE, device="cuda")
+
+
+def _facade_models(cfg):
+  from gpflowpilco_b200 import models as M
+  d, p = cfg["dynamics"], cfg["policy"]
+  L = d["Z"].shape[0]
+  drift = M.SVGP(M.SeparateIndependent([M.SquaredExponential(_dev(d["variance"][l]), _dev(d["lengthscales"][l])) for l in range(L)]),
+                 M.SeparateIndependentInducingVariables([M.InducingPoints(_dev(d["Z"][l])) for l in range(L)]),
+                 _dev(d["q_mu"]), _dev(d["q_sqrt"]), whiten=True, mean_function=M.Constant(_dev(d["mean_const"])))
+  pol_svgp = M.SVGP(M.SeparateIndependent([M.SquaredExponential(_dev(p["variance"][0]), _dev(p["lengthscales"][0]))]),
+                    M.SeparateIndependentInducingVariables([M.InducingPoints(_dev(p["Z"][0]))]), _dev(p["q_mu"]), _dev(p["q_sqrt"]),
+                    whiten=True, mean_function=M.Constant(_dev(p["mean_const"])))
+  link = M.BijectorChain([M.Scale(cfg["squash_scale"]), M.Shift(cfg["squash_shift"]), M.NormalCDF()])
+  policy = M.InverseLinkWrapper(M.KernelRegressor(pol_svgp), invlink=link)
+  return drift, policy
+
+
+def test_rules_one_at_a_time():
+  from gpflowpilco_b200.components import GaussianObjective, TrigonometricEncoder, sincos
+  from gpflowpilco_b200.moment_matching import GaussianMoments, moment_matching
+  from gpflowpilco_b200 import models as M
+  g = torch.Generator().manual_seed(0)
+  m = torch.randn(3, 4, dtype=DTYPE, generator=g)
+  S = generate_covariance(4, [3], 0.3, g)
+  x = GaussianMoments((_dev(m), _dev(S)), True)
+  ox = mo.GaussianMoments(m, S, True)
+  # encoder (upstream tests/test_components.py:69-104 checks this rule against MC; here against the oracle)
+  for active in [(1,), (2, 3), (0, 1, 2, 3)]:
+    a = moment_matching(x, TrigonometricEncoder(active))
+    b = mo.mm_encoder(ox, mo.TrigonometricEncoder(active))
+    scaled_close(a.y.mean(), b.y.mean(), 1e-13, "encoder mean")
+    scaled_close(a.y.covariance(), b.y.covariance(), 1e-12, "encoder cov")
+    scaled_close(a.cross_covariance(), b.cross_covariance(), 1e-12, "encoder cross")
+  # sincos / sin / cos
+  a, b = moment_matching(x, sincos), mo.mm_sincos(ox)
+  scaled_close(a.y.covariance(), b.y.covariance(), 1e-12, "sincos cov")
+  scaled_close(a.cross[0], b.cross[0], 1e-13, "sincos cross")
+  scaled_close(moment_matching(x, torch.cos).y.covariance(), mo.mm_cos(ox).y.covariance(), 1e-12, "cos cov")
+  scaled_close(moment_matching(x, torch.sin).cross[0], mo.mm_sin(ox).cross[0], 1e-13, "sin cross")
+  # squash chain on a 1-D Gaussian
+  x1 = GaussianMoments((_dev(m[:, :1]), _dev(S[:, :1, :1])), True)
+  link = M.BijectorChain([M.Scale(20 - 1e-5), M.Shift(-0.5), M.NormalCDF()])
+  a = moment_matching(x1, link)
+  b = mo.mm_squash(mo.GaussianMoments(m[:, :1], S[:, :1, :1], True), 20 - 1e-5)
+  scaled_close(a.y.mean(), b.y.mean(), 1e-13, "squash mean")
+  scaled_close(a.y.covariance(), b.y.covariance(), 1e-11, "squash var")
+  scaled_close(a.cross[0], b.cross[0], 1e-12, "squash cross")
+  # objective: expectation and samples (upstream tests/test_components.py:38-66)
+  W = torch.linalg.inv(generate_covariance(4, scale=0.5, gen=g))
+  t = torch.randn(4, dtype=DTYPE, generator=g)
+  obj, oobj = GaussianObjective(_dev(t), _dev(W)), mo.GaussianObjective(t, W)
+  scaled_close(obj(x), oobj(ox), 1e-12, "expected cost")
+  X = torch.randn(50, 4, dtype=DTYPE, generator=g)
+  scaled_close(obj(_dev(X)), oobj(X), 1e-13, "sample cost")
+
+
+def test_owens_t_against_scipy():
+  import ctypes
+  from scipy.special import owens_t
+  from gpflowpilco_b200 import _lib
+  h = np.linspace(-9, 9, 400)
+  a = np.random.default_rng(0).uniform(0.01, 1.0, 400)
+  out = torch.empty(400, dtype=DTYPE, device="cuda")
+  hd, ad = _dev(h), _dev(a)
+  _lib.check(_lib.load().gpp_owens_t(400, ctypes.c_void_p(hd.data_ptr()), ctypes.c_void_p(ad.data_ptr()), ctypes.c_void_p(out.data_ptr()), None))
+  assert float(np.abs(out.cpu().numpy() - owens_t(h, a)).max()) < 1e-15
+
+
+def test_kernel_expectation_signatures():
+  from gpflowpilco_b200 import models as M
+  from gpflowpilco_b200.utils.kernel_expectation import Gaussian, kernel_expectation
+  g = torch.Generator().manual_seed(1)
+  D, Mz, N = 3, 10, 2
+  mu = torch.randn(N, D, dtype=DTYPE, generator=g)
+  cov = generate_covariance(D, [N], 0.2, g)
+  ks = [ps.SEKernel(0.8, log_uniform([D], 0.5, 2.0, g)), ps.SEKernel(1.2, log_uniform([D], 0.5, 2.0, g))]
+  Zs = [torch.randn(Mz, D, dtype=DTYPE, generator=g) for _ in range(2)]
+  fk = [M.SquaredExponential(_dev(k.variance), _dev(k.lengthscales)) for k in ks]
+  fz = [M.InducingPoints(_dev(z)) for z in Zs]
+  p = Gaussian(_dev(mu), _dev(cov))
+  scaled_close(kernel_expectation(p, (fk[0], fz[0])), ps.eKxz(mu, cov, ks[0], Zs[0]), 1e-12, "eKxz")
+  scaled_close(kernel_expectation(p, (fk[0], fz[0]), (fk[1], fz[1])), ps.eKzxKxz(mu, cov, ks[0], Zs[0], ks[1], Zs[1]), 1e-11, "eKzxKxz")
+  mk, mz = M.SeparateIndependent(fk), M.SeparateIndependentInducingVariables(fz)
+  scaled_close(kernel_expectation(p, mk), ps.eKff_list(mu, ks), 1e-15, "eKff list")
+  scaled_close(kernel_expectation(p, (mk, mz)), ps.eKfu_list(mu, cov, ks, Zs), 1e-12, "eKfu list")
+  scaled_close(kernel_expectation(p, (mk, mz), (mk, mz)), ps.eKuffu_list(mu, cov, ks, Zs), 1e-11, "eKuffu list")
+
+
+def test_mm_closure_fused_equals_rule_by_rule_and_oracle():
+  from gpflowpilco_b200.components import GaussianObjective, TrigonometricEncoder
+  from gpflowpilco_b200.loops import EpisodeSpec, GaussianStateDistribution, MomentMatchingPILCO
+  cfg = synthetic.config1_cartpole(M=48, Mp=10)
+  drift, policy = _facade_models(cfg)
+  spec = EpisodeSpec(GaussianStateDistribution(_dev(cfg["m0"][0]), _dev(cfg["S0"][0])), horizon=0.6, step_size=0.1)
+  loop = MomentMatchingPILCO(spec, GaussianObjective(_dev(cfg["target"]), _dev(cfg["W"])), drift, policy, TrigonometricEncoder(cfg["active_dims"]))
+  assert spec.num_steps == 6
+  fused = loop.policy_loss_closure()()
+  stepwise = loop.policy_loss_closure(fused=False)()
+  dyn, pol = oracle_svgp(cfg["dynamics"]), oracle_svgp(cfg["policy"])
+  ref = ro.mm_rollout(torch.as_tensor(cfg["m0"]), torch.as_tensor(cfg["S0"]), 6, lambda s: gm.mm_svgp(s, dyn),
+                      lambda s: gm.mm_policy(s, pol, cfg["squash_scale"], cfg["squash_shift"]),
+                      mo.TrigonometricEncoder(cfg["active_dims"]), mo.GaussianObjective(cfg["target"], cfg["W"]))
+  scaled_close(fused, ref, 1e-7, "fused closure vs oracle")
+  scaled_close(stepwise, ref, 1e-7, "rule-by-rule closure vs oracle")
+
+
+def test_policy_sample_path_and_pathwise_closure():
+  from gpflowpilco_b200.components import GaussianObjective, TrigonometricEncoder
+  from gpflowpilco_b200.loops import EpisodeSpec, GaussianStateDistribution, PathwisePILCO
+  cfg = synthetic.config1_cartpole(M=32, Mp=10)
+  drift, policy = _facade_models(cfg)
+  g = torch.Generator().manual_seed(2)
+  e = torch.randn(9, 5, dtype=DTYPE, generator=g)
+  pol = oracle_svgp(cfg["policy"])
+  scaled_close(policy(_dev(e)), gm.policy_sample_path(pol, e, cfg["squash_scale"], cfg["squash_shift"]), 1e-10, "policy(e)")
+  spec = EpisodeSpec(GaussianStateDistribution(_dev(cfg["m0"][0]), _dev(cfg["S0"][0])), horizon=0.3, step_size=0.1)
+  loop = PathwisePILCO(spec, GaussianObjective(_dev(cfg["target"]), _dev(cfg["W"])), drift, policy, TrigonometricEncoder(cfg["active_dims"]))
+  closure = loop.policy_loss_closure(batch_size=64, num_bases=64, seed=5)
+  l1, l2 = closure(), closure()
+  assert l1.shape == (64,) and torch.isfinite(l1).all()
+  assert not torch.equal(l1, l2)          # fresh paths per call (upstream loops/pilco.py:281-284)
+  again = loop.policy_loss_closure(batch_size=64, num_bases=64, seed=5)()
+  assert torch.equal(l1, again)           # same seed -> identical draws
