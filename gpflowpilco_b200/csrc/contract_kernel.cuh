@@ -10,7 +10,7 @@
 //                        g_i = R^T z1'_i, r_i = c0 + z1'^T P1 z1'  (rows)  and  z2'_j, s_j = z2'^T P2 z2'  (columns)
 //                        into buffer b = k & 1; they also sum the lane partials of finished inputs (fixed order).
 //   consumer warps (NC)  lane l owns rows {l, l+32, ..} (RPT = T/32 register tile), warp w owns a slice of columns.
-//                        Per entry: 1 DADD + D DFMA + 16 FP64 (exp) + 1 DFMA.  The RPT row chains of a thread share
+//                        Per entry: 1 DADD + D DFMA + 10 FP64 (table exp, gpp_math.h) + 1 DFMA.  The RPT row chains of a thread share
 //                        their column operands, which makes ptxas interleave them (a dependent DFMA issues 8 cycles
 //                        after its producer, the pipe accepts one warp instruction every 2 cycles).
 // Shared-memory layouts make every warp access a broadcast or unit-stride (no bank conflicts):
@@ -43,7 +43,8 @@ struct ContractCfg {
   static constexpr int COL = CT + T * T;                        // [2][T][STRIDE]
   static constexpr int ROW = COL + 2 * T * ColLayout<D>::STRIDE;   // [2][D+2][T]
   static constexpr int RED = ROW + 2 * (D + 2) * T;             // [2][NC][32]
-  static constexpr int TOTAL = RED + 2 * NC * 32;               // doubles
+  static constexpr int ETAB = RED + 2 * NC * 32;                // [64][GPP_EXP_TAB_REP] replicated 2^(j/64) table (fast_exp_tab_n)
+  static constexpr int TOTAL = ETAB + 64 * GPP_EXP_TAB_REP;     // doubles
 };
 
 // barrier ids are immediates (a register id would make ptxas reserve all 16 hardware barriers for the CTA)
@@ -64,6 +65,41 @@ __device__ __forceinline__ void named_bar_arrive(int b, int count) {
   if (b) named_bar_arrive_imm<BASE + 1>(count); else named_bar_arrive_imm<BASE>(count);
 }
 
+// One work item = (slot, input chunk).  Both roles walk the same item sequence: thread 0 draws the next item from the global
+// counter and every thread of the CTA reads it between two CTA-wide barriers; the C tile load is shared too.
+struct ContractItem {
+  gpp_slot sl;
+  int slot_id, n0, K;
+  bool diag;
+};
+
+template <int D, int T, int NP, int NC>
+__device__ __forceinline__ bool contract_next_item(const ContractParams& p, double* Ct, int* s_item, ContractItem& it) {
+  constexpr int NT = ContractCfg<D, T, NP, NC>::NT;
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid == 0) *s_item = (int)atomicAdd(p.counter, 1u);
+  __syncthreads();
+  const int item = *s_item;
+  if (item >= p.nslots * p.nchunks) return false;
+  it.slot_id = item / p.nchunks;
+  const int chunk_id = item % p.nchunks;
+  it.sl = p.slots[it.slot_id];
+  it.n0 = chunk_id * p.chunk;
+  it.K = min(p.N, it.n0 + p.chunk) - it.n0;
+  it.diag = (it.sl.a == it.sl.b);
+  if (it.diag) {   // C is symmetric: read C[j][i] so that global reads and the later lane-wise smem reads are unit-stride
+    const double* Ca = p.C + (size_t)it.sl.a * p.M * p.M;
+    for (int idx = tid; idx < T * T; idx += NT) {
+      int jj = idx / T, ii = idx % T;
+      int jg = it.sl.tj * T + jj, ig = it.sl.ti * T + ii;
+      Ct[idx] = (jg < p.M && ig < p.M) ? Ca[(size_t)jg * p.M + ig] : 0.0;
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
 template <int D, int T, int NP, int NC>
 __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   using PP = PairPack<D>;
@@ -80,41 +116,20 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   double* colbuf = smem + CF::COL;
   double* rowbuf = smem + CF::ROW;
   double* red = smem + CF::RED;
+  double* etab = smem + CF::ETAB;
   __shared__ int s_item;
+  for (int i = threadIdx.x; i < 64 * GPP_EXP_TAB_REP; i += NT) etab[i] = kExp2Tab[i / GPP_EXP_TAB_REP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool producer = warp < NP;
-  const int cwarp = warp - NP;               // consumer warp index
-  // consumer column slice: T columns over NC warps, first (T % NC) warps take one more
-  const int cw = T / NC + ((cwarp >= 0 && cwarp < T % NC) ? 1 : 0);
-  const int c0 = cwarp * (T / NC) + min(max(cwarp, 0), T % NC);
-  const int nitems = p.nslots * p.nchunks;
+  ContractItem it;
 
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = (int)atomicAdd(p.counter, 1u);
-    __syncthreads();
-    const int item = s_item;
-    if (item >= nitems) break;
-    const int slot_id = item / p.nchunks, chunk_id = item % p.nchunks;
-    const gpp_slot sl = p.slots[slot_id];
-    const int n0 = chunk_id * p.chunk;
-    const int K = min(p.N, n0 + p.chunk) - n0;
-    const bool diag = (sl.a == sl.b);
-
-    if (diag) {   // C is symmetric: read C[j][i] so that global reads and the later lane-wise smem reads are unit-stride
-      const double* Ca = p.C + (size_t)sl.a * p.M * p.M;
-      for (int idx = tid; idx < T * T; idx += NT) {
-        int jj = idx / T, ii = idx % T;
-        int jg = sl.tj * T + jj, ig = sl.ti * T + ii;
-        Ct[idx] = (jg < p.M && ig < p.M) ? Ca[(size_t)jg * p.M + ig] : 0.0;
-      }
-    }
-    __syncthreads();
-
-    if (producer) {
-      // ---------------------------------------------------------------- producers
-      for (int k = 0; k < K + 2; ++k) {
+  if (warp < NP) {
+    // ------------------------------------------------------------------ producers (own copy of the item loop, then exit:
+    // the consumer loop below is then straight-line code for ptxas, which keeps its constants in uniform registers)
+    while (contract_next_item<D, T, NP, NC>(p, Ct, &s_item, it)) {
+      const gpp_slot sl = it.sl;
+      const bool diag = it.diag;
+      for (int k = 0; k < it.K + 2; ++k) {
         const int b = k & 1;
         if (k >= 2) {                        // consumers are done with input k-2 (buffer b): reduce its lane partials
           named_bar_sync<BAR_EMPTY>(b, NT);
@@ -124,11 +139,11 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
 #pragma unroll
             for (int w = 0; w < NC; ++w) s += rp[w * 32];
             s = warp_sum(s);
-            if (lane == 0) p.part[(size_t)(n0 + k - 2) * p.nslots + slot_id] = s;
+            if (lane == 0) p.part[(size_t)(it.n0 + k - 2) * p.nslots + it.slot_id] = s;
           }
         }
-        if (k >= K) continue;
-        const double* pk = p.packs + ((size_t)(n0 + k) * p.npairs + sl.pair) * PP::SIZE;
+        if (k >= it.K) continue;
+        const double* pk = p.packs + ((size_t)(it.n0 + k) * p.npairs + sl.pair) * PP::SIZE;
         double* rb = rowbuf + b * RBUF;
         double* cb = colbuf + b * CBUF;
         for (int st = tid; st < T; st += PT) {
@@ -188,53 +203,62 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
         __threadfence_block();
         named_bar_arrive<BAR_FULL>(b, NT);
       }
-    } else {
-      // ---------------------------------------------------------------- consumers
-      const double* ct = Ct + c0 * T + lane;
-      for (int k = 0; k < K; ++k) {
-        const int b = k & 1;
-        named_bar_sync<BAR_FULL>(b, NT);
-        const double* rb = rowbuf + b * RBUF + lane;
-        double g[RPT][D], r[RPT], acc[RPT];
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int cwarp = warp - NP;               // consumer warp index
+  // consumer column slice: T columns over NC warps, first (T % NC) warps take one more
+  const int cw = T / NC + (cwarp < T % NC ? 1 : 0);
+  const int c0 = cwarp * (T / NC) + min(cwarp, T % NC);
+  const double* ct = Ct + c0 * T + lane;
+  const double* etab_lane = etab + (lane & (GPP_EXP_TAB_REP - 1));
+  while (contract_next_item<D, T, NP, NC>(p, Ct, &s_item, it)) {
+    const bool diag = it.diag;
+    for (int k = 0; k < it.K; ++k) {
+      const int b = k & 1;
+      named_bar_sync<BAR_FULL>(b, NT);
+      const double* rb = rowbuf + b * RBUF + lane;
+      double g[RPT][D], r[RPT], acc[RPT];
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) {
+      for (int q = 0; q < RPT; ++q) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) g[q][d] = rb[d * T + 32 * q];
-          r[q] = rb[D * T + 32 * q];
-          acc[q] = 0.0;
-        }
-        const double* cb = colbuf + b * CBUF + c0 * CS;
-#pragma unroll 2
-        for (int jj = 0; jj < cw; ++jj) {
-          const double* c = cb + jj * CS;
-          double zc[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d) zc[d] = c[d];
-          const double sj = c[D];
-          double t[RPT];
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) t[q] = r[q] + sj;
-#pragma unroll
-          for (int d = 0; d < D; ++d)
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) t[q] = fma(g[q][d], zc[d], t[q]);
-          fast_exp_n<RPT>(t);
-          if (diag) {
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) acc[q] = fma(t[q], ct[jj * T + 32 * q], acc[q]);
-          } else {
-            const double wj = c[D + 1];
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) acc[q] = fma(t[q], wj, acc[q]);
-          }
-        }
-        double total = 0.0;
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) total += diag ? acc[q] : acc[q] * rb[(D + 1) * T + 32 * q];
-        red[b * DBUF + cwarp * 32 + lane] = total;
-        __threadfence_block();
-        named_bar_arrive<BAR_EMPTY>(b, NT);
+        for (int d = 0; d < D; ++d) g[q][d] = rb[d * T + 32 * q];
+        r[q] = rb[D * T + 32 * q];
+        acc[q] = 0.0;
       }
+      const double* cb = colbuf + b * CBUF + c0 * CS;
+#pragma unroll 2
+      for (int jj = 0; jj < cw; ++jj) {
+        const double* c = cb + jj * CS;
+        double zc[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) zc[d] = c[d];
+        const double sj = c[D];
+        double t[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) t[q] = r[q] + sj;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) t[q] = fma(g[q][d], zc[d], t[q]);
+        fast_exp_tab_n<RPT>(t, etab_lane);
+        if (diag) {
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) acc[q] = fma(t[q], ct[jj * T + 32 * q], acc[q]);
+        } else {
+          const double wj = c[D + 1];
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) acc[q] = fma(t[q], wj, acc[q]);
+        }
+      }
+      double total = 0.0;
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) total += diag ? acc[q] : acc[q] * rb[(D + 1) * T + 32 * q];
+      red[b * DBUF + cwarp * 32 + lane] = total;
+      __threadfence_block();
+      named_bar_arrive<BAR_EMPTY>(b, NT);
     }
   }
 }

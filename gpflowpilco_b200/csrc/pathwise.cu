@@ -51,34 +51,35 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 
 // cos(pi/2 * q) for K values in lock-step; q in quarter turns.
-static __constant__ double kCosC[7] = {0x1.0000000000000p+0, -0x1.3bd3cc9be458bp+0, 0x1.03c1f081b076ap-2, -0x1.55d3c7dbfb7afp-6,
-                                       0x1.e1f4fb5e72646p-11, -0x1.a6c9c0e8a7a20p-16, 0x1.f3db80db0de94p-22};
-static __constant__ double kSinC[7] = {0x1.921fb54442d18p+0, -0x1.4abbce625be41p-1, 0x1.466bc677587efp-4, -0x1.32d2cce2e5063p-8,
-                                       0x1.50782fd95b428p-13, -0x1.e30070fc48deap-19, 0x1.e3f34257daf3bp-25};
+//   q = 2 k + r, k = rint(q / 2), r in [-1, 1] (exact);  cos(pi/2 q) = (-1)^k cos(pi/2 r) = (-1)^k (P(r^2)^2 - 1),
+//   P(z) = sqrt(2) cos(pi/4 sqrt(z)): one degree-6 polynomial for every lane (the double-angle step replaces the
+//   per-quadrant sin/cos coefficient selects, which cost 14 ALU selects per value and made the loop issue-bound:
+//   profiles/r1_pathwise_full.txt).  11 FP64 ops, 2 integer ops; absolute error <= 8e-16.
+static __constant__ double kCosH[8] = {0x1.6a09e667f3bccp+0, -0x1.bea5b6072b1ecp-2, 0x1.6f5a49b29085dp-6, -0x1.e36ab0b62dd2bp-12,
+                                       0x1.54cb876c4eb32p-18, -0x1.2af4d2ca26f33p-25, 0x1.61741369cd96ep-33, 0.0};
 
 template <int K>
 __device__ __forceinline__ void cos_quarter_turns(double (&q)[K]) {
   const double MAGIC = 6755399441055744.0;
   double t[K], r[K], z[K], p[K];
-  bool odd[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) t[k] = q[k] + MAGIC;
+  for (int k = 0; k < K; ++k) t[k] = fma(q[k], 0.5, MAGIC);
 #pragma unroll
-  for (int k = 0; k < K; ++k) r[k] = q[k] - (t[k] - MAGIC);        // exact: r in [-1/2, 1/2]
+  for (int k = 0; k < K; ++k) r[k] = t[k] - MAGIC;
 #pragma unroll
-  for (int k = 0; k < K; ++k) { z[k] = r[k] * r[k]; odd[k] = lo_int(t[k]) & 1; }
+  for (int k = 0; k < K; ++k) r[k] = fma(r[k], -2.0, q[k]);        // exact: r in [-1, 1]
 #pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = odd[k] ? kSinC[6] : kCosC[6];
+  for (int k = 0; k < K; ++k) z[k] = r[k] * r[k];
 #pragma unroll
-  for (int j = 5; j >= 0; --j)
+  for (int k = 0; k < K; ++k) p[k] = fma(z[k], kCosH[6], kCosH[5]);
 #pragma unroll
-    for (int k = 0; k < K; ++k) p[k] = fma(p[k], z[k], odd[k] ? kSinC[j] : kCosC[j]);
+  for (int j = 4; j >= 0; --j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) p[k] = fma(p[k], z[k], kCosH[j]);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    // cos(x + n pi/2): n=0 -> C, 1 -> -r S, 2 -> -C, 3 -> r S
-    int n = lo_int(t[k]) & 3;
-    double val = odd[k] ? p[k] * r[k] : p[k];
-    q[k] = (n == 1 || n == 2) ? -val : val;
+    double val = fma(p[k], p[k], -1.0);
+    q[k] = make_double(hi_int(val) ^ (lo_int(t[k]) << 31), lo_int(val));   // (-1)^k through the sign bit
   }
 }
 
