@@ -49,6 +49,8 @@ SIGNATURES = {
     "gpp_microbench_fp64": (c_int, [c_int, c_int, c_int, _P, _P]),
     "gpp_mm_gp_predict_workspace_bytes": (c_size_t, [_P, c_int]),
     "gpp_mm_gp_predict_fwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_double, _P, c_size_t, _P, _P]),
+    "gpp_mm_gp_predict_bwd_workspace_bytes": (c_size_t, [_P, c_int]),
+    "gpp_mm_gp_predict_bwd": (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P, _P]),
 }
 
 _lib = None

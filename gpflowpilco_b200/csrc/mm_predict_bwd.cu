@@ -1,0 +1,540 @@
+// Backward of the fused moment-matched GP predict: given the adjoints of (f1, Sff, cross) return the adjoints of the input
+// moments (m, S).  Upstream obtains these by TensorFlow autodiff through gpflow_pilco/moment_matching/models.py:200-299 and
+// gpflow_pilco/utils/kernel_expectation.py:96-187; here they are closed form:
+//
+//   Psi2 part   d f2_ab / d mu = G (sum A e),  d f2_ab / d Sigma = 1/2 (G (sum A e e^T) G - (sum A) G),
+//               A = C_ab o Q_ab,  e_ij = A1 z1'_i + A2 z2'_j  (z' = z - mu),  G = (Sigma + V_ab)^-1,
+//               sum A e     = A1 r1_ab + A2 r1_ba,
+//               sum A e e^T = A1 R2_ab A1 + A2 R2_ba A2 + A1 X_ab A2 + (A1 X_ab A2)^T,
+//               with the ROW statistics of the ordered pair (a,b):  a_i = sum_j A_ij, u_i = sum_j A_ij z2'_j,
+//               S0 = sum_i a_i, r1 = sum_i a_i z1'_i, R2 = sum_i a_i z1'_i z1'_i^T, X = sum_i z1'_i u_i^T.
+//               Column statistics of (a,b) are the row statistics of (b,a) (Q_ba = Q_ab^T), so all L x L ordered pairs are
+//               contracted and no cross-thread column reduction is needed.
+//   Psi1 part   s = f1bar_l f1_l + crossbar_l . cross_l = sum_m w_m (f1bar + y . dz_m),  w = beta psi1, y = G1 crossbar,
+//               ds/dmu = G1 (sum w e dz) - (sum w) y,
+//               ds/dSigma = 1/2 (G1 (sum w e dz dz^T) G1 - (sum w e) G1) - 1/2 (y c^T + c y^T),  c = G1 sum w dz.
+//
+//   k_pack (ordered pairs) + k_psi1 (forward latent means)   -> k_bwd_prepare (un-mix W, Sff = f2 - f1 f1^T chain rule)
+//   -> k_contract_grad (thread per row, CTA per (input, ordered pair, 256-row block)) + k_psi1_bwd (warp per (input, latent))
+//   -> k_bwd_finalize (CTA per input: D x D algebra per unordered pair, fixed-order sums).
+// Gradients w.r.t. the model parameters are not produced: the dynamics model is constant during policy optimisation
+// (upstream differentiates w.r.t. policy.trainable_variables only, gpflow_pilco/utils/optimizers.py:52-56).
+#include <algorithm>
+
+#include "model.cuh"
+#include "predict_kernels.cuh"
+
+namespace gpp {
+
+constexpr int kGradRows = 256, kGradCols = 64;
+
+template <int D>
+struct GradStats {
+  static constexpr int TRI = D * (D + 1) / 2;
+  static constexpr int S0 = 0, R1 = 1, R2 = 1 + D, X = 1 + D + TRI;
+  static constexpr int SIZE = 1 + D + TRI + D * D;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kGradRows) k_contract_grad(const double* __restrict__ Z, const double* __restrict__ beta,
+                                                             const double* __restrict__ C, const double* __restrict__ packs,
+                                                             const double* __restrict__ omega, double* __restrict__ stats,
+                                                             int M, int L, int nrb) {
+  using PP = PairPack<D>;
+  using GS = GradStats<D>;
+  __shared__ double colz[kGradCols][D + 2];
+  __shared__ double pk[PP::SIZE];
+  __shared__ double red[kGradRows / 32][GS::SIZE];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rb = blockIdx.x % nrb;
+  const int p = (blockIdx.x / nrb) % (L * L);
+  const int n = blockIdx.x / (nrb * L * L);
+  const int a = p / L, b = p % L;
+  const bool diag = a == b;
+  double* out = stats + (((size_t)n * L * L + p) * nrb + rb) * GS::SIZE;
+  // pairs whose output adjoint is zero (e.g. diagonal-only covariance) are skipped; k_bwd_finalize skips them too
+  const double wgt = omega[((size_t)n * L + a) * L + b] + omega[((size_t)n * L + b) * L + a];
+  if (wgt == 0.0) return;
+  for (int i = tid; i < PP::SIZE; i += kGradRows) pk[i] = packs[((size_t)n * L * L + p) * PP::SIZE + i];
+  __syncthreads();
+  const int i = rb * kGradRows + tid;
+  const bool valid = i < M;
+  double z1[D], g[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) z1[d] = valid ? Z[((size_t)a * M + i) * D + d] - pk[PP::MU + d] : 0.0;
+#pragma unroll
+  for (int e = 0; e < D; ++e) {
+    double t = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) t = fma(z1[d], pk[PP::R + d * D + e], t);
+    g[e] = t;
+  }
+  const double ri = pk[PP::C0] + packed_quad<D>(pk + PP::P1, z1);
+  double ai = 0.0, u[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) u[d] = 0.0;
+  const double* Ca = C + (size_t)a * M * M;
+  for (int j0 = 0; j0 < M; j0 += kGradCols) {
+    __syncthreads();
+    if (tid < kGradCols && j0 + tid < M) {
+      const int j = j0 + tid;
+      double z2[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        z2[d] = Z[((size_t)b * M + j) * D + d] - pk[PP::MU + d];
+        colz[tid][d] = z2[d];
+      }
+      colz[tid][D] = packed_quad<D>(pk + PP::P2, z2);
+      colz[tid][D + 1] = beta[(size_t)b * M + j];
+    }
+    __syncthreads();
+    const int jn = min(kGradCols, M - j0);
+    if (valid) {
+      for (int jj = 0; jj < jn; ++jj) {
+        double t = ri + colz[jj][D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) t = fma(g[d], colz[jj][d], t);
+        const double w = diag ? Ca[(size_t)(j0 + jj) * M + i] : colz[jj][D + 1];   // C symmetric: C[j][i], coalesced over i
+        const double A = fast_exp(t) * w;
+        ai += A;
+#pragma unroll
+        for (int d = 0; d < D; ++d) u[d] = fma(A, colz[jj][d], u[d]);
+      }
+    }
+  }
+  if (!diag) {
+    const double bi = valid ? beta[(size_t)a * M + i] : 0.0;
+    ai *= bi;
+#pragma unroll
+    for (int d = 0; d < D; ++d) u[d] *= bi;
+  }
+  // row statistics -> fixed-order block reduction (lanes by shuffle, warps through shared memory)
+  auto put = [&](int k, double v) {
+    v = warp_sum(v);
+    if (lane == 0) red[warp][k] = v;
+  };
+  put(GS::S0, ai);
+#pragma unroll
+  for (int d = 0; d < D; ++d) put(GS::R1 + d, ai * z1[d]);
+  {
+    int t = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int e = d; e < D; ++e, ++t) put(GS::R2 + t, ai * z1[d] * z1[e]);
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int e = 0; e < D; ++e) put(GS::X + d * D + e, z1[d] * u[e]);
+  __syncthreads();
+  if (tid < GS::SIZE) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kGradRows / 32; ++w) s += red[w][tid];
+    out[tid] = s;
+  }
+}
+
+// un-mix the output adjoints to latent space and apply the chain rule of Sff = f2 - f1 f1^T (+ const)
+struct BwdPrepareParams {
+  const double *f1_bar, *Sff_bar, *cross_bar;   // [N,P], [N,P,P], [N,D,P]  (any may be null = zero)
+  const double* f1lat;                           // [N,L]
+  const double* W;                               // [P,L] or null
+  double *f1lat_bar, *crosslat_bar, *omega;      // [N,L], [N,D,L], [N,L,L]
+  int N, L, P, D, full_cov;
+};
+
+__global__ void k_bwd_prepare(BwdPrepareParams p) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int L = p.L, P = p.P, D = p.D;
+  double SL[GPP_MAX_L * GPP_MAX_L];
+  for (int l = 0; l < L; ++l)
+    for (int k = 0; k < L; ++k) {
+      double v = 0.0;
+      if (p.Sff_bar) {
+        const double* Sb = p.Sff_bar + (size_t)n * P * P;
+        if (p.W) {
+          for (int a = 0; a < P; ++a)
+            for (int b = 0; b < P; ++b)
+              if (p.full_cov || a == b) v = fma(p.W[a * L + l] * p.W[b * L + k], Sb[a * P + b], v);
+        } else if (p.full_cov || l == k) {
+          v = Sb[l * P + k];
+        }
+      }
+      SL[l * L + k] = v;
+      p.omega[((size_t)n * L + l) * L + k] = v;
+    }
+  const double* f1l = p.f1lat + (size_t)n * L;
+  for (int l = 0; l < L; ++l) {
+    double v = 0.0;
+    if (p.f1_bar) {
+      if (p.W) {
+        for (int o = 0; o < P; ++o) v = fma(p.W[o * L + l], p.f1_bar[(size_t)n * P + o], v);
+      } else {
+        v = p.f1_bar[(size_t)n * P + l];
+      }
+    }
+    for (int k = 0; k < L; ++k) v -= (SL[l * L + k] + SL[k * L + l]) * f1l[k];
+    p.f1lat_bar[(size_t)n * L + l] = v;
+    for (int d = 0; d < D; ++d) {
+      double c = 0.0;
+      if (p.cross_bar) {
+        const double* cb = p.cross_bar + ((size_t)n * D + d) * P;
+        if (p.W) {
+          for (int o = 0; o < P; ++o) c = fma(p.W[o * L + l], cb[o], c);
+        } else {
+          c = cb[l];
+        }
+      }
+      p.crosslat_bar[((size_t)n * D + d) * L + l] = c;
+    }
+  }
+}
+
+// G x for symmetric G = Li^T Li given the lower-triangular Li
+template <int D>
+__device__ __forceinline__ void gram_apply(const Mat<D>& Li, const double* x, double* out) {
+  double y[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k <= i; ++k) t = fma(Li(i, k), x[k], t);
+    y[i] = t;
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = d; i < D; ++i) t = fma(Li(i, d), y[i], t);
+    out[d] = t;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_psi1_bwd(const double* __restrict__ m, const double* __restrict__ S, int N, int L, int M,
+                                                  const double* __restrict__ Z, const double* __restrict__ ell,
+                                                  const double* __restrict__ var, const double* __restrict__ beta,
+                                                  const double* __restrict__ f1lat_bar, const double* __restrict__ crosslat_bar,
+                                                  double* __restrict__ gm /*[N,L,D]*/, double* __restrict__ gS /*[N,L,D,D]*/) {
+  constexpr int TRI = D * (D + 1) / 2;
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  double mu[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) mu[d] = m[(size_t)n * D + d];
+  for (int l = warp; l < L; l += nwarps) {
+    Mat<D> A, Li, G;
+    double half_log_v = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double e = ell[l * D + d];
+      half_log_v += log(e);
+#pragma unroll
+      for (int e2 = 0; e2 < D; ++e2) A(d, e2) = S[(size_t)n * D * D + d * D + e2] + (d == e2 ? e * e : 0.0);
+    }
+    cholesky<D>(A);
+    double log_det = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) log_det += log(A(d, d));
+    tri_inverse<D>(A, Li);
+    gram_inverse<D>(Li, G);
+    const double c0 = log(var[l]) + half_log_v - log_det;
+    const double fb = f1lat_bar[(size_t)n * L + l];
+    double cb[D], y[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) cb[d] = crosslat_bar[((size_t)n * D + d) * L + l];
+    gram_apply<D>(Li, cb, y);
+    double A0 = 0.0, B0 = 0.0, A1[D], B1[D], A2[TRI];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { A1[d] = 0.0; B1[d] = 0.0; }
+#pragma unroll
+    for (int t = 0; t < TRI; ++t) A2[t] = 0.0;
+    const double* Zl = Z + (size_t)l * M * D;
+    for (int j = lane; j < M; j += 32) {
+      double dz[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) dz[d] = Zl[(size_t)j * D + d] - mu[d];
+      double maha = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) t = fma(Li(i, k), dz[k], t);
+        maha = fma(t, t, maha);
+      }
+      const double w = beta[(size_t)l * M + j] * fast_exp(c0 - 0.5 * maha);
+      double e = fb;
+#pragma unroll
+      for (int d = 0; d < D; ++d) e = fma(y[d], dz[d], e);
+      const double we = w * e;
+      A0 += we;
+      B0 += w;
+      int t = 0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        A1[d] = fma(we, dz[d], A1[d]);
+        B1[d] = fma(w, dz[d], B1[d]);
+#pragma unroll
+        for (int e2 = d; e2 < D; ++e2, ++t) A2[t] = fma(we * dz[d], dz[e2], A2[t]);
+      }
+    }
+    A0 = warp_sum(A0);
+    B0 = warp_sum(B0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { A1[d] = warp_sum(A1[d]); B1[d] = warp_sum(B1[d]); }
+#pragma unroll
+    for (int t = 0; t < TRI; ++t) A2[t] = warp_sum(A2[t]);
+    if (lane == 0) {
+      double GA1[D], c[D];
+      gram_apply<D>(Li, A1, GA1);
+      gram_apply<D>(Li, B1, c);
+      double* om = gm + ((size_t)n * L + l) * D;
+      double* oS = gS + ((size_t)n * L + l) * D * D;
+#pragma unroll
+      for (int d = 0; d < D; ++d) om[d] = GA1[d] - B0 * y[d];
+      // T = A2 (full symmetric) ; GTG = G T G
+      double T[D * D], GT[D * D];
+      {
+        int t = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+          for (int e2 = d; e2 < D; ++e2, ++t) { T[d * D + e2] = A2[t]; T[e2 * D + d] = A2[t]; }
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double t = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) t = fma(G(i, k), T[k * D + j], t);
+          GT[i * D + j] = t;
+        }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double t = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) t = fma(GT[i * D + k], G(k, j), t);
+          oS[i * D + j] = 0.5 * (t - A0 * G(i, j)) - 0.5 * (y[i] * c[j] + c[i] * y[j]);
+        }
+    }
+  }
+}
+
+struct BwdFinalizeParams {
+  const double *m, *S;          // [N,D], [N,D,D]
+  const double* ell;            // [L,D]
+  const double* stats;          // [N,L*L,nrb,GS::SIZE]
+  const double* omega;          // [N,L,L]
+  const double *gm, *gS;        // psi1 contributions [N,L,D], [N,L,D,D]
+  double *m_bar, *S_bar;        // [N,D], [N,D,D]
+  int N, L, nrb;
+};
+
+template <int D>
+__global__ void __launch_bounds__(64) k_bwd_finalize(BwdFinalizeParams p) {
+  using GS = GradStats<D>;
+  constexpr int MAXP = GPP_MAX_L * (GPP_MAX_L + 1) / 2;
+  constexpr int CS = D + D * D;
+  __shared__ double contrib[MAXP][CS];
+  const int n = blockIdx.x, tid = threadIdx.x, L = p.L;
+  const int npairs = L * (L + 1) / 2;
+  for (int pr = tid; pr < npairs; pr += blockDim.x) {
+    // unordered pair index -> (a <= b)
+    int a = 0, rem = pr;
+    while (rem >= L - a) { rem -= L - a; ++a; }
+    const int b = a + rem;
+    double* out = contrib[pr];
+    const double wgt = (a == b) ? p.omega[((size_t)n * L + a) * L + a]
+                                : p.omega[((size_t)n * L + a) * L + b] + p.omega[((size_t)n * L + b) * L + a];
+    if (wgt == 0.0) {
+      for (int k = 0; k < CS; ++k) out[k] = 0.0;
+      continue;
+    }
+    double sab[GS::SIZE], sba[GS::SIZE];
+    for (int k = 0; k < GS::SIZE; ++k) {
+      double x = 0.0, y = 0.0;
+      for (int rb = 0; rb < p.nrb; ++rb) {
+        x += p.stats[(((size_t)n * L * L + a * L + b) * p.nrb + rb) * GS::SIZE + k];
+        y += p.stats[(((size_t)n * L * L + b * L + a) * p.nrb + rb) * GS::SIZE + k];
+      }
+      sab[k] = x;
+      sba[k] = y;
+    }
+    double A1[D], A2[D];
+    Mat<D> Sm, Li, G;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double v1 = p.ell[a * D + d] * p.ell[a * D + d], v2 = p.ell[b * D + d] * p.ell[b * D + d];
+      A1[d] = v2 / (v1 + v2);
+      A2[d] = v1 / (v1 + v2);
+#pragma unroll
+      for (int e = 0; e < D; ++e) Sm(d, e) = p.S[(size_t)n * D * D + d * D + e] + (d == e ? v1 * A1[d] : 0.0);
+    }
+    cholesky<D>(Sm);
+    tri_inverse<D>(Sm, Li);
+    gram_inverse<D>(Li, G);
+    double E1[D], E2[D * D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) E1[d] = A1[d] * sab[GS::R1 + d] + A2[d] * sba[GS::R1 + d];
+    {
+      double R2ab[D * D], R2ba[D * D];
+      int t = 0;
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int e = d; e < D; ++e, ++t) {
+          R2ab[d * D + e] = R2ab[e * D + d] = sab[GS::R2 + t];
+          R2ba[d * D + e] = R2ba[e * D + d] = sba[GS::R2 + t];
+        }
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int e = 0; e < D; ++e)
+          E2[d * D + e] = A1[d] * R2ab[d * D + e] * A1[e] + A2[d] * R2ba[d * D + e] * A2[e] +
+                          A1[d] * sab[GS::X + d * D + e] * A2[e] + A2[d] * sab[GS::X + e * D + d] * A1[e];
+    }
+    double dmu[D];
+    gram_apply<D>(Li, E1, dmu);
+#pragma unroll
+    for (int d = 0; d < D; ++d) out[d] = wgt * dmu[d];
+    double GT[D * D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) t = fma(G(i, k), E2[k * D + j], t);
+        GT[i * D + j] = t;
+      }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) t = fma(GT[i * D + k], G(k, j), t);
+        out[D + i * D + j] = wgt * 0.5 * (t - sab[GS::S0] * G(i, j));
+      }
+  }
+  __syncthreads();
+  for (int k = tid; k < CS; k += blockDim.x) {
+    double s = 0.0;
+    for (int pr = 0; pr < npairs; ++pr) s += contrib[pr][k];
+    for (int l = 0; l < L; ++l) s += (k < D) ? p.gm[((size_t)n * L + l) * D + k] : p.gS[((size_t)n * L + l) * D * D + (k - D)];
+    if (k < D) p.m_bar[(size_t)n * D + k] = s;
+    else p.S_bar[(size_t)n * D * D + (k - D)] = s;
+  }
+}
+
+static size_t bwd_align(size_t x) { return (x + 255) / 256 * 256; }
+
+struct BwdLayout {
+  size_t packs, stats, f1lat, crosslat, f1lat_bar, crosslat_bar, omega, gm, gS, total;
+  int nrb;
+};
+
+static BwdLayout bwd_layout(const gpp_gp_model* m, int N) {
+  BwdLayout lo{};
+  const int D = m->D, L = m->L;
+  size_t pack_doubles = 0, stat_doubles = 0;
+  switch (D) {
+#define GPP_CASE(d) case d: pack_doubles = PairPack<d>::SIZE; stat_doubles = GradStats<d>::SIZE; break;
+    GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+  }
+  lo.nrb = (m->M + kGradRows - 1) / kGradRows;
+  size_t off = 0;
+  auto take = [&](size_t doubles) { size_t o = off; off = bwd_align(off + doubles * sizeof(double)); return o; };
+  lo.packs = take(pack_doubles * L * L * N);
+  lo.stats = take(stat_doubles * L * L * lo.nrb * N);
+  lo.f1lat = take((size_t)L * N);
+  lo.crosslat = take((size_t)L * D * N);
+  lo.f1lat_bar = take((size_t)L * N);
+  lo.crosslat_bar = take((size_t)L * D * N);
+  lo.omega = take((size_t)L * L * N);
+  lo.gm = take((size_t)L * D * N);
+  lo.gS = take((size_t)L * D * D * N);
+  lo.total = off;
+  return lo;
+}
+
+template <int D>
+static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S, int N, const double* f1_bar, const double* Sff_bar,
+                       const double* cross_bar, int full_output_cov, double* m_bar, double* S_bar, char* ws, const BwdLayout& lo,
+                       int* info, cudaStream_t stream) {
+  const int L = m->L;
+  double* packs = (double*)(ws + lo.packs);
+  double* stats = (double*)(ws + lo.stats);
+  double* f1lat = (double*)(ws + lo.f1lat);
+  double* crosslat = (double*)(ws + lo.crosslat);
+  double* f1lat_bar = (double*)(ws + lo.f1lat_bar);
+  double* crosslat_bar = (double*)(ws + lo.crosslat_bar);
+  double* omega = (double*)(ws + lo.omega);
+  double* gm = (double*)(ws + lo.gm);
+  double* gS = (double*)(ws + lo.gS);
+  const int total = N * L * L;
+  k_pack<D><<<(total + 63) / 64, 64, 0, stream>>>(mu, S, N, m->ell, m->var, nullptr, L * L, L, packs, info);
+  k_psi1<D><<<N, 128, 0, stream>>>(mu, S, N, L, m->M, m->Z, m->ell, m->var, m->beta, f1lat, crosslat, info);
+  BwdPrepareParams bp;
+  bp.f1_bar = f1_bar; bp.Sff_bar = Sff_bar; bp.cross_bar = cross_bar; bp.f1lat = f1lat; bp.W = m->W;
+  bp.f1lat_bar = f1lat_bar; bp.crosslat_bar = crosslat_bar; bp.omega = omega;
+  bp.N = N; bp.L = L; bp.P = m->P; bp.D = D; bp.full_cov = full_output_cov;
+  k_bwd_prepare<<<(N + 63) / 64, 64, 0, stream>>>(bp);
+  profile_begin(stream);
+  k_contract_grad<D><<<N * L * L * lo.nrb, kGradRows, 0, stream>>>(m->Z, m->beta, m->C, packs, omega, stats, m->M, L, lo.nrb);
+  profile_end(stream);
+  k_psi1_bwd<D><<<N, 128, 0, stream>>>(mu, S, N, L, m->M, m->Z, m->ell, m->var, m->beta, f1lat_bar, crosslat_bar, gm, gS);
+  BwdFinalizeParams fp;
+  fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.omega = omega; fp.gm = gm; fp.gS = gS;
+  fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb;
+  k_bwd_finalize<D><<<N, 64, 0, stream>>>(fp);
+  count_launch(6);
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+// typed-stream alias used by the rollout backward
+int mm_predict_bwd_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, const double* f1_bar,
+                           const double* Sff_bar, const double* cross_bar, int full_output_cov, double* m_bar, double* S_bar,
+                           void* workspace, size_t workspace_bytes, int* info, cudaStream_t stream) {
+  return gpp_mm_gp_predict_bwd(model, m, S, N, f1_bar, Sff_bar, cross_bar, full_output_cov, m_bar, S_bar, workspace,
+                               workspace_bytes, info, (void*)stream);
+}
+
+}  // namespace gpp
+
+extern "C" {
+
+size_t gpp_mm_gp_predict_bwd_workspace_bytes(const gpp_gp_model* model, int N) {
+  if (!model || N <= 0) return 0;
+  return gpp::bwd_layout(model, N).total;
+}
+
+int gpp_mm_gp_predict_bwd(const gpp_gp_model* model, const double* m, const double* S, int N, const double* f1_bar,
+                          const double* Sff_bar, const double* cross_bar, int full_output_cov, double* m_bar, double* S_bar,
+                          void* workspace, size_t workspace_bytes, int* info, void* stream_) {
+  GPP_REQUIRE(model && m && S && m_bar && S_bar && workspace, GPP_ERR_NULL, "gpp_mm_gp_predict_bwd: null argument");
+  GPP_REQUIRE(N >= 1, GPP_ERR_BAD_SHAPE, "gpp_mm_gp_predict_bwd: N=%d", N);
+  gpp::BwdLayout lo = gpp::bwd_layout(model, N);
+  GPP_REQUIRE(workspace_bytes >= lo.total, GPP_ERR_WORKSPACE, "gpp_mm_gp_predict_bwd: workspace %zu < required %zu", workspace_bytes, lo.total);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  switch (model->D) {
+#define GPP_CASE(d) \
+  case d: return gpp::predict_bwd<d>(model, m, S, N, f1_bar, Sff_bar, cross_bar, full_output_cov, m_bar, S_bar, ws, lo, info, stream);
+    GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+    default:
+      gpp::set_error("gpp_mm_gp_predict_bwd: unsupported D=%d", model->D);
+      return GPP_ERR_UNSUPPORTED;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// k_pack and k_psi1: the per-input prologue kernels shared by the forward (mm_predict.cu) and backward (mm_predict_bwd.cu)
+// moment-matched GP predict.
+#pragma once
+#include "model.cuh"
+
+namespace gpp {
+
+// ---------------------------------------------------------------------------------------------------------
+// k_pack
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(64) k_pack(const double* __restrict__ m, const double* __restrict__ S, int N,
+                                             const double* __restrict__ ell, const double* __restrict__ var,
+                                             const int* __restrict__ pair_ab, int npairs, int L,
+                                             double* __restrict__ packs, int* info) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * npairs) return;
+  int n = idx / npairs, p = idx % npairs;
+  // pair table (a <= b, forward) or, with pair_ab == nullptr, all L x L ordered pairs (backward)
+  int a = pair_ab ? pair_ab[2 * p] : p / L, b = pair_ab ? pair_ab[2 * p + 1] : p % L;
+  double V1[D], V2[D], mu[D], Sg[D * D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    double e1 = ell[a * D + d], e2 = ell[b * D + d];
+    V1[d] = e1 * e1;
+    V2[d] = e2 * e2;
+    mu[d] = m[(size_t)n * D + d];
+  }
+#pragma unroll
+  for (int d = 0; d < D * D; ++d) Sg[d] = S[(size_t)n * D * D + d];
+  double out[PairPack<D>::SIZE];
+  bool ok = make_pair_pack<D>(mu, Sg, V1, V2, log(var[a] * var[b]), out);
+  if (!ok) flag_not_pd(info, n);
+  double* dst = packs + (size_t)idx * PairPack<D>::SIZE;
+#pragma unroll
+  for (int t = 0; t < PairPack<D>::SIZE; ++t) dst[t] = out[t];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_psi1: latent mean  f1[n,l] = sum_m beta_l[m] Psi1[n,m,l]  and  cross[n,:,l] = (S_n+Lambda_l)^-1 sum_m beta Psi1 (z_m - mu)
+//         (models.py:236 and :264-277; Psi1 is GPflow's eKxz)
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) k_psi1(const double* __restrict__ m, const double* __restrict__ S, int N, int L, int M,
+                                              const double* __restrict__ Z, const double* __restrict__ ell,
+                                              const double* __restrict__ var, const double* __restrict__ beta,
+                                              double* __restrict__ f1lat /*[N,L]*/, double* __restrict__ crosslat /*[N,D,L]*/,
+                                              int* info) {
+  int n = blockIdx.x;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  double mu[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) mu[d] = m[(size_t)n * D + d];
+  for (int l = warp; l < L; l += nwarps) {
+    Mat<D> A, Li;
+    double half_log_v = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      double e = ell[l * D + d];
+      half_log_v += log(e);
+#pragma unroll
+      for (int e2 = 0; e2 < D; ++e2) A(d, e2) = S[(size_t)n * D * D + d * D + e2] + (d == e2 ? e * e : 0.0);
+    }
+    bool ok = cholesky<D>(A);
+    if (!ok && lane == 0) flag_not_pd(info, n);
+    double log_det = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) log_det += log(A(d, d));
+    tri_inverse<D>(A, Li);
+    double c0 = log(var[l]) + half_log_v - log_det;
+    double acc = 0.0, vec[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) vec[d] = 0.0;
+    const double* Zl = Z + (size_t)l * M * D;
+    for (int j = lane; j < M; j += 32) {
+      double dz[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) dz[d] = Zl[(size_t)j * D + d] - mu[d];
+      double maha = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double y = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) y = fma(Li(i, k), dz[k], y);
+        maha = fma(y, y, maha);
+      }
+      double w = beta[(size_t)l * M + j] * fast_exp(c0 - 0.5 * maha);
+      acc += w;
+#pragma unroll
+      for (int d = 0; d < D; ++d) vec[d] = fma(w, dz[d], vec[d]);
+    }
+    acc = warp_sum(acc);
+#pragma unroll
+    for (int d = 0; d < D; ++d) vec[d] = warp_sum(vec[d]);
+    if (lane == 0) {
+      f1lat[(size_t)n * L + l] = acc;
+      // G vec with G = Li^T Li
+      double y[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) t = fma(Li(i, k), vec[k], t);
+        y[i] = t;
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = d; i < D; ++i) t = fma(Li(i, d), y[i], t);
+        crosslat[((size_t)n * D + d) * L + l] = t;
+      }
+    }
+  }
+}
+
+}  // namespace gpp

@@ -162,3 +162,31 @@ class GPModelHandle:
     if check:
       raise_if_not_pd(info, "mm_gp_predict")
     return f1, Sff, cross
+
+
+def _predict_bwd(self, m, S, f1_bar=None, Sff_bar=None, cross_bar=None, full_output_cov: bool = True, check: bool = True):
+  """Adjoints (m_bar [N,D], S_bar [N,D,D] symmetric) of `predict` given the output adjoints (None = zero)."""
+  m, S, f1_bar, Sff_bar, cross_bar = map(_c, (m, S, f1_bar, Sff_bar, cross_bar))
+  _dev_check(m, S, f1_bar, Sff_bar, cross_bar)
+  N = m.shape[0]
+  if m.shape != (N, self.D) or S.shape != (N, self.D, self.D):
+    raise ValueError(f"predict_bwd: expected m [N,{self.D}] and S [N,{self.D},{self.D}]")
+  for t, shape, name in ((f1_bar, (N, self.P), "f1_bar"), (Sff_bar, (N, self.P, self.P), "Sff_bar"), (cross_bar, (N, self.D, self.P), "cross_bar")):
+    if t is not None and tuple(t.shape) != shape:
+      raise ValueError(f"predict_bwd: {name} must have shape {shape}")
+  lib = _lib.load()
+  need = lib.gpp_mm_gp_predict_bwd_workspace_bytes(self._h, N)
+  if getattr(self, "_ws_bwd", None) is None or self._ws_bwd.numel() < need:
+    self._ws_bwd = torch.empty(need, dtype=torch.uint8, device=self.device)
+  m_bar = torch.empty(N, self.D, dtype=F64, device=self.device)
+  S_bar = torch.empty(N, self.D, self.D, dtype=F64, device=self.device)
+  info = _new_info(self.device)
+  _lib.check(lib.gpp_mm_gp_predict_bwd(self._h, _ptr(m), _ptr(S), N, _ptr(f1_bar), _ptr(Sff_bar), _ptr(cross_bar),
+                                       int(bool(full_output_cov)), _ptr(m_bar), _ptr(S_bar), _ptr(self._ws_bwd), self._ws_bwd.numel(),
+                                       _ptr(info), _stream()))
+  if check:
+    raise_if_not_pd(info, "mm_gp_predict_bwd")
+  return m_bar, S_bar
+
+
+GPModelHandle.predict_bwd = _predict_bwd

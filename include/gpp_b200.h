@@ -87,6 +87,16 @@ int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m /*[N,D]*/, 
                           int full_output_cov, double jitter,
                           void* workspace, size_t workspace_bytes, int* info, void* stream);
 
+/* Backward of gpp_mm_gp_predict_fwd (upstream: TensorFlow autodiff through moment_matching/models.py:200-299 and
+ * utils/kernel_expectation.py:96-187, driven by tape.gradient in utils/optimizers.py:52-56): given the adjoints of the
+ * outputs, f1_bar [N,P], Sff_bar [N,P,P] (only its diagonal is read when full_output_cov = 0), cross_bar [N,D,P] (any of
+ * the three may be NULL = zero), returns m_bar [N,D] and the SYMMETRIC S_bar [N,D,D].  Closed form: Psi2 is re-contracted
+ * with first/second-moment accumulators, never materialised.  Model parameters are treated as constants. */
+size_t gpp_mm_gp_predict_bwd_workspace_bytes(const gpp_gp_model* model, int N);
+int gpp_mm_gp_predict_bwd(const gpp_gp_model* model, const double* m, const double* S, int N,
+                          const double* f1_bar, const double* Sff_bar, const double* cross_bar, int full_output_cov,
+                          double* m_bar, double* S_bar, void* workspace, size_t workspace_bytes, int* info, void* stream);
+
 /* ---- small moment-matching rules, batched (one thread per Gaussian state) -----------------------------------
  *   gpp_mm_encoder    e = [sin x_a, cos x_a, x_b]: mean me [N,De], covariance See [N,De,De], Cxe = Cov(x,e) [N,Dx,De]
  *                     (upstream moment_matching/components.py:19-57 with maths.py:143-176; De = Dx + num_active)
