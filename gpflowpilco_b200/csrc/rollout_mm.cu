@@ -11,8 +11,7 @@
 //   GP predict   the fused kernels of mm_predict.cu on the N joint states
 //   k_step_post  one thread per rollout: Sxf = Sxd cross, Euler update (solvers.py:128-129), encoder rule on the new state,
 //                expected cost (components.py:30-37), loss accumulation.
-#include "mm_small.cuh"
-#include "model.cuh"
+#include "rollout_mm_common.cuh"
 
 namespace gpp {
 
@@ -76,192 +75,6 @@ __global__ void __launch_bounds__(128) k_policy_prepare(int Mp, int Dp, const do
   }
   __syncthreads();
   for (int i = tid; i < Mp; i += blockDim.x) beta[(size_t)r * Mp + i] = v[i];
-}
-
-// ---------------------------------------------------------------------------------------------------------
-struct RolloutMMParams {
-  EncoderSpec enc;
-  int N, Dx, De, D, L;       // D = De + 1 (scalar action), L = Dx outputs of the dynamics
-  int R, Mp;                 // policy sets (1 = shared, or N) and centres per policy
-  const double *pZ, *pEll, *pVar, *pBeta;   // [R,Mp,De], [R,De], [R], [R,Mp]
-  double scale, shift;
-  const double *target, *W;  // [De], [De,De]
-  double *m, *S, *loss;      // [N,Dx], [N,Dx,Dx], [N]   current state / accumulated loss
-  double *md, *Sd, *Sxd;     // [N,D], [N,D,D], [N,Dx,D]
-  double *f1, *Sff, *cross;  // [N,L], [N,L,L], [N,D,L]
-  double *traj_m, *traj_S;   // optional [H+1,N,Dx], [H+1,N,Dx,Dx]
-  int* info;
-};
-
-// k_step_pre: one CTA per rollout
-template <int DP>
-__global__ void __launch_bounds__(128) k_step_pre(RolloutMMParams p) {
-  using PP = PairPack<DP>;
-  __shared__ double me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
-  __shared__ double pack[PP::SIZE], Li1[DP * DP], c01;
-  __shared__ double red[4][DP + 2];
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Dx = p.Dx, De = p.De, D = p.D;
-  const int r = (p.R == 1) ? 0 : n;
-  const double* ell = p.pEll + (size_t)r * De;
-  const double var = p.pVar[r];
-  if (tid == 0) {
-    double m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
-    for (int i = 0; i < Dx; ++i) m[i] = p.m[(size_t)n * Dx + i];
-    for (int i = 0; i < Dx * Dx; ++i) S[i] = p.S[(size_t)n * Dx * Dx + i];
-    mm_encoder<double>(p.enc, m, S, me, See, Cxe);
-    // coefficient pack of the (policy kernel, policy kernel) pair and the Psi1 factorisation
-    double V[DP], mu[DP], Sg[DP * DP];
-    Mat<DP> A, Li;
-    double half_log_v = 0.0;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      V[d] = ell[d] * ell[d];
-      mu[d] = me[d];
-      half_log_v += log(ell[d]);
-#pragma unroll
-      for (int e = 0; e < DP; ++e) {
-        Sg[d * DP + e] = See[d * DP + e];
-        A(d, e) = See[d * DP + e] + (d == e ? V[d] : 0.0);
-      }
-    }
-    bool ok = make_pair_pack<DP>(mu, Sg, V, V, 2.0 * log(var), pack);
-    ok = cholesky<DP>(A) && ok;
-    if (!ok) flag_not_pd(p.info, n);
-    double log_det = 0.0;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) log_det += log(A(d, d));
-    tri_inverse<DP>(A, Li);
-#pragma unroll
-    for (int d = 0; d < DP * DP; ++d) Li1[d] = Li.a[d];
-    c01 = log(var) + half_log_v - log_det;
-  }
-  __syncthreads();
-  // ---- policy Psi1 terms: f1 = sum_i beta_i psi1_i, vec = sum_i beta_i psi1_i (z_i - me)
-  const double* Zp = p.pZ + (size_t)r * p.Mp * DP;
-  const double* beta = p.pBeta + (size_t)r * p.Mp;
-  double acc = 0.0, vec[DP];
-#pragma unroll
-  for (int d = 0; d < DP; ++d) vec[d] = 0.0;
-  for (int i = tid; i < p.Mp; i += blockDim.x) {
-    double dz[DP];
-#pragma unroll
-    for (int d = 0; d < DP; ++d) dz[d] = Zp[i * DP + d] - me[d];
-    double maha = 0.0;
-#pragma unroll
-    for (int a = 0; a < DP; ++a) {
-      double y = 0.0;
-#pragma unroll
-      for (int k = 0; k <= a; ++k) y = fma(Li1[a * DP + k], dz[k], y);
-      maha = fma(y, y, maha);
-    }
-    double w = beta[i] * fast_exp(c01 - 0.5 * maha);
-    acc += w;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) vec[d] = fma(w, dz[d], vec[d]);
-  }
-  // ---- policy Psi2 contraction: f2 = sum_ij beta_i beta_j Q_ij  (KernelRegressor: no model uncertainty, models.py:34-41)
-  double f2 = 0.0;
-  for (int i = tid; i < p.Mp; i += blockDim.x) {
-    double zr[DP], g[DP];
-#pragma unroll
-    for (int d = 0; d < DP; ++d) zr[d] = Zp[i * DP + d] - pack[PP::MU + d];
-#pragma unroll
-    for (int e = 0; e < DP; ++e) {
-      double t = 0.0;
-#pragma unroll
-      for (int d = 0; d < DP; ++d) t = fma(zr[d], pack[PP::R + d * DP + e], t);
-      g[e] = t;
-    }
-    double ri = pack[PP::C0] + packed_quad<DP>(pack + PP::P1, zr);
-    double row = 0.0;
-    for (int j = 0; j < p.Mp; ++j) {
-      double zc[DP];
-#pragma unroll
-      for (int d = 0; d < DP; ++d) zc[d] = Zp[j * DP + d] - pack[PP::MU + d];
-      double t = ri + packed_quad<DP>(pack + PP::P2, zc);
-#pragma unroll
-      for (int d = 0; d < DP; ++d) t = fma(g[d], zc[d], t);
-      row = fma(beta[j], fast_exp(t), row);
-    }
-    f2 = fma(beta[i], row, f2);
-  }
-  acc = warp_sum(acc);
-  f2 = warp_sum(f2);
-#pragma unroll
-  for (int d = 0; d < DP; ++d) vec[d] = warp_sum(vec[d]);
-  if (lane == 0) {
-    red[warp][0] = acc;
-    red[warp][1] = f2;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) red[warp][2 + d] = vec[d];
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double f1 = 0.0, f2s = 0.0, v[DP];
-#pragma unroll
-    for (int d = 0; d < DP; ++d) v[d] = 0.0;
-    for (int w = 0; w < 4; ++w) {
-      f1 += red[w][0];
-      f2s += red[w][1];
-#pragma unroll
-      for (int d = 0; d < DP; ++d) v[d] += red[w][2 + d];
-    }
-    // pre-inverted cross term of the regressor: (See + Lambda)^-1 vec  with (See+Lambda)^-1 = Li^T Li
-    double y[DP], cpre[DP];
-#pragma unroll
-    for (int a = 0; a < DP; ++a) {
-      double t = 0.0;
-#pragma unroll
-      for (int k = 0; k <= a; ++k) t = fma(Li1[a * DP + k], v[k], t);
-      y[a] = t;
-    }
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      double t = 0.0;
-#pragma unroll
-      for (int a = d; a < DP; ++a) t = fma(Li1[a * DP + d], y[a], t);
-      cpre[d] = t;
-    }
-    double vf = f2s - f1 * f1;
-    double mu_u, vu, gain;
-    mm_squash_1d<double>(f1, vf, p.scale, p.shift, mu_u, vu, gain);
-    // joint moments of d = (e, u)  (gaussian.py:53-63): Seu = See cpre gain
-    double seu[DP];
-#pragma unroll
-    for (int a = 0; a < DP; ++a) {
-      double t = 0.0;
-#pragma unroll
-      for (int b = 0; b < DP; ++b) t = fma(See[a * DP + b], cpre[b], t);
-      seu[a] = t * gain;
-    }
-    double* md = p.md + (size_t)n * D;
-    double* Sd = p.Sd + (size_t)n * D * D;
-    for (int a = 0; a < De; ++a) {
-      md[a] = me[a];
-      for (int b = 0; b < De; ++b) Sd[a * D + b] = See[a * De + b];
-      Sd[a * D + De] = seu[a];
-      Sd[De * D + a] = seu[a];
-    }
-    md[De] = mu_u;
-    Sd[De * D + De] = vu;
-    // Sxd = Cov(x, d): active rows through the encoder linearisation, inactive rows copied from S_d (forward_sde.py:112-124)
-    double* Sxd = p.Sxd + (size_t)n * Dx * D;
-    const int na = p.enc.na, nb = p.enc.nb();
-    for (int k = 0; k < na; ++k) {
-      int i = p.enc.active[k];
-      double sau = 0.0;
-      for (int b = 0; b < De; ++b) {
-        Sxd[i * D + b] = Cxe[i * De + b];
-        sau = fma(Cxe[i * De + b], cpre[b], sau);
-      }
-      Sxd[i * D + De] = sau * gain;
-    }
-    for (int j = 0; j < nb; ++j) {
-      int i = p.enc.inactive(j);
-      for (int b = 0; b < D; ++b) Sxd[i * D + b] = Sd[(2 * na + j) * D + b];
-    }
-  }
 }
 
 __global__ void k_step_post(RolloutMMParams p, int step) {

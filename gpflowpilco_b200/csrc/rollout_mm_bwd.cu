@@ -1,0 +1,459 @@
+// Backward of the moment-matched rollout: reverse sweep over the H steps of gpp_rollout_mm_fwd.
+//
+// Upstream differentiates the closure of MomentMatchingPILCO (gpflow_pilco/loops/pilco.py:192-220) with tape.gradient
+// w.r.t. policy.trainable_variables (gpflow_pilco/utils/optimizers.py:52-56).  Here, for t = H-1 .. 0, from the stored
+// trajectory (m_t, S_t):
+//   k_step_pre            recompute the pre stage of step t (md, Sd, Sxd)                       [rollout_mm_common.cuh]
+//   mm_predict_enqueue    recompute (f1, Sff, cross) of step t with the fused forward kernels   [mm_predict.cu]
+//   k_bwd_post            adjoint of (m_{t+1}, S_{t+1}) += loss_bar * d cost / d(m, S)  (dual numbers through the encoder and
+//                         expected-cost rules, one direction per lane), then the adjoint of the Euler moment update
+//                         (dynamics/solvers.py:128-129) and of Sxf = Sxd cross  (forward_sde.py:126)
+//   mm_predict_bwd        closed-form adjoint of the GP dynamics prediction                     [mm_predict_bwd.cu]
+//   k_bwd_pre             adjoint of the joint assembly (forward_sde.py:105-124, gaussian.py:53-63), of the squashing link
+//                         (2x2 Jacobian by dual numbers), closed-form adjoint of the policy's Psi1/Psi2 sums w.r.t. the
+//                         encoded moments AND the policy parameters (centres Z, weights beta = Kuu^-1 m, lengthscales),
+//                         then the encoder adjoint (dual numbers, one direction per thread).
+// Matrix adjoints follow one convention throughout: S_bar is symmetric and dLoss = sum_ij S_bar_ij dS_ij for symmetric dS.
+#include "dual.cuh"
+#include "rollout_mm_common.cuh"
+
+namespace gpp {
+
+int mm_predict_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
+                       double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
+                       int* info, cudaStream_t stream);   // mm_predict.cu
+int mm_predict_bwd_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, const double* f1_bar,
+                           const double* Sff_bar, const double* cross_bar, int full_output_cov, double* m_bar, double* S_bar,
+                           void* workspace, size_t workspace_bytes, int* info, cudaStream_t stream);   // mm_predict_bwd.cu
+
+struct RolloutBwdBuffers {
+  double *mb, *Sb;                                  // [N,Dx], [N,Dx,Dx]  running state adjoint
+  double *f1_bar, *Sff_bar, *cross_bar, *Sxd_bar;   // [N,L], [N,L,L], [N,D,L], [N,Dx,D]
+  double *md_bar, *Sd_bar;                          // [N,D], [N,D,D]
+  double *gZ, *gEll, *gBeta;                        // per-rollout parameter gradients [N,Mp,De], [N,De], [N,Mp]
+};
+
+// direction index k -> state-moment entry: k < Dx is m[k]; otherwise the symmetric pair (i <= j) of S
+__device__ __forceinline__ void direction_to_entry(int k, int Dx, int& i, int& j) {
+  int rem = k - Dx;
+  i = 0;
+  while (rem >= Dx - i) { rem -= Dx - i; ++i; }
+  j = i + rem;
+}
+
+// one warp per rollout
+__global__ void __launch_bounds__(32) k_bwd_post(RolloutMMParams p, const double* __restrict__ m_next, const double* __restrict__ S_next,
+                                                 const double* __restrict__ loss_bar, RolloutBwdBuffers bw) {
+  __shared__ double smb[GPP_SMALL_MAX], sSb[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  const int n = blockIdx.x, lane = threadIdx.x;
+  const int Dx = p.Dx, De = p.De, D = p.D, L = p.L;
+  for (int i = lane; i < Dx; i += 32) smb[i] = bw.mb[(size_t)n * Dx + i];
+  for (int i = lane; i < Dx * Dx; i += 32) sSb[i] = bw.Sb[(size_t)n * Dx * Dx + i];
+  __syncwarp();
+  const double lb = loss_bar ? loss_bar[n] : 1.0;
+  const int ndir = Dx + Dx * (Dx + 1) / 2;
+  for (int k = lane; k < ndir; k += 32) {
+    Dual m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
+    for (int i = 0; i < Dx; ++i) m[i] = Dual(m_next[(size_t)n * Dx + i]);
+    for (int i = 0; i < Dx * Dx; ++i) S[i] = Dual(S_next[(size_t)n * Dx * Dx + i]);
+    int di = 0, dj = 0;
+    if (k < Dx) {
+      m[k].d = 1.0;
+    } else {
+      direction_to_entry(k, Dx, di, dj);
+      S[di * Dx + dj].d = 1.0;
+      S[dj * Dx + di].d = 1.0;
+    }
+    Dual me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
+    mm_encoder<Dual>(p.enc, m, S, me, See, Cxe);
+    const Dual c = expected_cost<Dual>(De, me, See, p.target, p.W);
+    const double g = lb * c.d;
+    if (k < Dx) {
+      smb[k] += g;
+    } else if (di == dj) {
+      sSb[di * Dx + di] += g;
+    } else {
+      sSb[di * Dx + dj] += 0.5 * g;
+      sSb[dj * Dx + di] += 0.5 * g;
+    }
+  }
+  __syncwarp();
+  // Euler update m' = m + f1, S' = S + Sxf + Sxf^T + Sff with Sxf = Sxd cross  (dt = 1)
+  const double* cross = p.cross + (size_t)n * D * L;
+  const double* Sxd = p.Sxd + (size_t)n * Dx * D;
+  for (int l = lane; l < L; l += 32) bw.f1_bar[(size_t)n * L + l] = smb[l];
+  for (int t = lane; t < L * L; t += 32) bw.Sff_bar[(size_t)n * L * L + t] = sSb[t];
+  for (int t = lane; t < Dx * D; t += 32) {
+    const int i = t / D, b = t % D;
+    double v = 0.0;
+    for (int l = 0; l < L; ++l) v = fma(sSb[i * Dx + l] + sSb[l * Dx + i], cross[b * L + l], v);
+    bw.Sxd_bar[(size_t)n * Dx * D + t] = v;
+  }
+  for (int t = lane; t < D * L; t += 32) {
+    const int b = t / L, l = t % L;
+    double v = 0.0;
+    for (int i = 0; i < Dx; ++i) v = fma(Sxd[i * D + b], sSb[i * Dx + l] + sSb[l * Dx + i], v);
+    bw.cross_bar[(size_t)n * D * L + t] = v;
+  }
+  for (int i = lane; i < Dx; i += 32) bw.mb[(size_t)n * Dx + i] = smb[i];
+  for (int i = lane; i < Dx * Dx; i += 32) bw.Sb[(size_t)n * Dx * Dx + i] = sSb[i];
+}
+
+template <int DP>
+struct PreAdjoint {
+  double me_bar[DP], See_bar[DP * DP], Cxe_bar[GPP_SMALL_MAX * DP];
+  double f1b, f2b, cpre_bar[DP], y[DP];
+  double G1[DP * DP], G2[DP * DP];
+  double red[4][2 * DP + DP * DP];
+};
+
+template <int DP>
+__global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBuffers bw) {
+  using PP = PairPack<DP>;
+  constexpr int D = DP + 1;
+  constexpr int K = 2 * DP + DP * DP;      // block-reduced accumulators: mu [DP], ell [DP], Sigma [DP*DP]
+  __shared__ PreShared<DP> sh;
+  __shared__ PreAdjoint<DP> ad;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Dx = p.Dx;
+  const int r = (p.R == 1) ? 0 : n;
+  step_pre_forward<DP>(p, n, sh);
+
+  if (tid == 0) {
+    // ---- adjoint of the joint assembly: (md, Sd, Sxd) -> (me, See, Cxe, cpre, mu_u, vu, gain)
+    const double* md_bar = bw.md_bar + (size_t)n * D;
+    const double* Sxd_bar = bw.Sxd_bar + (size_t)n * Dx * D;
+    double Sdb[D * D];
+    for (int t = 0; t < D * D; ++t) Sdb[t] = bw.Sd_bar[(size_t)n * D * D + t];
+    const int na = p.enc.na, nb = p.enc.nb();
+    for (int j = 0; j < nb; ++j) {
+      const int i = p.enc.inactive(j);
+      for (int b = 0; b < D; ++b) Sdb[(2 * na + j) * D + b] += Sxd_bar[i * D + b];
+    }
+    double seu_bar[DP], gain_bar = 0.0;
+    for (int a = 0; a < DP; ++a) {
+      ad.me_bar[a] = md_bar[a];
+      ad.cpre_bar[a] = 0.0;
+      seu_bar[a] = Sdb[a * D + DP] + Sdb[DP * D + a];
+      for (int b = 0; b < DP; ++b) ad.See_bar[a * DP + b] = Sdb[a * D + b];
+    }
+    const double mu_u_bar = md_bar[DP], vu_bar = Sdb[DP * D + DP];
+    for (int t = 0; t < Dx * DP; ++t) ad.Cxe_bar[t] = 0.0;
+    for (int k = 0; k < na; ++k) {
+      const int i = p.enc.active[k];
+      double ri = 0.0;
+      for (int b = 0; b < DP; ++b) {
+        ad.Cxe_bar[i * DP + b] = Sxd_bar[i * D + b];
+        ri = fma(sh.Cxe[i * DP + b], sh.cpre[b], ri);
+      }
+      const double s = Sxd_bar[i * D + DP];
+      gain_bar = fma(s, ri, gain_bar);
+      for (int b = 0; b < DP; ++b) {
+        ad.Cxe_bar[i * DP + b] = fma(s * sh.gain, sh.cpre[b], ad.Cxe_bar[i * DP + b]);
+        ad.cpre_bar[b] = fma(s * sh.gain, sh.Cxe[i * DP + b], ad.cpre_bar[b]);
+      }
+    }
+    for (int a = 0; a < DP; ++a) {
+      double qa = 0.0;
+      for (int b = 0; b < DP; ++b) qa = fma(sh.See[a * DP + b], sh.cpre[b], qa);
+      gain_bar = fma(seu_bar[a], qa, gain_bar);
+      const double qb = seu_bar[a] * sh.gain;
+      for (int b = 0; b < DP; ++b) {
+        ad.See_bar[a * DP + b] = fma(qb, sh.cpre[b], ad.See_bar[a * DP + b]);
+        ad.cpre_bar[b] = fma(qb, sh.See[a * DP + b], ad.cpre_bar[b]);
+      }
+    }
+    // ---- squashing link: 2 x 3 Jacobian by dual numbers
+    Dual mu, vu, gn;
+    mm_squash_1d<Dual>(Dual(sh.f1, 1.0), Dual(sh.vf, 0.0), p.scale, p.shift, mu, vu, gn);
+    double f1b = mu_u_bar * mu.d + vu_bar * vu.d + gain_bar * gn.d;
+    mm_squash_1d<Dual>(Dual(sh.f1, 0.0), Dual(sh.vf, 1.0), p.scale, p.shift, mu, vu, gn);
+    const double vfb = mu_u_bar * mu.d + vu_bar * vu.d + gain_bar * gn.d;
+    ad.f2b = vfb;                          // vf = f2 - f1^2
+    ad.f1b = f1b - 2.0 * sh.f1 * vfb;
+    // ---- G1 = (See + Lambda)^-1, y = G1 cpre_bar, G2 = (See + Lambda/2)^-1
+    Mat<DP> Li, G, A2;
+    for (int t = 0; t < DP * DP; ++t) Li.a[t] = sh.Li1[t];
+    gram_inverse<DP>(Li, G);
+    const double* ell = p.pEll + (size_t)r * DP;
+    for (int a = 0; a < DP; ++a) {
+      double t = 0.0;
+      for (int b = 0; b < DP; ++b) {
+        ad.G1[a * DP + b] = G(a, b);
+        t = fma(G(a, b), ad.cpre_bar[b], t);
+        A2(a, b) = sh.See[a * DP + b] + (a == b ? 0.5 * ell[a] * ell[a] : 0.0);
+      }
+      ad.y[a] = t;
+    }
+    cholesky<DP>(A2);
+    tri_inverse<DP>(A2, Li);
+    gram_inverse<DP>(Li, G);
+    for (int t = 0; t < DP * DP; ++t) ad.G2[t] = G.a[t];
+  }
+  __syncthreads();
+
+  // ---- closed-form adjoint of the policy's Psi1 / Psi2 sums (rows over threads)
+  const double* Zp = p.pZ + (size_t)r * p.Mp * DP;
+  const double* beta = p.pBeta + (size_t)r * p.Mp;
+  const double* ell = p.pEll + (size_t)r * DP;
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  double* mu_acc = acc;
+  double* ell_acc = acc + DP;
+  double* sig_acc = acc + 2 * DP;
+  const double f1b = ad.f1b, f2b = ad.f2b;
+  for (int i = tid; i < p.Mp; i += blockDim.x) {
+    double zr[DP], zbar[DP], h[DP];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { zr[d] = Zp[i * DP + d] - sh.me[d]; zbar[d] = 0.0; }
+    // Psi1
+    double maha = 0.0, e = f1b;
+#pragma unroll
+    for (int a = 0; a < DP; ++a) {
+      double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < DP; ++b) t = fma(ad.G1[a * DP + b], zr[b], t);
+      h[a] = t;
+      maha = fma(t, zr[a], maha);
+      e = fma(ad.y[a], zr[a], e);
+    }
+    const double psi = fast_exp(sh.c01 - 0.5 * maha);
+    const double w = beta[i] * psi;
+    double beta_bar = psi * e;
+#pragma unroll
+    for (int a = 0; a < DP; ++a) {
+      const double t1 = w * (e * h[a] - ad.y[a]);
+      mu_acc[a] += t1;
+      zbar[a] -= t1;
+      double sdd = 0.0;
+#pragma unroll
+      for (int b = 0; b < DP; ++b) {
+        const double s = w * (0.5 * e * (h[a] * h[b] - ad.G1[a * DP + b]) - 0.5 * (ad.y[a] * h[b] + h[a] * ad.y[b]));
+        sig_acc[a * DP + b] += s;
+        if (a == b) sdd = s;
+      }
+      ell_acc[a] += 2.0 * ell[a] * sdd + w * e / ell[a];
+    }
+    // Psi2 (same kernel, same centres: V = Lambda/2, e_ij = (z_i + z_j)/2 - me)
+    double g0[DP];
+#pragma unroll
+    for (int e2 = 0; e2 < DP; ++e2) {
+      double t = 0.0;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) t = fma(zr[d], sh.pack[PP::R + d * DP + e2], t);
+      g0[e2] = t;
+    }
+    const double ri = sh.pack[PP::C0] + packed_quad<DP>(sh.pack + PP::P1, zr);
+    double rowQ = 0.0;
+    for (int j = 0; j < p.Mp; ++j) {
+      double zc[DP], ee[DP], g[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) { zc[d] = Zp[j * DP + d] - sh.me[d]; ee[d] = 0.5 * (zr[d] + zc[d]); }
+      double t = ri + packed_quad<DP>(sh.pack + PP::P2, zc);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) t = fma(g0[d], zc[d], t);
+      const double Q = fast_exp(t);
+      rowQ = fma(beta[j], Q, rowQ);
+      const double a = f2b * beta[i] * beta[j] * Q;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < DP; ++b) s = fma(ad.G2[d * DP + b], ee[b], s);
+        g[d] = s;
+      }
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const double dl = zr[d] - zc[d], il = 1.0 / ell[d];
+        mu_acc[d] = fma(a, g[d], mu_acc[d]);
+        zbar[d] = fma(a, -dl * il * il - g[d], zbar[d]);
+        ell_acc[d] = fma(a, il - 0.5 * ad.G2[d * DP + d] * ell[d] + 0.5 * dl * dl * il * il * il + 0.5 * g[d] * g[d] * ell[d], ell_acc[d]);
+#pragma unroll
+        for (int b = 0; b < DP; ++b) sig_acc[d * DP + b] = fma(a, 0.5 * (g[d] * g[b] - ad.G2[d * DP + b]), sig_acc[d * DP + b]);
+      }
+    }
+    beta_bar = fma(2.0 * f2b, rowQ, beta_bar);
+    bw.gBeta[(size_t)n * p.Mp + i] += beta_bar;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) bw.gZ[((size_t)n * p.Mp + i) * DP + d] += zbar[d];
+  }
+  // fixed-order block reduction of the K accumulators
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) ad.red[warp][k] = v;
+  }
+  __syncthreads();
+  if (tid < K) {
+    const double s = (ad.red[0][tid] + ad.red[1][tid]) + (ad.red[2][tid] + ad.red[3][tid]);
+    if (tid < DP) ad.me_bar[tid] += s;
+    else if (tid < 2 * DP) bw.gEll[(size_t)n * DP + (tid - DP)] += s;
+    else ad.See_bar[tid - 2 * DP] += s;
+  }
+  __syncthreads();
+
+  // ---- encoder adjoint: directional derivatives of <(me_bar, See_bar, Cxe_bar), encoder(m, S)>, one direction per thread
+  const int ndir = Dx + Dx * (Dx + 1) / 2;
+  if (tid < ndir) {
+    Dual m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
+    for (int i = 0; i < Dx; ++i) m[i] = Dual(p.m[(size_t)n * Dx + i]);
+    for (int i = 0; i < Dx * Dx; ++i) S[i] = Dual(p.S[(size_t)n * Dx * Dx + i]);
+    int di = 0, dj = 0;
+    if (tid < Dx) {
+      m[tid].d = 1.0;
+    } else {
+      direction_to_entry(tid, Dx, di, dj);
+      S[di * Dx + dj].d = 1.0;
+      S[dj * Dx + di].d = 1.0;
+    }
+    Dual me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
+    mm_encoder<Dual>(p.enc, m, S, me, See, Cxe);
+    double g = 0.0;
+    for (int a = 0; a < DP; ++a) g = fma(ad.me_bar[a], me[a].d, g);
+    for (int t = 0; t < DP * DP; ++t) g = fma(ad.See_bar[t], See[t].d, g);
+    for (int t = 0; t < Dx * DP; ++t) g = fma(ad.Cxe_bar[t], Cxe[t].d, g);
+    if (tid < Dx) {
+      bw.mb[(size_t)n * Dx + tid] += g;
+    } else if (di == dj) {
+      bw.Sb[(size_t)n * Dx * Dx + di * Dx + di] += g;
+    } else {
+      bw.Sb[(size_t)n * Dx * Dx + di * Dx + dj] += 0.5 * g;
+      bw.Sb[(size_t)n * Dx * Dx + dj * Dx + di] += 0.5 * g;
+    }
+  }
+}
+
+// out[r, k] = sum over the rollouts that used parameter set r (fixed order): R == N copies, R == 1 sums over n
+__global__ void k_reduce_param_grads(const double* __restrict__ g, int N, int R, int K, double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= R * K) return;
+  if (R == N) {
+    out[k] = g[k];
+  } else {
+    double s = 0.0;
+    for (int n = 0; n < N; ++n) s += g[(size_t)n * K + k];
+    out[k] = s;
+  }
+}
+
+struct RolloutBwdLayout {
+  size_t md, Sd, Sxd, f1, Sff, cross, mb, Sb, f1_bar, Sff_bar, cross_bar, Sxd_bar, md_bar, Sd_bar, gZ, gEll, gBeta, predict, predict_bwd, total;
+  size_t predict_bytes, predict_bwd_bytes;
+};
+
+static RolloutBwdLayout rollout_bwd_layout(const gpp_gp_model* dyn, int N, int Dx, int Mp) {
+  RolloutBwdLayout lo{};
+  const int D = dyn->D, L = dyn->P, De = D - 1;
+  size_t off = 0;
+  auto take = [&](size_t doubles) { size_t o = off; off = rollout_align_up(off + doubles * sizeof(double), 256); return o; };
+  lo.md = take((size_t)N * D);
+  lo.Sd = take((size_t)N * D * D);
+  lo.Sxd = take((size_t)N * Dx * D);
+  lo.f1 = take((size_t)N * L);
+  lo.Sff = take((size_t)N * L * L);
+  lo.cross = take((size_t)N * D * L);
+  lo.mb = take((size_t)N * Dx);
+  lo.Sb = take((size_t)N * Dx * Dx);
+  lo.f1_bar = take((size_t)N * L);
+  lo.Sff_bar = take((size_t)N * L * L);
+  lo.cross_bar = take((size_t)N * D * L);
+  lo.Sxd_bar = take((size_t)N * Dx * D);
+  lo.md_bar = take((size_t)N * D);
+  lo.Sd_bar = take((size_t)N * D * D);
+  lo.gZ = take((size_t)N * Mp * De);
+  lo.gEll = take((size_t)N * De);
+  lo.gBeta = take((size_t)N * Mp);
+  lo.predict_bytes = gpp_mm_gp_predict_workspace_bytes(dyn, N);
+  lo.predict_bwd_bytes = gpp_mm_gp_predict_bwd_workspace_bytes(dyn, N);
+  lo.predict = off;
+  off += rollout_align_up(lo.predict_bytes, 256);
+  lo.predict_bwd = off;
+  off += rollout_align_up(lo.predict_bwd_bytes, 256);
+  lo.total = off;
+  return lo;
+}
+
+}  // namespace gpp
+
+extern "C" {
+
+size_t gpp_rollout_mm_bwd_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx, int Mp) {
+  if (!dynamics || N <= 0 || Mp <= 0) return 0;
+  return gpp::rollout_bwd_layout(dynamics, N, Dx, Mp).total;
+}
+
+int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims /*host*/,
+                       int R, int Mp, const double* policy_Z, const double* policy_lengthscales, const double* policy_variance,
+                       const double* policy_beta, double squash_scale, double squash_shift,
+                       const double* cost_target, const double* cost_W, int H, const double* traj_m, const double* traj_S,
+                       const double* loss_bar, double* Z_bar, double* lengthscales_bar, double* beta_bar,
+                       double* m0_bar, double* S0_bar, void* workspace, size_t workspace_bytes, int* info, void* stream_) {
+  using namespace gpp;
+  GPP_REQUIRE(dynamics && policy_Z && policy_lengthscales && policy_variance && policy_beta && cost_target && cost_W && traj_m && traj_S &&
+                  Z_bar && lengthscales_bar && beta_bar && workspace, GPP_ERR_NULL, "gpp_rollout_mm_bwd: null argument");
+  GPP_REQUIRE(N >= 1 && H >= 0 && Dx >= 1 && Dx <= GPP_SMALL_MAX && Mp >= 1, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_bwd: bad sizes N=%d H=%d Dx=%d Mp=%d", N, H, Dx, Mp);
+  GPP_REQUIRE(num_active >= 0 && num_active <= 4 && num_active <= Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_bwd: bad number of encoded dims %d", num_active);
+  GPP_REQUIRE(R == 1 || R == N, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_bwd: R=%d must be 1 (shared policy) or N=%d", R, N);
+  RolloutMMParams p{};
+  p.enc.Dx = Dx; p.enc.na = num_active;
+  for (int k = 0; k < num_active; ++k) {
+    GPP_REQUIRE(active_dims[k] >= 0 && active_dims[k] < Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_bwd: active dim %d out of range", active_dims[k]);
+    p.enc.active[k] = active_dims[k];
+  }
+  p.N = N; p.Dx = Dx; p.De = Dx + num_active; p.D = p.De + 1; p.L = dynamics->P;
+  GPP_REQUIRE(p.De <= GPP_SMALL_MAX - 1, GPP_ERR_UNSUPPORTED, "gpp_rollout_mm_bwd: encoded dimension %d too large", p.De);
+  GPP_REQUIRE(dynamics->D == p.D && dynamics->P == Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_bwd: dynamics dims (%d in, %d out) do not match the state (%d, %d)",
+              dynamics->D, dynamics->P, p.D, Dx);
+  GPP_REQUIRE(Dx + Dx * (Dx + 1) / 2 <= 128, GPP_ERR_UNSUPPORTED, "gpp_rollout_mm_bwd: state dimension too large");
+  RolloutBwdLayout lo = rollout_bwd_layout(dynamics, N, Dx, Mp);
+  GPP_REQUIRE(workspace_bytes >= lo.total, GPP_ERR_WORKSPACE, "gpp_rollout_mm_bwd: workspace %zu < required %zu", workspace_bytes, lo.total);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  auto D_ = [&](size_t off) { return (double*)(ws + off); };
+  p.R = R; p.Mp = Mp; p.pZ = policy_Z; p.pEll = policy_lengthscales; p.pVar = policy_variance; p.pBeta = policy_beta;
+  p.scale = squash_scale; p.shift = squash_shift; p.target = cost_target; p.W = cost_W;
+  p.md = D_(lo.md); p.Sd = D_(lo.Sd); p.Sxd = D_(lo.Sxd); p.f1 = D_(lo.f1); p.Sff = D_(lo.Sff); p.cross = D_(lo.cross);
+  p.loss = nullptr; p.traj_m = nullptr; p.traj_S = nullptr; p.info = info;
+  RolloutBwdBuffers bw;
+  bw.mb = D_(lo.mb); bw.Sb = D_(lo.Sb); bw.f1_bar = D_(lo.f1_bar); bw.Sff_bar = D_(lo.Sff_bar); bw.cross_bar = D_(lo.cross_bar);
+  bw.Sxd_bar = D_(lo.Sxd_bar); bw.md_bar = D_(lo.md_bar); bw.Sd_bar = D_(lo.Sd_bar); bw.gZ = D_(lo.gZ); bw.gEll = D_(lo.gEll); bw.gBeta = D_(lo.gBeta);
+  // zero the running adjoint and the per-rollout parameter gradients (contiguous ranges of the workspace)
+  GPP_CUDA_OK(cudaMemsetAsync(ws + lo.mb, 0, lo.f1_bar - lo.mb, stream));
+  GPP_CUDA_OK(cudaMemsetAsync(ws + lo.gZ, 0, lo.predict - lo.gZ, stream));
+  const size_t sm = (size_t)N * Dx, sS = (size_t)N * Dx * Dx;
+  for (int t = H - 1; t >= 0; --t) {
+    p.m = const_cast<double*>(traj_m) + (size_t)t * sm;     // read-only in the kernels launched below
+    p.S = const_cast<double*>(traj_S) + (size_t)t * sS;
+    switch (p.De) {
+#define GPP_CASE(d) case d: k_step_pre<d><<<N, 128, 0, stream>>>(p); break;
+      GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7)
+#undef GPP_CASE
+      default: set_error("gpp_rollout_mm_bwd: unsupported encoded dimension %d", p.De); return GPP_ERR_UNSUPPORTED;
+    }
+    int rc = mm_predict_enqueue(dynamics, p.md, p.Sd, N, p.f1, p.Sff, p.cross, 1, 0.0, ws + lo.predict, lo.predict_bytes, info, stream);
+    if (rc != GPP_OK) return rc;
+    k_bwd_post<<<N, 32, 0, stream>>>(p, traj_m + (size_t)(t + 1) * sm, traj_S + (size_t)(t + 1) * sS, loss_bar, bw);
+    rc = mm_predict_bwd_enqueue(dynamics, p.md, p.Sd, N, bw.f1_bar, bw.Sff_bar, bw.cross_bar, 1, bw.md_bar, bw.Sd_bar,
+                                ws + lo.predict_bwd, lo.predict_bwd_bytes, info, stream);
+    if (rc != GPP_OK) return rc;
+    switch (p.De) {
+#define GPP_CASE(d) case d: k_bwd_pre<d><<<N, 128, 0, stream>>>(p, bw); break;
+      GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7)
+#undef GPP_CASE
+      default: break;
+    }
+    count_launch(3);
+  }
+  if (m0_bar) GPP_CUDA_OK(cudaMemcpyAsync(m0_bar, bw.mb, sizeof(double) * sm, cudaMemcpyDeviceToDevice, stream));
+  if (S0_bar) GPP_CUDA_OK(cudaMemcpyAsync(S0_bar, bw.Sb, sizeof(double) * sS, cudaMemcpyDeviceToDevice, stream));
+  const int De = p.De;
+  k_reduce_param_grads<<<(R * Mp * De + 127) / 128, 128, 0, stream>>>(bw.gZ, N, R, Mp * De, Z_bar);
+  k_reduce_param_grads<<<(R * De + 127) / 128, 128, 0, stream>>>(bw.gEll, N, R, De, lengthscales_bar);
+  k_reduce_param_grads<<<(R * Mp + 127) / 128, 128, 0, stream>>>(bw.gBeta, N, R, Mp, beta_bar);
+  count_launch(3);
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+}  // extern "C"

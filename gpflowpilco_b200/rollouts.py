@@ -94,3 +94,38 @@ def rollout_mm(dynamics: GPModelHandle, policy: PolicyParams, m0: torch.Tensor, 
   if check:
     raise_if_not_pd(info, "rollout_mm")
   return MMRolloutResult(loss, mf, Sf, tm, tS)
+
+
+def rollout_mm_bwd(dynamics: GPModelHandle, policy: PolicyParams, beta: torch.Tensor, traj_m: torch.Tensor, traj_S: torch.Tensor,
+                   active_dims: Sequence[int], cost_target: torch.Tensor, cost_W: torch.Tensor,
+                   loss_bar: Optional[torch.Tensor] = None, check: bool = True):
+  """Reverse sweep of `rollout_mm` from its stored trajectory: returns (Z_bar [R,Mp,De], lengthscales_bar [R,De] at fixed beta,
+  beta_bar [R,Mp], m0_bar [N,Dx], S0_bar [N,Dx,Dx]).  Upstream: tape.gradient through loops/pilco.py:192-220."""
+  traj_m, traj_S, cost_target, cost_W, beta, loss_bar = map(_c, (traj_m, traj_S, cost_target, cost_W, beta, loss_bar))
+  _dev_check(traj_m, traj_S, cost_target, cost_W, beta, loss_bar)
+  H1, N, Dx = traj_m.shape
+  na = len(active_dims)
+  De = Dx + na
+  R, Mp, Dp = policy.shape
+  if traj_S.shape != (H1, N, Dx, Dx) or Dp != De or beta.shape != (R, Mp):
+    raise ValueError("rollout_mm_bwd: inconsistent trajectory / policy shapes")
+  if loss_bar is not None and loss_bar.shape != (N,):
+    raise ValueError("rollout_mm_bwd: loss_bar must be [N]")
+  dev = traj_m.device
+  lib = _lib.load()
+  need = lib.gpp_rollout_mm_bwd_workspace_bytes(dynamics._h, N, Dx, Mp)
+  ws = torch.empty(need, dtype=torch.uint8, device=dev)
+  Zb = torch.empty(R, Mp, De, dtype=F64, device=dev)
+  eb = torch.empty(R, De, dtype=F64, device=dev)
+  bb = torch.empty(R, Mp, dtype=F64, device=dev)
+  m0b = torch.empty(N, Dx, dtype=F64, device=dev)
+  S0b = torch.empty(N, Dx, Dx, dtype=F64, device=dev)
+  info = _new_info(dev)
+  act = (ctypes.c_int * max(na, 1))(*active_dims)
+  _lib.check(lib.gpp_rollout_mm_bwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
+                                    _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
+                                    _ptr(cost_target), _ptr(cost_W), H1 - 1, _ptr(traj_m), _ptr(traj_S), _ptr(loss_bar),
+                                    _ptr(Zb), _ptr(eb), _ptr(bb), _ptr(m0b), _ptr(S0b), _ptr(ws), ws.numel(), _ptr(info), _stream()))
+  if check:
+    raise_if_not_pd(info, "rollout_mm_bwd")
+  return Zb, eb, bb, m0b, S0b

@@ -140,6 +140,21 @@ int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
                        double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final,
                        void* workspace, size_t workspace_bytes, int* info, void* stream);
 
+/* Backward of gpp_rollout_mm_fwd: reverse sweep over the H steps from the trajectory the forward stored (traj_m, traj_S as
+ * written by gpp_rollout_mm_fwd).  Upstream: tape.gradient(loss, policy.trainable_variables), utils/optimizers.py:52-56.
+ *   loss_bar [N] (NULL = ones)
+ *   -> Z_bar [R,Mp,De], lengthscales_bar [R,De]: gradients w.r.t. the policy centres / lengthscales AT FIXED beta,
+ *      beta_bar [R,Mp]: gradient w.r.t. beta = Kuu^-1 m (the caller chains beta to (Z, lengthscales, q_mu); the policy
+ *      variance is frozen upstream, loops/pilco.py:99-103), m0_bar [N,Dx], S0_bar [N,Dx,Dx] (symmetric; either may be NULL).
+ *   R = 1 sums the gradient over the N rollouts in a fixed order; R = N returns one gradient per restart. */
+size_t gpp_rollout_mm_bwd_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx, int Mp);
+int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims,
+                       int R, int Mp, const double* policy_Z, const double* policy_lengthscales,
+                       const double* policy_variance, const double* policy_beta, double squash_scale, double squash_shift,
+                       const double* cost_target, const double* cost_W, int H, const double* traj_m, const double* traj_S,
+                       const double* loss_bar, double* Z_bar, double* lengthscales_bar, double* beta_bar,
+                       double* m0_bar, double* S0_bar, void* workspace, size_t workspace_bytes, int* info, void* stream);
+
 /* ---- pathwise (sample-path) rollout ----------------------------------------------------------------------
  * replaces the closure body of PathwisePILCO._policy_loss_closure (upstream loops/pilco.py:263-303) for paths drawn by
  * gpflow_sampling's decoupled sampler (random-Fourier prior + canonical-basis update; contract in oracle/pathwise.py):

@@ -72,3 +72,75 @@ def test_mm_gp_predict_bwd_partial_adjoints_and_fd():
     fd[d] = (vals[0] - vals[1]) / (2 * eps)
   scaled_close(m_bar[0], fd, 1e-6, "m_bar vs finite differences")
   assert torch.allclose(S_bar, S_bar.transpose(-1, -2))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# moment-matched rollout: gradient of the loss w.r.t. the policy parameters and the initial moments
+# ---------------------------------------------------------------------------------------------------------
+def _oracle_rollout_grads(cfg, dynp, polp_list, m0, S0, H, loss_bar):
+  from oracle import psi_stats as ps
+  from oracle import rollout as ro
+  dyn = oracle_svgp(dynp)
+  enc = mo.TrigonometricEncoder(cfg["active_dims"])
+  obj = mo.GaussianObjective(cfg["target"], cfg["W"])
+  m0 = m0.clone().requires_grad_(True)
+  S0 = S0.clone().requires_grad_(True)
+  N = m0.shape[0]
+  leaves, losses = [], []
+  for n in range(N):
+    pp = polp_list[0] if len(polp_list) == 1 else polp_list[n]
+    if len(polp_list) == 1 and leaves:
+      Z, ell, q = leaves[0]
+    else:
+      Z = torch.as_tensor(pp["Z"][0]).clone().requires_grad_(True)
+      ell = torch.as_tensor(pp["lengthscales"][0]).clone().requires_grad_(True)
+      q = torch.as_tensor(pp["q_mu"]).clone().requires_grad_(True)
+      leaves.append((Z, ell, q))
+    pol = gm.SVGPModel([ps.SEKernel(float(pp["variance"][0]), ell)], [Z], q, torch.as_tensor(pp["q_sqrt"]), whiten=bool(pp["whiten"]),
+                       mean_const=torch.zeros(1, dtype=DTYPE))
+    loss = ro.mm_rollout(m0[n:n + 1], S0[n:n + 1], H, lambda s: gm.mm_svgp(s, dyn),
+                         lambda s: gm.mm_policy(s, pol, cfg["squash_scale"], cfg["squash_shift"]), enc, obj)
+    losses.append(loss[0])
+  total = (torch.stack(losses) * loss_bar).sum()
+  flat = [t for trip in leaves for t in trip]
+  grads = torch.autograd.grad(total, flat + [m0, S0])
+  gS0 = 0.5 * (grads[-1] + grads[-1].transpose(-1, -2))
+  trip = [grads[3 * i:3 * i + 3] for i in range(len(leaves))]
+  return torch.stack(losses).detach(), trip, grads[-2], gS0
+
+
+@pytest.mark.parametrize("shared_policy,whiten", [(True, True), (False, True), (True, False)])
+def test_rollout_mm_gradients_match_autograd(shared_policy, whiten):
+  from gpflowpilco_b200.autograd import rollout_mm_loss
+  N, H = 3, 4
+  g = torch.Generator().manual_seed(7)
+  dynp = synthetic.random_svgp(L=4, M=40, D=6, seed=21, whiten=True, z_scale=1.5)
+  dynp["q_mu"] = 0.2 * dynp["q_mu"]
+  dynp["mean_const"] = np.zeros(4)
+  R = 1 if shared_policy else N
+  pols = []
+  for r in range(R):
+    pp = synthetic.random_svgp(L=1, M=10, D=5, seed=60 + r, whiten=whiten)
+    pp["mean_const"] = np.zeros(1)
+    pols.append(pp)
+  m0 = torch.tensor([0.0, 2.5, 0.0, 0.0], dtype=DTYPE) + 0.3 * torch.randn(N, 4, dtype=DTYPE, generator=g)
+  S0 = generate_covariance(4, [N], 0.15, g)
+  cfg = dict(active_dims=(1,), target=np.array([0.0, 1.0, 0.0, 0.0, 0.0]), W=synthetic.config1_cartpole(M=8, Mp=4)["W"],
+             squash_scale=3.0, squash_shift=-0.5)
+  loss_bar = torch.randn(N, dtype=DTYPE, generator=g)
+  loss_ref, trip, gm0, gS0 = _oracle_rollout_grads(cfg, dynp, pols, m0, S0, H, loss_bar)
+
+  Z = _dev(np.stack([p["Z"][0] for p in pols])).requires_grad_(True)
+  ell = _dev(np.stack([p["lengthscales"][0] for p in pols])).requires_grad_(True)
+  q = _dev(np.stack([p["q_mu"][:, 0] for p in pols])).requires_grad_(True)
+  var = _dev(np.array([p["variance"][0] for p in pols]))
+  m0d, S0d = _dev(m0).requires_grad_(True), _dev(S0).requires_grad_(True)
+  loss = rollout_mm_loss(cuda_handle(dynp), Z, ell, var, q, m0d, S0d, H, cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]),
+                         squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"], whiten=whiten)
+  scaled_close(loss, loss_ref, 1e-6, "loss")
+  (loss * _dev(loss_bar)).sum().backward()
+  scaled_close(m0d.grad, gm0, 1e-6, "m0 gradient")
+  scaled_close(0.5 * (S0d.grad + S0d.grad.transpose(-1, -2)), gS0, 1e-6, "S0 gradient")
+  scaled_close(Z.grad, torch.stack([t[0] for t in trip]), 1e-6, "policy centre gradient")
+  scaled_close(ell.grad, torch.stack([t[1] for t in trip]), 1e-6, "policy lengthscale gradient")
+  scaled_close(q.grad, torch.stack([t[2][:, 0] for t in trip]), 1e-6, "policy q_mu gradient")
