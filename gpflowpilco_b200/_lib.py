@@ -42,6 +42,12 @@ SIGNATURES = {
     "gpp_rollout_pathwise_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
                                          _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
                                          _P, _P, _P, _P, _P]),
+    "gpp_rollout_pathwise_fwd_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
+                                              _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
+                                              _P, _P, _P, _P, _P, _P]),
+    "gpp_rollout_pathwise_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gpp_rollout_pathwise_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, _P, _P, c_double,
+                                         _P, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gpp_philox_raw": (c_int, [c_ulonglong, c_int, ctypes.c_uint, c_ulonglong, _P, _P]),
     "gpp_pathwise_draw_basis": (c_int, [c_int, c_int, c_int, c_ulonglong, _P, _P, _P]),
     "gpp_pathwise_draw_x0": (c_int, [c_int, c_ulonglong, c_int, _P, _P, c_ulonglong, _P, _P]),

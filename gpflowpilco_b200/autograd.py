@@ -79,3 +79,31 @@ def rollout_mm_loss(dynamics: GPModelHandle, Z: torch.Tensor, lengthscales: torc
   beta = policy_beta(Z, lengthscales, variance, q_mu, whiten, jitter)
   return _RolloutMM.apply(Z, lengthscales, beta, m0, S0, dynamics, variance, float(squash_scale), float(squash_shift), int(horizon),
                           tuple(active_dims), cost_target, cost_W)
+
+
+class _RolloutPathwise(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, Z, lengthscales, beta, x0, paths, variance, scale, shift, horizon, active_dims, target, W):
+    from gpflowpilco_b200.pathwise import rollout_pathwise
+    pol = PolicyParams(Z.detach(), lengthscales.detach(), variance, torch.zeros_like(beta), squash_scale=scale, squash_shift=shift)
+    loss, _, traj, jac = rollout_pathwise(paths, pol, x0.detach(), horizon, active_dims, target, W, beta=beta.detach(), save_for_backward=True)
+    ctx.save_for_backward(beta.detach(), traj, jac)
+    ctx.pol, ctx.active_dims, ctx.target, ctx.W = pol, tuple(active_dims), target, W
+    return loss
+
+  @staticmethod
+  def backward(ctx, loss_bar):
+    from gpflowpilco_b200.pathwise import rollout_pathwise_bwd
+    beta, traj, jac = ctx.saved_tensors
+    Zb, eb, bb, x0b = rollout_pathwise_bwd(ctx.pol, beta, traj, jac, ctx.active_dims, ctx.target, ctx.W, loss_bar=loss_bar.contiguous())
+    return Zb[None], eb[None], bb[None], x0b, None, None, None, None, None, None, None, None
+
+
+def rollout_pathwise_loss(paths, Z: torch.Tensor, lengthscales: torch.Tensor, variance: torch.Tensor, q_mu: torch.Tensor, x0: torch.Tensor,
+                          horizon: int, active_dims: Sequence[int], cost_target: torch.Tensor, cost_W: torch.Tensor,
+                          squash_scale: float = 1.0, squash_shift: float = -0.5, whiten: bool = True, jitter: float = 1e-6) -> torch.Tensor:
+  """loss[S] of the particle rollout on the function draws `paths` (upstream PathwisePILCO closure, loops/pilco.py:263-298),
+  differentiable w.r.t. the (single, shared) policy's Z [1,Mp,De], lengthscales [1,De], q_mu [1,Mp] and the initial states x0."""
+  beta = policy_beta(Z, lengthscales, variance, q_mu, whiten, jitter)
+  return _RolloutPathwise.apply(Z, lengthscales, beta, x0, paths, variance, float(squash_scale), float(squash_shift), int(horizon),
+                                tuple(active_dims), cost_target, cost_W)

@@ -83,6 +83,39 @@ __device__ __forceinline__ void cos_quarter_turns(double (&q)[K]) {
   }
 }
 
+// cos and sin of pi/2 * q in lock-step (gradient mode): sin(pi/2 r) = 2 sin(pi/4 r) cos(pi/4 r) = P(z) * (r * Qs(z)),
+// Qs(z) = sqrt(2) sin(pi/4 sqrt z) / sqrt z  (degree 6; abs. error <= 5e-16).  19 FP64 ops for the pair.
+static __constant__ double kSinH[8] = {0x1.1c5831add62e4p+0, -0x1.d3ba5c1c5f465p-4, 0x1.cda106381dcb8p-9, -0x1.b1e9f34807cbep-15,
+                                       0x1.dbd6f6b8a9057p-22, -0x1.5588a73e88afep-29, 0x1.5634879bdf5c2p-37, 0.0};
+
+template <int K>
+__device__ __forceinline__ void sincos_quarter_turns(double (&q)[K], double (&sn)[K]) {
+  const double MAGIC = 6755399441055744.0;
+  double t[K], r[K], z[K], p[K], s[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = fma(q[k], 0.5, MAGIC);
+#pragma unroll
+  for (int k = 0; k < K; ++k) r[k] = t[k] - MAGIC;
+#pragma unroll
+  for (int k = 0; k < K; ++k) r[k] = fma(r[k], -2.0, q[k]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) z[k] = r[k] * r[k];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { p[k] = fma(z[k], kCosH[6], kCosH[5]); s[k] = fma(z[k], kSinH[6], kSinH[5]); }
+#pragma unroll
+  for (int j = 4; j >= 0; --j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) { p[k] = fma(p[k], z[k], kCosH[j]); s[k] = fma(s[k], z[k], kSinH[j]); }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int sign = lo_int(t[k]) << 31;
+    double c = fma(p[k], p[k], -1.0);
+    double sv = p[k] * (r[k] * s[k]);
+    q[k] = make_double(hi_int(c) ^ sign, lo_int(c));
+    sn[k] = make_double(hi_int(sv) ^ sign, lo_int(sv));
+  }
+}
+
 constexpr int kPathP = 512;    // particles per CTA (one consumer thread each) -> 16 consumer warps + 1 producer warp
 constexpr int kPathTF = 8;    // feature rows per pipeline stage
 
@@ -106,6 +139,7 @@ struct PathwiseParams {
   double* loss;           // [S]
   double* x_final;        // [S][Dx]
   double* traj;           // optional [H+1][S][Dx]
+  double* jac;            // gradient mode: [H][L*D][ldS]  d f_l / d d_b of every particle-step (particle-minor)
 };
 
 template <int D, int P, int TF, int NS>
@@ -117,8 +151,8 @@ struct PathwiseCfg {
                                  sizeof(double) * (64 * (GPP_SMALL_MAX + 1) + 8 * GPP_SMALL_MAX * GPP_SMALL_MAX);
 };
 
-template <int D, int P, int TF, int NS>
-__global__ void __launch_bounds__(P + 32) k_pathwise_rollout(PathwiseParams p) {
+template <int D, int P, int TF, int NS, bool GRAD>
+__global__ void __launch_bounds__(P + 32, GRAD ? 2 : 1) k_pathwise_rollout(PathwiseParams p) {
   using CF = PathwiseCfg<D, P, TF, NS>;
   constexpr int BS = CF::BS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -224,6 +258,11 @@ __global__ void __launch_bounds__(P + 32) k_pathwise_rollout(PathwiseParams p) {
     double fx[GPP_SMALL_MAX];
     for (int l = 0; l < p.L; ++l) {
       double accw[4] = {0.0, 0.0, 0.0, 0.0}, accv[4] = {0.0, 0.0, 0.0, 0.0};
+      double jw[GRAD ? D : 1], jv[GRAD ? D : 1];     // gradient mode: sum_i w_i sin_i basis_i[d], sum_j v_j k_j (zs_j - ds)[d]
+      if (GRAD) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) { jw[d] = 0.0; jv[d] = 0.0; }
+      }
       for (int tile = 0; tile < tiles_f; ++tile, ++it) {
         const int st = (int)(it % NS);
         mbar_wait(&full[st], (unsigned)((it / NS) & 1));
@@ -238,9 +277,24 @@ __global__ void __launch_bounds__(P + 32) k_pathwise_rollout(PathwiseParams p) {
           for (int d = 0; d < D; ++d)
 #pragma unroll
             for (int k = 0; k < 4; ++k) q[k] = fma(bs[(f0 + k) * BS + d], dd[d], q[k]);
-          cos_quarter_turns<4>(q);
+          if (GRAD) {
+            double sn[4];
+            sincos_quarter_turns<4>(q, sn);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) accw[k] = fma(ws[(f0 + k) * P], q[k], accw[k]);
+            for (int k = 0; k < 4; ++k) {
+              const double w = ws[(f0 + k) * P];
+              accw[k] = fma(w, q[k], accw[k]);
+              sn[k] *= w;
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) jw[d] = fma(sn[k], bs[(f0 + k) * BS + d], jw[d]);
+          } else {
+            cos_quarter_turns<4>(q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) accw[k] = fma(ws[(f0 + k) * P], q[k], accw[k]);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
@@ -266,13 +320,32 @@ __global__ void __launch_bounds__(P + 32) k_pathwise_rollout(PathwiseParams p) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) q[k] *= -0.5;
           fast_exp_n<4>(q);
+          if (GRAD) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) accv[k] = fma(ws[(f0 + k) * P], q[k], accv[k]);
+            for (int k = 0; k < 4; ++k) {
+              q[k] *= ws[(f0 + k) * P];
+              accv[k] += q[k];
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) jv[d] = fma(q[k], bs[(f0 + k) * BS + d] - ds[d], jv[d]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) accv[k] = fma(ws[(f0 + k) * P], q[k], accv[k]);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
       }
       fx[l] = c_mean[l] + c_amp[l] * ((accw[0] + accw[1]) + (accw[2] + accw[3])) + c_var[l] * ((accv[0] + accv[1]) + (accv[2] + accv[3]));
+      if (GRAD && valid) {
+        // d f_l / d d_b = -(pi/2) amp_l sum_i w_i sin(pi/2 q_i) basis_i[b] + var_l sum_j v_j k_j (zs_j - ds)[b] / ell_l[b]
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          p.jac[((size_t)(t * p.L + l) * D + d) * p.ldS + s] =
+              -1.5707963267948966192 * c_amp[l] * jw[d] + c_var[l] * jv[d] * c_inv_ell[l * D + d];
+      }
     }
     for (int i = 0; i < Dx; ++i) x[i] += fx[i];                       // Euler, dt = 1, no diffusion (solvers.py:49-65)
     {
@@ -323,18 +396,19 @@ __global__ void k_pack_basis(int L, int F, int M, int Mpad, int D, int BS, const
   }
 }
 
-template <int D>
+template <int D, bool GRAD>
 static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
-  constexpr int P = kPathP, TF = kPathTF, NS = 4;
+  // gradient mode carries 2 D more accumulators per thread: half the particles per CTA (two CTAs per SM) keeps them in registers
+  constexpr int P = GRAD ? kPathP / 2 : kPathP, TF = kPathTF, NS = 4;
   using CF = PathwiseCfg<D, P, TF, NS>;
   static bool configured = false;
   if (!configured) {
-    GPP_CUDA_OK(cudaFuncSetAttribute(k_pathwise_rollout<D, P, TF, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+    GPP_CUDA_OK(cudaFuncSetAttribute(k_pathwise_rollout<D, P, TF, NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
     configured = true;
   }
   int grid = (p.S + P - 1) / P;
   profile_begin(stream);
-  k_pathwise_rollout<D, P, TF, NS><<<grid, P + 32, CF::SMEM, stream>>>(p);
+  k_pathwise_rollout<D, P, TF, NS, GRAD><<<grid, P + 32, CF::SMEM, stream>>>(p);
   profile_end(stream);
   count_launch();
   GPP_CUDA_OK(cudaGetLastError());
@@ -342,6 +416,39 @@ static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
 }
 
 }  // namespace gpp
+
+static int pathwise_fwd_impl(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
+                             const double* basis, const double* zbasis, const double* w, const double* v, const double* amp,
+                             const double* variance, const double* inv_lengthscales, const double* mean_const,
+                             int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                             double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                             const double* x0, double* loss, double* x_final, double* traj, double* jac, void* stream) {
+  using namespace gpp;
+  GPP_REQUIRE(basis && zbasis && w && v && amp && variance && inv_lengthscales && mean_const && policy_Zs && policy_inv_lengthscales &&
+                  policy_alpha && cost_target && cost_W && x0 && loss, GPP_ERR_NULL, "gpp_rollout_pathwise_fwd: null argument");
+  GPP_REQUIRE(S >= 1 && H >= 0 && L >= 1 && L <= GPP_SMALL_MAX && Dx >= 1 && Dx <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE,
+              "gpp_rollout_pathwise_fwd: bad sizes S=%d H=%d L=%d Dx=%d", S, H, L, Dx);
+  GPP_REQUIRE(L == Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: the drift must have one output per state dim (L=%d, Dx=%d)", L, Dx);
+  GPP_REQUIRE(F % kPathTF == 0 && Mpad % kPathTF == 0, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: F=%d and Mpad=%d must be multiples of %d", F, Mpad, kPathTF);
+  GPP_REQUIRE(ldS % kPathP == 0 && ldS >= S, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: ldS=%d must be a multiple of %d and >= S=%d", ldS, kPathP, S);
+  GPP_REQUIRE(Mp >= 1 && Mp <= 64, GPP_ERR_UNSUPPORTED, "gpp_rollout_pathwise_fwd: Mp=%d policy centres (max 64)", Mp);
+  GPP_REQUIRE(num_active >= 0 && num_active <= 4 && D == Dx + num_active + 1, GPP_ERR_BAD_SHAPE,
+              "gpp_rollout_pathwise_fwd: D=%d must be Dx + num_active + 1", D);
+  PathwiseParams p{};
+  p.enc.Dx = Dx; p.enc.na = num_active;
+  for (int k = 0; k < num_active; ++k) p.enc.active[k] = active_dims[k];
+  p.S = S; p.ldS = ldS; p.H = H; p.L = L; p.F = F; p.Mpad = Mpad; p.Dx = Dx; p.De = Dx + num_active; p.Mp = Mp;
+  p.basis = basis; p.zbasis = zbasis; p.w = w; p.v = v; p.amp = amp; p.var = variance; p.inv_ell = inv_lengthscales; p.mean = mean_const;
+  p.pZs = policy_Zs; p.pInvEll = policy_inv_lengthscales; p.pAlpha = policy_alpha; p.scale = squash_scale; p.shift = squash_shift;
+  p.target = cost_target; p.W = cost_W; p.x0 = x0; p.loss = loss; p.x_final = x_final; p.traj = traj; p.jac = jac;
+  switch (D) {
+#define GPP_CASE(d) case d: return jac ? launch_pathwise<d, true>(p, (cudaStream_t)stream) : launch_pathwise<d, false>(p, (cudaStream_t)stream);
+    GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+    default: set_error("gpp_rollout_pathwise_fwd: unsupported D=%d", D); return GPP_ERR_UNSUPPORTED;
+  }
+}
+
 
 extern "C" {
 
@@ -366,30 +473,21 @@ int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int 
                              int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
                              double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
                              const double* x0, double* loss, double* x_final, double* traj, void* stream) {
-  using namespace gpp;
-  GPP_REQUIRE(basis && zbasis && w && v && amp && variance && inv_lengthscales && mean_const && policy_Zs && policy_inv_lengthscales &&
-                  policy_alpha && cost_target && cost_W && x0 && loss, GPP_ERR_NULL, "gpp_rollout_pathwise_fwd: null argument");
-  GPP_REQUIRE(S >= 1 && H >= 0 && L >= 1 && L <= GPP_SMALL_MAX && Dx >= 1 && Dx <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE,
-              "gpp_rollout_pathwise_fwd: bad sizes S=%d H=%d L=%d Dx=%d", S, H, L, Dx);
-  GPP_REQUIRE(L == Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: the drift must have one output per state dim (L=%d, Dx=%d)", L, Dx);
-  GPP_REQUIRE(F % kPathTF == 0 && Mpad % kPathTF == 0, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: F=%d and Mpad=%d must be multiples of %d", F, Mpad, kPathTF);
-  GPP_REQUIRE(ldS % kPathP == 0 && ldS >= S, GPP_ERR_BAD_SHAPE, "gpp_rollout_pathwise_fwd: ldS=%d must be a multiple of %d and >= S=%d", ldS, kPathP, S);
-  GPP_REQUIRE(Mp >= 1 && Mp <= 64, GPP_ERR_UNSUPPORTED, "gpp_rollout_pathwise_fwd: Mp=%d policy centres (max 64)", Mp);
-  GPP_REQUIRE(num_active >= 0 && num_active <= 4 && D == Dx + num_active + 1, GPP_ERR_BAD_SHAPE,
-              "gpp_rollout_pathwise_fwd: D=%d must be Dx + num_active + 1", D);
-  PathwiseParams p{};
-  p.enc.Dx = Dx; p.enc.na = num_active;
-  for (int k = 0; k < num_active; ++k) p.enc.active[k] = active_dims[k];
-  p.S = S; p.ldS = ldS; p.H = H; p.L = L; p.F = F; p.Mpad = Mpad; p.Dx = Dx; p.De = Dx + num_active; p.Mp = Mp;
-  p.basis = basis; p.zbasis = zbasis; p.w = w; p.v = v; p.amp = amp; p.var = variance; p.inv_ell = inv_lengthscales; p.mean = mean_const;
-  p.pZs = policy_Zs; p.pInvEll = policy_inv_lengthscales; p.pAlpha = policy_alpha; p.scale = squash_scale; p.shift = squash_shift;
-  p.target = cost_target; p.W = cost_W; p.x0 = x0; p.loss = loss; p.x_final = x_final; p.traj = traj;
-  switch (D) {
-#define GPP_CASE(d) case d: return launch_pathwise<d>(p, (cudaStream_t)stream);
-    GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
-#undef GPP_CASE
-    default: set_error("gpp_rollout_pathwise_fwd: unsupported D=%d", D); return GPP_ERR_UNSUPPORTED;
-  }
+  return pathwise_fwd_impl(S, ldS, H, L, F, Mpad, D, Dx, num_active, active_dims, basis, zbasis, w, v, amp, variance, inv_lengthscales,
+                           mean_const, Mp, policy_Zs, policy_inv_lengthscales, policy_alpha, squash_scale, squash_shift, cost_target,
+                           cost_W, x0, loss, x_final, traj, nullptr, stream);
+}
+
+int gpp_rollout_pathwise_fwd_grad(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
+                                  const double* basis, const double* zbasis, const double* w, const double* v, const double* amp,
+                                  const double* variance, const double* inv_lengthscales, const double* mean_const,
+                                  int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                                  double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                                  const double* x0, double* loss, double* x_final, double* traj, double* jac, void* stream) {
+  GPP_REQUIRE(traj && jac, GPP_ERR_NULL, "gpp_rollout_pathwise_fwd_grad: traj and jac are required (they are what the backward reads)");
+  return pathwise_fwd_impl(S, ldS, H, L, F, Mpad, D, Dx, num_active, active_dims, basis, zbasis, w, v, amp, variance, inv_lengthscales,
+                           mean_const, Mp, policy_Zs, policy_inv_lengthscales, policy_alpha, squash_scale, squash_shift, cost_target,
+                           cost_W, x0, loss, x_final, traj, jac, stream);
 }
 
 }  // extern "C"

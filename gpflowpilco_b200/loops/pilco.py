@@ -107,7 +107,15 @@ class MomentMatchingPILCO(AbstractPILCO):
       st = np.asarray(solution_times, dtype=np.float64)
       unit_steps = abs(st[0] - initial_time - 1.0) < 1e-12 and (len(st) < 2 or np.allclose(np.diff(st), 1.0))
       if fused and unit_steps and self._fusable():
-        res = rollout_mm(svgp_handle(self.drift, True), self._policy_params(), mx, Sxx, len(st), self.encoder.active_dims,
+        pp = self._policy_params()
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (pp.Z, pp.lengthscales, pp.q_mu, mx, Sxx)):
+          # differentiable closure: upstream's tape.gradient(loss, policy.trainable_variables) (utils/optimizers.py:52-56)
+          # maps to gpp_rollout_mm_fwd + gpp_rollout_mm_bwd through the autograd shim
+          from gpflowpilco_b200.autograd import rollout_mm_loss
+          return rollout_mm_loss(svgp_handle(self.drift, True), pp.Z, pp.lengthscales, pp.variance, pp.q_mu, mx, Sxx, len(st),
+                                 self.encoder.active_dims, self.objective.target, self.objective.precis,
+                                 squash_scale=pp.squash_scale, squash_shift=pp.squash_shift, whiten=pp.whiten, jitter=pp.jitter)
+        res = rollout_mm(svgp_handle(self.drift, True), pp, mx, Sxx, len(st), self.encoder.active_dims,
                          self.objective.target, self.objective.precis)
         return res.loss
       loss = torch.zeros(mx.shape[:-1], dtype=mx.dtype, device=mx.device)

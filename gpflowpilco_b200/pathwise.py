@@ -119,8 +119,9 @@ def generate_paths(handle, num_samples: int, num_bases: int, seed: int, first_pa
 
 def rollout_pathwise(paths: PackedPaths, policy: PolicyParams, x0: torch.Tensor, horizon: int, active_dims: Sequence[int],
                      cost_target: torch.Tensor, cost_W: torch.Tensor, return_trajectory: bool = False,
-                     beta: Optional[torch.Tensor] = None):
-  """loss [S] (and final states / trajectory) of S particles, particle s evaluated on function draw s."""
+                     beta: Optional[torch.Tensor] = None, save_for_backward: bool = False):
+  """loss [S] (and final states / trajectory) of S particles, particle s evaluated on function draw s.
+  With save_for_backward the gradient-mode kernel runs and the result is (loss, x_final, traj, jac)."""
   x0, cost_target, cost_W = map(_c, (x0, cost_target, cost_W))
   _dev_check(x0, cost_target, cost_W)
   S, Dx = x0.shape
@@ -142,11 +143,49 @@ def rollout_pathwise(paths: PackedPaths, policy: PolicyParams, x0: torch.Tensor,
   dev = x0.device
   loss = torch.empty(S, dtype=F64, device=dev)
   xf = torch.empty(S, Dx, dtype=F64, device=dev)
-  traj = torch.empty(horizon + 1, S, Dx, dtype=F64, device=dev) if return_trajectory else None
+  traj = torch.empty(horizon + 1, S, Dx, dtype=F64, device=dev) if (return_trajectory or save_for_backward) else None
   act = (ctypes.c_int * max(na, 1))(*active_dims)
+  if save_for_backward:
+    jac = torch.empty(horizon, L * paths.D, ldS, dtype=F64, device=dev)
+    _lib.check(_lib.load().gpp_rollout_pathwise_fwd_grad(
+        S, ldS, int(horizon), L, F, Mpad, paths.D, Dx, na, act, _ptr(paths.basis), _ptr(paths.zbasis), _ptr(paths.w), _ptr(paths.v),
+        _ptr(paths.amp), _ptr(paths.variance), _ptr(paths.inv_lengthscales), _ptr(paths.mean_const), Mp, _ptr(pZs), _ptr(pinv),
+        _ptr(alpha), float(policy.squash_scale), float(policy.squash_shift), _ptr(cost_target), _ptr(cost_W), _ptr(x0), _ptr(loss),
+        _ptr(xf), _ptr(traj), _ptr(jac), _stream()))
+    return loss, xf, traj, jac
   _lib.check(_lib.load().gpp_rollout_pathwise_fwd(
       S, ldS, int(horizon), L, F, Mpad, paths.D, Dx, na, act, _ptr(paths.basis), _ptr(paths.zbasis), _ptr(paths.w), _ptr(paths.v),
       _ptr(paths.amp), _ptr(paths.variance), _ptr(paths.inv_lengthscales), _ptr(paths.mean_const), Mp, _ptr(pZs), _ptr(pinv),
       _ptr(alpha), float(policy.squash_scale), float(policy.squash_shift), _ptr(cost_target), _ptr(cost_W), _ptr(x0), _ptr(loss),
       _ptr(xf), _ptr(traj), _stream()))
   return loss, xf, traj
+
+
+def rollout_pathwise_bwd(policy: PolicyParams, beta: torch.Tensor, traj: torch.Tensor, jac: torch.Tensor, active_dims: Sequence[int],
+                         cost_target: torch.Tensor, cost_W: torch.Tensor, loss_bar: Optional[torch.Tensor] = None):
+  """Reverse sweep of the particle rollout from (traj, jac) saved by rollout_pathwise(save_for_backward=True): returns
+  (Z_bar [Mp,De], lengthscales_bar [De] at fixed beta, beta_bar [Mp], x0_bar [S,Dx]), summed over the particles."""
+  traj, jac, cost_target, cost_W, beta, loss_bar = map(_c, (traj, jac, cost_target, cost_W, beta, loss_bar))
+  _dev_check(traj, jac, cost_target, cost_W, beta, loss_bar)
+  H1, S, Dx = traj.shape
+  na = len(active_dims)
+  De = Dx + na
+  D = De + 1
+  R, Mp, Dp = policy.shape
+  H, LD, ldS = jac.shape
+  if R != 1 or Dp != De or H != H1 - 1 or LD != Dx * D:
+    raise ValueError("rollout_pathwise_bwd: inconsistent shapes")
+  dev = traj.device
+  lib = _lib.load()
+  need = lib.gpp_rollout_pathwise_bwd_workspace_bytes(S, Mp, De)
+  ws = torch.empty(need, dtype=torch.uint8, device=dev)
+  Zb = torch.empty(Mp, De, dtype=F64, device=dev)
+  eb = torch.empty(De, dtype=F64, device=dev)
+  bb = torch.empty(Mp, dtype=F64, device=dev)
+  x0b = torch.empty(S, Dx, dtype=F64, device=dev)
+  act = (ctypes.c_int * max(na, 1))(*active_dims)
+  _lib.check(lib.gpp_rollout_pathwise_bwd(S, ldS, H, Dx, D, Dx, na, act, Mp, _ptr(policy.Z[0].contiguous()), _ptr(policy.lengthscales[0].contiguous()),
+                                          float(policy.variance[0]), _ptr(beta[0].contiguous()), float(policy.squash_scale), _ptr(cost_target),
+                                          _ptr(cost_W), _ptr(traj), _ptr(jac), _ptr(loss_bar), _ptr(Zb), _ptr(eb), _ptr(bb), _ptr(x0b),
+                                          _ptr(ws), ws.numel(), _stream()))
+  return Zb, eb, bb, x0b

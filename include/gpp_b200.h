@@ -177,6 +177,27 @@ int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int 
                              double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
                              const double* x0, double* loss, double* x_final, double* traj, void* stream);
 
+/* Gradient mode of gpp_rollout_pathwise_fwd: same rollout, and while the weights stream past it also reduces
+ * jac [H, L*D, ldS] = d f_{s,l} / d d_b of every particle-step (the derivative of each particle's function draw w.r.t. its
+ * input).  traj [H+1,S,Dx] and jac are required: they are what gpp_rollout_pathwise_bwd reads. */
+int gpp_rollout_pathwise_fwd_grad(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
+                                  const double* basis, const double* zbasis, const double* w, const double* v, const double* amp,
+                                  const double* variance, const double* inv_lengthscales, const double* mean_const,
+                                  int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                                  double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                                  const double* x0, double* loss, double* x_final, double* traj, double* jac, void* stream);
+/* Backward of the pathwise closure (upstream: tape.gradient through loops/pilco.py:263-298): reverse sweep over traj / jac.
+ *   policy in its ORIGINAL parametrisation: Z [Mp,De], lengthscales [De], variance, beta = Kuu^-1 m [Mp];  loss_bar [S] (NULL = ones)
+ *   -> Z_bar [Mp,De], lengthscales_bar [De] (at fixed beta), beta_bar [Mp]: sums over the S particles in a fixed order;
+ *      x0_bar [S,Dx] (may be NULL). */
+size_t gpp_rollout_pathwise_bwd_workspace_bytes(int S, int Mp, int De);
+int gpp_rollout_pathwise_bwd(int S, int ldS, int H, int L, int D, int Dx, int num_active, const int* active_dims,
+                             int Mp, const double* policy_Z, const double* policy_lengthscales, double policy_variance,
+                             const double* policy_beta, double squash_scale, const double* cost_target, const double* cost_W,
+                             const double* traj, const double* jac, const double* loss_bar,
+                             double* Z_bar, double* lengthscales_bar, double* beta_bar, double* x0_bar,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- pathwise draws on the device (counter-based, sharding-invariant) --------------------------------------
  * Random streams: Philox4x32-10 keyed by (seed, stream, logical element index) with the GLOBAL particle index in the
  * element index (oracle/philox.py is the contract; raw words are bit-identical).  Replaces the set-up half of

@@ -144,3 +144,50 @@ def test_rollout_mm_gradients_match_autograd(shared_policy, whiten):
   scaled_close(Z.grad, torch.stack([t[0] for t in trip]), 1e-6, "policy centre gradient")
   scaled_close(ell.grad, torch.stack([t[1] for t in trip]), 1e-6, "policy lengthscale gradient")
   scaled_close(q.grad, torch.stack([t[2][:, 0] for t in trip]), 1e-6, "policy q_mu gradient")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pathwise particle rollout: gradient w.r.t. the policy parameters and the initial states
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,F,M,Mp,H", [(40, 64, 20, 6, 3), (300, 128, 40, 10, 4)])
+def test_rollout_pathwise_gradients_match_autograd(S, F, M, Mp, H):
+  from gpflowpilco_b200.autograd import rollout_pathwise_loss
+  from gpflowpilco_b200.pathwise import PackedPaths
+  from oracle import pathwise as pw
+  from oracle import psi_stats as ps
+  from oracle import rollout as ro
+  cfg = synthetic.config1_cartpole(M=M, Mp=Mp)
+  cfg["policy"]["q_mu"] = 200.0 * cfg["policy"]["q_mu"]
+  dyn = oracle_svgp(cfg["dynamics"])
+  paths = pw.generate_paths(dyn, F, 3, 0, S)
+  x0 = pw.draw_initial_states(torch.as_tensor(cfg["m0"][0]), torch.linalg.cholesky(torch.as_tensor(cfg["S0"][0])), 3, 0, S)
+  g = torch.Generator().manual_seed(1)
+  loss_bar = torch.randn(S, dtype=DTYPE, generator=g)
+  pp = cfg["policy"]
+  Z = torch.as_tensor(pp["Z"][0]).clone().requires_grad_(True)
+  ell = torch.as_tensor(pp["lengthscales"][0]).clone().requires_grad_(True)
+  q = torch.as_tensor(pp["q_mu"]).clone().requires_grad_(True)
+  x0r = x0.clone().requires_grad_(True)
+  pol = gm.SVGPModel([ps.SEKernel(float(pp["variance"][0]), ell)], [Z], q, torch.as_tensor(pp["q_sqrt"]), whiten=True,
+                     mean_const=torch.zeros(1, dtype=DTYPE))
+  enc = mo.TrigonometricEncoder(cfg["active_dims"])
+  obj = mo.GaussianObjective(cfg["target"], cfg["W"])
+  loss_ref = ro.pathwise_rollout(x0r, H, lambda eu: pw.evaluate_paths(dyn, paths, eu),
+                                 lambda e: gm.policy_sample_path(pol, e, cfg["squash_scale"], cfg["squash_shift"]), enc, obj)
+  gZ, gell, gq, gx0 = torch.autograd.grad((loss_ref * loss_bar).sum(), (Z, ell, q, x0r))
+
+  d = cfg["dynamics"]
+  packed = PackedPaths.from_sample_major(_dev(d["Z"]), _dev(d["lengthscales"]), _dev(d["variance"]), _dev(d["mean_const"]),
+                                         _dev(paths.omega), _dev(paths.phase), _dev(paths.w), _dev(paths.v))
+  Zd = _dev(pp["Z"]).requires_grad_(True)
+  elld = _dev(pp["lengthscales"]).requires_grad_(True)
+  qd = _dev(pp["q_mu"][:, 0][None]).requires_grad_(True)
+  x0d = _dev(x0).requires_grad_(True)
+  loss = rollout_pathwise_loss(packed, Zd, elld, _dev(pp["variance"]), qd, x0d, H, cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]),
+                               squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  scaled_close(loss, loss_ref.detach(), 1e-8, "loss")
+  (loss * _dev(loss_bar)).sum().backward()
+  scaled_close(x0d.grad, gx0, 1e-6, "x0 gradient")
+  scaled_close(Zd.grad[0], gZ, 1e-6, "policy centre gradient")
+  scaled_close(elld.grad[0], gell, 1e-6, "policy lengthscale gradient")
+  scaled_close(qd.grad[0], gq[:, 0], 1e-6, "policy q_mu gradient")

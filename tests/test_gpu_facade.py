@@ -142,3 +142,35 @@ def test_policy_sample_path_and_pathwise_closure():
   assert not torch.equal(l1, l2)          # fresh paths per call (upstream loops/pilco.py:281-284)
   again = loop.policy_loss_closure(batch_size=64, num_bases=64, seed=5)()
   assert torch.equal(l1, again)           # same seed -> identical draws
+
+
+def test_mm_closure_is_differentiable_like_upstream_tape_gradient():
+  """loss.backward() on the fused closure (upstream: tape.gradient(loss, policy.trainable_variables), optimizers.py:52-56)
+  agrees with central finite differences of the closure itself."""
+  from gpflowpilco_b200.components import GaussianObjective, TrigonometricEncoder
+  from gpflowpilco_b200.loops import EpisodeSpec, GaussianStateDistribution, MomentMatchingPILCO
+  cfg = synthetic.config1_cartpole(M=32, Mp=6)
+  cfg["policy"]["q_mu"] = 50.0 * cfg["policy"]["q_mu"]          # 1e-3 N(0,1) initial weights give a nearly flat loss
+  drift, policy = _facade_models(cfg)
+  svgp = policy.model.model
+  q_mu = svgp.q_mu.clone().requires_grad_(True)
+  svgp.q_mu = q_mu
+  spec = EpisodeSpec(GaussianStateDistribution(_dev(cfg["m0"][0]), _dev(cfg["S0"][0])), horizon=0.5, step_size=0.1)
+  loop = MomentMatchingPILCO(spec, GaussianObjective(_dev(cfg["target"]), _dev(cfg["W"])), drift, policy, TrigonometricEncoder(cfg["active_dims"]))
+  closure = loop.policy_loss_closure()
+  loss = closure()
+  assert loss.requires_grad
+  loss.sum().backward()
+  grad = q_mu.grad.clone()
+  fd = torch.zeros_like(grad)
+  eps = 1e-5
+  with torch.no_grad():
+    for i in range(q_mu.shape[0]):
+      vals = []
+      for sgn in (1.0, -1.0):
+        q2 = q_mu.detach().clone()
+        q2[i, 0] += sgn * eps
+        svgp.q_mu = q2
+        vals.append(float(closure().sum()))
+      fd[i, 0] = (vals[0] - vals[1]) / (2 * eps)
+  scaled_close(grad, fd, 1e-6, "d loss / d q_mu vs finite differences")
