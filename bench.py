@@ -48,6 +48,9 @@ def parse_args():
   ap.add_argument("--pathwise-particles", type=int, default=148 * 512, help="particles per GPU per launch (one wave of 512-particle CTAs)")
   ap.add_argument("--pathwise-horizon", type=int, default=100)
   ap.add_argument("--pathwise-bases", type=int, default=4096)
+  ap.add_argument("--no-policy-opt", action="store_true")
+  ap.add_argument("--restarts", type=int, default=64, help="policy restarts per GPU (config #5: 512 over 8 GPUs)")
+  ap.add_argument("--restart-horizon", type=int, default=100)
   return ap.parse_args()
 
 
@@ -229,6 +232,59 @@ def pathwise_section(dev, lib, pk, world):
   }
 
 
+def policy_opt_section(dev, lib, world):
+  """BASELINE config #5 (full PILCO policy-optimisation step): R policy restarts per GPU, cart-pole models of config #1
+  (M=256 dynamics, 30 policy centres), horizon H, forward + backward of the moment-matched rollout; restarts are sharded over
+  ranks, every rank receives loss[R_total] by all-gather.  Reports rollout-steps/s (forward + backward), whole job."""
+  import torch
+  import torch.distributed as dist
+  from gpflowpilco_b200 import distributed as gd
+  from gpflowpilco_b200 import ops, synthetic
+  args = ARGS
+  R, H = args.restarts, args.restart_horizon
+  cfg = synthetic.config1_cartpole()
+  T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+  d, p = cfg["dynamics"], cfg["policy"]
+  handle = ops.GPModelHandle(T(d["Z"]), T(d["lengthscales"]), T(d["variance"]), T(d["q_mu"]), T(d["q_sqrt"]), whiten=True,
+                             mean_const=T(d["mean_const"]))
+  Rt = R * world
+  g = torch.Generator().manual_seed(5)
+  Z = T(p["Z"]).repeat(Rt, 1, 1) + 0.3 * torch.randn(Rt, *p["Z"].shape[1:], dtype=torch.float64, generator=g).to(dev)
+  ell = T(p["lengthscales"]).repeat(Rt, 1) * torch.exp(torch.empty(Rt, 1, dtype=torch.float64).uniform_(-0.7, 0.7, generator=g)).to(dev)
+  q = 1e-3 * torch.randn(Rt, p["Z"].shape[1], dtype=torch.float64, generator=g).to(dev)
+  var = T(p["variance"]).repeat(Rt)
+  def step():
+    return gd.mm_restart_losses_and_grads(handle, Z, ell, var, q, T(cfg["m0"]), T(cfg["S0"]), H, cfg["active_dims"], T(cfg["target"]),
+                                          T(cfg["W"]), cfg["squash_scale"], cfg["squash_shift"])
+  step()
+  times = []
+  launches0 = lib.gpp_launch_count()
+  for _ in range(2):
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses, _, grads = step()
+    e1.record()
+    e1.synchronize()
+    times.append(e0.elapsed_time(e1))
+  launches = (lib.gpp_launch_count() - launches0) // 2
+  t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  sec = float(t[0]) * 1e-3
+  M, L, D = d["Z"].shape[1], 4, 6
+  flop_per_step = 4 * (L * (L + 1) // 2) * M * M * (2 * D + 26)      # SURVEY §8d: fwd + bwd counted as 4 x forward
+  return {"metric": "mm_policy_opt_rollout_steps_per_s", "value": Rt * H / sec, "unit": "rollout_steps/s (forward+backward)",
+          "config": {"workload": "config#5 policy-optimisation step", "restarts_per_gpu": R, "horizon": H, "dynamics_inducing": M,
+                     "policy_centres": int(p["Z"].shape[1]), "collective": "all-gather of loss[R] (uneven-safe), gradients stay sharded"},
+          "ms_per_opt_step": 1e3 * sec, "gpu_launches_per_opt_step": int(launches), "mean_loss": float(losses.mean()),
+          "grad_norm": float(grads[0].norm()),
+          "roofline": {"bound": "fp64", "achieved": Rt * H * flop_per_step / sec / 1e12 / world, "unit": "TFLOP/s per GPU",
+                       "algorithmic": f"{flop_per_step} flop per rollout-step (4 x forward, SURVEY 8d)"}}
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
@@ -363,6 +419,7 @@ def run_b200(args):
 
   # second half of the metric; every rank takes part (its particles are sharded by global index)
   pathwise = None if args.no_pathwise else pathwise_section(dev, lib, pk, world)
+  policy_opt = None if args.no_policy_opt else policy_opt_section(dev, lib, world)
 
   if rank == 0:
     kern_s = float(np.mean(kern_ms)) * 1e-3
@@ -386,6 +443,8 @@ def run_b200(args):
     }
     if pathwise is not None:
       line["pathwise"] = pathwise
+    if policy_opt is not None:
+      line["policy_opt_step"] = policy_opt
     if not args.no_cpu_baseline:
       small = {k: (v[:64] if k in ("mu", "cov") else v) for k, v in cfg.items()}
       rate, sample, _ = time_cpu(small, args.cpu_baseline_seconds, reference_form=True)

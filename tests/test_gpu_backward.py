@@ -191,3 +191,32 @@ def test_rollout_pathwise_gradients_match_autograd(S, F, M, Mp, H):
   scaled_close(Zd.grad[0], gZ, 1e-6, "policy centre gradient")
   scaled_close(elld.grad[0], gell, 1e-6, "policy lengthscale gradient")
   scaled_close(qd.grad[0], gq[:, 0], 1e-6, "policy q_mu gradient")
+
+
+def test_sharded_closures_single_process_and_chunk_invariance():
+  """distributed.py on one GPU (no process group): the pathwise mean cost / gradient do not depend on how the particles
+  are chunked (the same property that makes them independent of the number of ranks: Philox streams are keyed by the
+  global particle index), and the restart-sharded MM closure returns per-restart losses and gradients."""
+  from gpflowpilco_b200 import distributed as gd
+  cfg = synthetic.config1_cartpole(M=32, Mp=8)
+  cfg["policy"]["q_mu"] = 100.0 * cfg["policy"]["q_mu"]
+  pp = cfg["policy"]
+  h = cuda_handle(cfg["dynamics"])
+  args = (h, _dev(pp["Z"]), _dev(pp["lengthscales"]), _dev(pp["variance"]), _dev(pp["q_mu"][:, 0][None]), _dev(cfg["m0"][0]), _dev(cfg["S0"][0]))
+  kw = dict(total_particles=700, num_bases=64, seed=4, horizon=3, active_dims=cfg["active_dims"], cost_target=_dev(cfg["target"]),
+            cost_W=_dev(cfg["W"]), squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  l1, g1 = gd.pathwise_policy_loss_and_grad(*args, **kw, max_particles_per_launch=1024)
+  l2, g2 = gd.pathwise_policy_loss_and_grad(*args, **kw, max_particles_per_launch=256)
+  assert abs(float(l1) - float(l2)) <= 1e-12 * abs(float(l1))
+  for a, b in zip(g1, g2):
+    scaled_close(b, a, 1e-10, "chunked vs single-launch gradient")
+  R = 3
+  g = torch.Generator().manual_seed(0)
+  Z = _dev(pp["Z"]).repeat(R, 1, 1) + 0.1 * _dev(torch.randn(R, *pp["Z"].shape[1:], dtype=DTYPE, generator=g))
+  ell = _dev(pp["lengthscales"]).repeat(R, 1)
+  q = _dev(pp["q_mu"][:, 0][None]).repeat(R, 1)
+  var = _dev(pp["variance"]).repeat(R)
+  losses, (start, count), grads = gd.mm_restart_losses_and_grads(h, Z, ell, var, q, _dev(cfg["m0"]), _dev(cfg["S0"]), 4, cfg["active_dims"],
+                                                                 _dev(cfg["target"]), _dev(cfg["W"]), cfg["squash_scale"], cfg["squash_shift"])
+  assert losses.shape == (R,) and (start, count) == (0, R) and grads[0].shape == Z.shape and torch.isfinite(grads[0]).all()
+  assert float((losses[1:] - losses[0]).abs().max()) > 0     # different restarts, different losses
