@@ -171,6 +171,7 @@ def time_cpu(cfg, seconds: float, reference_form: bool, steps: int = 1):
 
 
 ARGS = None
+_emit = print
 
 
 def pathwise_section(dev, lib, pk, world):
@@ -305,7 +306,7 @@ def run_reference(args):
       "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "note": "upstream needs tensorflow/gpflow (absent): timed is oracle/, its line-by-line CPU restatement",
   }
-  print(json.dumps(line))
+  _emit(json.dumps(line))
 
 
 def run_b200(args):
@@ -452,15 +453,23 @@ def run_b200(args):
       import torch as _t
       line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port", "sample": sample,
                               "reassociated_form": {"value": rate2, "sample": sample2}}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
 
 
 def main():
-  global ARGS
+  global ARGS, _emit
   args = parse_args()
   ARGS = args
+  # the contract is ONE JSON line on stdout: libraries that print to fd 1 (NCCL prints its version there) are sent to stderr,
+  # and the line itself is written to the saved descriptor
+  sys.stdout.flush()
+  real_stdout = os.dup(1)
+  os.dup2(2, 1)
+
+  def _emit(line: str):
+    os.write(real_stdout, (line + "\n").encode())
   if args.impl == "reference":
     run_reference(args)
   else:

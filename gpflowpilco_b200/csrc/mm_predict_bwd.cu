@@ -39,19 +39,22 @@ template <int D>
 __global__ void __launch_bounds__(kGradRows) k_contract_grad(const double* __restrict__ Z, const double* __restrict__ beta,
                                                              const double* __restrict__ C, const double* __restrict__ packs,
                                                              const double* __restrict__ omega, double* __restrict__ stats,
-                                                             int M, int L, int nrb) {
+                                                             int M, int L, int nrb, int ncb, int cols_per_block) {
   using PP = PairPack<D>;
   using GS = GradStats<D>;
   __shared__ double colz[kGradCols][D + 2];
   __shared__ double pk[PP::SIZE];
   __shared__ double red[kGradRows / 32][GS::SIZE];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rb = blockIdx.x % nrb;
-  const int p = (blockIdx.x / nrb) % (L * L);
-  const int n = blockIdx.x / (nrb * L * L);
+  // a CTA owns 256 rows x one block of columns; row statistics are linear in the column partial sums, so the column blocks
+  // of a row block are simply added up by k_bwd_finalize (fixed order)
+  const int cb = blockIdx.x % ncb;
+  const int rb = (blockIdx.x / ncb) % nrb;
+  const int p = (blockIdx.x / (ncb * nrb)) % (L * L);
+  const int n = blockIdx.x / (ncb * nrb * L * L);
   const int a = p / L, b = p % L;
   const bool diag = a == b;
-  double* out = stats + (((size_t)n * L * L + p) * nrb + rb) * GS::SIZE;
+  double* out = stats + ((((size_t)n * L * L + p) * nrb + rb) * ncb + cb) * GS::SIZE;
   // pairs whose output adjoint is zero (e.g. diagonal-only covariance) are skipped; k_bwd_finalize skips them too
   const double wgt = omega[((size_t)n * L + a) * L + b] + omega[((size_t)n * L + b) * L + a];
   if (wgt == 0.0) return;
@@ -74,9 +77,10 @@ __global__ void __launch_bounds__(kGradRows) k_contract_grad(const double* __res
 #pragma unroll
   for (int d = 0; d < D; ++d) u[d] = 0.0;
   const double* Ca = C + (size_t)a * M * M;
-  for (int j0 = 0; j0 < M; j0 += kGradCols) {
+  const int jbeg = cb * cols_per_block, jend = min(M, jbeg + cols_per_block);
+  for (int j0 = jbeg; j0 < jend; j0 += kGradCols) {
     __syncthreads();
-    if (tid < kGradCols && j0 + tid < M) {
+    if (tid < kGradCols && j0 + tid < jend) {
       const int j = j0 + tid;
       double z2[D];
 #pragma unroll
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(kGradRows) k_contract_grad(const double* __res
       colz[tid][D + 1] = beta[(size_t)b * M + j];
     }
     __syncthreads();
-    const int jn = min(kGradCols, M - j0);
+    const int jn = min(kGradCols, jend - j0);
     if (valid) {
       for (int jj = 0; jj < jn; ++jj) {
         double t = ri + colz[jj][D];
@@ -437,7 +441,7 @@ static size_t bwd_align(size_t x) { return (x + 255) / 256 * 256; }
 
 struct BwdLayout {
   size_t packs, stats, f1lat, crosslat, f1lat_bar, crosslat_bar, omega, gm, gS, total;
-  int nrb;
+  int nrb, ncb, cols_per_block;
 };
 
 static BwdLayout bwd_layout(const gpp_gp_model* m, int N) {
@@ -450,10 +454,16 @@ static BwdLayout bwd_layout(const gpp_gp_model* m, int N) {
 #undef GPP_CASE
   }
   lo.nrb = (m->M + kGradRows - 1) / kGradRows;
+  // split the columns so that the grid has ~16 CTAs per SM (the kernel is a serial loop over its columns per thread)
+  const int max_cb = (m->M + kGradCols - 1) / kGradCols;
+  const long long ctas = (long long)N * L * L * lo.nrb;
+  lo.ncb = (int)std::min<long long>(max_cb, std::max<long long>(1, (16LL * num_sms() + ctas - 1) / ctas));
+  lo.cols_per_block = ((m->M + lo.ncb - 1) / lo.ncb + kGradCols - 1) / kGradCols * kGradCols;
+  lo.ncb = (m->M + lo.cols_per_block - 1) / lo.cols_per_block;
   size_t off = 0;
   auto take = [&](size_t doubles) { size_t o = off; off = bwd_align(off + doubles * sizeof(double)); return o; };
   lo.packs = take(pack_doubles * L * L * N);
-  lo.stats = take(stat_doubles * L * L * lo.nrb * N);
+  lo.stats = take(stat_doubles * L * L * lo.nrb * lo.ncb * N);
   lo.f1lat = take((size_t)L * N);
   lo.crosslat = take((size_t)L * D * N);
   lo.f1lat_bar = take((size_t)L * N);
@@ -488,12 +498,13 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   bp.N = N; bp.L = L; bp.P = m->P; bp.D = D; bp.full_cov = full_output_cov;
   k_bwd_prepare<<<(N + 63) / 64, 64, 0, stream>>>(bp);
   profile_begin(stream);
-  k_contract_grad<D><<<N * L * L * lo.nrb, kGradRows, 0, stream>>>(m->Z, m->beta, m->C, packs, omega, stats, m->M, L, lo.nrb);
+  k_contract_grad<D><<<N * L * L * lo.nrb * lo.ncb, kGradRows, 0, stream>>>(m->Z, m->beta, m->C, packs, omega, stats, m->M, L, lo.nrb, lo.ncb,
+                                                                            lo.cols_per_block);
   profile_end(stream);
   k_psi1_bwd<D><<<N, 128, 0, stream>>>(mu, S, N, L, m->M, m->Z, m->ell, m->var, m->beta, f1lat_bar, crosslat_bar, gm, gS);
   BwdFinalizeParams fp;
   fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.omega = omega; fp.gm = gm; fp.gS = gS;
-  fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb;
+  fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb * lo.ncb;
   k_bwd_finalize<D><<<N, 64, 0, stream>>>(fp);
   count_launch(6);
   GPP_CUDA_OK(cudaGetLastError());
