@@ -69,16 +69,19 @@ __global__ void __launch_bounds__(64) k_pack_single(const double* __restrict__ m
 
 // grid (column strips of CT columns, n); 128 threads, each owns 2 adjacent columns of the strip and walks all rows.
 template <int D>
-__global__ void __launch_bounds__(128) k_ekzxkxz(const double* __restrict__ packs, const double* __restrict__ Z1, int M1,
+__global__ void __launch_bounds__(128, 4) k_ekzxkxz(const double* __restrict__ packs, const double* __restrict__ Z1, int M1,
                                                  const double* __restrict__ Z2, int M2, double* __restrict__ out) {
   using PP = PairPack<D>;
   constexpr int RT = 64;                 // rows staged per pass
   constexpr int RS = (D + 1 + 1) & ~1;   // z1'[D], r
   __shared__ __align__(16) double pk[PP::SIZE];
   __shared__ __align__(16) double rowbuf[RT * RS];
+  __shared__ double etab[64 * GPP_EXP_TAB_REP];   // replicated 2^(j/64) table of the 10-op exp (gpp_math.h)
   const int n = blockIdx.y, tid = threadIdx.x;
   for (int t = tid; t < PP::SIZE; t += blockDim.x) pk[t] = packs[(size_t)n * PP::SIZE + t];
+  for (int t = tid; t < 64 * GPP_EXP_TAB_REP; t += blockDim.x) etab[t] = kExp2Tab[t / GPP_EXP_TAB_REP];
   __syncthreads();
+  const double* etab_lane = etab + (tid & (GPP_EXP_TAB_REP - 1));
   const int j0 = (blockIdx.x * 128 + tid) * 2;
   const bool pair_ok = ((M2 & 1) == 0);          // 16-byte aligned pair stores need an even row length
   double g[2][D], s[2];
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(128) k_ekzxkxz(const double* __restrict__ pack
         t[2] = fma(rb1[d], g[0][d], t[2]);
         t[3] = fma(rb1[d], g[1][d], t[3]);
       }
-      fast_exp_n<4>(t);
+      fast_exp_tab_n<4>(t, etab_lane);
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         if (ii + rr >= rows) break;
