@@ -44,7 +44,8 @@ struct ContractCfg {
   static constexpr int ROW = COL + 2 * T * ColLayout<D>::STRIDE;   // [2][D+2][T]
   static constexpr int RED = ROW + 2 * (D + 2) * T;             // [2][NC][32]
   static constexpr int ETAB = RED + 2 * NC * 32;                // [64][GPP_EXP_TAB_REP] replicated 2^(j/64) table (fast_exp_tab_n)
-  static constexpr int TOTAL = ETAB + 64 * GPP_EXP_TAB_REP;     // doubles
+  static constexpr int PKBUF = ETAB + 64 * GPP_EXP_TAB_REP;     // [2][PairPack<D>::SIZE] coefficient packs of the inputs in flight
+  static constexpr int TOTAL = PKBUF + 2 * PairPack<D>::SIZE;   // doubles
 };
 
 // barrier ids are immediates (a register id would make ptxas reserve all 16 hardware barriers for the CTA)
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   constexpr int RPT = T / 32;                // rows per consumer thread
   constexpr int CS = ColLayout<D>::STRIDE;
   constexpr int RBUF = (D + 2) * T, CBUF = T * CS, DBUF = NC * 32;
-  constexpr int BAR_FULL = 1, BAR_EMPTY = 3;  // named barriers 1,2 (full) and 3,4 (empty); 0 is __syncthreads
+  constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_PROD = 5;  // named barriers 1,2 (full), 3,4 (empty), 5 (producers); 0 is __syncthreads
   static_assert(T % 32 == 0, "rows of a tile are covered by 32 lanes x RPT");
 
   extern __shared__ __align__(16) double smem[];
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   double* rowbuf = smem + CF::ROW;
   double* red = smem + CF::RED;
   double* etab = smem + CF::ETAB;
+  double* pkbuf = smem + CF::PKBUF;
   __shared__ int s_item;
   for (int i = threadIdx.x; i < 64 * GPP_EXP_TAB_REP; i += NT) etab[i] = kExp2Tab[i / GPP_EXP_TAB_REP];
 
@@ -126,9 +128,27 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   if (warp < NP) {
     // ------------------------------------------------------------------ producers (own copy of the item loop, then exit:
     // the consumer loop below is then straight-line code for ptxas, which keeps its constants in uniform registers)
+    static_assert(PT == T, "one producer thread per tile row / column");
+    constexpr int NPV = (PP::SIZE + PT - 1) / PT;   // pack elements staged per producer thread
     while (contract_next_item<D, T, NP, NC>(p, Ct, &s_item, it)) {
       const gpp_slot sl = it.sl;
       const bool diag = it.diag;
+      // the tile's centres and weights do not change over the chunk: keep this thread's row and column in registers
+      const int ig = sl.ti * T + tid, jg = sl.tj * T + tid;
+      double zrow[D], zcol[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        zrow[d] = ig < p.M ? p.Z[((size_t)sl.a * p.M + ig) * D + d] : 0.0;
+        zcol[d] = jg < p.M ? p.Z[((size_t)sl.b * p.M + jg) * D + d] : 0.0;
+      }
+      const double brow = (!diag && ig < p.M) ? p.beta[(size_t)sl.a * p.M + ig] : 0.0;
+      const double bcol = (!diag && jg < p.M) ? p.beta[(size_t)sl.b * p.M + jg] : 0.0;
+      // coefficient pack of input k: one element per thread, loaded one input ahead, staged in shared memory (double buffered)
+      const double* pk0 = p.packs + ((size_t)it.n0 * p.npairs + sl.pair) * PP::SIZE;
+      const size_t pk_stride = (size_t)p.npairs * PP::SIZE;
+      double pv[NPV];
+#pragma unroll
+      for (int q = 0; q < NPV; ++q) pv[q] = tid + q * PT < PP::SIZE ? pk0[tid + q * PT] : 0.0;
       for (int k = 0; k < it.K + 2; ++k) {
         const int b = k & 1;
         if (k >= 2) {                        // consumers are done with input k-2 (buffer b): reduce its lane partials
@@ -143,62 +163,43 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
           }
         }
         if (k >= it.K) continue;
-        const double* pk = p.packs + ((size_t)(it.n0 + k) * p.npairs + sl.pair) * PP::SIZE;
+        double* pk = pkbuf + b * PP::SIZE;
+#pragma unroll
+        for (int q = 0; q < NPV; ++q)
+          if (tid + q * PT < PP::SIZE) pk[tid + q * PT] = pv[q];
+        named_bar_sync_imm<BAR_PROD>(PT);   // producers only: pack k visible; pack k-2 (same buffer) no longer read
+        if (k + 1 < it.K) {
+#pragma unroll
+          for (int q = 0; q < NPV; ++q)
+            if (tid + q * PT < PP::SIZE) pv[q] = pk0[(size_t)(k + 1) * pk_stride + tid + q * PT];
+        }
         double* rb = rowbuf + b * RBUF;
         double* cb = colbuf + b * CBUF;
-        for (int st = tid; st < T; st += PT) {
-          // row st of the tile
-          {
-            const int ig = sl.ti * T + st;
-            double zc[D];
+        {
+          // row `tid` of the tile
+          double zc[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d)
-              zc[d] = (ig < p.M ? p.Z[((size_t)sl.a * p.M + ig) * D + d] : 0.0) - __ldg(pk + PP::MU + d);
+          for (int d = 0; d < D; ++d) zc[d] = zrow[d] - pk[PP::MU + d];
 #pragma unroll
-            for (int e = 0; e < D; ++e) {
-              double t = 0.0;
+          for (int e = 0; e < D; ++e) {
+            double t = 0.0;
 #pragma unroll
-              for (int d = 0; d < D; ++d) t = fma(zc[d], __ldg(pk + PP::R + d * D + e), t);
-              rb[e * T + st] = t;
-            }
-            double q = __ldg(pk + PP::C0);
-            {
-              int t = 0;
-#pragma unroll
-              for (int d = 0; d < D; ++d) {
-                double row = 0.0;
-#pragma unroll
-                for (int e = d; e < D; ++e, ++t) row = fma(__ldg(pk + PP::P1 + t), zc[e], row);
-                q = fma(row, zc[d], q);
-              }
-            }
-            rb[D * T + st] = q;
-            rb[(D + 1) * T + st] = (!diag && ig < p.M) ? p.beta[(size_t)sl.a * p.M + ig] : 0.0;
+            for (int d = 0; d < D; ++d) t = fma(zc[d], pk[PP::R + d * D + e], t);
+            rb[e * T + tid] = t;
           }
-          // column st of the tile
-          {
-            const int jg = sl.tj * T + st;
-            double zc[D];
+          rb[D * T + tid] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
+          rb[(D + 1) * T + tid] = brow;
+        }
+        {
+          // column `tid` of the tile
+          double zc[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d)
-              zc[d] = (jg < p.M ? p.Z[((size_t)sl.b * p.M + jg) * D + d] : 0.0) - __ldg(pk + PP::MU + d);
-            double q = 0.0;
-            {
-              int t = 0;
+          for (int d = 0; d < D; ++d) zc[d] = zcol[d] - pk[PP::MU + d];
+          double* dst = cb + tid * CS;
 #pragma unroll
-              for (int d = 0; d < D; ++d) {
-                double row = 0.0;
-#pragma unroll
-                for (int e = d; e < D; ++e, ++t) row = fma(__ldg(pk + PP::P2 + t), zc[e], row);
-                q = fma(row, zc[d], q);
-              }
-            }
-            double* dst = cb + st * CS;
-#pragma unroll
-            for (int d = 0; d < D; ++d) dst[d] = zc[d];
-            dst[D] = q;
-            dst[D + 1] = (!diag && jg < p.M) ? p.beta[(size_t)sl.b * p.M + jg] : 0.0;
-          }
+          for (int d = 0; d < D; ++d) dst[d] = zc[d];
+          dst[D] = packed_quad<D>(pk + PP::P2, zc);
+          dst[D + 1] = bcol;
         }
         __threadfence_block();
         named_bar_arrive<BAR_FULL>(b, NT);
