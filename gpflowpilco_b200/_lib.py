@@ -35,7 +35,10 @@ SIGNATURES = {
                                    _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "gpp_rollout_mm_bwd_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
     "gpp_rollout_mm_bwd": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_double, c_double,
-                                   _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
+                                   _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
+    "gpp_rollout_mm_saved_doubles": (c_size_t, [_P, c_int, c_int, c_int]),
+    "gpp_rollout_mm_fwd_save": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_double, c_double,
+                                        _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "gpp_pathwise_tile": (c_int, []),
     "gpp_pathwise_particles_per_cta": (c_int, []),
     "gpp_pathwise_pack_basis": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),

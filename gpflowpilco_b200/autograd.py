@@ -57,16 +57,16 @@ class _RolloutMM(torch.autograd.Function):
   @staticmethod
   def forward(ctx, Z, lengthscales, beta, m0, S0, dynamics, variance, scale, shift, horizon, active_dims, target, W):
     pol = PolicyParams(Z.detach(), lengthscales.detach(), variance, torch.zeros_like(beta), squash_scale=scale, squash_shift=shift)
-    res = rollout_mm(dynamics, pol, m0.detach(), S0.detach(), horizon, active_dims, target, W, return_trajectory=True, beta=beta.detach())
-    ctx.save_for_backward(beta.detach(), res.traj_m, res.traj_S)
+    res = rollout_mm(dynamics, pol, m0.detach(), S0.detach(), horizon, active_dims, target, W, beta=beta.detach(), save_for_backward=True)
+    ctx.save_for_backward(beta.detach(), res.traj_m, res.traj_S, res.saved)
     ctx.pol, ctx.dynamics, ctx.active_dims, ctx.target, ctx.W = pol, dynamics, tuple(active_dims), target, W
     return res.loss
 
   @staticmethod
   def backward(ctx, loss_bar):
-    beta, traj_m, traj_S = ctx.saved_tensors
+    beta, traj_m, traj_S, saved = ctx.saved_tensors
     Zb, eb, bb, m0b, S0b = rollout_mm_bwd(ctx.dynamics, ctx.pol, beta, traj_m, traj_S, ctx.active_dims, ctx.target, ctx.W,
-                                          loss_bar=loss_bar.contiguous())
+                                          loss_bar=loss_bar.contiguous(), saved=saved)
     return Zb, eb, bb, m0b, S0b, None, None, None, None, None, None, None, None
 
 

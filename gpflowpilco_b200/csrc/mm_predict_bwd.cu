@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(kGradRows) k_contract_grad(const double* __res
   __shared__ double colz[kGradCols][D + 2];
   __shared__ double pk[PP::SIZE];
   __shared__ double red[kGradRows / 32][GS::SIZE];
+  __shared__ double etab[64 * GPP_EXP_TAB_REP];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = tid; t < 64 * GPP_EXP_TAB_REP; t += kGradRows) etab[t] = kExp2Tab[t / GPP_EXP_TAB_REP];
+  const double* etab_lane = etab + (lane & (GPP_EXP_TAB_REP - 1));
   // a CTA owns 256 rows x one block of columns; row statistics are linear in the column partial sums, so the column blocks
   // of a row block are simply added up by k_bwd_finalize (fixed order)
   const int cb = blockIdx.x % ncb;
@@ -99,7 +102,9 @@ __global__ void __launch_bounds__(kGradRows) k_contract_grad(const double* __res
 #pragma unroll
         for (int d = 0; d < D; ++d) t = fma(g[d], colz[jj][d], t);
         const double w = diag ? Ca[(size_t)(j0 + jj) * M + i] : colz[jj][D + 1];   // C symmetric: C[j][i], coalesced over i
-        const double A = fast_exp(t) * w;
+        double ex[1] = {t};
+        fast_exp_tab_n<1>(ex, etab_lane);
+        const double A = ex[0] * w;
         ai += A;
 #pragma unroll
         for (int d = 0; d < D; ++d) u[d] = fma(A, colz[jj][d], u[d]);

@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(128) k_policy_prepare(int Mp, int Dp, const do
   for (int i = tid; i < Mp; i += blockDim.x) beta[(size_t)r * Mp + i] = v[i];
 }
 
-__global__ void k_step_post(RolloutMMParams p, int step) {
+constexpr int kCostRing = 32;   // steps whose costs are evaluated by one k_cost_ring launch
+
+__global__ void k_step_post(RolloutMMParams p, int step, double* __restrict__ ring_m, double* __restrict__ ring_S) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= p.N) return;
   const int Dx = p.Dx, De = p.De, D = p.D, L = p.L;
@@ -100,9 +102,34 @@ __global__ void k_step_post(RolloutMMParams p, int step) {
     for (int i = 0; i < Dx; ++i) p.traj_m[((size_t)(step + 1) * p.N + n) * Dx + i] = m[i];
     for (int i = 0; i < Dx * Dx; ++i) p.traj_S[((size_t)(step + 1) * p.N + n) * Dx * Dx + i] = S[i];
   }
+  // the expected cost of the new state is evaluated later, for a whole ring of steps at once (k_cost_ring): it does not feed
+  // back into the state, so the serial LU / determinant of every step stays off the critical path of the rollout
+  const int slot = step % kCostRing;
+  for (int i = 0; i < Dx; ++i) ring_m[((size_t)slot * p.N + n) * Dx + i] = m[i];
+  for (int i = 0; i < Dx * Dx; ++i) ring_S[((size_t)slot * p.N + n) * Dx * Dx + i] = S[i];
+}
+
+// expected cost of `count` ring slots x N rollouts, one thread each  (upstream loops/pilco.py:199-205 with components.py:30-37)
+__global__ void k_cost_ring(RolloutMMParams p, const double* __restrict__ ring_m, const double* __restrict__ ring_S, int count,
+                            double* __restrict__ costbuf) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * p.N) return;
+  const int Dx = p.Dx;
+  double m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  for (int i = 0; i < Dx; ++i) m[i] = ring_m[(size_t)idx * Dx + i];
+  for (int i = 0; i < Dx * Dx; ++i) S[i] = ring_S[(size_t)idx * Dx * Dx + i];
   double me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
   mm_encoder<double>(p.enc, m, S, me, See, Cxe);
-  p.loss[n] += expected_cost<double>(De, me, See, p.target, p.W);
+  costbuf[idx] = expected_cost<double>(p.De, me, See, p.target, p.W);
+}
+
+// loss[n] += costs of the ring slots in step order (fixed summation order: same result as a per-step accumulation)
+__global__ void k_cost_accumulate(int N, int count, const double* __restrict__ costbuf, double* __restrict__ loss) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double acc = loss[n];
+  for (int t = 0; t < count; ++t) acc += costbuf[(size_t)t * N + n];
+  loss[n] = acc;
 }
 
 __global__ void k_rollout_init(RolloutMMParams p, const double* m0, const double* S0) {
@@ -125,7 +152,7 @@ __global__ void k_rollout_init(RolloutMMParams p, const double* m0, const double
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct RolloutLayout {
-  size_t m, S, md, Sd, Sxd, f1, Sff, cross, predict, total, predict_bytes;
+  size_t m, S, md, Sd, Sxd, f1, Sff, cross, ring_m, ring_S, costbuf, predict, total, predict_bytes;
 };
 
 static RolloutLayout rollout_layout(const gpp_gp_model* dyn, int N, int Dx) {
@@ -141,6 +168,9 @@ static RolloutLayout rollout_layout(const gpp_gp_model* dyn, int N, int Dx) {
   lo.f1 = take((size_t)N * L);
   lo.Sff = take((size_t)N * L * L);
   lo.cross = take((size_t)N * D * L);
+  lo.ring_m = take((size_t)kCostRing * N * Dx);
+  lo.ring_S = take((size_t)kCostRing * N * Dx * Dx);
+  lo.costbuf = take((size_t)kCostRing * N);
   lo.predict = off;
   lo.predict_bytes = gpp_mm_gp_predict_workspace_bytes(dyn, N);
   lo.total = off + align_up(lo.predict_bytes, 256);
@@ -149,32 +179,12 @@ static RolloutLayout rollout_layout(const gpp_gp_model* dyn, int N, int Dx) {
 
 }  // namespace gpp
 
-extern "C" {
-
-int gpp_policy_prepare(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance,
-                       const double* q_mu, int whiten, double jitter, double* beta, int* info, void* stream) {
-  GPP_REQUIRE(Z && lengthscales && variance && q_mu && beta, GPP_ERR_NULL, "gpp_policy_prepare: null argument");
-  GPP_REQUIRE(R >= 1 && Mp >= 1 && Dp >= 1, GPP_ERR_BAD_SHAPE, "gpp_policy_prepare: bad sizes R=%d Mp=%d Dp=%d", R, Mp, Dp);
-  size_t smem = sizeof(double) * ((size_t)Mp * (Mp + 1) + Mp);
-  GPP_REQUIRE(smem <= 200 * 1024, GPP_ERR_UNSUPPORTED, "gpp_policy_prepare: Mp=%d too large for the in-CTA Cholesky (use gpp_gp_model_create)", Mp);
-  if (smem > 48 * 1024) GPP_CUDA_OK(cudaFuncSetAttribute(gpp::k_policy_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gpp::k_policy_prepare<<<R, 128, smem, (cudaStream_t)stream>>>(Mp, Dp, Z, lengthscales, variance, q_mu, whiten, jitter, beta, info);
-  gpp::count_launch();
-  GPP_CUDA_OK(cudaGetLastError());
-  return GPP_OK;
-}
-
-size_t gpp_rollout_mm_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx) {
-  if (!dynamics || N <= 0) return 0;
-  return gpp::rollout_layout(dynamics, N, Dx).total;
-}
-
-int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims /*host*/,
-                       int R, int Mp, const double* policy_Z, const double* policy_lengthscales, const double* policy_variance,
-                       const double* policy_beta, double squash_scale, double squash_shift,
-                       const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
-                       double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final,
-                       void* workspace, size_t workspace_bytes, int* info, void* stream_) {
+static int rollout_mm_fwd_impl(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims /*host*/,
+                               int R, int Mp, const double* policy_Z, const double* policy_lengthscales, const double* policy_variance,
+                               const double* policy_beta, double squash_scale, double squash_shift,
+                               const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
+                               double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final, double* saved,
+                               void* workspace, size_t workspace_bytes, int* info, void* stream_) {
   using namespace gpp;
   GPP_REQUIRE(dynamics && policy_Z && policy_lengthscales && policy_variance && policy_beta && cost_target && cost_W && m0 && S0 &&
                   loss && workspace, GPP_ERR_NULL, "gpp_rollout_mm_fwd: null argument");
@@ -206,7 +216,15 @@ int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
   const int tb = 64, gb = (N + tb - 1) / tb;
   k_rollout_init<<<gb, tb, 0, stream>>>(p, m0, S0);
   count_launch();
+  const RolloutSaved sv(N, Dx, p.D, p.L);
+  double* ring_m = (double*)(ws + lo.ring_m);
+  double* ring_S = (double*)(ws + lo.ring_S);
+  double* costbuf = (double*)(ws + lo.costbuf);
   for (int t = 0; t < H; ++t) {
+    if (saved) {   // the joint moments, Cov(x, d) and the pre-inverted cross term of every step are written where the backward reads them
+      double* base = saved + (size_t)t * sv.per_step;
+      p.md = base + sv.md; p.Sd = base + sv.Sd; p.Sxd = base + sv.Sxd; p.cross = base + sv.cross;
+    }
     switch (p.De) {
 #define GPP_CASE(d) case d: k_step_pre<d><<<N, 128, 0, stream>>>(p); break;
       GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7)
@@ -216,13 +234,68 @@ int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
     count_launch();
     int rc = mm_predict_enqueue(dynamics, p.md, p.Sd, N, p.f1, p.Sff, p.cross, 1, 0.0, ws + lo.predict, lo.predict_bytes, info, stream);
     if (rc != GPP_OK) return rc;
-    k_step_post<<<gb, tb, 0, stream>>>(p, t);
+    k_step_post<<<gb, tb, 0, stream>>>(p, t, ring_m, ring_S);
     count_launch();
+    if ((t + 1) % kCostRing == 0 || t == H - 1) {
+      const int count = t % kCostRing + 1;
+      k_cost_ring<<<(count * N + 63) / 64, 64, 0, stream>>>(p, ring_m, ring_S, count, costbuf);
+      k_cost_accumulate<<<gb, tb, 0, stream>>>(N, count, costbuf, loss);
+      count_launch(2);
+    }
   }
   if (m_final) GPP_CUDA_OK(cudaMemcpyAsync(m_final, p.m, sizeof(double) * N * Dx, cudaMemcpyDeviceToDevice, stream));
   if (S_final) GPP_CUDA_OK(cudaMemcpyAsync(S_final, p.S, sizeof(double) * N * Dx * Dx, cudaMemcpyDeviceToDevice, stream));
   GPP_CUDA_OK(cudaGetLastError());
   return GPP_OK;
+}
+
+
+extern "C" {
+
+int gpp_policy_prepare(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance,
+                       const double* q_mu, int whiten, double jitter, double* beta, int* info, void* stream) {
+  GPP_REQUIRE(Z && lengthscales && variance && q_mu && beta, GPP_ERR_NULL, "gpp_policy_prepare: null argument");
+  GPP_REQUIRE(R >= 1 && Mp >= 1 && Dp >= 1, GPP_ERR_BAD_SHAPE, "gpp_policy_prepare: bad sizes R=%d Mp=%d Dp=%d", R, Mp, Dp);
+  size_t smem = sizeof(double) * ((size_t)Mp * (Mp + 1) + Mp);
+  GPP_REQUIRE(smem <= 200 * 1024, GPP_ERR_UNSUPPORTED, "gpp_policy_prepare: Mp=%d too large for the in-CTA Cholesky (use gpp_gp_model_create)", Mp);
+  if (smem > 48 * 1024) GPP_CUDA_OK(cudaFuncSetAttribute(gpp::k_policy_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gpp::k_policy_prepare<<<R, 128, smem, (cudaStream_t)stream>>>(Mp, Dp, Z, lengthscales, variance, q_mu, whiten, jitter, beta, info);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+size_t gpp_rollout_mm_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx) {
+  if (!dynamics || N <= 0) return 0;
+  return gpp::rollout_layout(dynamics, N, Dx).total;
+}
+
+size_t gpp_rollout_mm_saved_doubles(const gpp_gp_model* dynamics, int N, int Dx, int H) {
+  if (!dynamics || N <= 0 || H < 0) return 0;
+  return gpp::RolloutSaved(N, Dx, dynamics->D, dynamics->P).per_step * (size_t)H;
+}
+
+int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims /*host*/,
+                       int R, int Mp, const double* policy_Z, const double* policy_lengthscales, const double* policy_variance,
+                       const double* policy_beta, double squash_scale, double squash_shift,
+                       const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
+                       double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final,
+                       void* workspace, size_t workspace_bytes, int* info, void* stream) {
+  return rollout_mm_fwd_impl(dynamics, N, Dx, num_active, active_dims, R, Mp, policy_Z, policy_lengthscales, policy_variance, policy_beta,
+                             squash_scale, squash_shift, cost_target, cost_W, H, m0, S0, loss, traj_m, traj_S, m_final, S_final, nullptr,
+                             workspace, workspace_bytes, info, stream);
+}
+
+int gpp_rollout_mm_fwd_save(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims /*host*/,
+                            int R, int Mp, const double* policy_Z, const double* policy_lengthscales, const double* policy_variance,
+                            const double* policy_beta, double squash_scale, double squash_shift,
+                            const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
+                            double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final, double* saved,
+                            void* workspace, size_t workspace_bytes, int* info, void* stream) {
+  GPP_REQUIRE(traj_m && traj_S && saved, GPP_ERR_NULL, "gpp_rollout_mm_fwd_save: traj_m, traj_S and saved are required (the backward reads them)");
+  return rollout_mm_fwd_impl(dynamics, N, Dx, num_active, active_dims, R, Mp, policy_Z, policy_lengthscales, policy_variance, policy_beta,
+                             squash_scale, squash_shift, cost_target, cost_W, H, m0, S0, loss, traj_m, traj_S, m_final, S_final, saved,
+                             workspace, workspace_bytes, info, stream);
 }
 
 }  // extern "C"

@@ -5,8 +5,9 @@
 // trajectory (m_t, S_t):
 //   k_step_pre            recompute the pre stage of step t (md, Sd, Sxd)                       [rollout_mm_common.cuh]
 //   mm_predict_enqueue    recompute (f1, Sff, cross) of step t with the fused forward kernels   [mm_predict.cu]
-//   k_bwd_post            adjoint of (m_{t+1}, S_{t+1}) += loss_bar * d cost / d(m, S)  (dual numbers through the encoder and
-//                         expected-cost rules, one direction per lane), then the adjoint of the Euler moment update
+//   k_cost_grad_ring      d cost / d(m, S) of 32 consecutive trajectory states at once (dual numbers through the encoder and
+//                         expected-cost rules, one (state, rollout, direction) per thread)
+//   k_bwd_post            adjoint of (m_{t+1}, S_{t+1}) += loss_bar * that gradient, then the adjoint of the Euler moment update
 //                         (dynamics/solvers.py:128-129) and of Sxf = Sxd cross  (forward_sde.py:126)
 //   mm_predict_bwd        closed-form adjoint of the GP dynamics prediction                     [mm_predict_bwd.cu]
 //   k_bwd_pre             adjoint of the joint assembly (forward_sde.py:105-124, gaussian.py:53-63), of the squashing link
@@ -41,40 +42,58 @@ __device__ __forceinline__ void direction_to_entry(int k, int Dx, int& i, int& j
   j = i + rem;
 }
 
+constexpr int kGradRing = 32;   // steps whose cost gradients are evaluated by one k_cost_grad_ring launch
+
+// d cost / d(m, S) of `count` consecutive trajectory states x N rollouts x ndir directions, one thread each: forward-mode dual
+// numbers through the same templated encoder / expected-cost code as the forward pass.  The states are known from the stored
+// trajectory, so all of a ring's gradients are computed in one parallel launch instead of serially inside the sweep.
+__global__ void k_cost_grad_ring(RolloutMMParams p, const double* __restrict__ tm, const double* __restrict__ tS, int count, int ndir,
+                                 double* __restrict__ cg /*[count,N,ndir]*/) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * p.N * ndir) return;
+  const int k = idx % ndir;
+  const size_t sn = idx / ndir;                 // (slot, rollout) flattened: trajectory states are [t, n] contiguous
+  const int Dx = p.Dx;
+  Dual m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  for (int i = 0; i < Dx; ++i) m[i] = Dual(tm[sn * Dx + i]);
+  for (int i = 0; i < Dx * Dx; ++i) S[i] = Dual(tS[sn * Dx * Dx + i]);
+  if (k < Dx) {
+    m[k].d = 1.0;
+  } else {
+    int di, dj;
+    direction_to_entry(k, Dx, di, dj);
+    S[di * Dx + dj].d = 1.0;
+    S[dj * Dx + di].d = 1.0;
+  }
+  Dual me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  mm_encoder<Dual>(p.enc, m, S, me, See, Cxe);
+  cg[idx] = expected_cost<Dual>(p.De, me, See, p.target, p.W).d;
+}
+
 // one warp per rollout
-__global__ void __launch_bounds__(32) k_bwd_post(RolloutMMParams p, const double* __restrict__ m_next, const double* __restrict__ S_next,
+__global__ void __launch_bounds__(32) k_bwd_post(RolloutMMParams p, const double* __restrict__ cg /*[N,ndir] of state t+1*/,
                                                  const double* __restrict__ loss_bar, RolloutBwdBuffers bw) {
   __shared__ double smb[GPP_SMALL_MAX], sSb[GPP_SMALL_MAX * GPP_SMALL_MAX];
   const int n = blockIdx.x, lane = threadIdx.x;
-  const int Dx = p.Dx, De = p.De, D = p.D, L = p.L;
+  const int Dx = p.Dx, D = p.D, L = p.L;
   for (int i = lane; i < Dx; i += 32) smb[i] = bw.mb[(size_t)n * Dx + i];
   for (int i = lane; i < Dx * Dx; i += 32) sSb[i] = bw.Sb[(size_t)n * Dx * Dx + i];
   __syncwarp();
   const double lb = loss_bar ? loss_bar[n] : 1.0;
   const int ndir = Dx + Dx * (Dx + 1) / 2;
   for (int k = lane; k < ndir; k += 32) {
-    Dual m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
-    for (int i = 0; i < Dx; ++i) m[i] = Dual(m_next[(size_t)n * Dx + i]);
-    for (int i = 0; i < Dx * Dx; ++i) S[i] = Dual(S_next[(size_t)n * Dx * Dx + i]);
-    int di = 0, dj = 0;
-    if (k < Dx) {
-      m[k].d = 1.0;
-    } else {
-      direction_to_entry(k, Dx, di, dj);
-      S[di * Dx + dj].d = 1.0;
-      S[dj * Dx + di].d = 1.0;
-    }
-    Dual me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
-    mm_encoder<Dual>(p.enc, m, S, me, See, Cxe);
-    const Dual c = expected_cost<Dual>(De, me, See, p.target, p.W);
-    const double g = lb * c.d;
+    const double g = lb * cg[(size_t)n * ndir + k];
     if (k < Dx) {
       smb[k] += g;
-    } else if (di == dj) {
-      sSb[di * Dx + di] += g;
     } else {
-      sSb[di * Dx + dj] += 0.5 * g;
-      sSb[dj * Dx + di] += 0.5 * g;
+      int di, dj;
+      direction_to_entry(k, Dx, di, dj);
+      if (di == dj) {
+        sSb[di * Dx + di] += g;
+      } else {
+        sSb[di * Dx + dj] += 0.5 * g;
+        sSb[dj * Dx + di] += 0.5 * g;
+      }
     }
   }
   __syncwarp();
@@ -338,7 +357,7 @@ __global__ void k_reduce_param_grads(const double* __restrict__ g, int N, int R,
 }
 
 struct RolloutBwdLayout {
-  size_t md, Sd, Sxd, f1, Sff, cross, mb, Sb, f1_bar, Sff_bar, cross_bar, Sxd_bar, md_bar, Sd_bar, gZ, gEll, gBeta, predict, predict_bwd, total;
+  size_t md, Sd, Sxd, f1, Sff, cross, mb, Sb, f1_bar, Sff_bar, cross_bar, Sxd_bar, md_bar, Sd_bar, gZ, gEll, gBeta, cg, predict, predict_bwd, total;
   size_t predict_bytes, predict_bwd_bytes;
 };
 
@@ -364,6 +383,7 @@ static RolloutBwdLayout rollout_bwd_layout(const gpp_gp_model* dyn, int N, int D
   lo.gZ = take((size_t)N * Mp * De);
   lo.gEll = take((size_t)N * De);
   lo.gBeta = take((size_t)N * Mp);
+  lo.cg = take((size_t)kGradRing * N * (Dx + Dx * (Dx + 1) / 2));
   lo.predict_bytes = gpp_mm_gp_predict_workspace_bytes(dyn, N);
   lo.predict_bwd_bytes = gpp_mm_gp_predict_bwd_workspace_bytes(dyn, N);
   lo.predict = off;
@@ -387,7 +407,7 @@ int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
                        int R, int Mp, const double* policy_Z, const double* policy_lengthscales, const double* policy_variance,
                        const double* policy_beta, double squash_scale, double squash_shift,
                        const double* cost_target, const double* cost_W, int H, const double* traj_m, const double* traj_S,
-                       const double* loss_bar, double* Z_bar, double* lengthscales_bar, double* beta_bar,
+                       const double* saved, const double* loss_bar, double* Z_bar, double* lengthscales_bar, double* beta_bar,
                        double* m0_bar, double* S0_bar, void* workspace, size_t workspace_bytes, int* info, void* stream_) {
   using namespace gpp;
   GPP_REQUIRE(dynamics && policy_Z && policy_lengthscales && policy_variance && policy_beta && cost_target && cost_W && traj_m && traj_S &&
@@ -420,20 +440,37 @@ int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
   bw.Sxd_bar = D_(lo.Sxd_bar); bw.md_bar = D_(lo.md_bar); bw.Sd_bar = D_(lo.Sd_bar); bw.gZ = D_(lo.gZ); bw.gEll = D_(lo.gEll); bw.gBeta = D_(lo.gBeta);
   // zero the running adjoint and the per-rollout parameter gradients (contiguous ranges of the workspace)
   GPP_CUDA_OK(cudaMemsetAsync(ws + lo.mb, 0, lo.f1_bar - lo.mb, stream));
-  GPP_CUDA_OK(cudaMemsetAsync(ws + lo.gZ, 0, lo.predict - lo.gZ, stream));
+  GPP_CUDA_OK(cudaMemsetAsync(ws + lo.gZ, 0, lo.cg - lo.gZ, stream));
   const size_t sm = (size_t)N * Dx, sS = (size_t)N * Dx * Dx;
+  GPP_REQUIRE(p.De >= 1 && p.De <= 7, GPP_ERR_UNSUPPORTED, "gpp_rollout_mm_bwd: unsupported encoded dimension %d", p.De);
+  const RolloutSaved sv(N, Dx, p.D, p.L);
+  const int ndir = Dx + Dx * (Dx + 1) / 2;
+  double* cg = D_(lo.cg);
   for (int t = H - 1; t >= 0; --t) {
+    if (t == H - 1 || (t + 1) % kGradRing == 0) {   // cost gradients of the states t+1 of this ring of steps, one launch
+      const int t0 = t / kGradRing * kGradRing, count = t - t0 + 1;
+      const int total = count * N * ndir;
+      k_cost_grad_ring<<<(total + 63) / 64, 64, 0, stream>>>(p, traj_m + (size_t)(t0 + 1) * sm, traj_S + (size_t)(t0 + 1) * sS, count, ndir, cg);
+      count_launch();
+    }
     p.m = const_cast<double*>(traj_m) + (size_t)t * sm;     // read-only in the kernels launched below
     p.S = const_cast<double*>(traj_S) + (size_t)t * sS;
-    switch (p.De) {
+    int rc = GPP_OK;
+    if (saved) {   // step t's joint moments, Cov(x, d) and cross term as the forward stored them (read-only here)
+      double* base = const_cast<double*>(saved) + (size_t)t * sv.per_step;
+      p.md = base + sv.md; p.Sd = base + sv.Sd; p.Sxd = base + sv.Sxd; p.cross = base + sv.cross;
+    } else {       // recompute them: pre stage + fused forward predict
+      switch (p.De) {
 #define GPP_CASE(d) case d: k_step_pre<d><<<N, 128, 0, stream>>>(p); break;
-      GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7)
+        GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7)
 #undef GPP_CASE
-      default: set_error("gpp_rollout_mm_bwd: unsupported encoded dimension %d", p.De); return GPP_ERR_UNSUPPORTED;
+        default: break;
+      }
+      count_launch();
+      rc = mm_predict_enqueue(dynamics, p.md, p.Sd, N, p.f1, p.Sff, p.cross, 1, 0.0, ws + lo.predict, lo.predict_bytes, info, stream);
+      if (rc != GPP_OK) return rc;
     }
-    int rc = mm_predict_enqueue(dynamics, p.md, p.Sd, N, p.f1, p.Sff, p.cross, 1, 0.0, ws + lo.predict, lo.predict_bytes, info, stream);
-    if (rc != GPP_OK) return rc;
-    k_bwd_post<<<N, 32, 0, stream>>>(p, traj_m + (size_t)(t + 1) * sm, traj_S + (size_t)(t + 1) * sS, loss_bar, bw);
+    k_bwd_post<<<N, 32, 0, stream>>>(p, cg + (size_t)(t % kGradRing) * N * ndir, loss_bar, bw);
     rc = mm_predict_bwd_enqueue(dynamics, p.md, p.Sd, N, bw.f1_bar, bw.Sff_bar, bw.cross_bar, 1, bw.md_bar, bw.Sd_bar,
                                 ws + lo.predict_bwd, lo.predict_bwd_bytes, info, stream);
     if (rc != GPP_OK) return rc;
@@ -443,7 +480,7 @@ int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
 #undef GPP_CASE
       default: break;
     }
-    count_launch(3);
+    count_launch(2);
   }
   if (m0_bar) GPP_CUDA_OK(cudaMemcpyAsync(m0_bar, bw.mb, sizeof(double) * sm, cudaMemcpyDeviceToDevice, stream));
   if (S0_bar) GPP_CUDA_OK(cudaMemcpyAsync(S0_bar, bw.Sb, sizeof(double) * sS, cudaMemcpyDeviceToDevice, stream));

@@ -222,4 +222,17 @@ __global__ void __launch_bounds__(128) k_step_pre(RolloutMMParams p) {
 
 inline size_t rollout_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// per-step block of the optional `saved` buffer of gpp_rollout_mm_fwd_save (offsets in doubles):
+//   md [N,D] | Sd [N,D,D] | Sxd [N,Dx,D] | cross [N,D,L]
+struct RolloutSaved {
+  size_t md, Sd, Sxd, cross, per_step;
+  RolloutSaved(int N, int Dx, int D, int L) {
+    md = 0;
+    Sd = md + (size_t)N * D;
+    Sxd = Sd + (size_t)N * D * D;
+    cross = Sxd + (size_t)N * Dx * D;
+    per_step = cross + (size_t)N * D * L;
+  }
+};
+
 }  // namespace gpp

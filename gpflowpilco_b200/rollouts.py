@@ -54,11 +54,12 @@ class MMRolloutResult:
   S_final: torch.Tensor                   # [N,Dx,Dx]
   traj_m: Optional[torch.Tensor] = None   # [H+1,N,Dx]
   traj_S: Optional[torch.Tensor] = None   # [H+1,N,Dx,Dx]
+  saved: Optional[torch.Tensor] = None    # per-step joint moments / cross terms kept for the backward
 
 
 def rollout_mm(dynamics: GPModelHandle, policy: PolicyParams, m0: torch.Tensor, S0: torch.Tensor, horizon: int,
                active_dims: Sequence[int], cost_target: torch.Tensor, cost_W: torch.Tensor, return_trajectory: bool = False,
-               beta: Optional[torch.Tensor] = None, check: bool = True) -> MMRolloutResult:
+               beta: Optional[torch.Tensor] = None, check: bool = True, save_for_backward: bool = False) -> MMRolloutResult:
   """Moment-matched rollout + expected cost for N initial Gaussian states (upstream loops/pilco.py:192-220)."""
   m0, S0, cost_target, cost_W = map(_c, (m0, S0, cost_target, cost_W))
   _dev_check(m0, S0, cost_target, cost_W)
@@ -83,10 +84,20 @@ def rollout_mm(dynamics: GPModelHandle, policy: PolicyParams, m0: torch.Tensor, 
   loss = torch.empty(N, dtype=F64, device=dev)
   mf = torch.empty(N, Dx, dtype=F64, device=dev)
   Sf = torch.empty(N, Dx, Dx, dtype=F64, device=dev)
-  tm = torch.empty(horizon + 1, N, Dx, dtype=F64, device=dev) if return_trajectory else None
-  tS = torch.empty(horizon + 1, N, Dx, Dx, dtype=F64, device=dev) if return_trajectory else None
+  keep = return_trajectory or save_for_backward
+  tm = torch.empty(horizon + 1, N, Dx, dtype=F64, device=dev) if keep else None
+  tS = torch.empty(horizon + 1, N, Dx, Dx, dtype=F64, device=dev) if keep else None
   info = _new_info(dev)
   act = (ctypes.c_int * max(na, 1))(*active_dims)
+  if save_for_backward:
+    saved = torch.empty(lib.gpp_rollout_mm_saved_doubles(dynamics._h, N, Dx, int(horizon)), dtype=F64, device=dev)
+    _lib.check(lib.gpp_rollout_mm_fwd_save(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
+                                           _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
+                                           _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
+                                           _ptr(mf), _ptr(Sf), _ptr(saved), _ptr(ws), ws.numel(), _ptr(info), _stream()))
+    if check:
+      raise_if_not_pd(info, "rollout_mm")
+    return MMRolloutResult(loss, mf, Sf, tm, tS, saved)
   _lib.check(lib.gpp_rollout_mm_fwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
                                     _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
                                     _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
@@ -98,7 +109,7 @@ def rollout_mm(dynamics: GPModelHandle, policy: PolicyParams, m0: torch.Tensor, 
 
 def rollout_mm_bwd(dynamics: GPModelHandle, policy: PolicyParams, beta: torch.Tensor, traj_m: torch.Tensor, traj_S: torch.Tensor,
                    active_dims: Sequence[int], cost_target: torch.Tensor, cost_W: torch.Tensor,
-                   loss_bar: Optional[torch.Tensor] = None, check: bool = True):
+                   loss_bar: Optional[torch.Tensor] = None, check: bool = True, saved: Optional[torch.Tensor] = None):
   """Reverse sweep of `rollout_mm` from its stored trajectory: returns (Z_bar [R,Mp,De], lengthscales_bar [R,De] at fixed beta,
   beta_bar [R,Mp], m0_bar [N,Dx], S0_bar [N,Dx,Dx]).  Upstream: tape.gradient through loops/pilco.py:192-220."""
   traj_m, traj_S, cost_target, cost_W, beta, loss_bar = map(_c, (traj_m, traj_S, cost_target, cost_W, beta, loss_bar))
@@ -113,6 +124,8 @@ def rollout_mm_bwd(dynamics: GPModelHandle, policy: PolicyParams, beta: torch.Te
     raise ValueError("rollout_mm_bwd: loss_bar must be [N]")
   dev = traj_m.device
   lib = _lib.load()
+  if saved is not None and (not saved.is_cuda or saved.numel() != lib.gpp_rollout_mm_saved_doubles(dynamics._h, N, Dx, H1 - 1)):
+    raise ValueError("rollout_mm_bwd: `saved` does not match this rollout")
   need = lib.gpp_rollout_mm_bwd_workspace_bytes(dynamics._h, N, Dx, Mp)
   ws = torch.empty(need, dtype=torch.uint8, device=dev)
   Zb = torch.empty(R, Mp, De, dtype=F64, device=dev)
@@ -124,7 +137,7 @@ def rollout_mm_bwd(dynamics: GPModelHandle, policy: PolicyParams, beta: torch.Te
   act = (ctypes.c_int * max(na, 1))(*active_dims)
   _lib.check(lib.gpp_rollout_mm_bwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
                                     _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
-                                    _ptr(cost_target), _ptr(cost_W), H1 - 1, _ptr(traj_m), _ptr(traj_S), _ptr(loss_bar),
+                                    _ptr(cost_target), _ptr(cost_W), H1 - 1, _ptr(traj_m), _ptr(traj_S), _ptr(saved), _ptr(loss_bar),
                                     _ptr(Zb), _ptr(eb), _ptr(bb), _ptr(m0b), _ptr(S0b), _ptr(ws), ws.numel(), _ptr(info), _stream()))
   if check:
     raise_if_not_pd(info, "rollout_mm_bwd")

@@ -148,11 +148,21 @@ int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
  *      variance is frozen upstream, loops/pilco.py:99-103), m0_bar [N,Dx], S0_bar [N,Dx,Dx] (symmetric; either may be NULL).
  *   R = 1 sums the gradient over the N rollouts in a fixed order; R = N returns one gradient per restart. */
 size_t gpp_rollout_mm_bwd_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx, int Mp);
+/* Forward that also keeps, for every step, what the backward would otherwise recompute (joint moments of (e, u), Cov(x, d),
+ * pre-inverted cross term): saved [gpp_rollout_mm_saved_doubles(dynamics, N, Dx, H)] doubles; traj_m / traj_S are required.
+ * Pass the buffer to gpp_rollout_mm_bwd (`saved`; NULL there = recompute from the trajectory). */
+size_t gpp_rollout_mm_saved_doubles(const gpp_gp_model* dynamics, int N, int Dx, int H);
+int gpp_rollout_mm_fwd_save(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims,
+                            int R, int Mp, const double* policy_Z, const double* policy_lengthscales,
+                            const double* policy_variance, const double* policy_beta, double squash_scale, double squash_shift,
+                            const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
+                            double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final, double* saved,
+                            void* workspace, size_t workspace_bytes, int* info, void* stream);
 int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims,
                        int R, int Mp, const double* policy_Z, const double* policy_lengthscales,
                        const double* policy_variance, const double* policy_beta, double squash_scale, double squash_shift,
                        const double* cost_target, const double* cost_W, int H, const double* traj_m, const double* traj_S,
-                       const double* loss_bar, double* Z_bar, double* lengthscales_bar, double* beta_bar,
+                       const double* saved, const double* loss_bar, double* Z_bar, double* lengthscales_bar, double* beta_bar,
                        double* m0_bar, double* S0_bar, void* workspace, size_t workspace_bytes, int* info, void* stream);
 
 /* ---- pathwise (sample-path) rollout ----------------------------------------------------------------------
