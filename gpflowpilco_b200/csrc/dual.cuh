@@ -41,4 +41,11 @@ __device__ __forceinline__ Dual s_sqrt(Dual x) { double r = sqrt(x.v); return Du
 __device__ __forceinline__ Dual s_erfc(Dual x) { return Dual(erfc(x.v), -1.1283791670955125739 * exp(-x.v * x.v) * x.d); }
 __device__ __forceinline__ double s_value(Dual x) { return x.v; }
 
+// Owen's T with known value: tangent from the closed-form partials (mm_small.cuh)
+__device__ __forceinline__ Dual owens_t_given(Dual h, Dual a, double t0) {
+  const double dh = -0.5 * 0.39894228040143267794 * exp(-0.5 * h.v * h.v) * erf(a.v * h.v * 0.70710678118654752440);
+  const double da = exp(-0.5 * h.v * h.v * (1.0 + a.v * a.v)) * 0.15915494309189535 / (1.0 + a.v * a.v);
+  return Dual(t0, dh * h.d + da * a.d);
+}
+
 }  // namespace gpp

@@ -120,19 +120,43 @@ __device__ void mm_encoder(const EncoderSpec& es, const S* m, const S* Sx /*[Dx]
   }
 }
 
+// Owen's T evaluated by the 32 lanes of a warp (one Gauss-Legendre node each); every lane returns the sum
+__device__ __forceinline__ double owens_t_warp(double h, double a) {
+  const int lane = threadIdx.x & 31, k = lane >> 1;
+  const double half = 0.5 * a;
+  const double x = half * (1.0 + ((lane & 1) ? kGL32_X[k] : -kGL32_X[k]));
+  const double d = x * x + 1.0;
+  double v = exp(-0.5 * h * h * d) / d * kGL32_W[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v * half * 0.15915494309189535;
+}
+
+// T(h, a) as a scalar of type S when its VALUE t0 is already known: double -> t0; dual number -> value t0 with the tangent from
+// the closed-form partials dT/dh = -phi(h) erf(a h / sqrt 2) / 2, dT/da = exp(-h^2 (1 + a^2) / 2) / (2 pi (1 + a^2))  
+__device__ __forceinline__ double owens_t_given(double, double, double t0) { return t0; }
+
 // ---- squashing link  u = scale * (Phi(f) + shift)  applied to a 1-D Gaussian f ~ N(mf, vf) -----------------------------------
 // returns mean, variance of u and d = Cov(f,f)^-1 Cov(f,u)  (chain of bijectors.py:37-69, maths.py:47-78)
-template <typename S>
-__device__ void mm_squash_1d(S mf, S vf, double scale, double shift, S& mu, S& vu, S& gain) {
+// USE_T0: Owen's T value supplied by the caller (owens_t_warp) instead of the serial 32-node quadrature
+template <typename S, bool USE_T0 = false>
+__device__ void mm_squash_1d(S mf, S vf, double scale, double shift, S& mu, S& vu, S& gain, double t0 = 0.0) {
   S vw = vf + 1.0;
   S isq = S(1.0) / s_sqrt(vw);
   S h = isq * mf;
   S y1 = ndtr(h);
-  S y2 = y1 - owens_t(h, S(1.0) / s_sqrt(vf * 2.0 + 1.0)) * 2.0;       // E[Phi^2]   (bijectors.py:57-58)
+  S a = S(1.0) / s_sqrt(vf * 2.0 + 1.0);
+  S y2 = y1 - (USE_T0 ? owens_t_given(h, a, t0) : owens_t(h, a)) * 2.0;       // E[Phi^2]   (bijectors.py:57-58)
   S phi = s_exp(h * h * (-0.5)) * 0.39894228040143267794;
   mu = (y1 + shift) * scale;
   vu = (y2 - y1 * y1) * (scale * scale);
   gain = isq * phi * scale;
+}
+
+// (h, a) of the squashing rule, for callers that evaluate Owen's T cooperatively first
+__device__ __forceinline__ void squash_owens_args(double mf, double vf, double& h, double& a) {
+  h = mf / sqrt(vf + 1.0);
+  a = 1.0 / sqrt(2.0 * vf + 1.0);
 }
 
 // ---- general small linear algebra (runtime n <= GPP_SMALL_MAX) ----------------------------------------------------------------

@@ -184,9 +184,9 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
     }
     // ---- squashing link: 2 x 3 Jacobian by dual numbers
     Dual mu, vu, gn;
-    mm_squash_1d<Dual>(Dual(sh.f1, 1.0), Dual(sh.vf, 0.0), p.scale, p.shift, mu, vu, gn);
-    double f1b = mu_u_bar * mu.d + vu_bar * vu.d + gain_bar * gn.d;
-    mm_squash_1d<Dual>(Dual(sh.f1, 0.0), Dual(sh.vf, 1.0), p.scale, p.shift, mu, vu, gn);
+    mm_squash_1d<Dual, true>(Dual(sh.f1, 1.0), Dual(sh.vf, 0.0), p.scale, p.shift, mu, vu, gn, sh.t0);   // Owen's T: value from the
+    double f1b = mu_u_bar * mu.d + vu_bar * vu.d + gain_bar * gn.d;                                       // forward, closed-form partials
+    mm_squash_1d<Dual, true>(Dual(sh.f1, 0.0), Dual(sh.vf, 1.0), p.scale, p.shift, mu, vu, gn, sh.t0);
     const double vfb = mu_u_bar * mu.d + vu_bar * vu.d + gain_bar * gn.d;
     ad.f2b = vfb;                          // vf = f2 - f1^2
     ad.f1b = f1b - 2.0 * sh.f1 * vfb;
@@ -222,37 +222,44 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
   double* ell_acc = acc + DP;
   double* sig_acc = acc + 2 * DP;
   const double f1b = ad.f1b, f2b = ad.f2b;
-  for (int i = tid; i < p.Mp; i += blockDim.x) {
+  // thread = (row i, quarter c of the columns); the 4 threads of a row are neighbouring lanes and combine their row sums by shuffle
+  const int nwork = (4 * p.Mp + 31) / 32 * 32;     // whole warps iterate together (shuffles below)
+  for (int idx = tid; idx < nwork; idx += blockDim.x) {
+    const bool live = idx < 4 * p.Mp;
+    const int i = live ? idx >> 2 : 0, c = idx & 3;
     double zr[DP], zbar[DP], h[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) { zr[d] = Zp[i * DP + d] - sh.me[d]; zbar[d] = 0.0; }
-    // Psi1
-    double maha = 0.0, e = f1b;
+    double beta_bar = 0.0;
+    if (live && c == 0) {
+      // Psi1
+      double maha = 0.0, e = f1b;
 #pragma unroll
-    for (int a = 0; a < DP; ++a) {
-      double t = 0.0;
+      for (int a = 0; a < DP; ++a) {
+        double t = 0.0;
 #pragma unroll
-      for (int b = 0; b < DP; ++b) t = fma(ad.G1[a * DP + b], zr[b], t);
-      h[a] = t;
-      maha = fma(t, zr[a], maha);
-      e = fma(ad.y[a], zr[a], e);
-    }
-    const double psi = fast_exp(sh.c01 - 0.5 * maha);
-    const double w = beta[i] * psi;
-    double beta_bar = psi * e;
-#pragma unroll
-    for (int a = 0; a < DP; ++a) {
-      const double t1 = w * (e * h[a] - ad.y[a]);
-      mu_acc[a] += t1;
-      zbar[a] -= t1;
-      double sdd = 0.0;
-#pragma unroll
-      for (int b = 0; b < DP; ++b) {
-        const double s = w * (0.5 * e * (h[a] * h[b] - ad.G1[a * DP + b]) - 0.5 * (ad.y[a] * h[b] + h[a] * ad.y[b]));
-        sig_acc[a * DP + b] += s;
-        if (a == b) sdd = s;
+        for (int b = 0; b < DP; ++b) t = fma(ad.G1[a * DP + b], zr[b], t);
+        h[a] = t;
+        maha = fma(t, zr[a], maha);
+        e = fma(ad.y[a], zr[a], e);
       }
-      ell_acc[a] += 2.0 * ell[a] * sdd + w * e / ell[a];
+      const double psi = fast_exp(sh.c01 - 0.5 * maha);
+      const double w = beta[i] * psi;
+      beta_bar = psi * e;
+#pragma unroll
+      for (int a = 0; a < DP; ++a) {
+        const double t1 = w * (e * h[a] - ad.y[a]);
+        mu_acc[a] += t1;
+        zbar[a] -= t1;
+        double sdd = 0.0;
+#pragma unroll
+        for (int b = 0; b < DP; ++b) {
+          const double s = w * (0.5 * e * (h[a] * h[b] - ad.G1[a * DP + b]) - 0.5 * (ad.y[a] * h[b] + h[a] * ad.y[b]));
+          sig_acc[a * DP + b] += s;
+          if (a == b) sdd = s;
+        }
+        ell_acc[a] += 2.0 * ell[a] * sdd + w * e / ell[a];
+      }
     }
     // Psi2 (same kernel, same centres: V = Lambda/2, e_ij = (z_i + z_j)/2 - me)
     double g0[DP];
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
     }
     const double ri = sh.pack[PP::C0] + packed_quad<DP>(sh.pack + PP::P1, zr);
     double rowQ = 0.0;
-    for (int j = 0; j < p.Mp; ++j) {
+    for (int j = c; live && j < p.Mp; j += 4) {
       double zc[DP], ee[DP], g[DP];
 #pragma unroll
       for (int d = 0; d < DP; ++d) { zc[d] = Zp[j * DP + d] - sh.me[d]; ee[d] = 0.5 * (zr[d] + zc[d]); }
@@ -293,9 +300,19 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
       }
     }
     beta_bar = fma(2.0 * f2b, rowQ, beta_bar);
-    bw.gBeta[(size_t)n * p.Mp + i] += beta_bar;
+    // combine the 4 quarters of the row (fixed order) and let quarter 0 write
+    beta_bar += __shfl_xor_sync(0xffffffffu, beta_bar, 1);
+    beta_bar += __shfl_xor_sync(0xffffffffu, beta_bar, 2);
 #pragma unroll
-    for (int d = 0; d < DP; ++d) bw.gZ[((size_t)n * p.Mp + i) * DP + d] += zbar[d];
+    for (int d = 0; d < DP; ++d) {
+      zbar[d] += __shfl_xor_sync(0xffffffffu, zbar[d], 1);
+      zbar[d] += __shfl_xor_sync(0xffffffffu, zbar[d], 2);
+    }
+    if (live && c == 0) {
+      bw.gBeta[(size_t)n * p.Mp + i] += beta_bar;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) bw.gZ[((size_t)n * p.Mp + i) * DP + d] += zbar[d];
+    }
   }
   // fixed-order block reduction of the K accumulators
 #pragma unroll

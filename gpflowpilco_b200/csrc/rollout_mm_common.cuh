@@ -30,6 +30,7 @@ struct PreShared {
   double c01;                        // log(var) + sum log ell - log det chol(See + Lambda)
   double red[4][DP + 2];
   double f1, f2, vf, mu_u, vu, gain; // policy mean / second moment / variance, squashed action moments, link gain
+  double t0;                         // Owen's T(h, a) of the squashing rule (warp-evaluated; the backward reuses it)
   double vec[DP], cpre[DP], seu[DP]; // sum beta psi1 (z - me), (See+Lambda)^-1 vec, Cov(e, u)
 };
 
@@ -98,8 +99,10 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
     for (int d = 0; d < DP; ++d) vec[d] = fma(w, dz[d], vec[d]);
   }
   // ---- policy Psi2 contraction: f2 = sum_ij beta_i beta_j Q_ij  (KernelRegressor: no model uncertainty, models.py:34-41)
+  //      thread = (row i, quarter c of the columns): 4 threads share a row so that all 128 threads work at Mp = 30
   double f2 = 0.0;
-  for (int i = tid; i < p.Mp; i += blockDim.x) {
+  for (int idx = tid; idx < 4 * p.Mp; idx += blockDim.x) {
+    const int i = idx >> 2, c = idx & 3;
     double zr[DP], g[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) zr[d] = Zp[i * DP + d] - sh.pack[PP::MU + d];
@@ -112,7 +115,7 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
     }
     double ri = sh.pack[PP::C0] + packed_quad<DP>(sh.pack + PP::P1, zr);
     double row = 0.0;
-    for (int j = 0; j < p.Mp; ++j) {
+    for (int j = c; j < p.Mp; j += 4) {
       double zc[DP];
 #pragma unroll
       for (int d = 0; d < DP; ++d) zc[d] = Zp[j * DP + d] - sh.pack[PP::MU + d];
@@ -134,46 +137,55 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
     for (int d = 0; d < DP; ++d) sh.red[warp][2 + d] = vec[d];
   }
   __syncthreads();
-  if (tid == 0) {
-    double f1 = 0.0, f2s = 0.0, v[DP];
-#pragma unroll
-    for (int d = 0; d < DP; ++d) v[d] = 0.0;
+  if (warp == 0) {
+    double f1 = 0.0, f2s = 0.0;
     for (int w = 0; w < 4; ++w) {
       f1 += sh.red[w][0];
       f2s += sh.red[w][1];
-#pragma unroll
-      for (int d = 0; d < DP; ++d) v[d] += sh.red[w][2 + d];
     }
-    // pre-inverted cross term of the regressor: (See + Lambda)^-1 vec  with (See+Lambda)^-1 = Li^T Li
-    double y[DP];
+    const double vf = f2s - f1 * f1;
+    double h, a;
+    squash_owens_args(f1, vf, h, a);
+    const double t0 = owens_t_warp(h, a);      // the 32-node quadrature of E[Phi^2], one node per lane
+    if (lane == 0) {
+      double v[DP];
 #pragma unroll
-    for (int a = 0; a < DP; ++a) {
-      double t = 0.0;
+      for (int d = 0; d < DP; ++d) v[d] = 0.0;
+      for (int w = 0; w < 4; ++w)
 #pragma unroll
-      for (int k = 0; k <= a; ++k) t = fma(sh.Li1[a * DP + k], v[k], t);
-      y[a] = t;
-    }
+        for (int d = 0; d < DP; ++d) v[d] += sh.red[w][2 + d];
+      // pre-inverted cross term of the regressor: (See + Lambda)^-1 vec  with (See+Lambda)^-1 = Li^T Li
+      double y[DP];
 #pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      double t = 0.0;
+      for (int a2 = 0; a2 < DP; ++a2) {
+        double t = 0.0;
 #pragma unroll
-      for (int a = d; a < DP; ++a) t = fma(sh.Li1[a * DP + d], y[a], t);
-      sh.cpre[d] = t;
-      sh.vec[d] = v[d];
-    }
-    sh.f1 = f1;
-    sh.f2 = f2s;
-    sh.vf = f2s - f1 * f1;
-    double mu_u, vu, gain;
-    mm_squash_1d<double>(f1, sh.vf, p.scale, p.shift, mu_u, vu, gain);
-    sh.mu_u = mu_u; sh.vu = vu; sh.gain = gain;
-    // joint moments of d = (e, u)  (gaussian.py:53-63): Seu = See cpre gain
+        for (int k = 0; k <= a2; ++k) t = fma(sh.Li1[a2 * DP + k], v[k], t);
+        y[a2] = t;
+      }
 #pragma unroll
-    for (int a = 0; a < DP; ++a) {
-      double t = 0.0;
+      for (int d = 0; d < DP; ++d) {
+        double t = 0.0;
 #pragma unroll
-      for (int b = 0; b < DP; ++b) t = fma(sh.See[a * DP + b], sh.cpre[b], t);
-      sh.seu[a] = t * gain;
+        for (int a2 = d; a2 < DP; ++a2) t = fma(sh.Li1[a2 * DP + d], y[a2], t);
+        sh.cpre[d] = t;
+        sh.vec[d] = v[d];
+      }
+      sh.f1 = f1;
+      sh.f2 = f2s;
+      sh.vf = vf;
+      sh.t0 = t0;
+      double mu_u, vu, gain;
+      mm_squash_1d<double, true>(f1, vf, p.scale, p.shift, mu_u, vu, gain, t0);
+      sh.mu_u = mu_u; sh.vu = vu; sh.gain = gain;
+      // joint moments of d = (e, u)  (gaussian.py:53-63): Seu = See cpre gain
+#pragma unroll
+      for (int a2 = 0; a2 < DP; ++a2) {
+        double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < DP; ++b) t = fma(sh.See[a2 * DP + b], sh.cpre[b], t);
+        sh.seu[a2] = t * gain;
+      }
     }
   }
   __syncthreads();
