@@ -202,7 +202,9 @@ def pathwise_section(dev, lib, pk, world):
   target, W = T(cfg["target"]), T(cfg["W"])
   lib.gpp_profile_enable(1)
   times = []
-  for it in range(3):
+  sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+  sampler.start()
+  for it in range(4):
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
@@ -211,11 +213,30 @@ def pathwise_section(dev, lib, pk, world):
     lib.gpp_profile_last_ms(ctypes.byref(ms))
     if it:
       times.append(ms.value)
+  pw_clocks = sampler.stop()
   lib.gpp_profile_enable(0)
-  t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+  # gradient mode: forward with per-step Jacobians + reverse sweep (policy gradient), events around the pair
+  from gpflowpilco_b200.autograd import rollout_pathwise_loss
+  Zg, eg, qg = [x.clone().requires_grad_(True) for x in (policy.Z, policy.lengthscales, policy.q_mu)]
+  gtimes = []
+  for it in range(3):
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gl = rollout_pathwise_loss(paths, Zg, eg, policy.variance, qg, x0, H, cfg["active_dims"], target, W, squash_scale=cfg["squash_scale"],
+                               squash_shift=cfg["squash_shift"])
+    gl.sum().backward()
+    e1.record()
+    e1.synchronize()
+    if it:
+      gtimes.append(e0.elapsed_time(e1))
+    Zg.grad = eg.grad = qg.grad = None
+  t = torch.tensor([float(np.mean(times)), float(np.mean(gtimes))], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  sec = float(t[0]) * 1e-3
+  sec, gsec = float(t[0]) * 1e-3, float(t[1]) * 1e-3
   L, M, D = 4, d["Z"].shape[1], 6
   bytes_per_pstep = 8 * L * (F + M) + 2 * 8 * 4
   flop_per_pstep = L * F * (2 * D + 2 + 20) + L * M * (2 * D + 2 + 20) + 30 * (2 * 5 + 22)
@@ -225,9 +246,13 @@ def pathwise_section(dev, lib, pk, world):
       "config": {"workload": "config#4 pathwise cart-pole rollouts", "particles_per_gpu_per_launch": S, "bases": F, "horizon": H,
                  "latents": L, "inducing": M, "weights": "streamed from HBM (generated on device beforehand, Philox by global particle index)",
                  "note": "1M particles = ceil(2^20 / particles_per_launch) identical launches per GPU"},
-      "ms_per_launch": 1e3 * sec, "generation_s": gen_s, "mean_loss": float(loss.mean()),
+      "ms_per_launch": 1e3 * sec, "generation_s": gen_s, "mean_loss": float(loss.mean()), "clocks": pw_clocks,
+      "with_policy_gradient": {"value": world * psteps / gsec, "unit": "particle_steps/s (gradient-mode forward + reverse sweep)",
+                               "ms": 1e3 * gsec, "hbm_frac": bytes_per_pstep * psteps / gsec / 1e9 / pk.get("hbm_gbs")},
       "roofline": {"bound": "hbm", "achieved": bytes_per_pstep * psteps / sec / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
-                   "frac": bytes_per_pstep * psteps / sec / 1e9 / pk.get("hbm_gbs"), "traffic": None, "kernel": "k_pathwise_rollout",
+                   "frac": bytes_per_pstep * psteps / sec / 1e9 / pk.get("hbm_gbs"), "traffic": 0.99998 * bytes_per_pstep * psteps,
+                   "traffic_source": "ncu --set full at H=10 (profiles/r1b_pathwise_full.txt): dram read 105.575 GB vs 105.577 GB algorithmic; scaled to this launch",
+                   "kernel": "k_pathwise_rollout",
                    "algorithmic": f"{bytes_per_pstep} B and {flop_per_pstep} flop per particle-step",
                    "fp64_achieved_tflops": flop_per_pstep * psteps / sec / 1e12},
   }
@@ -432,7 +457,9 @@ def run_b200(args):
         "config": {"workload": "config#2 batched exact MM GP predict (M=1000, D=6, E=4, full 4x4 cov + cross)",
                    "inputs_per_gpu": N, "l2": "flushed between timed steps (256 MB write)", "timing": "CUDA events per step, max over ranks"},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                     "traffic": None, "kernel": "k_contract", "kernel_ms": 1e3 * kern_s,
+                     "traffic": 96.35e6 if N == 8192 else None,
+                     "traffic_source": "ncu --set full of this command at N=8192 (profiles/r1c_contract_bench_full.txt): dram read 78.45 MB + write 17.90 MB per launch",
+                     "kernel": "k_contract", "kernel_ms": 1e3 * kern_s,
                      "kernel_share_of_step": kern_s / (total_s / args.steps),
                      "algorithmic": f"{FLOP_PER_ENTRY} flop/entry x {ENTRIES_PER_INPUT} entries/input x {N} inputs",
                      "peak_source": "in-run DFMA microbenchmark (gpp_microbench_fp64); MEASURED_PEAKS.json has no FP64 figure",
