@@ -3,18 +3,23 @@
 // Work item = (kernel pair (a,b), T x T tile of the M x M index space, chunk of inputs).  Persistent CTAs pull
 // items from an atomic counter.  A CTA keeps the tile of C_a (diagonal pairs) in shared memory for the whole
 // chunk.  Warps are specialised and hand data over through double-buffered shared memory with named barriers
-// (bar.arrive / bar.sync), so there is NO CTA-wide barrier per input and the warps drift apart: shared-memory
-// bursts of one warp hide behind the FP64 work of the others.
+// (bar.arrive / bar.sync), so there is NO CTA-wide barrier per input and the warps drift apart.
 //
-//   producer warps (NP)  one input ahead: read the (n, pair) coefficient pack from L2, compute
-//                        g_i = R^T z1'_i, r_i = c0 + z1'^T P1 z1'  (rows)  and  z2'_j, s_j = z2'^T P2 z2'  (columns)
-//                        into buffer b = k & 1; they also sum the lane partials of finished inputs (fixed order).
-//   consumer warps (NC)  lane l owns rows {l, l+32, ..} (RPT = T/32 register tile), warp w owns a slice of columns.
-//                        Per entry: 1 DADD + D DFMA + 10 FP64 (table exp, gpp_math.h) + 1 DFMA.  The RPT row chains of a thread share
-//                        their column operands, which makes ptxas interleave them (a dependent DFMA issues 8 cycles
-//                        after its producer, the pipe accepts one warp instruction every 2 cycles).
-// Shared-memory layouts make every warp access a broadcast or unit-stride (no bank conflicts):
-//   Ct[j][i] (i fastest), rowbuf[b][field][i] (structure of arrays), colbuf[b][j][field] (broadcast reads).
+//   producer warps (NP)  one input ahead: stage the (n, pair) coefficient pack in shared memory and write, for their tile row
+//                        and column, the EXTENDED vectors  A_i = [g_i (D), r_i, 1, 0..],  B_j = [z2'_j (D), 1, s_j, 0..]
+//                        (g_i = R^T z1'_i, r_i = c0 + z1'^T P1 z1', s_j = z2'^T P2 z2'), so that the whole exponent is one
+//                        inner product  log Q_ij = A_i . B_j  of length K = 4 KS.  They also sum the lane partials of
+//                        finished inputs (fixed order).
+//   consumer warps (NC)  warp w owns the 8-row strip w of the tile.  The exponent of an 8 x 8 block of entries is KS
+//                        `mma.sync.m8n8k4.f64` instructions (SASS DMMA): on B200 DMMA runs on the FP64 pipe at the DFMA rate
+//                        (37.1 vs 36.1 TFLOP/s, scripts/microbench/dmma.cu) but takes its operands from 4 registers per 512
+//                        flop, whereas the scalar form needs D three-register DFMAs per entry, each of which costs 3 issue
+//                        cycles instead of 2 (scripts/microbench/fp64_pipe.cu).  Each lane then holds 2 entries of one row
+//                        (adjacent columns): table exp (10 FP64 ops, gpp_math.h) and one DFMA each into the contraction with
+//                        C_a[i][j..j+1] (one 128-bit shared load) or beta_b[j..j+1].
+// Shared-memory layouts make every warp access unit-stride or bank-conflict free:
+//   rowA[b][ks][row][4], colB[b][ks][col][4]   a warp's 32 fragment elements of one k-step are 256 contiguous bytes
+//   Ct[i][j] with row stride T + 8 doubles      8 rows x 4 column pairs per 128-bit load: quarter-warps hit disjoint banks
 #pragma once
 
 namespace gpp {
@@ -31,22 +36,31 @@ struct ContractParams {
 };
 
 template <int D>
-struct ColLayout {
-  static constexpr int STRIDE = (D + 2 + 1) & ~1;   // z2'[D], s_j, w_j  (even => 16-byte records)
+struct ExtLayout {
+  static constexpr int KS = (D + 2 + 3) / 4;        // k-steps of 4: g/z (D), then (r_i, 1) . (1, s_j)
 };
 
 template <int D, int T, int NP, int NC>
 struct ContractCfg {
+  static_assert(NC * 8 == T, "one consumer warp per 8-row strip of the tile");
+  static constexpr int KS = ExtLayout<D>::KS;
+  static constexpr int LDC = T + 8;                             // row stride of the C tile (bank spreading for 128-bit loads)
   static constexpr int NT = 32 * (NP + NC);
   static constexpr int PT = 32 * NP;                            // producer threads
-  static constexpr int CT = 0;                                  // [T][T]
-  static constexpr int COL = CT + T * T;                        // [2][T][STRIDE]
-  static constexpr int ROW = COL + 2 * T * ColLayout<D>::STRIDE;   // [2][D+2][T]
-  static constexpr int RED = ROW + 2 * (D + 2) * T;             // [2][NC][32]
+  static constexpr int CT = 0;                                  // [T][LDC]
+  static constexpr int COL = CT + T * LDC;                      // [2][KS][T][4]
+  static constexpr int ROW = COL + 2 * KS * T * 4;              // [2][KS][T][4]
+  static constexpr int WGT = ROW + 2 * KS * T * 4;              // [2][2][T]  beta of the rows / columns (off-diagonal pairs)
+  static constexpr int RED = WGT + 2 * 2 * T;                   // [2][NC][32]
   static constexpr int ETAB = RED + 2 * NC * 32;                // [64][GPP_EXP_TAB_REP] replicated 2^(j/64) table (fast_exp_tab_n)
   static constexpr int PKBUF = ETAB + 64 * GPP_EXP_TAB_REP;     // [2][PairPack<D>::SIZE] coefficient packs of the inputs in flight
   static constexpr int TOTAL = PKBUF + 2 * PairPack<D>::SIZE;   // doubles
 };
+
+// D (8x8) += A (8x4, row) * B (4x8, col), FP64: lane l holds A[l>>2][l&3], B[l&3][l>>2], D[l>>2][2(l&3) + {0,1}]
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 
 // barrier ids are immediates (a register id would make ptxas reserve all 16 hardware barriers for the CTA)
 template <int ID>
@@ -89,12 +103,13 @@ __device__ __forceinline__ bool contract_next_item(const ContractParams& p, doub
   it.n0 = chunk_id * p.chunk;
   it.K = min(p.N, it.n0 + p.chunk) - it.n0;
   it.diag = (it.sl.a == it.sl.b);
-  if (it.diag) {   // C is symmetric: read C[j][i] so that global reads and the later lane-wise smem reads are unit-stride
+  if (it.diag) {
+    constexpr int LDC = ContractCfg<D, T, NP, NC>::LDC;
     const double* Ca = p.C + (size_t)it.sl.a * p.M * p.M;
     for (int idx = tid; idx < T * T; idx += NT) {
-      int jj = idx / T, ii = idx % T;
-      int jg = it.sl.tj * T + jj, ig = it.sl.ti * T + ii;
-      Ct[idx] = (jg < p.M && ig < p.M) ? Ca[(size_t)jg * p.M + ig] : 0.0;
+      int ii = idx / T, jj = idx % T;
+      int ig = it.sl.ti * T + ii, jg = it.sl.tj * T + jj;
+      Ct[ii * LDC + jj] = (jg < p.M && ig < p.M) ? Ca[(size_t)ig * p.M + jg] : 0.0;
     }
   }
   __syncthreads();
@@ -105,17 +120,17 @@ template <int D, int T, int NP, int NC>
 __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   using PP = PairPack<D>;
   using CF = ContractCfg<D, T, NP, NC>;
-  constexpr int NT = CF::NT, PT = CF::PT;
-  constexpr int RPT = T / 32;                // rows per consumer thread
-  constexpr int CS = ColLayout<D>::STRIDE;
-  constexpr int RBUF = (D + 2) * T, CBUF = T * CS, DBUF = NC * 32;
+  constexpr int NT = CF::NT, PT = CF::PT, KS = CF::KS, LDC = CF::LDC;
+  constexpr int FBUF = KS * T * 4, WBUF = 2 * T, DBUF = NC * 32;
   constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_PROD = 5;  // named barriers 1,2 (full), 3,4 (empty), 5 (producers); 0 is __syncthreads
-  static_assert(T % 32 == 0, "rows of a tile are covered by 32 lanes x RPT");
+  static_assert(PT == T, "one producer thread per tile row / column");
+  static_assert((T / 8) % 2 == 0, "column groups are processed in pairs");
 
   extern __shared__ __align__(16) double smem[];
   double* Ct = smem + CF::CT;
-  double* colbuf = smem + CF::COL;
-  double* rowbuf = smem + CF::ROW;
+  double* colB = smem + CF::COL;
+  double* rowA = smem + CF::ROW;
+  double* wgt = smem + CF::WGT;
   double* red = smem + CF::RED;
   double* etab = smem + CF::ETAB;
   double* pkbuf = smem + CF::PKBUF;
@@ -126,9 +141,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   ContractItem it;
 
   if (warp < NP) {
-    // ------------------------------------------------------------------ producers (own copy of the item loop, then exit:
-    // the consumer loop below is then straight-line code for ptxas, which keeps its constants in uniform registers)
-    static_assert(PT == T, "one producer thread per tile row / column");
+    // ------------------------------------------------------------------ producers (own copy of the item loop, then exit)
     constexpr int NPV = (PP::SIZE + PT - 1) / PT;   // pack elements staged per producer thread
     while (contract_next_item<D, T, NP, NC>(p, Ct, &s_item, it)) {
       const gpp_slot sl = it.sl;
@@ -143,7 +156,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
       }
       const double brow = (!diag && ig < p.M) ? p.beta[(size_t)sl.a * p.M + ig] : 0.0;
       const double bcol = (!diag && jg < p.M) ? p.beta[(size_t)sl.b * p.M + jg] : 0.0;
-      // coefficient pack of input k: one element per thread, loaded one input ahead, staged in shared memory (double buffered)
+      // coefficient pack of input k: loaded one input ahead, staged in shared memory (double buffered)
       const double* pk0 = p.packs + ((size_t)it.n0 * p.npairs + sl.pair) * PP::SIZE;
       const size_t pk_stride = (size_t)p.npairs * PP::SIZE;
       double pv[NPV];
@@ -173,10 +186,9 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
           for (int q = 0; q < NPV; ++q)
             if (tid + q * PT < PP::SIZE) pv[q] = pk0[(size_t)(k + 1) * pk_stride + tid + q * PT];
         }
-        double* rb = rowbuf + b * RBUF;
-        double* cb = colbuf + b * CBUF;
+        double ext[4 * KS];
         {
-          // row `tid` of the tile
+          // row `tid` of the tile: A = [g (D), r, 1, 0..]
           double zc[D];
 #pragma unroll
           for (int d = 0; d < D; ++d) zc[d] = zrow[d] - pk[PP::MU + d];
@@ -185,21 +197,33 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
             double t = 0.0;
 #pragma unroll
             for (int d = 0; d < D; ++d) t = fma(zc[d], pk[PP::R + d * D + e], t);
-            rb[e * T + tid] = t;
+            ext[e] = t;
           }
-          rb[D * T + tid] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
-          rb[(D + 1) * T + tid] = brow;
+          ext[D] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
+          ext[D + 1] = 1.0;
+#pragma unroll
+          for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
+          double* ra = rowA + b * FBUF + tid * 4;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int q = 0; q < 4; q += 2)
+              *reinterpret_cast<double2*>(ra + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
+          wgt[b * WBUF + tid] = brow;
         }
         {
-          // column `tid` of the tile
-          double zc[D];
+          // column `tid` of the tile: B = [z2' (D), 1, s, 0..]
 #pragma unroll
-          for (int d = 0; d < D; ++d) zc[d] = zcol[d] - pk[PP::MU + d];
-          double* dst = cb + tid * CS;
+          for (int d = 0; d < D; ++d) ext[d] = zcol[d] - pk[PP::MU + d];
+          ext[D + 1] = packed_quad<D>(pk + PP::P2, ext);
+          ext[D] = 1.0;
+          double* cb = colB + b * FBUF + tid * 4;
 #pragma unroll
-          for (int d = 0; d < D; ++d) dst[d] = zc[d];
-          dst[D] = packed_quad<D>(pk + PP::P2, zc);
-          dst[D + 1] = bcol;
+          for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int q = 0; q < 4; q += 2)
+              *reinterpret_cast<double2*>(cb + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
+          wgt[b * WBUF + T + tid] = bcol;
         }
         __threadfence_block();
         named_bar_arrive<BAR_FULL>(b, NT);
@@ -208,56 +232,49 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
     return;
   }
 
-  // -------------------------------------------------------------------- consumers
-  const int cwarp = warp - NP;               // consumer warp index
-  // consumer column slice: T columns over NC warps, first (T % NC) warps take one more
-  const int cw = T / NC + (cwarp < T % NC ? 1 : 0);
-  const int c0 = cwarp * (T / NC) + min(cwarp, T % NC);
-  const double* ct = Ct + c0 * T + lane;
+  // -------------------------------------------------------------------- consumers: warp = 8-row strip of the tile
+  const int strip = warp - NP;
+  const int row = strip * 8 + (lane >> 2);           // this lane's row of the tile
+  const int cpair = 2 * (lane & 3);                  // its column pair inside an 8-column group
+  const double* ct = Ct + row * LDC + cpair;
   const double* etab_lane = etab + (lane & (GPP_EXP_TAB_REP - 1));
   while (contract_next_item<D, T, NP, NC>(p, Ct, &s_item, it)) {
     const bool diag = it.diag;
     for (int k = 0; k < it.K; ++k) {
       const int b = k & 1;
       named_bar_sync<BAR_FULL>(b, NT);
-      const double* rb = rowbuf + b * RBUF + lane;
-      double g[RPT][D], r[RPT], acc[RPT];
+      const double* ra = rowA + b * FBUF + strip * 32 + lane;
+      const double* cb = colB + b * FBUF + lane;
+      const double* wc = wgt + b * WBUF + T + cpair;
+      double a[KS];
 #pragma unroll
-      for (int q = 0; q < RPT; ++q) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) g[q][d] = rb[d * T + 32 * q];
-        r[q] = rb[D * T + 32 * q];
-        acc[q] = 0.0;
-      }
-      const double* cb = colbuf + b * CBUF + c0 * CS;
+      for (int ks = 0; ks < KS; ++ks) a[ks] = ra[ks * T * 4];
+      double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 2
-      for (int jj = 0; jj < cw; ++jj) {
-        const double* c = cb + jj * CS;
-        double zc[D];
+      for (int cg = 0; cg < T / 8; cg += 2) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int d = 0; d < D; ++d) zc[d] = c[d];
-        const double sj = c[D];
-        double t[RPT];
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) t[q] = r[q] + sj;
-#pragma unroll
-        for (int d = 0; d < D; ++d)
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) t[q] = fma(g[q][d], zc[d], t[q]);
-        fast_exp_tab_n<RPT>(t, etab_lane);
-        if (diag) {
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) acc[q] = fma(t[q], ct[jj * T + 32 * q], acc[q]);
-        } else {
-          const double wj = c[D + 1];
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) acc[q] = fma(t[q], wj, acc[q]);
+        for (int ks = 0; ks < KS; ++ks) {
+          dmma_m8n8k4(t[0], t[1], a[ks], cb[ks * T * 4 + cg * 32]);
+          dmma_m8n8k4(t[2], t[3], a[ks], cb[ks * T * 4 + cg * 32 + 32]);
         }
+        fast_exp_tab_n<4>(t, etab_lane);
+        double2 w0, w1;
+        if (diag) {
+          w0 = *reinterpret_cast<const double2*>(ct + cg * 8);
+          w1 = *reinterpret_cast<const double2*>(ct + cg * 8 + 8);
+        } else {
+          w0 = *reinterpret_cast<const double2*>(wc + cg * 8);
+          w1 = *reinterpret_cast<const double2*>(wc + cg * 8 + 8);
+        }
+        acc0 = fma(t[0], w0.x, acc0);
+        acc1 = fma(t[2], w1.x, acc1);
+        acc0 = fma(t[1], w0.y, acc0);
+        acc1 = fma(t[3], w1.y, acc1);
       }
-      double total = 0.0;
-#pragma unroll
-      for (int q = 0; q < RPT; ++q) total += diag ? acc[q] : acc[q] * rb[(D + 1) * T + 32 * q];
-      red[b * DBUF + cwarp * 32 + lane] = total;
+      double total = acc0 + acc1;
+      if (!diag) total *= wgt[b * WBUF + row];
+      red[b * DBUF + strip * 32 + lane] = total;
       __threadfence_block();
       named_bar_arrive<BAR_EMPTY>(b, NT);
     }

@@ -191,7 +191,7 @@ static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S,
   cp.Z = m->Z; cp.beta = m->beta; cp.C = m->C; cp.packs = packs; cp.part = part; cp.slots = tab.d_slots;
   cp.counter = counter; cp.N = N; cp.M = m->M; cp.L = m->L; cp.npairs = tab.npairs; cp.nslots = tab.nslots;
   cp.nchunks = pl.nchunks; cp.chunk = pl.chunk;
-  int rc = pl.tile_idx ? launch_contract<D, 128, 4, 12>(cp, stream) : launch_contract<D, 64, 2, 8>(cp, stream);
+  int rc = pl.tile_idx ? launch_contract<D, 128, 4, 16>(cp, stream) : launch_contract<D, 64, 2, 8>(cp, stream);
   if (rc != GPP_OK) return rc;
   FinalizeParams fp;
   fp.part = part; fp.slots = tab.d_slots; fp.pair_start = tab.d_pair_start; fp.pair_ab = tab.d_pair_ab;
