@@ -80,6 +80,56 @@ __device__ __forceinline__ void named_bar_arrive(int b, int count) {
   if (b) named_bar_arrive_imm<BASE + 1>(count); else named_bar_arrive_imm<BASE>(count);
 }
 
+// exp for the contraction loop: same table-driven algorithm as fast_exp_tab_n (gpp_math.h), with the integer tail written for
+// the issue port (every non-FP64 instruction issued beside the FP64 pipe costs ~0.8 cycles, fp64_pipe.cu):
+//   * the argument is clamped to >= -707 by an unsigned min on its high word (1 op) instead of selecting 0 afterwards
+//     (4 ops): entries below exp(-707) ~ 1e-307 are numerically zero in the contraction either way;
+//   * table address = lane base + ((n & 63) << 7) and exponent insert = hi + ((n >> 6) << 20), 2 ops each.
+// `tab_addr` is the shared-space byte address of this lane's table replica (etab + (lane & 15)).
+template <int K>
+__device__ __forceinline__ void exp_tab_contract(double (&x)[K], unsigned tab_addr) {
+  const double MAGIC = 6755399441055744.0;
+  double t[K], r[K], p[K], s2[K], tj[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    unsigned hi = (unsigned)__double2hiint(x[k]);
+    hi = min(hi, 0xC0861800u);                                   // x >= -707 (positive x: hi < 2^31, untouched)
+    x[k] = __hiloint2double((int)hi, __double2loint(x[k]));
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = fma(x[k], kExpT[0], MAGIC);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    unsigned addr;
+    asm("{\n\t.reg .b32 m;\n\tand.b32 m, %1, 63;\n\tshl.b32 m, m, 7;\n\tadd.u32 %0, m, %2;\n\t}" : "=r"(addr) : "r"(__double2loint(t[k])), "r"(tab_addr));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj[k]) : "r"(addr));
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) r[k] = t[k] - MAGIC;
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = fma(r[k], kExpT[1], x[k]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) r[k] = fma(r[k], kExpT[2], p[k]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) s2[k] = r[k] * r[k];
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = fma(r[k], kExpT[6], kExpT[5]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], kExpT[4]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], kExpT[3]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = fma(p[k], s2[k], r[k]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) p[k] = fma(tj[k], p[k], tj[k]);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int hi2;
+    asm("{\n\t.reg .s32 e;\n\tshr.s32 e, %1, 6;\n\tmad.lo.s32 %0, e, 1048576, %2;\n\t}" : "=r"(hi2) : "r"(__double2loint(t[k])), "r"(__double2hiint(p[k])));
+    x[k] = __hiloint2double(hi2, __double2loint(p[k]));
+  }
+}
+
 // One work item = (slot, input chunk).  Both roles walk the same item sequence: thread 0 draws the next item from the global
 // counter and every thread of the CTA reads it between two CTA-wide barriers; the C tile load is shared too.
 struct ContractItem {
@@ -237,7 +287,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   const int row = strip * 8 + (lane >> 2);           // this lane's row of the tile
   const int cpair = 2 * (lane & 3);                  // its column pair inside an 8-column group
   const double* ct = Ct + row * LDC + cpair;
-  const double* etab_lane = etab + (lane & (GPP_EXP_TAB_REP - 1));
+  const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (GPP_EXP_TAB_REP - 1)));
   while (contract_next_item<D, T, NP, NC>(p, Ct, &s_item, it)) {
     const bool diag = it.diag;
     for (int k = 0; k < it.K; ++k) {
@@ -245,7 +295,8 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
       named_bar_sync<BAR_FULL>(b, NT);
       const double* ra = rowA + b * FBUF + strip * 32 + lane;
       const double* cb = colB + b * FBUF + lane;
-      const double* wc = wgt + b * WBUF + T + cpair;
+      // contraction weights of this lane's row: C_a[i][j..] (diagonal pairs) or beta_b[j..]; both advance 8 doubles per column group
+      const double* wsrc = diag ? ct : wgt + b * WBUF + T + cpair;
       double a[KS];
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) a[ks] = ra[ks * T * 4];
@@ -258,15 +309,9 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
           dmma_m8n8k4(t[0], t[1], a[ks], cb[ks * T * 4 + cg * 32]);
           dmma_m8n8k4(t[2], t[3], a[ks], cb[ks * T * 4 + cg * 32 + 32]);
         }
-        fast_exp_tab_n<4>(t, etab_lane);
-        double2 w0, w1;
-        if (diag) {
-          w0 = *reinterpret_cast<const double2*>(ct + cg * 8);
-          w1 = *reinterpret_cast<const double2*>(ct + cg * 8 + 8);
-        } else {
-          w0 = *reinterpret_cast<const double2*>(wc + cg * 8);
-          w1 = *reinterpret_cast<const double2*>(wc + cg * 8 + 8);
-        }
+        exp_tab_contract<4>(t, etab_lane);
+        const double2 w0 = *reinterpret_cast<const double2*>(wsrc + cg * 8);
+        const double2 w1 = *reinterpret_cast<const double2*>(wsrc + cg * 8 + 8);
         acc0 = fma(t[0], w0.x, acc0);
         acc1 = fma(t[2], w1.x, acc1);
         acc0 = fma(t[1], w0.y, acc0);
