@@ -45,6 +45,7 @@ struct ContractCfg {
   static_assert(NC * 8 == T, "one consumer warp per 8-row strip of the tile");
   static constexpr int KS = ExtLayout<D>::KS;
   static constexpr int LDC = T + 8;                             // row stride of the C tile (bank spreading for 128-bit loads)
+  static constexpr int REP = KS <= 2 ? 16 : 8;                  // replication of the exp table
   static constexpr int NT = 32 * (NP + NC);
   static constexpr int PT = 32 * NP;                            // producer threads
   static constexpr int CT = 0;                                  // [T][LDC]
@@ -52,8 +53,8 @@ struct ContractCfg {
   static constexpr int ROW = COL + 2 * KS * T * 4;              // [2][KS][T][4]
   static constexpr int WGT = ROW + 2 * KS * T * 4;              // [2][2][T]  beta of the rows / columns (off-diagonal pairs)
   static constexpr int RED = WGT + 2 * 2 * T;                   // [2][NC][32]
-  static constexpr int ETAB = RED + 2 * NC * 32;                // [64][GPP_EXP_TAB_REP] replicated 2^(j/64) table (fast_exp_tab_n)
-  static constexpr int PKBUF = ETAB + 64 * GPP_EXP_TAB_REP;     // [2][PairPack<D>::SIZE] coefficient packs of the inputs in flight
+  static constexpr int ETAB = RED + 2 * NC * 32;                // [256][REP] replicated 2^(j/256) table (exp_tab_contract)
+  static constexpr int PKBUF = ETAB + 256 * REP;                // [2][PairPack<D>::SIZE] coefficient packs of the inputs in flight
   static constexpr int TOTAL = PKBUF + 2 * PairPack<D>::SIZE;   // doubles
 };
 
@@ -80,16 +81,22 @@ __device__ __forceinline__ void named_bar_arrive(int b, int count) {
   if (b) named_bar_arrive_imm<BASE + 1>(count); else named_bar_arrive_imm<BASE>(count);
 }
 
-// exp for the contraction loop: same table-driven algorithm as fast_exp_tab_n (gpp_math.h), with the integer tail written for
-// the issue port (every non-FP64 instruction issued beside the FP64 pipe costs ~0.8 cycles, fp64_pipe.cu):
+// exp for the contraction loop: the 256-entry table algorithm of gpp_math.h (exp_tab256_ref: 8 FP64-pipe ops), with the integer
+// tail written for the issue port (every non-FP64 instruction issued beside the FP64 pipe costs ~0.8 cycles, fp64_pipe.cu):
 //   * the argument is clamped to >= -707 by an unsigned min on its high word (1 op) instead of selecting 0 afterwards
 //     (4 ops): entries below exp(-707) ~ 1e-307 are numerically zero in the contraction either way;
-//   * table address = lane base + ((n & 63) << 7) and exponent insert = hi + ((n >> 6) << 20), 2 ops each.
-// `tab_addr` is the shared-space byte address of this lane's table replica (etab + (lane & 15)).
-template <int K>
+//   * table address = lane base + ((n & 255) << 7) and exponent insert = hi + ((n >> 8) << 20), 2 ops each.
+// `tab_addr` is the shared-space byte address of this lane's table replica (etab + (lane & (REP-1))); entry j of replica c lives at
+// etab[j * REP + c]: with REP = 16 the 64-bit loads of a half-warp hit 16 distinct bank pairs whatever the j's are (REP = 8,
+// used when D >= 7 needs the shared memory for a third k-step, allows 2-way conflicts).
+constexpr int kContractTab = 256;
+
+template <int K, int REP>
 __device__ __forceinline__ void exp_tab_contract(double (&x)[K], unsigned tab_addr) {
+  constexpr int SHIFT = REP == 16 ? 7 : 6;      // entry stride in bytes: 8 * REP
+  static_assert(REP == 16 || REP == 8, "table replication");
   const double MAGIC = 6755399441055744.0;
-  double t[K], r[K], p[K], s2[K], tj[K];
+  double t[K], r[K], q[K], tj[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     unsigned hi = (unsigned)__double2hiint(x[k]);
@@ -97,36 +104,32 @@ __device__ __forceinline__ void exp_tab_contract(double (&x)[K], unsigned tab_ad
     x[k] = __hiloint2double((int)hi, __double2loint(x[k]));
   }
 #pragma unroll
-  for (int k = 0; k < K; ++k) t[k] = fma(x[k], kExpT[0], MAGIC);
+  for (int k = 0; k < K; ++k) t[k] = fma(x[k], kExpT256[0], MAGIC);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     unsigned addr;
-    asm("{\n\t.reg .b32 m;\n\tand.b32 m, %1, 63;\n\tshl.b32 m, m, 7;\n\tadd.u32 %0, m, %2;\n\t}" : "=r"(addr) : "r"(__double2loint(t[k])), "r"(tab_addr));
+    asm("{\n\t.reg .b32 m;\n\tand.b32 m, %1, 255;\n\tshl.b32 m, m, %3;\n\tadd.u32 %0, m, %2;\n\t}" : "=r"(addr) : "r"(__double2loint(t[k])), "r"(tab_addr), "n"(SHIFT));
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj[k]) : "r"(addr));
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) r[k] = t[k] - MAGIC;
 #pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma(r[k], kExpT[1], x[k]);
+  for (int k = 0; k < K; ++k) r[k] = fma(r[k], kExpT256[1], x[k]);
 #pragma unroll
-  for (int k = 0; k < K; ++k) r[k] = fma(r[k], kExpT[2], p[k]);
+  for (int k = 0; k < K; ++k) q[k] = fma(r[k], kExpT256[4], kExpT256[3]);
 #pragma unroll
-  for (int k = 0; k < K; ++k) s2[k] = r[k] * r[k];
+  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], kExpT256[2]);
 #pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma(r[k], kExpT[6], kExpT[5]);
+  for (int k = 0; k < K; ++k) q[k] = fma(q[k], r[k], 1.0);
 #pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], kExpT[4]);
+  for (int k = 0; k < K; ++k) q[k] = q[k] * r[k];                 // exp(r) - 1
 #pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma(p[k], r[k], kExpT[3]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma(p[k], s2[k], r[k]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma(tj[k], p[k], tj[k]);
+  for (int k = 0; k < K; ++k) q[k] = fma(tj[k], q[k], tj[k]);      // T_j exp(r)
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     int hi2;
-    asm("{\n\t.reg .s32 e;\n\tshr.s32 e, %1, 6;\n\tmad.lo.s32 %0, e, 1048576, %2;\n\t}" : "=r"(hi2) : "r"(__double2loint(t[k])), "r"(__double2hiint(p[k])));
-    x[k] = __hiloint2double(hi2, __double2loint(p[k]));
+    asm("{\n\t.reg .s32 e;\n\tshr.s32 e, %1, 8;\n\tmad.lo.s32 %0, e, 1048576, %2;\n\t}" : "=r"(hi2) : "r"(__double2loint(t[k])), "r"(__double2hiint(q[k])));
+    x[k] = __hiloint2double(hi2, __double2loint(q[k]));
   }
 }
 
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   double* etab = smem + CF::ETAB;
   double* pkbuf = smem + CF::PKBUF;
   __shared__ int s_item;
-  for (int i = threadIdx.x; i < 64 * GPP_EXP_TAB_REP; i += NT) etab[i] = kExp2Tab[i / GPP_EXP_TAB_REP];
+  for (int i = threadIdx.x; i < kContractTab * CF::REP; i += NT) etab[i] = kExp2Tab256[i / CF::REP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ContractItem it;
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   const int row = strip * 8 + (lane >> 2);           // this lane's row of the tile
   const int cpair = 2 * (lane & 3);                  // its column pair inside an 8-column group
   const double* ct = Ct + row * LDC + cpair;
-  const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (GPP_EXP_TAB_REP - 1)));
+  const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (CF::REP - 1)));
   while (contract_next_item<D, T, NP, NC>(p, Ct, &s_item, it)) {
     const bool diag = it.diag;
     for (int k = 0; k < it.K; ++k) {
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
           dmma_m8n8k4(t[0], t[1], a[ks], cb[ks * T * 4 + cg * 32]);
           dmma_m8n8k4(t[2], t[3], a[ks], cb[ks * T * 4 + cg * 32 + 32]);
         }
-        exp_tab_contract<4>(t, etab_lane);
+        exp_tab_contract<4, CF::REP>(t, etab_lane);
         const double2 w0 = *reinterpret_cast<const double2*>(wsrc + cg * 8);
         const double2 w1 = *reinterpret_cast<const double2*>(wsrc + cg * 8 + 8);
         acc0 = fma(t[0], w0.x, acc0);

@@ -227,6 +227,37 @@ GPP_HD void fast_exp_tab_n(double (&x)[K], const double* tab) {
   for (int k = 0; k < K; ++k) x[k] = exp_tab_in_range(x[k]) ? exp_tab_scale(p[k], n[k]) : 0.0;   // x < -707: exactly 0
 }
 
+// 256-entry variant for the contraction kernel: n = rint(x 256/ln 2), |r| <= ln2/512 = 0.00135, degree-4 Taylor (truncation
+// 3.8e-17), and a single full-precision ln2/256 constant in the reduction: r = fma(n, -ln2/256, x) is exact up to one rounding,
+// the constant's own error shifts r by |n| 2.4e-19 <= |x| 9e-17, i.e. by less than the rounding error x already carries.
+// 8 FP64-pipe ops.  exp_tab256_core returns p = T_j exp(r) in [1, 2) and n; the caller scales by 2^(n >> 8).
+GPP_EXP_TABLE kExp2Tab256[256] = {
+#include "exp2_tab256.inc"
+};
+GPP_EXP_TABLE kExpT256[8] = {
+    0x1.71547652b82fep+8,     // 0  256 log2(e)
+    -0x1.62e42fefa39efp-9,    // 1  -ln2/256
+    0.5,                      // 2  1/2!
+    0x1.5555555555555p-3,     // 3  1/3!
+    0x1.5555555555555p-5,     // 4  1/4!
+    0.0, 0.0, 0.0};
+
+// host-testable scalar reference of the 256-entry algorithm (same operation order as the device loop)
+GPP_HD double exp_tab256_ref(double x) {
+  const double MAGIC = 6755399441055744.0;
+  double t = fma_(x, kExpT256[0], MAGIC);
+  int32_t n = lo_int(t);
+  double nd = t - MAGIC;
+  double r = fma_(nd, kExpT256[1], x);
+  double q = fma_(r, kExpT256[4], kExpT256[3]);
+  q = fma_(q, r, kExpT256[2]);
+  q = fma_(q, r, 1.0);
+  double em1 = q * r;
+  double tj = kExp2Tab256[n & 255];
+  double p = fma_(tj, em1, tj);
+  return make_double(hi_int(p) + ((n >> 8) << 20), lo_int(p));
+}
+
 // ---------------------------------------------------------------------------------------------
 // D x D helpers, row-major in registers.  All loops fully unrolled (D is compile-time).
 // ---------------------------------------------------------------------------------------------
