@@ -3,8 +3,8 @@
 // Psi2 replaces `_E`, gpflow_pilco/utils/kernel_expectation.py:72-187.  The reference builds >= 4 [N,M1,M2]
 // temporaries (tile of Z, two triangular solves, a K=D matmul, two exp tensors); here each entry is produced
 // once from  log Q_ij = r_i + s_j + z1'_i^T R z2'_j  (common.cuh) and written with 128-bit coalesced stores.
-// The kernel is HBM-write bound (8 B/entry) with the FP64 pipe a close second (D + 17 FP64 ops/entry).
-#include "common.cuh"
+// The kernel is HBM-write bound (8 B/entry); the FP64 pipe (KS/32 DMMA + 8 FP64 ops per entry) is a close second.
+#include "mma_exp.cuh"
 
 namespace gpp {
 
@@ -67,81 +67,158 @@ __global__ void __launch_bounds__(64) k_pack_single(const double* __restrict__ m
   for (int t = 0; t < PairPack<D>::SIZE; ++t) packs[(size_t)n * PairPack<D>::SIZE + t] = out[t];
 }
 
-// grid (column strips of CT columns, n); 128 threads, each owns 2 adjacent columns of the strip and walks all rows.
+// Psi2, materialised.  CTA = (input n, block of 128 rows), 16 warps; warp w owns the 8-row strip w and walks all columns in
+// blocks of 128.  With the extended vectors A_i, B_j (mma_exp.cuh) the exponent of an 8 x 8 block of entries is KS
+// mma.sync.m8n8k4.f64 (DMMA) instructions; each lane then holds two horizontally adjacent entries: table exp (8 FP64 ops each)
+// and one 128-bit streaming store.  Rows are prepared once per CTA, columns once per column block by all 512 threads
+// (4 threads per column share the quadratic form).  Measured: DMMA runs at the DFMA rate on B200 but needs 4 register operands
+// per 512 flop instead of 3 per 2 (scripts/microbench/dmma.cu, fp64_pipe.cu).
+constexpr int kPsi2Rows = 128, kPsi2Cols = 128, kPsi2Threads = 512;
+
 template <int D>
-__global__ void __launch_bounds__(128, 4) k_ekzxkxz(const double* __restrict__ packs, const double* __restrict__ Z1, int M1,
-                                                 const double* __restrict__ Z2, int M2, double* __restrict__ out) {
+struct Psi2Cfg {
+  // when carrying (r_i, 1).(1, s_j) inside the inner product would cost a whole extra k-step (D = 3, 4, 7, 8), the two scalars are
+  // added into the DMMA accumulator instead (1 DADD per entry)
+  static constexpr bool EXCL = (D + 3) / 4 < ExtLayout<D>::KS;
+  static constexpr int KS = EXCL ? (D + 3) / 4 : ExtLayout<D>::KS;
+  static constexpr int REP = 16;
+  static constexpr int PK = 0;                                   // coefficient pack
+  static constexpr int ROWA = (PairPack<D>::SIZE + 1) & ~1;      // [KS][128][4]
+  static constexpr int COLB = ROWA + KS * kPsi2Rows * 4;         // [2][KS][128][4]
+  static constexpr int ETAB = COLB + 2 * KS * kPsi2Cols * 4;     // [256][REP]
+  static constexpr int ROWR = ETAB + 256 * REP;                  // [128] r_i        (EXCL only)
+  static constexpr int COLS = ROWR + kPsi2Rows;                  // [2][128] s_j     (EXCL only)
+  static constexpr int TOTAL = COLS + 2 * kPsi2Cols;             // doubles
+};
+
+template <int D>
+__global__ void __launch_bounds__(kPsi2Threads, 2) k_ekzxkxz(const double* __restrict__ packs, const double* __restrict__ Z1, int M1,
+                                                             const double* __restrict__ Z2, int M2, double* __restrict__ out) {
   using PP = PairPack<D>;
-  constexpr int RT = 64;                 // rows staged per pass
-  constexpr int RS = (D + 1 + 1) & ~1;   // z1'[D], r
-  __shared__ __align__(16) double pk[PP::SIZE];
-  __shared__ __align__(16) double rowbuf[RT * RS];
-  __shared__ double etab[64 * GPP_EXP_TAB_REP];   // replicated 2^(j/64) table of the 10-op exp (gpp_math.h)
-  const int n = blockIdx.y, tid = threadIdx.x;
-  for (int t = tid; t < PP::SIZE; t += blockDim.x) pk[t] = packs[(size_t)n * PP::SIZE + t];
-  for (int t = tid; t < 64 * GPP_EXP_TAB_REP; t += blockDim.x) etab[t] = kExp2Tab[t / GPP_EXP_TAB_REP];
+  using CF = Psi2Cfg<D>;
+  constexpr int KS = CF::KS, FB = KS * kPsi2Cols * 4;
+  extern __shared__ __align__(16) double smem[];
+  double* pk = smem + CF::PK;
+  double* rowA = smem + CF::ROWA;
+  double* colB = smem + CF::COLB;
+  double* etab = smem + CF::ETAB;
+  double* rowR = smem + CF::ROWR;
+  double* colS = smem + CF::COLS;
+  constexpr bool EXCL = CF::EXCL;
+  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * kPsi2Rows;
+  for (int t = tid; t < PP::SIZE; t += kPsi2Threads) pk[t] = packs[(size_t)n * PP::SIZE + t];
+  for (int t = tid; t < 256 * CF::REP; t += kPsi2Threads) etab[t] = kExp2Tab256[t / CF::REP];
   __syncthreads();
-  const double* etab_lane = etab + (tid & (GPP_EXP_TAB_REP - 1));
-  const int j0 = (blockIdx.x * 128 + tid) * 2;
-  const bool pair_ok = ((M2 & 1) == 0);          // 16-byte aligned pair stores need an even row length
-  double g[2][D], s[2];
+  if (tid < kPsi2Rows) {   // A_i of row i0 + tid
+    const int i = i0 + tid;
+    double zc[D], ext[4 * KS];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    int j = j0 + c;
+    for (int d = 0; d < D; ++d) zc[d] = (i < M1 ? Z1[(size_t)i * D + d] : 0.0) - pk[PP::MU + d];
+#pragma unroll
+    for (int e = 0; e < D; ++e) {
+      double t = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) t = fma(zc[d], pk[PP::R + d * D + e], t);
+      ext[e] = t;
+    }
+    const double ri = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
+    if (EXCL) {
+      rowR[tid] = ri;
+#pragma unroll
+      for (int e = D; e < 4 * KS; ++e) ext[e] = 0.0;
+    } else {
+      ext[D] = ri;
+      ext[D + 1] = 1.0;
+#pragma unroll
+      for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rowA[(ks * kPsi2Rows + tid) * 4 + q] = ext[ks * 4 + q];
+  }
+  // column block `cbk` -> colB[buf]: thread = (column, quarter); the quarters share the quadratic form z2'^T P2 z2' by shuffle
+  auto prepare_columns = [&](int cbk, int buf) {
+    const int jl = tid >> 2, q = tid & 3, j = cbk * kPsi2Cols + jl;
     double zc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) zc[d] = (j < M2 ? Z2[(size_t)j * D + d] : 0.0) - pk[PP::MU + d];
-    s[c] = packed_quad<D>(pk + PP::P2, zc);
+    double part = 0.0;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {       // g = R z2'
-      double t = 0.0;
+    for (int d = 0; d < D; ++d) {
+      if ((d & 3) == q) {
+        double rowsum = 0.0;
 #pragma unroll
-      for (int e = 0; e < D; ++e) t = fma(pk[PP::R + d * D + e], zc[e], t);
-      g[c][d] = t;
-    }
-  }
-  double* outn = out + (size_t)n * M1 * M2;
-  for (int i0 = 0; i0 < M1; i0 += RT) {
-    __syncthreads();
-    if (tid < RT) {
-      int i = i0 + tid;
-      double zr[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) zr[d] = (i < M1 ? Z1[(size_t)i * D + d] : 0.0) - pk[PP::MU + d];
-      double r = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zr);
-#pragma unroll
-      for (int d = 0; d < D; ++d) rowbuf[tid * RS + d] = zr[d];
-      rowbuf[tid * RS + D] = r;
-    }
-    __syncthreads();
-    const int rows = min(RT, M1 - i0);
-    if (j0 >= M2) continue;
-    // 2 rows x 2 columns in lock-step (4 independent FP64 chains per thread); rowbuf is zero-padded past M1
-#pragma unroll 1
-    for (int ii = 0; ii < rows; ii += 2) {
-      const double* rb0 = rowbuf + ii * RS;
-      const double* rb1 = rb0 + RS;
-      double t[4] = {rb0[D] + s[0], rb0[D] + s[1], rb1[D] + s[0], rb1[D] + s[1]};
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        t[0] = fma(rb0[d], g[0][d], t[0]);
-        t[1] = fma(rb0[d], g[1][d], t[1]);
-        t[2] = fma(rb1[d], g[0][d], t[2]);
-        t[3] = fma(rb1[d], g[1][d], t[3]);
+        for (int e = d; e < D; ++e) rowsum = fma(pk[PP::P2 + d * D - d * (d - 1) / 2 + (e - d)], zc[e], rowsum);
+        part = fma(rowsum, zc[d], part);
       }
-      fast_exp_tab_n<4>(t, etab_lane);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (q < KS) {
+      double* dst = colB + buf * FB + (q * kPsi2Cols + jl) * 4;
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        if (ii + rr >= rows) break;
-        double* dst = outn + (size_t)(i0 + ii + rr) * M2 + j0;
-        if (pair_ok) {
-          __stcs(reinterpret_cast<double2*>(dst), make_double2(t[2 * rr], t[2 * rr + 1]));   // streaming: never re-read
-        } else {
-          __stcs(dst, t[2 * rr]);
-          if (j0 + 1 < M2) __stcs(dst + 1, t[2 * rr + 1]);
+      for (int c = 0; c < 4; ++c) {
+        const int e = 4 * q + c;                 // B_j = [z2' (D), 1, s_j, 0..]
+        double v = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) v = (e == d) ? zc[d] : v;
+        if (!EXCL) v = (e == D) ? 1.0 : ((e == D + 1) ? part : v);
+        dst[c] = v;
+      }
+    }
+    if (EXCL && q == 3) colS[buf * kPsi2Cols + jl] = part;
+  };
+  prepare_columns(0, 0);
+  __syncthreads();
+  double a[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) a[ks] = rowA[(ks * kPsi2Rows + warp * 8) * 4 + lane];
+  const int row = i0 + warp * 8 + (lane >> 2);
+  const int cpair = 2 * (lane & 3);
+  const double ri = EXCL ? rowR[warp * 8 + (lane >> 2)] : 0.0;
+  const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (CF::REP - 1)));
+  const bool pair_ok = ((M2 & 1) == 0);          // 16-byte aligned pair stores need an even row length
+  double* outrow = out + ((size_t)n * M1 + row) * M2;
+  const int ncb = (M2 + kPsi2Cols - 1) / kPsi2Cols;
+  for (int cbk = 0; cbk < ncb; ++cbk) {
+    const int buf = cbk & 1;
+    if (cbk + 1 < ncb) prepare_columns(cbk + 1, buf ^ 1);      // next block's columns into the other buffer
+    const double* cb = colB + buf * FB + lane;
+#pragma unroll 2
+    for (int cg = 0; cg < kPsi2Cols / 8; cg += 2) {
+      double t[4] = {0.0, 0.0, 0.0, 0.0};
+      if (EXCL) {
+        const double2 s0 = *reinterpret_cast<const double2*>(colS + buf * kPsi2Cols + cg * 8 + cpair);
+        const double2 s1 = *reinterpret_cast<const double2*>(colS + buf * kPsi2Cols + cg * 8 + 8 + cpair);
+        t[0] = ri + s0.x; t[1] = ri + s0.y; t[2] = ri + s1.x; t[3] = ri + s1.y;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        dmma_m8n8k4(t[0], t[1], a[ks], cb[(ks * kPsi2Cols + cg * 8) * 4]);
+        dmma_m8n8k4(t[2], t[3], a[ks], cb[(ks * kPsi2Cols + cg * 8 + 8) * 4]);
+      }
+      bool tiny[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tiny[k] = (unsigned)__double2hiint(t[k]) > 0xC0861800u;   // log Q < -707: exactly 0
+      exp_tab_contract<4, CF::REP>(t, etab_lane);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] = tiny[k] ? 0.0 : t[k];
+      if (row < M1) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = cbk * kPsi2Cols + (cg + u) * 8 + cpair;
+          if (pair_ok && j + 1 < M2) {
+            __stcs(reinterpret_cast<double2*>(outrow + j), make_double2(t[2 * u], t[2 * u + 1]));   // streaming: never re-read
+          } else {
+            if (j < M2) __stcs(outrow + j, t[2 * u]);
+            if (j + 1 < M2) __stcs(outrow + j + 1, t[2 * u + 1]);
+          }
         }
       }
     }
+    __syncthreads();   // next block's columns complete; this block's buffer free for the block after next
   }
 }
 
@@ -162,9 +239,15 @@ static int run_ekzxkxz(const double* mu, const double* cov, int N, const double*
   double* packs = nullptr;
   GPP_CUDA_OK(cudaMallocAsync(&packs, sizeof(double) * PairPack<D>::SIZE * (size_t)N, stream));
   k_pack_single<D><<<(N + 63) / 64, 64, 0, stream>>>(mu, cov, N, ell1, ell2, log(var1 * var2), packs, info);
-  dim3 grid((M2 + 255) / 256, N);
+  dim3 grid((M1 + kPsi2Rows - 1) / kPsi2Rows, N);
+  const size_t smem = sizeof(double) * Psi2Cfg<D>::TOTAL;
+  static bool configured = false;
+  if (!configured) {
+    GPP_CUDA_OK(cudaFuncSetAttribute(k_ekzxkxz<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
   profile_begin(stream);
-  k_ekzxkxz<D><<<grid, 128, 0, stream>>>(packs, Z1, M1, Z2, M2, out);
+  k_ekzxkxz<D><<<grid, kPsi2Threads, smem, stream>>>(packs, Z1, M1, Z2, M2, out);
   profile_end(stream);
   count_launch(2);
   GPP_CUDA_OK(cudaGetLastError());
