@@ -317,6 +317,8 @@ def run_reference(args):
   if rank != 0:
     return
   import torch
+  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core this process may run on
+  torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
   cfg = build_workload(min(args.inputs, 256), 0)
   total = args.steps + args.warmup
   budget = 150.0
@@ -473,7 +475,7 @@ def run_b200(args):
       line["pathwise"] = pathwise
     if policy_opt is not None:
       line["policy_opt_step"] = policy_opt
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (rank 0), on a bounded sample
       small = {k: (v[:64] if k in ("mu", "cov") else v) for k, v in cfg.items()}
       rate, sample, _ = time_cpu(small, args.cpu_baseline_seconds, reference_form=True)
       rate2, sample2, _ = time_cpu(small, args.cpu_baseline_seconds / 2, reference_form=False)

@@ -9,13 +9,14 @@
 //   k_psi1     one warp per (n, latent): Psi1 contracted with beta -> latent mean and pre-inverted cross term
 //   k_contract persistent CTAs pull (pair, tile, input-chunk) items; a CTA keeps one T x T tile of C_a
 //              (= beta beta^T - B, diagonal pairs) or the beta vectors (off-diagonal pairs) on chip and streams
-//              inputs through it: per entry 1 DADD + D DFMA (bilinear form) + 15 FP64 ops (exp) + 1 DFMA
-//              (contraction).  Diagonal pairs use the symmetry Q_aa = Q_aa^T (upper tiles only, weight 2).
+//              inputs through it: per 8 x 8 block of entries 2 DMMA (exponents), then per entry 8 FP64 ops (table exp)
+//              + 1 DFMA (contraction).  Diagonal pairs use the symmetry Q_aa = Q_aa^T (upper tiles only, weight 2).
 //   k_finalize per input: deterministic fixed-order sum of the tile partials, Sff = f2 - f1 f1^T + diag(var),
 //              optional W mixing (LinearCoregionalization, models.py:279-286), mean constant, jitter.
 //
-// FP64 throughout (the reference is float64; 1e-6 relative parity target).  The tensor cores are not used:
-// the contraction is a Hadamard-weighted reduction of an elementwise exp, not a GEMM.
+// FP64 throughout (the reference is float64; 1e-6 relative parity target).  The only GEMM-shaped piece — the exponent of
+// every entry as an inner product of extended row / column vectors — runs on the FP64 tensor path (mma.sync.m8n8k4.f64, SASS
+// DMMA); the contraction itself is a Hadamard-weighted reduction of an elementwise exp, not a GEMM.
 #include <algorithm>
 
 #include "model.cuh"
