@@ -1,6 +1,7 @@
 // Batched entry points for the small moment-matching rules (one thread per Gaussian state), used by the Python
 // façade when the rules are applied one at a time (moment_matching(x, encoder), moment_matching(x, bijector), objective(x))
 // instead of through the fused rollout.  Same device code as the rollout kernels (mm_small.cuh).
+#include "bvn.cuh"
 #include "mm_small.cuh"
 
 namespace gpp {
@@ -44,6 +45,27 @@ __global__ void k_cost_samples(int N, int De, const double* e, const double* tar
   out[n] = sample_cost(De, le, target, W);
 }
 
+// u = scale (Phi(f) + shift) for an A-dimensional Gaussian f ~ N(mf, Sf): one thread per (state, i, j) entry of the covariance.
+// E[Phi(f_i) Phi(f_j)] = BVN(-9 < w_i < h_i, -9 < w_j < h_j; rho_ij) with h = mf / sqrt(1 + diag Sf), rho_ij = Sf_ij /
+// sqrt((1 + v_i)(1 + v_j)) — including i = j — and the lower limit -9 of upstream moment_matching/bijectors.py:59-63.
+__global__ void k_mm_squash_nd(int N, int A, const double* __restrict__ mf, const double* __restrict__ Sf, double scale, double shift,
+                               double* __restrict__ mu, double* __restrict__ Su, double* __restrict__ gain) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * A * A) return;
+  const int j = idx % A, i = (idx / A) % A, n = idx / (A * A);
+  const double* S = Sf + (size_t)n * A * A;
+  const double vi = S[i * A + i], vj = S[j * A + j];
+  const double qi = rsqrt(vi + 1.0), qj = rsqrt(vj + 1.0);
+  const double hi = mf[(size_t)n * A + i] * qi, hj = mf[(size_t)n * A + j] * qj;
+  const double y1i = bvn_ndtr(hi), y1j = bvn_ndtr(hj);
+  const double y2 = bvn_box(-9.0, hi, -9.0, hj, S[i * A + j] * qi * qj);
+  Su[idx] = (y2 - y1i * y1j) * scale * scale;
+  if (i == j) {
+    mu[(size_t)n * A + i] = (y1i + shift) * scale;
+    gain[(size_t)n * A + i] = qi * 0.39894228040143267794 * exp(-0.5 * hi * hi) * scale;
+  }
+}
+
 __global__ void k_owens_t(int N, const double* h, const double* a, double* out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n < N) out[n] = owens_t<double>(h[n], a[n]);
@@ -75,6 +97,18 @@ int gpp_mm_squash(int N, const double* mf, const double* vf, double scale, doubl
   GPP_REQUIRE(mf && vf && mu && vu && gain, GPP_ERR_NULL, "gpp_mm_squash: null argument");
   if (N <= 0) return GPP_OK;
   gpp::k_mm_squash<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(N, mf, vf, scale, shift, mu, vu, gain);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+int gpp_mm_squash_nd(int N, int A, const double* mf, const double* Sf, double scale, double shift, double* mu, double* Su, double* gain,
+                     void* stream) {
+  GPP_REQUIRE(mf && Sf && mu && Su && gain, GPP_ERR_NULL, "gpp_mm_squash_nd: null argument");
+  GPP_REQUIRE(A >= 1 && A <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE, "gpp_mm_squash_nd: A=%d", A);
+  if (N <= 0) return GPP_OK;
+  const long long total = (long long)N * A * A;
+  gpp::k_mm_squash_nd<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(N, A, mf, Sf, scale, shift, mu, Su, gain);
   gpp::count_launch();
   GPP_CUDA_OK(cudaGetLastError());
   return GPP_OK;

@@ -115,17 +115,25 @@ def _mm_scale(x, bijector: Scale, **kwargs):
 
 @dispatcher.register(GaussianMoments, NormalCDF)
 def _mm_gauss_ndtr(x, _):
-  """y = Phi(x) for a 1-D Gaussian (upstream bijectors.py:37-58, the owens_t branch).  The multi-dimensional branch
-  (Genz BVN, bijectors.py:59-63) is not on the cart-pole path and is not implemented on the device yet."""
-  if x.ndim != 1:
-    raise NotImplementedError("NormalCDF moment matching is implemented for 1-D inputs (scalar actions)")
-  mf, vf = _c(x.mean()[:, 0]), _c(x.covariance()[:, 0, 0])
-  _dev_check(mf, vf)
-  N = mf.shape[0]
-  mu, vu, gain = (torch.empty(N, dtype=F64, device=mf.device) for _ in range(3))
-  _lib.check(_lib.load().gpp_mm_squash(N, _ptr(mf), _ptr(vf), 1.0, 0.0, _ptr(mu), _ptr(vu), _ptr(gain), _stream()))
-  y = GaussianMoments(moments=(mu[:, None], vu[:, None, None]), centered=True)
-  return GaussianMatch(x=x, y=y, cross=(gain[:, None, None], True))
+  """y = Phi(x): the 1-D owens_t branch (upstream bijectors.py:37-58) and the multi-dimensional branch with Genz's bivariate
+  normal probabilities (bijectors.py:59-63, utils/bvn.py:67-232), both on the device."""
+  lib = _lib.load()
+  if x.ndim == 1:
+    mf, vf = _c(x.mean()[:, 0]), _c(x.covariance()[:, 0, 0])
+    _dev_check(mf, vf)
+    N = mf.shape[0]
+    mu, vu, gain = (torch.empty(N, dtype=F64, device=mf.device) for _ in range(3))
+    _lib.check(lib.gpp_mm_squash(N, _ptr(mf), _ptr(vf), 1.0, 0.0, _ptr(mu), _ptr(vu), _ptr(gain), _stream()))
+    y = GaussianMoments(moments=(mu[:, None], vu[:, None, None]), centered=True)
+    return GaussianMatch(x=x, y=y, cross=(gain[:, None, None], True))
+  mf, Sf = _c(x.mean()), _c(x.covariance())
+  _dev_check(mf, Sf)
+  N, A = mf.shape
+  mu = torch.empty(N, A, dtype=F64, device=mf.device)
+  Su = torch.empty(N, A, A, dtype=F64, device=mf.device)
+  gain = torch.empty(N, A, dtype=F64, device=mf.device)
+  _lib.check(lib.gpp_mm_squash_nd(N, A, _ptr(mf), _ptr(Sf), 1.0, 0.0, _ptr(mu), _ptr(Su), _ptr(gain), _stream()))
+  return GaussianMatch(x=x, y=GaussianMoments(moments=(mu, Su), centered=True), cross=(torch.diag_embed(gain), True))
 
 
 # ---- encoder --------------------------------------------------------------------------------------------

@@ -102,6 +102,9 @@ int gpp_mm_gp_predict_bwd(const gpp_gp_model* model, const double* m, const doub
  *                     (upstream moment_matching/components.py:19-57 with maths.py:143-176; De = Dx + num_active)
  *   gpp_mm_squash     u = scale (Phi(f) + shift), f ~ N(mf, vf): mean, variance and gain = Cov(f,f)^-1 Cov(f,u)
  *                     (upstream moment_matching/bijectors.py:21-69 chained with maths.py:47-78; Owen's T on device)
+ *   gpp_mm_squash_nd  the same link on an A-dimensional Gaussian f ~ N(mf [N,A], Sf [N,A,A]): mean mu [N,A], covariance Su [N,A,A],
+ *                     diagonal gain [N,A]; E[Phi(f_i) Phi(f_j)] by Genz's bivariate normal probabilities with upstream's lower
+ *                     limit -9 (upstream moment_matching/bijectors.py:59-63 with utils/bvn.py:67-232)
  *   gpp_cost_gaussian E[-exp(-1/2 (e-t)^T W (e-t))] for e ~ N(me, See)   (upstream components.py:30-37)
  *   gpp_cost_samples  -exp(-1/2 (e-t)^T W (e-t))                           (upstream components.py:39-41)
  *   gpp_owens_t       Owen's T(h, a), 0 < a <= 1 (stands in for tfp.math.owens_t, upstream bijectors.py:15,58) */
@@ -109,6 +112,8 @@ int gpp_mm_encoder(int N, int Dx, int num_active, const int* active_dims /*host*
                    double* me, double* See, double* Cxe, void* stream);
 int gpp_mm_squash(int N, const double* mf, const double* vf, double scale, double shift, double* mu, double* vu, double* gain,
                   void* stream);
+int gpp_mm_squash_nd(int N, int A, const double* mf, const double* Sf, double scale, double shift, double* mu, double* Su, double* gain,
+                     void* stream);
 int gpp_cost_gaussian(int N, int De, const double* me, const double* See, const double* target, const double* W, double* out,
                       void* stream);
 int gpp_cost_samples(int N, int De, const double* e, const double* target, const double* W, double* out, void* stream);

@@ -211,7 +211,7 @@ def multiply(a, b, **kw):
 math = types.SimpleNamespace(
     add=add, subtract=subtract, multiply=multiply, cos=_un(np.cos), sin=_un(np.sin), exp=_un(np.exp), log=_un(np.log),
     square=_un(np.square), sqrt=_un(np.sqrt), rsqrt=_un(lambda x: 1.0 / np.sqrt(x)), reciprocal=_un(lambda x: 1.0 / x),
-    erfc=_un(sps.erfc), erf=_un(sps.erf), l2_normalize=_l2_normalize, abs=_un(np.abs),
+    erfc=_un(sps.erfc), erf=_un(sps.erf), l2_normalize=_l2_normalize, abs=_un(np.abs), asin=_un(np.arcsin),
 )
 
 
@@ -314,6 +314,9 @@ def build_module():
                        einsum=lambda eq, *a, **kw: T(np.einsum(eq, *[np.asarray(v) for v in a])),
                        clip_by_value=lambda x, lo, hi, **kw: T(np.clip(np.asarray(x), lo, hi)),
                        logical_and=np.logical_and, logical_or=np.logical_or, logical_not=np.logical_not, equal=np.equal,
+                       constant=lambda v, dtype=None, **kw: T(np.asarray(v, dtype=np.float64 if dtype is None else dtype)),
+                       sign=_un(np.sign), maximum=lambda a, b, **kw: T(np.maximum(np.asarray(a), np.asarray(b))),
+                       minimum=lambda a, b, **kw: T(np.minimum(np.asarray(a), np.asarray(b))),
                        ).items():
     setattr(tf, name, fn)
   return tf

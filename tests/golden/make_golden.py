@@ -6,6 +6,7 @@ Each fixture stores seeded inputs and the outputs upstream's own functions produ
   mm_models.npz  moment_matching(x, GPR | SVGP single-output | SVGP SeparateIndependent | SVGP LinearCoregionalization),
                  full and diagonal output covariance   (upstream moment_matching/models.py:44-299)
   rules.npz      sincos / sin / cos rules, TrigonometricEncoder rule, Chain[Scale,Shift,NormalCDF] rule, GaussianObjective
+  squash_nd.npz  Chain[Scale,Shift,NormalCDF] on 2-D / 3-D Gaussians: the Genz bivariate-normal branch (bijectors.py:59-63, utils/bvn.py)
   rollout.npz    forward_sde (encoder + squashed RBF policy + SVGP drift) stepped by MomentMatchingEuler with the loss
                  callback of loops/pilco.py:199-205 (5 steps), trajectory of moments and the accumulated loss
 The pathwise sampler is a third-party package absent from the tree: no golden vectors for it (parity unpinned).
@@ -153,6 +154,32 @@ def main(reference_root="/root/reference"):
   Xs = rng.standard_normal((20, 4))
   out.update(obj_W=Wc, obj_target=tgt, obj_expected=A(obj(x4)), obj_X=Xs, obj_samples=A(obj(tf.convert_to_tensor(Xs))))
   np.savez(os.path.join(OUT, "rules.npz"), **out)
+
+  # ---------------------------------------------------------------- multi-dimensional squashing link (Genz BVN branch)
+  # upstream moment_matching/bijectors.py:59-63 with utils/bvn.py:67-232; one state per call so that upstream's batch-wide choice of
+  # the Gauss-Legendre order (bvn.py:221-228) is the per-state choice; cases cover all three orders and the |rho| >= 0.925 branch
+  rng = np.random.default_rng(23)
+  out = {}
+  for tag, Adim, corr in (("a2_weak", 2, 0.1), ("a2_mid", 2, 0.6), ("a2_strong", 2, 0.97), ("a3_mid", 3, 0.5), ("a3_strong", 3, 0.96)):
+    n = 3
+    ms, Ss, means, covs, pres = [], [], [], [], []
+    for i in range(n):
+      m = rng.standard_normal(Adim)
+      sd = np.exp(rng.uniform(np.log(0.5), np.log(3.0), Adim))     # large variances make rho = S_ij / sqrt((1+v_i)(1+v_j)) approach corr
+      C = np.full((Adim, Adim), corr) + (1 - corr) * np.eye(Adim)
+      if i == 1 and Adim == 2:
+        C[0, 1] = C[1, 0] = -corr
+      S = C * sd[:, None] * sd[None, :] * (25.0 if "strong" in tag else 1.0)
+      x = GaussianMoments(moments=(tf.convert_to_tensor(m[None]), tf.convert_to_tensor(S[None])), centered=True)
+      with np.errstate(all="ignore"):
+        mm = moment_matching(x, tfb.Chain(bijectors=[tfb.Scale(scale=tf.cast(3.0, np.float64)), tfb.Shift(shift=tf.cast(-0.5, np.float64)),
+                                                     tfb.NormalCDF()]))
+      ms.append(m); Ss.append(S); means.append(A(mm.y.mean())[0]); covs.append(A(mm.y.covariance())[0])
+      pres.append(A(mm.cross_covariance(preinv=True))[0])
+    out.update({f"{tag}_m": np.stack(ms), f"{tag}_S": np.stack(Ss), f"{tag}_mean": np.stack(means), f"{tag}_cov": np.stack(covs),
+                f"{tag}_cross_pre": np.stack(pres)})
+  out.update(scale=3.0, shift=-0.5)
+  np.savez(os.path.join(OUT, "squash_nd.npz"), **out)
 
   # ---------------------------------------------------------------- rollout (forward_sde + MomentMatchingEuler + loss callback)
   from gpflowpilco_b200 import synthetic

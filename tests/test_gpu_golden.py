@@ -108,3 +108,18 @@ def test_rollout_golden():
   scaled_close(res.traj_m, torch.as_tensor(g["traj_m"]), 1e-8, "trajectory means")
   scaled_close(res.traj_S, torch.as_tensor(g["traj_S"]), 1e-6, "trajectory covariances")
   scaled_close(res.loss, torch.as_tensor(g["loss"]), 1e-7, "loss")
+
+
+def test_squash_nd_golden():
+  """Multi-dimensional squashing link on the device (Genz BVN branch) against upstream's outputs (tests/golden/squash_nd.npz),
+  through the reference-facing Chain[Scale, Shift, NormalCDF] bijector, batched over the states."""
+  from gpflowpilco_b200 import models as M
+  from gpflowpilco_b200.moment_matching import GaussianMoments, moment_matching
+  g = load("squash_nd.npz")
+  link = M.BijectorChain([M.Scale(float(g["scale"])), M.Shift(float(g["shift"])), M.NormalCDF()])
+  for tag in ("a2_weak", "a2_mid", "a2_strong", "a3_mid", "a3_strong"):
+    x = GaussianMoments((_dev(g[f"{tag}_m"]), _dev(g[f"{tag}_S"])), True)
+    mm = moment_matching(x, link)
+    scaled_close(mm.y.mean(), torch.as_tensor(g[f"{tag}_mean"]), 1e-9, f"{tag} mean")
+    scaled_close(mm.y.covariance(), torch.as_tensor(g[f"{tag}_cov"]), 1e-9, f"{tag} cov")
+    scaled_close(mm.cross_covariance(preinv=True), torch.as_tensor(g[f"{tag}_cross_pre"]), 1e-9, f"{tag} cross (pre-inverted)")
