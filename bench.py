@@ -170,6 +170,32 @@ def time_cpu(cfg, seconds: float, reference_form: bool, steps: int = 1):
   return n / best, f"{n} of the {cfg['mu'].shape[0]} inputs of config #2 per step, {form}, torch float64, {torch.get_num_threads()} threads", 1e3 * float(np.mean(times))
 
 
+def time_cpu_rollout(cfg, H):
+  """CPU restatement of config #1 (oracle, upstream triangular-solve form, forward only): seconds per rollout, best of 2."""
+  import torch
+  from oracle import gp_models as gm
+  from oracle import moments as mo
+  from oracle import psi_stats as ps
+  from oracle import rollout as ro
+
+  def model(pp):
+    L = pp["Z"].shape[0]
+    ks = [ps.SEKernel(float(pp["variance"][l]), torch.as_tensor(pp["lengthscales"][l])) for l in range(L)]
+    return gm.SVGPModel(ks, [torch.as_tensor(pp["Z"][l]) for l in range(L)], torch.as_tensor(pp["q_mu"]), torch.as_tensor(pp["q_sqrt"]),
+                        whiten=bool(pp["whiten"]), mean_const=torch.as_tensor(pp["mean_const"]))
+  dyn, pol = model(cfg["dynamics"]), model(cfg["policy"])
+  enc = mo.TrigonometricEncoder(cfg["active_dims"])
+  obj = mo.GaussianObjective(cfg["target"], cfg["W"])
+  best, loss = 1e9, None
+  for _ in range(2):
+    t0 = time.perf_counter()
+    loss = ro.mm_rollout(torch.as_tensor(cfg["m0"]), torch.as_tensor(cfg["S0"]), H, lambda s: gm.mm_svgp(s, dyn),
+                         lambda s: gm.mm_policy(s, pol, cfg["squash_scale"], cfg["squash_shift"]), enc, obj)
+    best = min(best, time.perf_counter() - t0)
+  return {"forward_ms": 1e3 * best, "rollout_steps_per_s_forward": H / best, "loss": float(loss[0]), "kind": "port",
+          "cores": torch.get_num_threads(), "sample": "the whole config #1 rollout, oracle in upstream's triangular-solve form"}
+
+
 ARGS = None
 _emit = print
 
@@ -300,12 +326,38 @@ def policy_opt_section(dev, lib, world):
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   sec = float(t[0]) * 1e-3
+  # BASELINE config #1 (the reference's own CPU-runnable case): one cart-pole rollout, N = 1, H = 30, forward and forward+backward
+  from gpflowpilco_b200.autograd import rollout_mm_loss
+  H1 = cfg["horizon"]
+  Z1 = T(p["Z"]).clone().requires_grad_(True)
+  q1 = T(p["q_mu"][:, 0][None]).clone().requires_grad_(True)
+  e1_ = T(p["lengthscales"]).clone().requires_grad_(True)
+  c1 = {"fwd_ms": [], "fwd_bwd_ms": []}
+  for it in range(4):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    l1 = rollout_mm_loss(handle, Z1, e1_, T(p["variance"]), q1, T(cfg["m0"]), T(cfg["S0"]), H1, cfg["active_dims"], T(cfg["target"]), T(cfg["W"]),
+                         squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+    ev[1].record()
+    l1.sum().backward()
+    ev[2].record()
+    torch.cuda.synchronize()
+    if it:
+      c1["fwd_ms"].append(ev[0].elapsed_time(ev[1]))
+      c1["fwd_bwd_ms"].append(ev[0].elapsed_time(ev[2]))
+    Z1.grad = q1.grad = e1_.grad = None
+  config1 = {"workload": "config#1 cart-pole MM rollout, N=1, H=%d, M=256 dynamics, 30 policy centres" % H1,
+             "forward_ms": float(np.mean(c1["fwd_ms"])), "forward_backward_ms": float(np.mean(c1["fwd_bwd_ms"])),
+             "rollout_steps_per_s_forward": H1 / float(np.mean(c1["fwd_ms"])) * 1e3, "loss": float(l1.detach()[0])}
+  if world == 1 and not args.no_cpu_baseline:
+    config1["cpu"] = time_cpu_rollout(cfg, H1)
   M, L, D = d["Z"].shape[1], 4, 6
   flop_per_step = 4 * (L * (L + 1) // 2) * M * M * (2 * D + 26)      # fwd + bwd counted as 4 x forward
   return {"metric": "mm_policy_opt_rollout_steps_per_s", "value": Rt * H / sec, "unit": "rollout_steps/s (forward+backward)",
           "config": {"workload": "config#5 policy-optimisation step", "restarts_per_gpu": R, "horizon": H, "dynamics_inducing": M,
                      "policy_centres": int(p["Z"].shape[1]), "collective": "all-gather of loss[R] (uneven-safe), gradients stay sharded"},
           "ms_per_opt_step": 1e3 * sec, "gpu_launches_per_opt_step": int(launches), "mean_loss": float(losses.mean()),
+          "config1_rollout": config1,
           "grad_norm": float(grads[0].norm()),
           "roofline": {"bound": "fp64", "achieved": Rt * H * flop_per_step / sec / 1e12 / world, "unit": "TFLOP/s per GPU",
                        "algorithmic": f"{flop_per_step} flop per rollout-step (4 x forward, SURVEY 8d)"}}
