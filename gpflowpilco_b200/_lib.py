@@ -31,6 +31,7 @@ SIGNATURES = {
     "gpp_cost_samples": (c_int, [c_int, c_int, _P, _P, _P, _P, _P]),
     "gpp_owens_t": (c_int, [c_int, _P, _P, _P, _P]),
     "gpp_policy_prepare": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_double, _P, _P, _P]),
+    "gpp_policy_prepare_bwd": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_double, _P, _P, _P, _P]),
     "gpp_rollout_mm_workspace_bytes": (c_size_t, [_P, c_int, c_int]),
     "gpp_rollout_mm_fwd": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_double, c_double,
                                    _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),

@@ -77,6 +77,138 @@ __global__ void __launch_bounds__(128) k_policy_prepare(int Mp, int Dp, const do
   for (int i = tid; i < Mp; i += blockDim.x) beta[(size_t)r * Mp + i] = v[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// adjoint of k_policy_prepare: beta_bar -> (q_mu_bar, Z_bar +=, lengthscales_bar +=) through beta = Kuu^-1 m.
+//   not whitened: w = Kuu^-1 beta_bar,  q_bar = w,  K_bar = -(w beta^T + beta w^T)/2
+//   whitened (beta = L^-T q): w = L^-1 beta_bar, q_bar = w, L_bar = -tril(beta w^T), P = Phi(L^T L_bar) (lower triangle, halved
+//                             diagonal), K_bar = L^-T (P + P^T)/2 L^-1   (reverse-mode Cholesky)
+//   K_ij = var exp(-|z_i - z_j|^2_ell / 2):  Z_bar_id -= sum_j 2 K_bar_ij K_ij (z_id - z_jd) / ell_d^2,
+//                                            ell_bar_d += sum_ij K_bar_ij K_ij (z_id - z_jd)^2 / ell_d^3
+// One CTA per parameter set, three Mp x Mp matrices in shared memory (upstream: TF autodiff through gpflow.covariances.Kuu,
+// tf.linalg.cholesky and the triangular solves of moment_matching/models.py:216-235).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_policy_prepare_bwd(int Mp, int Dp, const double* __restrict__ Z, const double* __restrict__ ell,
+                                                            const double* __restrict__ var, const double* __restrict__ beta,
+                                                            const double* __restrict__ beta_bar, int whiten, double jitter,
+                                                            double* __restrict__ Z_bar, double* __restrict__ ell_bar, double* __restrict__ q_bar) {
+  extern __shared__ double sm[];
+  const int ld = Mp + 1;
+  double* Lm = sm;                 // Cholesky factor of Kuu (lower)
+  double* A = Lm + Mp * ld;        // K_bar
+  double* B = A + Mp * ld;         // scratch
+  double* w = B + Mp * ld;
+  double* b = w + Mp;
+  const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const double* Zr = Z + (size_t)r * Mp * Dp;
+  const double* er = ell + (size_t)r * Dp;
+  for (int idx = tid; idx < Mp * Mp; idx += nt) {
+    const int i = idx / Mp, j = idx % Mp;
+    double acc = 0.0;
+    for (int d = 0; d < Dp; ++d) {
+      const double t = (Zr[i * Dp + d] - Zr[j * Dp + d]) / er[d];
+      acc = fma(t, t, acc);
+    }
+    const double k = var[r] * exp(-0.5 * acc);
+    B[i * ld + j] = k;                                   // kernel matrix without jitter (needed again at the end)
+    Lm[i * ld + j] = k + (i == j ? jitter : 0.0);
+  }
+  for (int i = tid; i < Mp; i += nt) { w[i] = beta_bar[(size_t)r * Mp + i]; b[i] = beta[(size_t)r * Mp + i]; }
+  __syncthreads();
+  for (int j = 0; j < Mp; ++j) {                         // right-looking Cholesky, as in k_policy_prepare
+    if (tid == 0) Lm[j * ld + j] = sqrt(Lm[j * ld + j]);
+    __syncthreads();
+    const double djj = Lm[j * ld + j];
+    for (int i = j + 1 + tid; i < Mp; i += nt) Lm[i * ld + j] /= djj;
+    __syncthreads();
+    for (int idx = tid; idx < (Mp - j - 1) * (Mp - j - 1); idx += nt) {
+      const int a = j + 1 + idx / (Mp - j - 1), c = j + 1 + idx % (Mp - j - 1);
+      if (c <= a) Lm[a * ld + c] -= Lm[a * ld + j] * Lm[c * ld + j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    for (int i = 0; i < Mp; ++i) {                       // w = L^-1 beta_bar
+      double t = w[i];
+      for (int k = 0; k < i; ++k) t -= Lm[i * ld + k] * w[k];
+      w[i] = t / Lm[i * ld + i];
+    }
+    if (!whiten)
+      for (int i = Mp - 1; i >= 0; --i) {                // w = L^-T w = Kuu^-1 beta_bar
+        double t = w[i];
+        for (int k = i + 1; k < Mp; ++k) t -= Lm[k * ld + i] * w[k];
+        w[i] = t / Lm[i * ld + i];
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < Mp; i += nt) q_bar[(size_t)r * Mp + i] = w[i];
+  if (!whiten) {
+    for (int idx = tid; idx < Mp * Mp; idx += nt) {
+      const int i = idx / Mp, j = idx % Mp;
+      A[i * ld + j] = -0.5 * (w[i] * b[j] + b[i] * w[j]);
+    }
+    __syncthreads();
+  } else {
+    // P = Phi(L^T L_bar), L_bar = -tril(beta w^T):  P_ij = -sum_{k >= i} L_ki b_k w_j  (i >= j)
+    double* P = A;
+    for (int idx = tid; idx < Mp * Mp; idx += nt) {
+      const int i = idx / Mp, j = idx % Mp;
+      double v = 0.0;
+      if (i >= j) {
+        for (int k = i; k < Mp; ++k) v = fma(Lm[k * ld + i], b[k], v);
+        v *= -w[j];
+        if (i == j) v *= 0.5;
+      }
+      P[i * ld + j] = v;
+    }
+    __syncthreads();
+    // S = (P + P^T)/2 (symmetric) -> X = L^-T S, one column per thread; then K_bar = L^-T X^T
+    double* X = B;                    // scratch: the kernel matrix kept in B is recomputed after the two solves
+    for (int c = tid; c < Mp; c += nt) {
+      for (int i = Mp - 1; i >= 0; --i) {
+        double t = 0.5 * (P[i * ld + c] + P[c * ld + i]);
+        for (int k = i + 1; k < Mp; ++k) t -= Lm[k * ld + i] * X[k * ld + c];
+        X[i * ld + c] = t / Lm[i * ld + i];
+      }
+    }
+    __syncthreads();
+    for (int c = tid; c < Mp; c += nt) {                 // column c of K_bar = L^-T (row c of X)^T
+      for (int i = Mp - 1; i >= 0; --i) {
+        double t = X[c * ld + i];
+        for (int k = i + 1; k < Mp; ++k) t -= Lm[k * ld + i] * A[k * ld + c];
+        A[i * ld + c] = t / Lm[i * ld + i];
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < Mp * Mp; idx += nt) {      // B <- kernel matrix again
+      const int i = idx / Mp, j = idx % Mp;
+      double acc = 0.0;
+      for (int d = 0; d < Dp; ++d) {
+        const double t = (Zr[i * Dp + d] - Zr[j * Dp + d]) / er[d];
+        acc = fma(t, t, acc);
+      }
+      B[i * ld + j] = var[r] * exp(-0.5 * acc);
+    }
+    __syncthreads();
+  }
+  // G = K_bar o K, then the centre and lengthscale gradients (fixed summation order)
+  for (int idx = tid; idx < Mp * Dp; idx += nt) {
+    const int i = idx / Dp, d = idx % Dp;
+    double acc = 0.0;
+    for (int j = 0; j < Mp; ++j)
+      acc = fma((A[i * ld + j] + A[j * ld + i]) * B[i * ld + j], Zr[i * Dp + d] - Zr[j * Dp + d], acc);
+    Z_bar[(size_t)r * Mp * Dp + idx] -= acc / (er[d] * er[d]);
+  }
+  for (int d = tid; d < Dp; d += nt) {
+    double acc = 0.0;
+    for (int i = 0; i < Mp; ++i)
+      for (int j = 0; j < Mp; ++j) {
+        const double df = Zr[i * Dp + d] - Zr[j * Dp + d];
+        acc = fma(A[i * ld + j] * B[i * ld + j], df * df, acc);
+      }
+    ell_bar[(size_t)r * Dp + d] += acc / (er[d] * er[d] * er[d]);
+  }
+}
+
 constexpr int kCostRing = 32;   // steps whose costs are evaluated by one k_cost_ring launch
 
 __global__ void k_step_post(RolloutMMParams p, int step, double* __restrict__ ring_m, double* __restrict__ ring_S) {
@@ -260,6 +392,22 @@ int gpp_policy_prepare(int R, int Mp, int Dp, const double* Z, const double* len
   GPP_REQUIRE(smem <= 200 * 1024, GPP_ERR_UNSUPPORTED, "gpp_policy_prepare: Mp=%d too large for the in-CTA Cholesky (use gpp_gp_model_create)", Mp);
   if (smem > 48 * 1024) GPP_CUDA_OK(cudaFuncSetAttribute(gpp::k_policy_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gpp::k_policy_prepare<<<R, 128, smem, (cudaStream_t)stream>>>(Mp, Dp, Z, lengthscales, variance, q_mu, whiten, jitter, beta, info);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+int gpp_policy_prepare_bwd(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance, const double* beta,
+                           const double* beta_bar, int whiten, double jitter, double* Z_bar, double* lengthscales_bar, double* q_mu_bar,
+                           void* stream) {
+  GPP_REQUIRE(Z && lengthscales && variance && beta && beta_bar && Z_bar && lengthscales_bar && q_mu_bar, GPP_ERR_NULL,
+              "gpp_policy_prepare_bwd: null argument");
+  GPP_REQUIRE(R >= 1 && Mp >= 1 && Dp >= 1, GPP_ERR_BAD_SHAPE, "gpp_policy_prepare_bwd: bad sizes R=%d Mp=%d Dp=%d", R, Mp, Dp);
+  size_t smem = sizeof(double) * (3 * (size_t)Mp * (Mp + 1) + 2 * Mp);
+  GPP_REQUIRE(smem <= 200 * 1024, GPP_ERR_UNSUPPORTED, "gpp_policy_prepare_bwd: Mp=%d too large for the in-CTA Cholesky adjoint", Mp);
+  if (smem > 48 * 1024) GPP_CUDA_OK(cudaFuncSetAttribute(gpp::k_policy_prepare_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gpp::k_policy_prepare_bwd<<<R, 128, smem, (cudaStream_t)stream>>>(Mp, Dp, Z, lengthscales, variance, beta, beta_bar, whiten, jitter, Z_bar,
+                                                                    lengthscales_bar, q_mu_bar);
   gpp::count_launch();
   GPP_CUDA_OK(cudaGetLastError());
   return GPP_OK;

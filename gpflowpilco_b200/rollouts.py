@@ -47,6 +47,21 @@ class PolicyParams:
     return out
 
 
+def policy_beta_bwd(policy: PolicyParams, beta: torch.Tensor, beta_bar: torch.Tensor, Z_bar: torch.Tensor, lengthscales_bar: torch.Tensor):
+  """Chain beta_bar through beta = Kuu^-1 m on the device: returns q_mu_bar [R,Mp] and ADDS the Kuu contributions into
+  Z_bar / lengthscales_bar (gpp_policy_prepare_bwd)."""
+  beta, beta_bar = _c(beta), _c(beta_bar)
+  _dev_check(beta, beta_bar, Z_bar, lengthscales_bar)
+  if not (Z_bar.is_contiguous() and lengthscales_bar.is_contiguous()):
+    raise ValueError("policy_beta_bwd: gradient buffers must be contiguous (they are updated in place)")
+  R, Mp, Dp = policy.shape
+  q_bar = torch.empty(R, Mp, dtype=F64, device=beta.device)
+  _lib.check(_lib.load().gpp_policy_prepare_bwd(R, Mp, Dp, _ptr(policy.Z), _ptr(policy.lengthscales), _ptr(policy.variance), _ptr(beta),
+                                                _ptr(beta_bar), int(policy.whiten), float(policy.jitter), _ptr(Z_bar), _ptr(lengthscales_bar),
+                                                _ptr(q_bar), _stream()))
+  return q_bar
+
+
 @dataclass
 class MMRolloutResult:
   loss: torch.Tensor                      # [N]

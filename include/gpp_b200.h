@@ -126,6 +126,13 @@ int gpp_owens_t(int N, const double* h, const double* a, double* out, void* stre
 int gpp_policy_prepare(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance,
                        const double* q_mu, int whiten, double jitter, double* beta, int* info, void* stream);
 
+/* Adjoint of gpp_policy_prepare: beta_bar [R,Mp] -> q_mu_bar [R,Mp] (written) and the contributions through Kuu to
+ * Z_bar [R,Mp,Dp] and lengthscales_bar [R,Dp] (ADDED to what the buffers hold, e.g. the fixed-beta gradients returned by
+ * gpp_rollout_mm_bwd / gpp_rollout_pathwise_bwd).  Upstream: TF autodiff through Kuu, its Cholesky and the triangular solves. */
+int gpp_policy_prepare_bwd(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance,
+                           const double* beta, const double* beta_bar, int whiten, double jitter,
+                           double* Z_bar, double* lengthscales_bar, double* q_mu_bar, void* stream);
+
 /* ---- moment-matched rollout ------------------------------------------------------------------------------
  * replaces the closure body of MomentMatchingPILCO._policy_loss_closure (upstream loops/pilco.py:192-220): H steps of
  * forward_sde (dynamics/forward_sde.py:95-137: TrigonometricEncoder -> InverseLinkWrapper(KernelRegressor) with the
