@@ -130,9 +130,9 @@ static Plan make_plan(const gpp_gp_model* m, int N, int full_output_cov) {
   const gpp_gp_model::SlotTable& big = m->tables[1][pl.diag_only];
   pl.tile_idx = ((long long)big.nslots * N >= 8LL * sms && m->M >= 128) ? 1 : 0;
   const gpp_gp_model::SlotTable& tab = m->tables[pl.tile_idx][pl.diag_only];
-  // aim for ~64 items per SM (dynamic scheduling tail <= ~1.5%), but keep chunks >= 8 inputs to amortise the tile load
+  // aim for ~64 items per SM (dynamic scheduling tail <= ~1.5%), but keep chunks >= 4 inputs to amortise the tile load
   long long want_items = 64LL * sms;
-  int nchunks = (int)std::max(1LL, std::min<long long>((want_items + tab.nslots - 1) / tab.nslots, (N + 7) / 8));
+  int nchunks = (int)std::max(1LL, std::min<long long>((want_items + tab.nslots - 1) / tab.nslots, (N + 3) / 4));
   pl.chunk = (N + nchunks - 1) / nchunks;
   pl.nchunks = (N + pl.chunk - 1) / pl.chunk;
   const int D = m->D;
