@@ -15,18 +15,19 @@
 //               ds/dSigma = 1/2 (G1 (sum w e dz dz^T) G1 - (sum w e) G1) - 1/2 (y c^T + c y^T),  c = G1 sum w dz.
 //
 //   k_pack (ordered pairs) + k_psi1 (forward latent means)   -> k_bwd_prepare (un-mix W, Sff = f2 - f1 f1^T chain rule)
-//   -> k_contract_grad (thread per row, CTA per (input, ordered pair, 256-row block)) + k_psi1_bwd (warp per (input, latent))
+//   -> k_contract_grad (DMMA exponents, warp per 8-row strip, CTA per (input, ordered pair, 128-row block)) + k_psi1_bwd (warp per (input, latent))
 //   -> k_bwd_finalize (CTA per input: D x D algebra per unordered pair, fixed-order sums).
 // Gradients w.r.t. the model parameters are not produced: the dynamics model is constant during policy optimisation
 // (upstream differentiates w.r.t. policy.trainable_variables only, gpflow_pilco/utils/optimizers.py:52-56).
 #include <algorithm>
 
+#include "mma_exp.cuh"
 #include "model.cuh"
 #include "predict_kernels.cuh"
 
 namespace gpp {
 
-constexpr int kGradRows = 256, kGradCols = 64;
+constexpr int kGradRows = 128, kGradCols = 128, kGradThreads = 512;
 
 template <int D>
 struct GradStats {
@@ -36,111 +37,210 @@ struct GradStats {
 };
 
 template <int D>
-__global__ void __launch_bounds__(kGradRows) k_contract_grad(const double* __restrict__ Z, const double* __restrict__ beta,
-                                                             const double* __restrict__ C, const double* __restrict__ packs,
-                                                             const double* __restrict__ omega, double* __restrict__ stats,
-                                                             int M, int L, int nrb, int ncb, int cols_per_block) {
+struct GradCfg {
+  static constexpr int KS = ExtLayout<D>::KS;
+  static constexpr int REP = 16;
+  static constexpr int PK = 0;                                   // coefficient pack
+  static constexpr int ROWA = (PairPack<D>::SIZE + 1) & ~1;      // [KS][128][4]
+  static constexpr int COLB = ROWA + KS * kGradRows * 4;         // [2][KS][128][4]
+  static constexpr int COLW = COLB + 2 * KS * kGradCols * 4;     // [2][128] beta_b of the columns (off-diagonal pairs)
+  static constexpr int ETAB = COLW + 2 * kGradCols;              // [256][REP]
+  static constexpr int RED = ETAB + 256 * REP;                   // [16][GradStats::SIZE]
+  static constexpr int TOTAL = RED + (kGradThreads / 32) * GradStats<D>::SIZE;   // doubles
+};
+
+// Row statistics of one ordered pair: CTA = (input n, ordered pair p, block of 128 rows), 16 warps, warp w = 8-row strip w, all
+// columns in blocks of 128.  Same DMMA scheme as the forward kernels (mma_exp.cuh): the exponents of an 8 x 8 block are KS
+// mma.sync.m8n8k4.f64, each lane then holds two entries of ONE row, so the row sums a_i = sum_j A_ij and u_i = sum_j A_ij z2'_j
+// (A = C o Q, or beta_a beta_b^T o Q) accumulate in 1 + D registers per lane and are completed by two shuffles across the 4
+// lanes of a row.
+template <int D>
+__global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double* __restrict__ Z, const double* __restrict__ beta,
+                                                                   const double* __restrict__ C, const double* __restrict__ packs,
+                                                                   const double* __restrict__ omega, double* __restrict__ stats,
+                                                                   int M, int L, int nrb) {
   using PP = PairPack<D>;
   using GS = GradStats<D>;
-  __shared__ double colz[kGradCols][D + 2];
-  __shared__ double pk[PP::SIZE];
-  __shared__ double red[kGradRows / 32][GS::SIZE];
-  __shared__ double etab[64 * GPP_EXP_TAB_REP];
+  using CF = GradCfg<D>;
+  constexpr int KS = CF::KS, FB = KS * kGradCols * 4;
+  extern __shared__ __align__(16) double smem[];
+  double* pk = smem + CF::PK;
+  double* rowA = smem + CF::ROWA;
+  double* colB = smem + CF::COLB;
+  double* colW = smem + CF::COLW;
+  double* etab = smem + CF::ETAB;
+  double* red = smem + CF::RED;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int t = tid; t < 64 * GPP_EXP_TAB_REP; t += kGradRows) etab[t] = kExp2Tab[t / GPP_EXP_TAB_REP];
-  const double* etab_lane = etab + (lane & (GPP_EXP_TAB_REP - 1));
-  // a CTA owns 256 rows x one block of columns; row statistics are linear in the column partial sums, so the column blocks
-  // of a row block are simply added up by k_bwd_finalize (fixed order)
-  const int cb = blockIdx.x % ncb;
-  const int rb = (blockIdx.x / ncb) % nrb;
-  const int p = (blockIdx.x / (ncb * nrb)) % (L * L);
-  const int n = blockIdx.x / (ncb * nrb * L * L);
+  const int rb = blockIdx.x % nrb;
+  const int p = (blockIdx.x / nrb) % (L * L);
+  const int n = blockIdx.x / (nrb * L * L);
   const int a = p / L, b = p % L;
   const bool diag = a == b;
-  double* out = stats + ((((size_t)n * L * L + p) * nrb + rb) * ncb + cb) * GS::SIZE;
+  double* out = stats + (((size_t)n * L * L + p) * nrb + rb) * GS::SIZE;
   // pairs whose output adjoint is zero (e.g. diagonal-only covariance) are skipped; k_bwd_finalize skips them too
   const double wgt = omega[((size_t)n * L + a) * L + b] + omega[((size_t)n * L + b) * L + a];
   if (wgt == 0.0) return;
-  for (int i = tid; i < PP::SIZE; i += kGradRows) pk[i] = packs[((size_t)n * L * L + p) * PP::SIZE + i];
+  for (int t = tid; t < PP::SIZE; t += kGradThreads) pk[t] = packs[((size_t)n * L * L + p) * PP::SIZE + t];
+  for (int t = tid; t < 256 * CF::REP; t += kGradThreads) etab[t] = kExp2Tab256[t / CF::REP];
   __syncthreads();
-  const int i = rb * kGradRows + tid;
-  const bool valid = i < M;
-  double z1[D], g[D];
+  const int i0 = rb * kGradRows;
+  if (tid < kGradRows) {   // A_i of row i0 + tid
+    const int i = i0 + tid;
+    double zc[D], ext[4 * KS];
 #pragma unroll
-  for (int d = 0; d < D; ++d) z1[d] = valid ? Z[((size_t)a * M + i) * D + d] - pk[PP::MU + d] : 0.0;
+    for (int d = 0; d < D; ++d) zc[d] = (i < M ? Z[((size_t)a * M + i) * D + d] : 0.0) - pk[PP::MU + d];
 #pragma unroll
-  for (int e = 0; e < D; ++e) {
-    double t = 0.0;
+    for (int e = 0; e < D; ++e) {
+      double t = 0.0;
 #pragma unroll
-    for (int d = 0; d < D; ++d) t = fma(z1[d], pk[PP::R + d * D + e], t);
-    g[e] = t;
-  }
-  const double ri = pk[PP::C0] + packed_quad<D>(pk + PP::P1, z1);
-  double ai = 0.0, u[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) u[d] = 0.0;
-  const double* Ca = C + (size_t)a * M * M;
-  const int jbeg = cb * cols_per_block, jend = min(M, jbeg + cols_per_block);
-  for (int j0 = jbeg; j0 < jend; j0 += kGradCols) {
-    __syncthreads();
-    if (tid < kGradCols && j0 + tid < jend) {
-      const int j = j0 + tid;
-      double z2[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        z2[d] = Z[((size_t)b * M + j) * D + d] - pk[PP::MU + d];
-        colz[tid][d] = z2[d];
-      }
-      colz[tid][D] = packed_quad<D>(pk + PP::P2, z2);
-      colz[tid][D + 1] = beta[(size_t)b * M + j];
+      for (int d = 0; d < D; ++d) t = fma(zc[d], pk[PP::R + d * D + e], t);
+      ext[e] = t;
     }
-    __syncthreads();
-    const int jn = min(kGradCols, jend - j0);
-    if (valid) {
-      for (int jj = 0; jj < jn; ++jj) {
-        double t = ri + colz[jj][D];
+    ext[D] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
+    ext[D + 1] = 1.0;
 #pragma unroll
-        for (int d = 0; d < D; ++d) t = fma(g[d], colz[jj][d], t);
-        const double w = diag ? Ca[(size_t)(j0 + jj) * M + i] : colz[jj][D + 1];   // C symmetric: C[j][i], coalesced over i
-        double ex[1] = {t};
-        fast_exp_tab_n<1>(ex, etab_lane);
-        const double A = ex[0] * w;
-        ai += A;
+    for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
 #pragma unroll
-        for (int d = 0; d < D; ++d) u[d] = fma(A, colz[jj][d], u[d]);
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rowA[(ks * kGradRows + tid) * 4 + q] = ext[ks * 4 + q];
+  }
+  // column block -> colB[buf] (thread = (column, quarter), as in k_ekzxkxz) and the columns' beta_b -> colW[buf]
+  auto prepare_columns = [&](int cbk, int buf) {
+    const int jl = tid >> 2, q = tid & 3, j = cbk * kGradCols + jl;
+    double zc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) zc[d] = (j < M ? Z[((size_t)b * M + j) * D + d] : 0.0) - pk[PP::MU + d];
+    double part = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if ((d & 3) == q) {
+        double rowsum = 0.0;
+#pragma unroll
+        for (int e = d; e < D; ++e) rowsum = fma(pk[PP::P2 + d * D - d * (d - 1) / 2 + (e - d)], zc[e], rowsum);
+        part = fma(rowsum, zc[d], part);
       }
     }
-  }
-  if (!diag) {
-    const double bi = valid ? beta[(size_t)a * M + i] : 0.0;
-    ai *= bi;
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (q < KS) {
+      double* dst = colB + buf * FB + (q * kGradCols + jl) * 4;
 #pragma unroll
-    for (int d = 0; d < D; ++d) u[d] *= bi;
-  }
-  // row statistics -> fixed-order block reduction (lanes by shuffle, warps through shared memory)
-  auto put = [&](int k, double v) {
-    v = warp_sum(v);
-    if (lane == 0) red[warp][k] = v;
+      for (int c = 0; c < 4; ++c) {
+        const int e = 4 * q + c;                 // B_j = [z2' (D), 1, s_j, 0..]
+        double v = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) v = (e == d) ? zc[d] : v;
+        v = (e == D) ? 1.0 : ((e == D + 1) ? part : v);
+        dst[c] = v;
+      }
+    }
+    if (q == 3) colW[buf * kGradCols + jl] = (j < M) ? beta[(size_t)b * M + j] : 0.0;
   };
-  put(GS::S0, ai);
+  prepare_columns(0, 0);
+  __syncthreads();
+  double af[KS];
 #pragma unroll
-  for (int d = 0; d < D; ++d) put(GS::R1 + d, ai * z1[d]);
-  {
-    int t = 0;
+  for (int ks = 0; ks < KS; ++ks) af[ks] = rowA[(ks * kGradRows + warp * 8) * 4 + lane];
+  const int rloc = warp * 8 + (lane >> 2);
+  const int row = i0 + rloc;
+  const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (CF::REP - 1)));
+  const double* Crow = C + (size_t)a * M * M + (size_t)min(row, M - 1) * M;   // C symmetric: row `row`, contiguous over columns
+  // U = A Z2' accumulates on the tensor path too.  The exponent DMMA's output column n is mapped to the PHYSICAL column
+  // pi(n) = (n >> 1) + 4 (n & 1) of the 8-column group, so that the two entries a lane (r, c) receives are A[r][c] and A[r][4 + c]:
+  // exactly the A-operand fragments of the two k-slices of  U += A Z2'  — no layout conversion.  The B operand is Z2' as stored in
+  // the columns' B vectors (lane (n, k) reads dimension n of column k).  Since B_j[D] = 1, the row sum a_i = sum_j A_ij is column
+  // D of U (D <= 7).
+  constexpr bool ROWSUM_IN_U = D <= 7;
+  double u0 = 0.0, u1 = 0.0, ai = 0.0;       // U[row][2c], U[row][2c+1] (c = lane & 3), scalar row sum when D = 8
+  const int grp = lane & ~3, c4 = lane & 3;
+  const int nn = lane >> 2;
+  const int boff = (((nn >> 1) + 4 * (nn & 1)) * 4) + c4;                // exponent B fragment: ext index k = c4 of column pi(n)
+  const int zoff = ((lane >> 4) * kGradCols) * 4 + ((lane >> 2) & 3);    // U B fragment: dimension n -> k-step n >> 2, element n & 3
+  const int ncb = (M + kGradCols - 1) / kGradCols;
+  for (int cbk = 0; cbk < ncb; ++cbk) {
+    const int buf = cbk & 1;
+    if (cbk + 1 < ncb) prepare_columns(cbk + 1, buf ^ 1);
+    const double* cb = colB + buf * FB;
+    for (int cg = 0; cg < kGradCols / 8; cg += 2) {
+      double t[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int d = 0; d < D; ++d)
+      for (int ks = 0; ks < KS; ++ks) {
+        dmma_m8n8k4(t[0], t[1], af[ks], cb[(ks * kGradCols + cg * 8) * 4 + boff]);
+        dmma_m8n8k4(t[2], t[3], af[ks], cb[(ks * kGradCols + cg * 8 + 8) * 4 + boff]);
+      }
+      exp_tab_contract<4, CF::REP>(t, etab_lane);
 #pragma unroll
-      for (int e = d; e < D; ++e, ++t) put(GS::R2 + t, ai * z1[d] * z1[e]);
+      for (int uu = 0; uu < 2; ++uu) {
+        const int jl = (cg + uu) * 8 + c4, j = cbk * kGradCols + jl;      // this lane's columns: j and j + 4
+        double w0, w1;
+        if (diag) {
+          w0 = j < M ? Crow[j] : 0.0;
+          w1 = j + 4 < M ? Crow[j + 4] : 0.0;
+        } else {
+          w0 = colW[buf * kGradCols + jl];
+          w1 = colW[buf * kGradCols + jl + 4];
+        }
+        const double A0 = t[2 * uu] * w0, A1 = t[2 * uu + 1] * w1;     // A[row][j], A[row][j + 4]
+        if (!ROWSUM_IN_U) ai += A0 + A1;
+        const double* zb = cb + jl * 4 + zoff;                           // Z2'[column 8 (cg+uu) + k][dimension n], k = c4
+        dmma_m8n8k4(u0, u1, A0, zb[0]);
+        dmma_m8n8k4(u0, u1, A1, zb[16]);
+      }
+    }
+    __syncthreads();
   }
-#pragma unroll
-  for (int d = 0; d < D; ++d)
-#pragma unroll
-    for (int e = 0; e < D; ++e) put(GS::X + d * D + e, z1[d] * u[e]);
+  // lane (r, c) holds U[r][2c], U[r][2c+1]: park each row's (a_i, u_i, z1'_i) in shared memory (the column buffers are free now),
+  // then one thread per (statistic, 16-row chunk) forms the row products and sums them in a fixed order
+  constexpr int RW = 2 * D + 2;              // per row: a, u[D], z1'[D], pad
+  double* rows = colB;                       // 128 x RW doubles <= 2 KS 128 4
+  static_assert(kGradRows * RW <= 2 * KS * kGradCols * 4, "row scratch fits in the column buffers");
+  {
+    const bool valid = row < M;
+    const double rs = valid ? (diag ? 1.0 : beta[(size_t)a * M + row]) : 0.0;   // rows beyond M carry weight 0
+    double* rw = rows + rloc * RW;
+    if (2 * c4 < D) rw[1 + 2 * c4] = u0 * rs;
+    if (2 * c4 + 1 < D) rw[1 + 2 * c4 + 1] = u1 * rs;
+    if (ROWSUM_IN_U) {
+      if (2 * c4 == D) rw[0] = u0 * rs;
+      if (2 * c4 + 1 == D) rw[0] = u1 * rs;
+    } else {
+      ai += __shfl_xor_sync(0xffffffffu, ai, 1);
+      ai += __shfl_xor_sync(0xffffffffu, ai, 2);
+      if (c4 == 0) rw[0] = ai * rs;
+    }
+    for (int d = c4; d < D; d += 4) rw[1 + D + d] = valid ? Z[((size_t)a * M + row) * D + d] - pk[PP::MU + d] : 0.0;
+  }
+  __syncthreads();
+  constexpr int CH = kGradThreads / 64;      // 8 chunks of 16 rows when SIZE <= 64; statistics beyond 64 loop
+  for (int k = tid & 63; k < GS::SIZE; k += 64) {
+    const int q = tid >> 6;
+    // statistic k: S0 = sum a;  R1[d] = sum a z[d];  R2[d,e] = sum a z[d] z[e];  X[d,e] = sum z[d] u[e]
+    int kind, d1 = 0, d2 = 0;
+    if (k == GS::S0) kind = 0;
+    else if (k < GS::R2) { kind = 1; d1 = k - GS::R1; }
+    else if (k < GS::X) {
+      kind = 2;
+      int t = k - GS::R2;
+      while (t >= D - d1) { t -= D - d1; ++d1; }
+      d2 = d1 + t;
+    } else { kind = 3; d1 = (k - GS::X) / D; d2 = (k - GS::X) % D; }
+    double acc = 0.0;
+    for (int r = q * (kGradRows / CH); r < (q + 1) * (kGradRows / CH); ++r) {
+      const double* rw = rows + r * RW;
+      const double av = rw[0];
+      if (kind == 0) acc += av;
+      else if (kind == 1) acc = fma(av, rw[1 + D + d1], acc);
+      else if (kind == 2) acc = fma(av * rw[1 + D + d1], rw[1 + D + d2], acc);
+      else acc = fma(rw[1 + D + d1], rw[1 + d2], acc);
+    }
+    red[q * GS::SIZE + k] = acc;
+  }
   __syncthreads();
   if (tid < GS::SIZE) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kGradRows / 32; ++w) s += red[w][tid];
+    for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
     out[tid] = s;
   }
 }
@@ -446,7 +546,7 @@ static size_t bwd_align(size_t x) { return (x + 255) / 256 * 256; }
 
 struct BwdLayout {
   size_t packs, stats, f1lat, crosslat, f1lat_bar, crosslat_bar, omega, gm, gS, total;
-  int nrb, ncb, cols_per_block;
+  int nrb;
 };
 
 static BwdLayout bwd_layout(const gpp_gp_model* m, int N) {
@@ -459,16 +559,10 @@ static BwdLayout bwd_layout(const gpp_gp_model* m, int N) {
 #undef GPP_CASE
   }
   lo.nrb = (m->M + kGradRows - 1) / kGradRows;
-  // split the columns so that the grid has ~16 CTAs per SM (the kernel is a serial loop over its columns per thread)
-  const int max_cb = (m->M + kGradCols - 1) / kGradCols;
-  const long long ctas = (long long)N * L * L * lo.nrb;
-  lo.ncb = (int)std::min<long long>(max_cb, std::max<long long>(1, (16LL * num_sms() + ctas - 1) / ctas));
-  lo.cols_per_block = ((m->M + lo.ncb - 1) / lo.ncb + kGradCols - 1) / kGradCols * kGradCols;
-  lo.ncb = (m->M + lo.cols_per_block - 1) / lo.cols_per_block;
   size_t off = 0;
   auto take = [&](size_t doubles) { size_t o = off; off = bwd_align(off + doubles * sizeof(double)); return o; };
   lo.packs = take(pack_doubles * L * L * N);
-  lo.stats = take(stat_doubles * L * L * lo.nrb * lo.ncb * N);
+  lo.stats = take(stat_doubles * L * L * lo.nrb * N);
   lo.f1lat = take((size_t)L * N);
   lo.crosslat = take((size_t)L * D * N);
   lo.f1lat_bar = take((size_t)L * N);
@@ -503,13 +597,20 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   bp.N = N; bp.L = L; bp.P = m->P; bp.D = D; bp.full_cov = full_output_cov;
   k_bwd_prepare<<<(N + 63) / 64, 64, 0, stream>>>(bp);
   profile_begin(stream);
-  k_contract_grad<D><<<N * L * L * lo.nrb * lo.ncb, kGradRows, 0, stream>>>(m->Z, m->beta, m->C, packs, omega, stats, m->M, L, lo.nrb, lo.ncb,
-                                                                            lo.cols_per_block);
+  {
+    const size_t smem = sizeof(double) * GradCfg<D>::TOTAL;
+    static bool configured = false;
+    if (!configured) {
+      GPP_CUDA_OK(cudaFuncSetAttribute(k_contract_grad<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    k_contract_grad<D><<<N * L * L * lo.nrb, kGradThreads, smem, stream>>>(m->Z, m->beta, m->C, packs, omega, stats, m->M, L, lo.nrb);
+  }
   profile_end(stream);
   k_psi1_bwd<D><<<N, 128, 0, stream>>>(mu, S, N, L, m->M, m->Z, m->ell, m->var, m->beta, f1lat_bar, crosslat_bar, gm, gS);
   BwdFinalizeParams fp;
   fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.omega = omega; fp.gm = gm; fp.gS = gS;
-  fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb * lo.ncb;
+  fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb;
   k_bwd_finalize<D><<<N, 64, 0, stream>>>(fp);
   count_launch(6);
   GPP_CUDA_OK(cudaGetLastError());
