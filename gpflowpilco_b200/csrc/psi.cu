@@ -261,10 +261,10 @@ extern "C" {
 
 int gpp_ekxz(const double* mu, const double* cov, int N, int D, const double* Z, int M, const double* lengthscales,
              double variance, double* out, int* info, void* stream) {
-  GPP_REQUIRE(mu && cov && Z && lengthscales && out, GPP_ERR_NULL, "gpp_ekxz: null argument");
   GPP_REQUIRE(N >= 0 && M >= 0 && D >= 1, GPP_ERR_BAD_SHAPE, "gpp_ekxz: bad sizes N=%d M=%d D=%d", N, M, D);
   GPP_REQUIRE(N <= 65535, GPP_ERR_UNSUPPORTED, "gpp_ekxz: N=%d > 65535 inputs per call", N);
-  if (N == 0 || M == 0) return GPP_OK;
+  if (N == 0 || M == 0) return GPP_OK;      // empty batch: nothing to do (the array pointers may be null)
+  GPP_REQUIRE(mu && cov && Z && lengthscales && out, GPP_ERR_NULL, "gpp_ekxz: null argument");
   switch (D) {
 #define GPP_CASE(d) case d: return gpp::run_ekxz<d>(mu, cov, N, Z, M, lengthscales, variance, out, info, (cudaStream_t)stream);
     GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
@@ -276,12 +276,12 @@ int gpp_ekxz(const double* mu, const double* cov, int N, int D, const double* Z,
 int gpp_ekzxkxz(const double* mu, const double* cov, int N, int D, const double* Z1, int M1, const double* lengthscales1,
                 double variance1, const double* Z2, int M2, const double* lengthscales2, double variance2, double* out,
                 int* info, void* stream) {
-  GPP_REQUIRE(mu && cov && Z1 && lengthscales1 && out, GPP_ERR_NULL, "gpp_ekzxkxz: null argument");
   if (!Z2) { Z2 = Z1; M2 = M1; }
   if (!lengthscales2) { lengthscales2 = lengthscales1; variance2 = variance1; }
   GPP_REQUIRE(N >= 0 && M1 >= 0 && M2 >= 0 && D >= 1, GPP_ERR_BAD_SHAPE, "gpp_ekzxkxz: bad sizes N=%d M1=%d M2=%d D=%d", N, M1, M2, D);
   GPP_REQUIRE(N <= 65535, GPP_ERR_UNSUPPORTED, "gpp_ekzxkxz: N=%d > 65535 inputs per call", N);
-  if (N == 0 || M1 == 0 || M2 == 0) return GPP_OK;
+  if (N == 0 || M1 == 0 || M2 == 0) return GPP_OK;      // empty batch: nothing to do (the array pointers may be null)
+  GPP_REQUIRE(mu && cov && Z1 && lengthscales1 && out, GPP_ERR_NULL, "gpp_ekzxkxz: null argument");
   switch (D) {
 #define GPP_CASE(d) \
   case d: return gpp::run_ekzxkxz<d>(mu, cov, N, Z1, M1, lengthscales1, variance1, Z2, M2, lengthscales2, variance2, out, info, (cudaStream_t)stream);

@@ -32,7 +32,9 @@ def _oracle_predict_grads(params, mu, cov, f1_bar, Sff_bar, cross_bar, full_cov,
 
 @pytest.mark.parametrize("L,M,D,whiten,coreg,full_cov", [(1, 24, 3, True, False, True), (3, 40, 4, False, False, True),
                                                          (4, 64, 6, True, False, True), (2, 300, 5, True, False, True),
-                                                         (3, 33, 4, True, True, True), (3, 40, 4, True, False, False)])
+                                                         (3, 33, 4, True, True, True), (3, 40, 4, True, False, False),
+                                                         (2, 130, 7, True, False, True), (2, 50, 8, False, False, True),
+                                                         (1, 17, 1, True, False, True), (2, 31, 2, True, False, True)])
 def test_mm_gp_predict_bwd_matches_autograd(L, M, D, whiten, coreg, full_cov):
   params = synthetic.random_svgp(L=L, M=M, D=D, seed=5, whiten=whiten, P=(L + 1 if coreg else None))
   gen = torch.Generator().manual_seed(11)

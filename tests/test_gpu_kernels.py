@@ -38,7 +38,8 @@ def test_ekxz(D, M, N):
   scaled_close(out, ref, 1e-12, "ekxz")
 
 
-@pytest.mark.parametrize("D,M1,M2,N", [(1, 5, 4, 2), (2, 32, 32, 1), (4, 16, 33, 3), (6, 70, 64, 2), (8, 129, 100, 2)])
+@pytest.mark.parametrize("D,M1,M2,N", [(1, 5, 4, 2), (2, 32, 32, 1), (4, 16, 33, 3), (6, 70, 64, 2), (8, 129, 100, 2), (3, 140, 257, 2),
+                                       (5, 1, 1, 1), (7, 300, 131, 3)])
 def test_ekzxkxz_generic(D, M1, M2, N):
   from gpflowpilco_b200 import ops
   mu, cov, g = _inputs(N, D, 200 + D)
@@ -104,6 +105,8 @@ def test_model_weights(whiten, unc):
     (3, 130, 3, 2, True, False, None),
     (2, 70, 8, 2, True, True, None),
     (1, 9, 1, 4, False, True, None),
+    (2, 150, 7, 9, True, True, None),      # D = 7: three k-steps of the exponent inner product
+    (2, 40, 2, 3, True, True, None),       # D = 2: a single k-step
 ])
 def test_mm_gp_predict_vs_reference_form(L, M, D, N, whiten, unc, P):
   """CUDA O(M^2) path vs the oracle's triangular-solve form (upstream moment_matching/models.py:200-299)."""
@@ -193,3 +196,17 @@ def test_config2_shape_subsample():
   scaled_close(f1, ref.y.mean(), 1e-7, "f1")
   scaled_close(Sff, ref.y.covariance(), 1e-6, "Sff")
   scaled_close(cross, ref.cross[0], 1e-7, "cross")
+
+
+def test_empty_and_degenerate_batches():
+  """N = 0 / M = 0 are no-ops, a single inducing point and a single input work, odd row lengths take the scalar-store path."""
+  from gpflowpilco_b200 import ops
+  mu, cov, g = _inputs(2, 3, 5)
+  Z = torch.randn(1, 3, dtype=DTYPE, generator=g)
+  k = ps.SEKernel(1.1, log_uniform([3], 0.3, 3.0, g))
+  out = ops.ekzxkxz(_dev(mu), _dev(cov), _dev(Z), _dev(k.lengthscales), float(k.variance))
+  scaled_close(out, ps.eKzxKxz(mu, cov, k, Z), 1e-12, "M = 1")
+  empty = ops.ekzxkxz(_dev(mu[:0]), _dev(cov[:0]), _dev(Z), _dev(k.lengthscales), float(k.variance))
+  assert empty.shape == (0, 1, 1)
+  e1 = ops.ekxz(_dev(mu[:0]), _dev(cov[:0]), _dev(Z), _dev(k.lengthscales), float(k.variance))
+  assert e1.shape == (0, 1)
