@@ -49,6 +49,7 @@ def parse_args():
   ap.add_argument("--pathwise-horizon", type=int, default=100)
   ap.add_argument("--pathwise-bases", type=int, default=4096)
   ap.add_argument("--no-policy-opt", action="store_true")
+  ap.add_argument("--no-psi2", action="store_true")
   ap.add_argument("--restarts", type=int, default=64, help="policy restarts per GPU (config #5: 512 over 8 GPUs)")
   ap.add_argument("--restart-horizon", type=int, default=100)
   return ap.parse_args()
@@ -284,6 +285,39 @@ def pathwise_section(dev, lib, pk, world):
   }
 
 
+def psi2_section(dev, lib, pk):
+  """BASELINE config #3 (kernel-expectation stress): materialised eKzxKxz, M = 2048 inducing points, D = 8, two kernels / two inducing
+  sets, on 256 of the 1024 Gaussian inputs per launch (8.6 GB written; the full config is 4 such launches)."""
+  import torch
+  from gpflowpilco_b200 import ops, synthetic
+  c3 = synthetic.config3_psi2_stress(N=256)
+  T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+  mu3, cov3 = T(c3["mu"]), T(c3["cov"])
+  args = (mu3, cov3, T(c3["Z1"]), T(c3["lengthscales1"]), c3["variance1"], T(c3["Z2"]), T(c3["lengthscales2"]), c3["variance2"])
+  lib.gpp_profile_enable(1)
+  kms, tms = [], []
+  for it in range(4):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = ops.ekzxkxz(*args, check=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = ctypes.c_float()
+    lib.gpp_profile_last_ms(ctypes.byref(ms))
+    if it:
+      kms.append(ms.value)
+      tms.append(e0.elapsed_time(e1))
+    nbytes = out.numel() * 8
+    del out
+  lib.gpp_profile_enable(0)
+  ks, ts = float(np.mean(kms)) * 1e-3, float(np.mean(tms)) * 1e-3
+  return {"metric": "psi2_entries_per_s", "value": nbytes / 8 / ts, "unit": "entries/s (whole call: pack + column vectors + main kernel + allocation)",
+          "config": {"workload": "config#3 Psi2 stress", "inputs_per_launch": 256, "inducing": 2048, "dims": 8},
+          "roofline": {"bound": "hbm", "achieved": nbytes / ks / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s", "frac": nbytes / ks / 1e9 / pk.get("hbm_gbs"),
+                       "traffic": 8.54e9, "traffic_source": "ncu --set full (profiles/r1b_psi2_final_full.txt): dram write 8.54 GB per launch = algorithmic 8.59 GB",
+                       "kernel": "k_ekzxkxz", "kernel_ms": 1e3 * ks, "call_ms": 1e3 * ts, "algorithmic": "8 B written per entry"}}
+
+
 def policy_opt_section(dev, lib, world):
   """BASELINE config #5 (full PILCO policy-optimisation step): R policy restarts per GPU, cart-pole models of config #1
   (M=256 dynamics, 30 policy centres), horizon H, forward + backward of the moment-matched rollout; restarts are sharded over
@@ -500,6 +534,7 @@ def run_b200(args):
   # second half of the metric; every rank takes part (its particles are sharded by global index)
   pathwise = None if args.no_pathwise else pathwise_section(dev, lib, pk, world)
   policy_opt = None if args.no_policy_opt else policy_opt_section(dev, lib, world)
+  psi2 = psi2_section(dev, lib, pk) if (rank == 0 and not args.no_psi2) else None
 
   if rank == 0:
     kern_s = float(np.mean(kern_ms)) * 1e-3
@@ -527,6 +562,8 @@ def run_b200(args):
       line["pathwise"] = pathwise
     if policy_opt is not None:
       line["policy_opt_step"] = policy_opt
+    if psi2 is not None:
+      line["psi2"] = psi2
     if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (rank 0), on a bounded sample
       small = {k: (v[:64] if k in ("mu", "cov") else v) for k, v in cfg.items()}
       rate, sample, _ = time_cpu(small, args.cpu_baseline_seconds, reference_form=True)

@@ -91,9 +91,55 @@ struct Psi2Cfg {
   static constexpr int TOTAL = COLS + 2 * kPsi2Cols;             // doubles
 };
 
+// B vectors (and, in the EXCL layout, s_j) of every column block of every input, written once as images of the main kernel's
+// shared-memory column buffer [KS][128][4] (+ [128]); the 16 row-block CTAs of an input then copy instead of recomputing them.
+// CTA = (column block, input): thread = (column, quarter); the quarters share the quadratic form z2'^T P2 z2' by shuffle.
+template <int D>
+__global__ void __launch_bounds__(kPsi2Threads) k_psi2_cols(const double* __restrict__ packs, const double* __restrict__ Z2, int M2,
+                                                            double* __restrict__ colext) {
+  using PP = PairPack<D>;
+  using CF = Psi2Cfg<D>;
+  constexpr int KS = CF::KS, FB = KS * kPsi2Cols * 4, IMG = FB + kPsi2Cols;
+  constexpr bool EXCL = CF::EXCL;
+  __shared__ double pk[PP::SIZE];
+  const int cbk = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  for (int t = tid; t < PP::SIZE; t += kPsi2Threads) pk[t] = packs[(size_t)n * PP::SIZE + t];
+  __syncthreads();
+  double* img = colext + ((size_t)n * gridDim.x + cbk) * IMG;
+  const int jl = tid >> 2, q = tid & 3, j = cbk * kPsi2Cols + jl;
+  double zc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) zc[d] = (j < M2 ? Z2[(size_t)j * D + d] : 0.0) - pk[PP::MU + d];
+  double part = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    if ((d & 3) == q) {
+      double rowsum = 0.0;
+#pragma unroll
+      for (int e = d; e < D; ++e) rowsum = fma(pk[PP::P2 + d * D - d * (d - 1) / 2 + (e - d)], zc[e], rowsum);
+      part = fma(rowsum, zc[d], part);
+    }
+  }
+  part += __shfl_xor_sync(0xffffffffu, part, 1);
+  part += __shfl_xor_sync(0xffffffffu, part, 2);
+  if (q < KS) {
+    double* dst = img + (q * kPsi2Cols + jl) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int e = 4 * q + c;                 // B_j = [z2' (D), 1, s_j, 0..]
+      double v = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) v = (e == d) ? zc[d] : v;
+      if (!EXCL) v = (e == D) ? 1.0 : ((e == D + 1) ? part : v);
+      dst[c] = v;
+    }
+  }
+  if (q == 3) img[FB + jl] = part;
+}
+
 template <int D>
 __global__ void __launch_bounds__(kPsi2Threads, 2) k_ekzxkxz(const double* __restrict__ packs, const double* __restrict__ Z1, int M1,
-                                                             const double* __restrict__ Z2, int M2, double* __restrict__ out) {
+                                                             const double* __restrict__ colext, int M2, double* __restrict__ out) {
   using PP = PairPack<D>;
   using CF = Psi2Cfg<D>;
   constexpr int KS = CF::KS, FB = KS * kPsi2Cols * 4;
@@ -138,37 +184,13 @@ __global__ void __launch_bounds__(kPsi2Threads, 2) k_ekzxkxz(const double* __res
 #pragma unroll
       for (int q = 0; q < 4; ++q) rowA[(ks * kPsi2Rows + tid) * 4 + q] = ext[ks * 4 + q];
   }
-  // column block `cbk` -> colB[buf]: thread = (column, quarter); the quarters share the quadratic form z2'^T P2 z2' by shuffle
+  // column block `cbk` -> colB[buf] / colS[buf]: copy the image k_psi2_cols prepared (L2-resident: shared by the input's row blocks)
+  const int ncb = (M2 + kPsi2Cols - 1) / kPsi2Cols;
   auto prepare_columns = [&](int cbk, int buf) {
-    const int jl = tid >> 2, q = tid & 3, j = cbk * kPsi2Cols + jl;
-    double zc[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) zc[d] = (j < M2 ? Z2[(size_t)j * D + d] : 0.0) - pk[PP::MU + d];
-    double part = 0.0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      if ((d & 3) == q) {
-        double rowsum = 0.0;
-#pragma unroll
-        for (int e = d; e < D; ++e) rowsum = fma(pk[PP::P2 + d * D - d * (d - 1) / 2 + (e - d)], zc[e], rowsum);
-        part = fma(rowsum, zc[d], part);
-      }
-    }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    if (q < KS) {
-      double* dst = colB + buf * FB + (q * kPsi2Cols + jl) * 4;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int e = 4 * q + c;                 // B_j = [z2' (D), 1, s_j, 0..]
-        double v = 0.0;
-#pragma unroll
-        for (int d = 0; d < D; ++d) v = (e == d) ? zc[d] : v;
-        if (!EXCL) v = (e == D) ? 1.0 : ((e == D + 1) ? part : v);
-        dst[c] = v;
-      }
-    }
-    if (EXCL && q == 3) colS[buf * kPsi2Cols + jl] = part;
+    constexpr int IMG = FB + kPsi2Cols;
+    const double* img = colext + ((size_t)n * ncb + cbk) * IMG;
+    for (int t = tid; t < FB; t += kPsi2Threads) colB[buf * FB + t] = img[t];
+    if (EXCL && tid < kPsi2Cols) colS[buf * kPsi2Cols + tid] = img[FB + tid];
   };
   prepare_columns(0, 0);
   __syncthreads();
@@ -181,7 +203,6 @@ __global__ void __launch_bounds__(kPsi2Threads, 2) k_ekzxkxz(const double* __res
   const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (CF::REP - 1)));
   const bool pair_ok = ((M2 & 1) == 0);          // 16-byte aligned pair stores need an even row length
   double* outrow = out + ((size_t)n * M1 + row) * M2;
-  const int ncb = (M2 + kPsi2Cols - 1) / kPsi2Cols;
   for (int cbk = 0; cbk < ncb; ++cbk) {
     const int buf = cbk & 1;
     if (cbk + 1 < ncb) prepare_columns(cbk + 1, buf ^ 1);      // next block's columns into the other buffer
@@ -240,6 +261,12 @@ static int run_ekzxkxz(const double* mu, const double* cov, int N, const double*
   GPP_CUDA_OK(cudaMallocAsync(&packs, sizeof(double) * PairPack<D>::SIZE * (size_t)N, stream));
   k_pack_single<D><<<(N + 63) / 64, 64, 0, stream>>>(mu, cov, N, ell1, ell2, log(var1 * var2), packs, info);
   dim3 grid((M1 + kPsi2Rows - 1) / kPsi2Rows, N);
+  const int ncb = (M2 + kPsi2Cols - 1) / kPsi2Cols;
+  const size_t img = (size_t)Psi2Cfg<D>::KS * kPsi2Cols * 4 + kPsi2Cols;
+  double* colext = nullptr;
+  GPP_CUDA_OK(cudaMallocAsync(&colext, sizeof(double) * img * ncb * (size_t)N, stream));
+  k_psi2_cols<D><<<dim3(ncb, N), kPsi2Threads, 0, stream>>>(packs, Z2, M2, colext);
+  count_launch();
   const size_t smem = sizeof(double) * Psi2Cfg<D>::TOTAL;
   static bool configured = false;
   if (!configured) {
@@ -247,10 +274,11 @@ static int run_ekzxkxz(const double* mu, const double* cov, int N, const double*
     configured = true;
   }
   profile_begin(stream);
-  k_ekzxkxz<D><<<grid, kPsi2Threads, smem, stream>>>(packs, Z1, M1, Z2, M2, out);
+  k_ekzxkxz<D><<<grid, kPsi2Threads, smem, stream>>>(packs, Z1, M1, colext, M2, out);
   profile_end(stream);
   count_launch(2);
   GPP_CUDA_OK(cudaGetLastError());
+  GPP_CUDA_OK(cudaFreeAsync(colext, stream));
   GPP_CUDA_OK(cudaFreeAsync(packs, stream));
   return GPP_OK;
 }
