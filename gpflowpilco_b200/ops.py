@@ -65,8 +65,8 @@ def ekxz(mu, cov, Z, lengthscales, variance: float, check: bool = True) -> torch
 
 
 def ekzxkxz(mu, cov, Z1, lengthscales1, variance1: float, Z2=None, lengthscales2=None, variance2: Optional[float] = None,
-            check: bool = True) -> torch.Tensor:
-  """Psi2 [N,M1,M2] (replaces upstream utils/kernel_expectation.py:72-187)."""
+            check: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """Psi2 [N,M1,M2] (replaces upstream utils/kernel_expectation.py:72-187).  `out`: optional caller-owned result buffer."""
   mu, cov, Z1, lengthscales1, Z2, lengthscales2 = map(_c, (mu, cov, Z1, lengthscales1, Z2, lengthscales2))
   _dev_check(mu, cov, Z1, lengthscales1, Z2, lengthscales2)
   N, D = mu.shape
@@ -76,7 +76,10 @@ def ekzxkxz(mu, cov, Z1, lengthscales1, variance1: float, Z2=None, lengthscales2
     raise ValueError("ekzxkxz: inconsistent shapes")
   if (lengthscales2 is None) != (variance2 is None):
     raise ValueError("ekzxkxz: lengthscales2 and variance2 go together")
-  out = torch.empty(N, M1, M2, dtype=F64, device=mu.device)
+  if out is None:
+    out = torch.empty(N, M1, M2, dtype=F64, device=mu.device)
+  elif tuple(out.shape) != (N, M1, M2) or out.dtype != F64 or not out.is_cuda or not out.is_contiguous():
+    raise ValueError("ekzxkxz: `out` must be a contiguous CUDA float64 tensor of shape [N,M1,M2]")
   info = _new_info(mu.device)
   _lib.check(_lib.load().gpp_ekzxkxz(_ptr(mu), _ptr(cov), N, D, _ptr(Z1), M1, _ptr(lengthscales1), float(variance1),
                                      _ptr(Z2), M2, _ptr(lengthscales2), float(variance2 or 0.0), _ptr(out), _ptr(info),
