@@ -150,84 +150,11 @@ GPP_HD void fast_exp_n(double (&x)[K]) {
   }
 }
 
-// Table-driven exp: exp(x) = 2^k T[j] P(r),  n = rint(x 64/ln 2), k = n >> 6, j = n & 63, r = x - n ln2/64 (|r| <= 0.0055),
-// P = degree-5 Taylor (truncation 3.5e-17).  10 FP64-pipe ops (vs 16 for fast_exp_n) + one table load.
-// `tab` points at a copy of kExp2Tab replicated GPP_EXP_TAB_REP times with entry j of replica c at tab[j*REP + c]; on the
-// device the kernels keep it in shared memory and pass tab + (lane & 15): the 64-bit loads of a half-warp then hit 16
-// distinct bank pairs whatever the j's are (conflict-free).  Same domain contract as fast_exp_n.
+// Table-driven exp for the Psi2 kernels: exp(x) = 2^k T[j] P(r) with a 2^(j/256) table kept in shared memory, replicated
+// GPP_EXP_TAB_REP times (entry j of replica c at tab[j*REP + c]; a lane uses replica lane & (REP-1), so the 64-bit loads of a
+// half-warp hit 16 distinct bank pairs whatever the j's are).  Device loop: mma_exp.cuh (exp_tab_contract).
 #define GPP_EXP_TAB_REP 16
-GPP_EXP_TABLE kExp2Tab[64] = {
-    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
-    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
-    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
-    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
-    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
-    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
-    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
-    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
-    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
-    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
-    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
-    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
-    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
-    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
-    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
-    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
-GPP_EXP_TABLE kExpT[8] = {
-    0x1.71547652b82fep+6,     // 0  64 log2(e)
-    -0x1.62e42fee00000p-7,    // 1  -ln2/64 hi (fdlibm split / 64: 32 significant bits, n*hi exact for |n| < 2^20)
-    -0x1.a39ef35793c76p-39,   // 2  -ln2/64 lo
-    0.5,                      // 3  1/2!
-    0x1.5555555555555p-3,     // 4  1/3!
-    0x1.5555555555555p-5,     // 5  1/4!
-    0x1.1111111111111p-7,     // 6  1/5!
-    0.0};
-
-// core: p = T_j exp(r) (unscaled, in [0.99, 2.02)), n = rint(x 64 log2 e)
-template <int K>
-GPP_HD void exp_tab_core(const double (&x)[K], const double* tab, double (&p)[K], int32_t (&n)[K]) {
-  const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: the low word of t holds n = rint(x * 64 log2 e)
-  double t[K], r[K], s2[K], tj[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) t[k] = fma_(x[k], kExpT[0], MAGIC);
-#pragma unroll
-  for (int k = 0; k < K; ++k) { n[k] = lo_int(t[k]); tj[k] = tab[(n[k] & 63) * GPP_EXP_TAB_REP]; }
-#pragma unroll
-  for (int k = 0; k < K; ++k) r[k] = t[k] - MAGIC;
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma_(r[k], kExpT[1], x[k]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) r[k] = fma_(r[k], kExpT[2], p[k]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) s2[k] = r[k] * r[k];
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma_(r[k], kExpT[6], kExpT[5]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma_(p[k], r[k], kExpT[4]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma_(p[k], r[k], kExpT[3]);
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma_(p[k], s2[k], r[k]);      // exp(r) - 1
-#pragma unroll
-  for (int k = 0; k < K; ++k) p[k] = fma_(tj[k], p[k], tj[k]);     // T_j exp(r)
-}
-
-// scale by 2^(n >> 6) through the exponent field (no clamp: callers only use the result when x >= -707, for which
-// n >> 6 >= -1020 and p >= 0.99, so the result is a normal number)
-GPP_HD double exp_tab_scale(double p, int32_t n) { return make_double(hi_int(p) + ((n >> 6) << 20), lo_int(p)); }
-// x >= -707 ?  (hi word of -707.0 is 0xC0861800; the unsigned compare also rejects -inf, NaN-with-sign and huge negatives)
-GPP_HD bool exp_tab_in_range(double x) { return !((uint32_t)hi_int(x) > 0xC0861800u); }
-
-template <int K>
-GPP_HD void fast_exp_tab_n(double (&x)[K], const double* tab) {
-  double p[K];
-  int32_t n[K];
-  exp_tab_core<K>(x, tab, p, n);
-#pragma unroll
-  for (int k = 0; k < K; ++k) x[k] = exp_tab_in_range(x[k]) ? exp_tab_scale(p[k], n[k]) : 0.0;   // x < -707: exactly 0
-}
-
-// 256-entry variant for the contraction kernel: n = rint(x 256/ln 2), |r| <= ln2/512 = 0.00135, degree-4 Taylor (truncation
+// n = rint(x 256/ln 2), |r| <= ln2/512 = 0.00135, degree-4 Taylor (truncation
 // 3.8e-17), and a single full-precision ln2/256 constant in the reduction: r = fma(n, -ln2/256, x) is exact up to one rounding,
 // the constant's own error shifts r by |n| 2.4e-19 <= |x| 9e-17, i.e. by less than the rounding error x already carries.
 // 8 FP64-pipe ops.  exp_tab256_core returns p = T_j exp(r) in [1, 2) and n; the caller scales by 2^(n >> 8).

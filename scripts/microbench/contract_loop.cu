@@ -1,4 +1,4 @@
-// Microbenchmark of the k_contract consumer inner loop in isolation (developer tool).
+// Microbenchmark of the SCALAR (pre-DMMA) k_contract consumer inner loop in isolation (developer tool; history of DESIGN.md §4.1).
 // Same data layout as the real kernel; no producers, no barriers: measures the FP64 loop's own ceiling.
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -54,8 +54,6 @@ __global__ void __launch_bounds__(512) k(int reps, int ncons_warps, int first_co
   double* Ct = smem;                 // [T][T]
   double* colbuf = Ct + T * T;       // [T][CS]
   double* rowbuf = colbuf + T * CS;  // [D+2][T]
-  double* etab = rowbuf + (D + 2) * T;  // [64][16] replicated exp2 table
-  for (int i = threadIdx.x; i < 64 * GPP_EXP_TAB_REP; i += blockDim.x) etab[i] = gpp::kExp2Tab[i / GPP_EXP_TAB_REP];
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) Ct[i] = seed[i & 1023] * 1e-3;
   for (int i = threadIdx.x; i < T * CS; i += blockDim.x) colbuf[i] = -0.01 * seed[(i * 7) & 1023];
   for (int i = threadIdx.x; i < (D + 2) * T; i += blockDim.x) rowbuf[i] = 0.02 * seed[(i * 3) & 1023];
@@ -98,8 +96,6 @@ __global__ void __launch_bounds__(512) k(int reps, int ncons_warps, int first_co
 #endif
 #if VARIANT == 0
       gpp::fast_exp_n<RPT>(t);
-#elif VARIANT == 5
-      gpp::fast_exp_tab_n<RPT>(t, etab + (lane & 15));
 #else
       exp_v1<RPT>(t);
 #endif
@@ -129,7 +125,7 @@ int main() {
                    0x1.6c16c1788bd90p-10, 0x1.a01a01a7c41d5p-13, 0x1.a019b90d2ae7ap-16, 0x1.71de0dae63bb3p-19,
                    0x1.289185613a3d6p-22, 0x1.af38a9b0ec855p-26, 0};
   cudaMemcpyToSymbol(kC, hc, sizeof(hc));
-  size_t smem = sizeof(double) * (T * T + T * CS + (D + 2) * T + 64 * GPP_EXP_TAB_REP);
+  size_t smem = sizeof(double) * (T * T + T * CS + (D + 2) * T);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int reps = 400;
   int cfgs[4][2] = {{16, 0}, {12, 4}, {12, 0}, {8, 0}};
