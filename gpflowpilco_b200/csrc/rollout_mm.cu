@@ -9,8 +9,11 @@
 //   k_step_pre   one CTA per rollout: encoder rule, policy moment matching (Psi1/Psi2 of the small policy GP done by the
 //                CTA's threads), squashing link, joint moments of d = (e,u), and Sxd = Cov(x, d) rows (forward_sde.py:105-124)
 //   GP predict   the fused kernels of mm_predict.cu on the N joint states
-//   k_step_post  one thread per rollout: Sxf = Sxd cross, Euler update (solvers.py:128-129), encoder rule on the new state,
-//                expected cost (components.py:30-37), loss accumulation.
+//   k_step_post  one thread per rollout: Sxf = Sxd cross, Euler update (solvers.py:128-129); the new state also goes into a ring
+//   k_cost_ring + k_cost_accumulate   every 32 steps: encoder rule + expected cost (components.py:30-37) of the ring's states in
+//                one parallel launch, added to the loss in step order (the cost does not feed back into the state).
+// gpp_rollout_mm_fwd_save additionally keeps each step's (md, Sd, Sxd, cross) for gpp_rollout_mm_bwd (rollout_mm_bwd.cu);
+// gpp_policy_prepare / gpp_policy_prepare_bwd map the policy's q_mu to beta = Kuu^-1 m and back.
 #include "rollout_mm_common.cuh"
 
 namespace gpp {

@@ -2,9 +2,10 @@
 //
 // Upstream differentiates the closure of MomentMatchingPILCO (gpflow_pilco/loops/pilco.py:192-220) with tape.gradient
 // w.r.t. policy.trainable_variables (gpflow_pilco/utils/optimizers.py:52-56).  Here, for t = H-1 .. 0, from the stored
-// trajectory (m_t, S_t):
+// trajectory (m_t, S_t) and the per-step (md, Sd, Sxd, cross) kept by gpp_rollout_mm_fwd_save — or, without them:
 //   k_step_pre            recompute the pre stage of step t (md, Sd, Sxd)                       [rollout_mm_common.cuh]
 //   mm_predict_enqueue    recompute (f1, Sff, cross) of step t with the fused forward kernels   [mm_predict.cu]
+// then
 //   k_cost_grad_ring      d cost / d(m, S) of 32 consecutive trajectory states at once (dual numbers through the encoder and
 //                         expected-cost rules, one (state, rollout, direction) per thread)
 //   k_bwd_post            adjoint of (m_{t+1}, S_{t+1}) += loss_bar * that gradient, then the adjoint of the Euler moment update
