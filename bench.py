@@ -48,6 +48,8 @@ def parse_args():
   ap.add_argument("--pathwise-particles", type=int, default=148 * 512, help="particles per GPU per launch (one wave of 512-particle CTAs)")
   ap.add_argument("--pathwise-horizon", type=int, default=100)
   ap.add_argument("--pathwise-bases", type=int, default=4096)
+  ap.add_argument("--no-pathwise-full", dest="pathwise_full", action="store_false",
+                  help="skip the run of all 2^20 particles of config #4 (about 4 s on one GPU, split over the ranks)")
   ap.add_argument("--no-policy-opt", action="store_true")
   ap.add_argument("--no-psi2", action="store_true")
   ap.add_argument("--restarts", type=int, default=64, help="policy restarts per GPU (config #5: 512 over 8 GPUs)")
@@ -260,6 +262,37 @@ def pathwise_section(dev, lib, pk, world):
     if it:
       gtimes.append(e0.elapsed_time(e1))
     Zg.grad = eg.grad = qg.grad = None
+  # the whole of config #4: 2^20 particles over all ranks, in chunks of one wave each; path generation (Philox draws + the
+  # update-weight solve, on the device) and the rollout of every chunk are inside the timed region
+  full = None
+  if args.pathwise_full:
+    total_particles = 2 ** 20
+    per_rank = total_particles // world
+    first = rank * per_rank
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    done, acc_loss = 0, torch.zeros((), dtype=torch.float64, device=dev)
+    while done < per_rank:
+      n = min(S, per_rank - done)
+      if n == S:
+        generate_paths(handle, n, F, seed=0, first_particle=first + done, out=paths)
+        pth = paths
+      else:
+        pth = generate_paths(handle, n, F, seed=0, first_particle=first + done)
+      xs = draw_initial_states(T(cfg["m0"][0]), T(cfg["S0"][0]), 0, first + done, n)
+      l_, _, _ = rollout_pathwise(pth, policy, xs, H, cfg["active_dims"], target, W, beta=beta)
+      acc_loss = acc_loss + l_.sum()
+      done += n
+    if world > 1:
+      dist.all_reduce(acc_loss)                       # the one collective of the pathwise closure: the summed cost
+    torch.cuda.synchronize()
+    tf_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
+    full = {"particles": total_particles, "horizon": H, "seconds": float(tf_[0]), "particle_steps_per_s": total_particles * H / float(tf_[0]),
+            "mean_loss": float(acc_loss) / total_particles, "includes": "device-side path generation of every chunk + rollouts + cost all-reduce"}
   t = torch.tensor([float(np.mean(times)), float(np.mean(gtimes))], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -274,6 +307,7 @@ def pathwise_section(dev, lib, pk, world):
                  "latents": L, "inducing": M, "weights": "streamed from HBM (generated on device beforehand, Philox by global particle index)",
                  "note": "1M particles = ceil(2^20 / particles_per_launch) identical launches per GPU"},
       "ms_per_launch": 1e3 * sec, "generation_s": gen_s, "mean_loss": float(loss.mean()), "clocks": pw_clocks,
+      "full_config4": full,
       "with_policy_gradient": {"value": world * psteps / gsec, "unit": "particle_steps/s (gradient-mode forward + reverse sweep)",
                                "ms": 1e3 * gsec, "hbm_frac": bytes_per_pstep * psteps / gsec / 1e9 / pk.get("hbm_gbs")},
       "roofline": {"bound": "hbm", "achieved": bytes_per_pstep * psteps / sec / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
