@@ -117,6 +117,7 @@ __device__ __forceinline__ void sincos_quarter_turns(double (&q)[K], double (&sn
 }
 
 constexpr int kPathP = 512;    // particles per CTA (one consumer thread each) -> 16 consumer warps + 1 producer warp
+constexpr int kPathPGrad = 256;   // gradient mode
 constexpr int kPathTF = 8;    // feature rows per pipeline stage
 
 struct PathwiseParams {
@@ -152,7 +153,7 @@ struct PathwiseCfg {
 };
 
 template <int D, int P, int TF, int NS, bool GRAD>
-__global__ void __launch_bounds__(P + 32, GRAD ? 2 : 1) k_pathwise_rollout(PathwiseParams p) {
+__global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p) {
   using CF = PathwiseCfg<D, P, TF, NS>;
   constexpr int BS = CF::BS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(P + 32, GRAD ? 2 : 1) k_pathwise_rollout(Pathw
   if (warp == P / 32) {
     // ------------------------------------------------------------------ producer warp (one elected lane)
     if (lane == 0) {
-      const unsigned bytes = (unsigned)(sizeof(double) * CF::STAGE_DOUBLES);
+      const int pcount = min(P, p.ldS - s0);        // particles this CTA really has columns for (last CTA of a launch)
+      const unsigned bytes = (unsigned)(sizeof(double) * (TF * BS + TF * pcount));
       long it = 0;
       for (int t = 0; t < p.H; ++t)
         for (int l = 0; l < p.L; ++l)
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(P + 32, GRAD ? 2 : 1) k_pathwise_rollout(Pathw
             bulk_g2s(sb, bsrc, (unsigned)(sizeof(double) * TF * BS), &full[st]);
 #pragma unroll 1
             for (int f = 0; f < TF; ++f)
-              bulk_g2s(sb + TF * BS + f * P, wsrc + (size_t)f * p.ldS, (unsigned)(sizeof(double) * P), &full[st]);
+              bulk_g2s(sb + TF * BS + f * P, wsrc + (size_t)f * p.ldS, (unsigned)(sizeof(double) * pcount), &full[st]);
           }
     }
     return;
@@ -398,8 +400,9 @@ __global__ void k_pack_basis(int L, int F, int M, int Mpad, int D, int BS, const
 
 template <int D, bool GRAD>
 static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
-  // gradient mode carries 2 D more accumulators per thread: half the particles per CTA (two CTAs per SM) keeps them in registers
-  constexpr int P = GRAD ? kPathP / 2 : kPathP, TF = kPathTF, NS = 4;
+  // gradient mode carries 2 D more accumulators per thread: 256-particle CTAs (8 consumer warps + the producer, one CTA per SM)
+  // keep them in registers without spills (168 registers); measured faster than 2 spilling CTAs per SM or 480-particle CTAs
+  constexpr int P = GRAD ? kPathPGrad : kPathP, TF = kPathTF, NS = 4;
   using CF = PathwiseCfg<D, P, TF, NS>;
   static bool configured = false;
   if (!configured) {
