@@ -123,13 +123,13 @@ class GPModelHandle:
     return self._params
 
   def __del__(self):
-    h = getattr(self, "_h", None)
-    if h is not None and h.value:
-      try:
+    try:                                  # at interpreter shutdown module globals (ctypes, _lib) may already be gone
+      h = getattr(self, "_h", None)
+      if h is not None and h.value:
         _lib.load().gpp_gp_model_destroy(h)
-      except Exception:
-        pass
-      self._h = ctypes.c_void_p()
+        self._h = None
+    except Exception:
+      pass
 
   def weights(self):
     """(beta [L,M], C [L,M,M]) copies, for tests."""

@@ -101,3 +101,27 @@ def test_batched_rollout_random_models(shared_policy):
   scaled_close(res.loss, torch.cat(losses), 1e-7, "loss")
   scaled_close(res.m_final, torch.cat([f[0] for f in finals]), 1e-7, "final means")
   scaled_close(res.S_final, torch.cat([f[1] for f in finals]), 1e-6, "final covariances")
+
+
+def test_rollout_is_capturable_in_a_cuda_graph():
+  """The C entry points only enqueue kernels / memsets on the caller's stream (no allocation, no synchronisation), so a whole
+  H-step rollout can be captured once and replayed: the replay reproduces the eager result bit for bit."""
+  from gpflowpilco_b200.rollouts import rollout_mm
+  cfg = synthetic.config1_cartpole(M=48, Mp=10)
+  h = cuda_handle(cfg["dynamics"])
+  pol = _policy_params(cfg["policy"], cfg["squash_scale"], cfg["squash_shift"])
+  beta = pol.beta()
+  m0, S0, tgt, W = _dev(cfg["m0"]), _dev(cfg["S0"]), _dev(cfg["target"]), _dev(cfg["W"])
+  run = lambda: rollout_mm(h, pol, m0, S0, 8, cfg["active_dims"], tgt, W, beta=beta, check=False).loss
+  eager = run().clone()
+  side = torch.cuda.Stream()
+  with torch.cuda.stream(side):
+    run()
+  torch.cuda.synchronize()
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(graph):
+    out = run()
+  out.zero_()
+  graph.replay()
+  torch.cuda.synchronize()
+  assert torch.equal(out, eager)
