@@ -46,6 +46,8 @@ def main():
   loop = MomentMatchingPILCO(spec, GaussianObjective(T(cfg["target"]), T(cfg["W"])), drift, policy, TrigonometricEncoder(cfg["active_dims"]))
   closure = loop.policy_loss_closure()
   opt = GradientDescent(step_limit=args.steps, optimizer_factory=lambda vs: torch.optim.Adam(vs, lr=1e-2), transform=clip_by_global_norm(1.0))
+  closure().sum().backward()                     # warm-up: CUDA context, lazy module load, handle build
+  pol.q_mu.grad = Zvar.grad = None
   t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
   t0.record()
   hist = opt.minimize(closure, [pol.q_mu, Zvar])
