@@ -8,18 +8,19 @@
 //               sum A e e^T = A1 R2_ab A1 + A2 R2_ba A2 + A1 X_ab A2 + (A1 X_ab A2)^T,
 //               with the ROW statistics of the ordered pair (a,b):  a_i = sum_j A_ij, u_i = sum_j A_ij z2'_j,
 //               S0 = sum_i a_i, r1 = sum_i a_i z1'_i, R2 = sum_i a_i z1'_i z1'_i^T, X = sum_i z1'_i u_i^T.
-//               Column statistics of (a,b) are the row statistics of (b,a) (Q_ba = Q_ab^T), so all L x L ordered pairs are
-//               contracted and no cross-thread column reduction is needed.
+//               Column statistics of (a,b) are the row statistics of (b,a) (Q_ba = Q_ab^T); of those only r1_ba = sum_i u_i and
+//               R2_ba = sum_j (sum_i A_ij) z2'_j z2'_j^T are needed beyond the row pass, so each unordered pair is contracted once.
 //   Psi1 part   s = f1bar_l f1_l + crossbar_l . cross_l = sum_m w_m (f1bar + y . dz_m),  w = beta psi1, y = G1 crossbar,
 //               ds/dmu = G1 (sum w e dz) - (sum w) y,
 //               ds/dSigma = 1/2 (G1 (sum w e dz dz^T) G1 - (sum w e) G1) - 1/2 (y c^T + c y^T),  c = G1 sum w dz.
 //
 //   k_pack (ordered pairs) + k_psi1 (forward latent means)   -> k_bwd_prepare (un-mix W, Sff = f2 - f1 f1^T chain rule)
-//   -> k_contract_grad (DMMA exponents, warp per 8-row strip, CTA per (input, ordered pair, 128-row block)) + k_psi1_bwd (warp per (input, latent))
+//   -> k_contract_grad (DMMA exponents, warp per 8-row strip, CTA per (input, unordered pair, 128-row block)) + k_psi1_bwd (warp per (input, latent))
 //   -> k_bwd_finalize (CTA per input: D x D algebra per unordered pair, fixed-order sums).
 // Gradients w.r.t. the model parameters are not produced: the dynamics model is constant during policy optimisation
 // (upstream differentiates w.r.t. policy.trainable_variables only, gpflow_pilco/utils/optimizers.py:52-56).
 #include <algorithm>
+#include <type_traits>
 
 #include "mma_exp.cuh"
 #include "model.cuh"
@@ -39,21 +40,27 @@ struct GradStats {
 template <int D>
 struct GradCfg {
   static constexpr int KS = ExtLayout<D>::KS;
-  static constexpr int REP = 16;
+  static constexpr int REP = KS <= 2 ? 16 : 8;
+  static constexpr int NW = kGradThreads / 32;
   static constexpr int PK = 0;                                   // coefficient pack
   static constexpr int ROWA = (PairPack<D>::SIZE + 1) & ~1;      // [KS][128][4]
   static constexpr int COLB = ROWA + KS * kGradRows * 4;         // [2][KS][128][4]
   static constexpr int COLW = COLB + 2 * KS * kGradCols * 4;     // [2][128] beta_b of the columns (off-diagonal pairs)
   static constexpr int ETAB = COLW + 2 * kGradCols;              // [256][REP]
-  static constexpr int RED = ETAB + 256 * REP;                   // [16][GradStats::SIZE]
-  static constexpr int TOTAL = RED + (kGradThreads / 32) * GradStats<D>::SIZE;   // doubles
+  static constexpr int RED = ETAB + 256 * REP;                   // [8][GradStats::SIZE]
+  static constexpr int CSUM = RED + (kGradThreads / 64) * GradStats<D>::SIZE;   // [2][16][128] per-warp column sums (off-diagonal pairs)
+  static constexpr int COLA = CSUM + 2 * NW * kGradCols;         // [ncb * 128] column sums a'_j of this row block
+  static constexpr int FIXED = COLA;                             // + ncb * 128 doubles at launch
 };
 
-// Row statistics of one ordered pair: CTA = (input n, ordered pair p, block of 128 rows), 16 warps, warp w = 8-row strip w, all
-// columns in blocks of 128.  Same DMMA scheme as the forward kernels (mma_exp.cuh): the exponents of an 8 x 8 block are KS
-// mma.sync.m8n8k4.f64, each lane then holds two entries of ONE row, so the row sums a_i = sum_j A_ij and u_i = sum_j A_ij z2'_j
-// (A = C o Q, or beta_a beta_b^T o Q) accumulate in 1 + D registers per lane and are completed by two shuffles across the 4
-// lanes of a row.
+// Statistics of one UNORDERED pair {a <= b}: CTA = (input n, pair, block of 128 rows of latent a), 16 warps, warp w = 8-row strip w,
+// all columns (rows of latent b) in blocks of 128.  Same DMMA scheme as the forward kernels (mma_exp.cuh): the exponents of an
+// 8 x 8 block are KS mma.sync.m8n8k4.f64, each lane then holds entries of ONE row, and the row sums a_i = sum_j A_ij,
+// u_i = sum_j A_ij z2'_j (A = C o Q, or beta_a beta_b^T o Q) accumulate on the tensor path as well.
+// For a < b the statistics of the ordered pair (b, a) follow from the same entries (Q_ba = Q_ab^T, same centre mu):
+//   S0_ba = S0_ab,  X_ba = X_ab^T,  r1_ba = sum_i u_i,  R2_ba = sum_j a'_j z2'_j z2'_j^T  with the COLUMN sums a'_j = sum_i A_ij,
+// so only a'_j is extra: a 3-level transpose-reduce over the 8 row lanes (8 shuffles per 16 columns), one store per warp and
+// column into shared memory, summed over the 16 strips in a fixed order.  The exponentials of (b, a) are never evaluated.
 template <int D>
 __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double* __restrict__ Z, const double* __restrict__ beta,
                                                                    const double* __restrict__ C, const double* __restrict__ packs,
@@ -70,12 +77,18 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
   double* colW = smem + CF::COLW;
   double* etab = smem + CF::ETAB;
   double* red = smem + CF::RED;
+  double* csum = smem + CF::CSUM;
+  double* colA = smem + CF::COLA;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int npairs = L * (L + 1) / 2;
   const int rb = blockIdx.x % nrb;
-  const int p = (blockIdx.x / nrb) % (L * L);
-  const int n = blockIdx.x / (nrb * L * L);
-  const int a = p / L, b = p % L;
+  const int pr = (blockIdx.x / nrb) % npairs;
+  const int n = blockIdx.x / (nrb * npairs);
+  int a = 0, b = pr;                           // unordered pair index -> (a <= b), rows of the upper triangle in order
+  while (b >= L - a) { b -= L - a; ++a; }
+  b += a;
   const bool diag = a == b;
+  const int p = a * L + b;
   double* out = stats + (((size_t)n * L * L + p) * nrb + rb) * GS::SIZE;
   // pairs whose output adjoint is zero (e.g. diagonal-only covariance) are skipped; k_bwd_finalize skips them too
   const double wgt = omega[((size_t)n * L + a) * L + b] + omega[((size_t)n * L + b) * L + a];
@@ -137,6 +150,16 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
     }
     if (q == 3) colW[buf * kGradCols + jl] = (j < M) ? beta[(size_t)b * M + j] : 0.0;
   };
+  // off-diagonal pairs: a'_j of column block cbk = sum over the 16 strips, in strip order
+  auto fold_column_sums = [&](int cbk) {
+    if (tid < kGradCols) {
+      const double* src = csum + (cbk & 1) * CF::NW * kGradCols + tid;
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < CF::NW; ++w) s += src[w * kGradCols];
+      colA[cbk * kGradCols + tid] = s;
+    }
+  };
   prepare_columns(0, 0);
   __syncthreads();
   double af[KS];
@@ -146,6 +169,8 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
   const int row = i0 + rloc;
   const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (CF::REP - 1)));
   const double* Crow = C + (size_t)a * M * M + (size_t)min(row, M - 1) * M;   // C symmetric: row `row`, contiguous over columns
+  // row weight: off-diagonal pairs apply beta_a[row] inside the loop (the column sums need it); diagonal pairs only mask rows >= M
+  const double rs = row < M ? (diag ? 1.0 : beta[(size_t)a * M + row]) : 0.0;
   // U = A Z2' accumulates on the tensor path too.  The exponent DMMA's output column n is mapped to the PHYSICAL column
   // pi(n) = (n >> 1) + 4 (n & 1) of the 8-column group, so that the two entries a lane (r, c) receives are A[r][c] and A[r][4 + c]:
   // exactly the A-operand fragments of the two k-slices of  U += A Z2'  — no layout conversion.  The B operand is Z2' as stored in
@@ -153,70 +178,91 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
   // D of U (D <= 7).
   constexpr bool ROWSUM_IN_U = D <= 7;
   double u0 = 0.0, u1 = 0.0, ai = 0.0;       // U[row][2c], U[row][2c+1] (c = lane & 3), scalar row sum when D = 8
-  const int grp = lane & ~3, c4 = lane & 3;
+  const int c4 = lane & 3;
   const int nn = lane >> 2;
   const int boff = (((nn >> 1) + 4 * (nn & 1)) * 4) + c4;                // exponent B fragment: ext index k = c4 of column pi(n)
   const int zoff = ((lane >> 4) * kGradCols) * 4 + ((lane >> 2) & 3);    // U B fragment: dimension n -> k-step n >> 2, element n & 3
   const int ncb = (M + kGradCols - 1) / kGradCols;
-  for (int cbk = 0; cbk < ncb; ++cbk) {
-    const int buf = cbk & 1;
-    if (cbk + 1 < ncb) prepare_columns(cbk + 1, buf ^ 1);
-    const double* cb = colB + buf * FB;
-    for (int cg = 0; cg < kGradCols / 8; cg += 2) {
-      double t[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool b2 = lane & 4, b3 = lane & 8;
+  const int csoff = warp * kGradCols + (b2 ? 8 : 0) + (b3 ? 4 : 0) + c4;    // this lane's column after the transpose-reduce
+  auto main_loop = [&](auto diag_tag) {
+    constexpr bool DIAG = decltype(diag_tag)::value;
+    for (int cbk = 0; cbk < ncb; ++cbk) {
+      const int buf = cbk & 1;
+      if (cbk + 1 < ncb) prepare_columns(cbk + 1, buf ^ 1);
+      if (!DIAG && cbk > 0) fold_column_sums(cbk - 1);
+      const double* cb = colB + buf * FB;
+      double* cs = csum + buf * CF::NW * kGradCols + csoff;
+#pragma unroll 1
+      for (int cg = 0; cg < kGradCols / 8; cg += 2) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        dmma_m8n8k4(t[0], t[1], af[ks], cb[(ks * kGradCols + cg * 8) * 4 + boff]);
-        dmma_m8n8k4(t[2], t[3], af[ks], cb[(ks * kGradCols + cg * 8 + 8) * 4 + boff]);
-      }
-      exp_tab_contract<4, CF::REP>(t, etab_lane);
-#pragma unroll
-      for (int uu = 0; uu < 2; ++uu) {
-        const int jl = (cg + uu) * 8 + c4, j = cbk * kGradCols + jl;      // this lane's columns: j and j + 4
-        double w0, w1;
-        if (diag) {
-          w0 = j < M ? Crow[j] : 0.0;
-          w1 = j + 4 < M ? Crow[j + 4] : 0.0;
-        } else {
-          w0 = colW[buf * kGradCols + jl];
-          w1 = colW[buf * kGradCols + jl + 4];
+        for (int ks = 0; ks < KS; ++ks) {
+          dmma_m8n8k4(t[0], t[1], af[ks], cb[(ks * kGradCols + cg * 8) * 4 + boff]);
+          dmma_m8n8k4(t[2], t[3], af[ks], cb[(ks * kGradCols + cg * 8 + 8) * 4 + boff]);
         }
-        const double A0 = t[2 * uu] * w0, A1 = t[2 * uu + 1] * w1;     // A[row][j], A[row][j + 4]
-        if (!ROWSUM_IN_U) ai += A0 + A1;
-        const double* zb = cb + jl * 4 + zoff;                           // Z2'[column 8 (cg+uu) + k][dimension n], k = c4
-        dmma_m8n8k4(u0, u1, A0, zb[0]);
-        dmma_m8n8k4(u0, u1, A1, zb[16]);
+        exp_tab_contract<4, CF::REP>(t, etab_lane);
+        double A[4];
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+          const int jl = (cg + uu) * 8 + c4, j = cbk * kGradCols + jl;      // this lane's columns: j and j + 4
+          double w0, w1;
+          if (DIAG) {
+            w0 = j < M ? Crow[j] : 0.0;
+            w1 = j + 4 < M ? Crow[j + 4] : 0.0;
+          } else {
+            w0 = colW[buf * kGradCols + jl] * rs;
+            w1 = colW[buf * kGradCols + jl + 4] * rs;
+          }
+          A[2 * uu] = t[2 * uu] * w0;                                      // A[row][j], A[row][j + 4]
+          A[2 * uu + 1] = t[2 * uu + 1] * w1;
+          if (!ROWSUM_IN_U) ai += A[2 * uu] + A[2 * uu + 1];
+          const double* zb = cb + jl * 4 + zoff;                           // Z2'[column 8 (cg+uu) + k][dimension n], k = c4
+          dmma_m8n8k4(u0, u1, A[2 * uu], zb[0]);
+          dmma_m8n8k4(u0, u1, A[2 * uu + 1], zb[16]);
+        }
+        if (!DIAG) {
+          // column sums over the strip's 8 rows (lane bits 2..4): halve the live values at each level
+          const double k0 = b2 ? A[2] : A[0], k1 = b2 ? A[3] : A[1];
+          const double s0 = b2 ? A[0] : A[2], s1 = b2 ? A[1] : A[3];
+          const double h0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);     // block uu = b2, columns c4 and c4 + 4
+          const double h1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 4);
+          double v = (b3 ? h1 : h0) + __shfl_xor_sync(0xffffffffu, b3 ? h0 : h1, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (lane < 16) cs[cg * 8] = v;                                   // column 8 (cg + b2) + 4 b3 + c4
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
-  }
+  };
+  if (diag) main_loop(std::true_type{});
+  else main_loop(std::false_type{});
   // lane (r, c) holds U[r][2c], U[r][2c+1]: park each row's (a_i, u_i, z1'_i) in shared memory (the column buffers are free now),
   // then one thread per (statistic, 16-row chunk) forms the row products and sums them in a fixed order
   constexpr int RW = 2 * D + 2;              // per row: a, u[D], z1'[D], pad
   double* rows = colB;                       // 128 x RW doubles <= 2 KS 128 4
   static_assert(kGradRows * RW <= 2 * KS * kGradCols * 4, "row scratch fits in the column buffers");
   {
-    const bool valid = row < M;
-    const double rs = valid ? (diag ? 1.0 : beta[(size_t)a * M + row]) : 0.0;   // rows beyond M carry weight 0
+    const double re = diag ? rs : 1.0;       // off-diagonal rows are already weighted
     double* rw = rows + rloc * RW;
-    if (2 * c4 < D) rw[1 + 2 * c4] = u0 * rs;
-    if (2 * c4 + 1 < D) rw[1 + 2 * c4 + 1] = u1 * rs;
+    if (2 * c4 < D) rw[1 + 2 * c4] = u0 * re;
+    if (2 * c4 + 1 < D) rw[1 + 2 * c4 + 1] = u1 * re;
     if (ROWSUM_IN_U) {
-      if (2 * c4 == D) rw[0] = u0 * rs;
-      if (2 * c4 + 1 == D) rw[0] = u1 * rs;
+      if (2 * c4 == D) rw[0] = u0 * re;
+      if (2 * c4 + 1 == D) rw[0] = u1 * re;
     } else {
       ai += __shfl_xor_sync(0xffffffffu, ai, 1);
       ai += __shfl_xor_sync(0xffffffffu, ai, 2);
-      if (c4 == 0) rw[0] = ai * rs;
+      if (c4 == 0) rw[0] = ai * re;
     }
-    for (int d = c4; d < D; d += 4) rw[1 + D + d] = valid ? Z[((size_t)a * M + row) * D + d] - pk[PP::MU + d] : 0.0;
+    for (int d = c4; d < D; d += 4) rw[1 + D + d] = row < M ? Z[((size_t)a * M + row) * D + d] - pk[PP::MU + d] : 0.0;
   }
+  if (!diag) fold_column_sums(ncb - 1);
   __syncthreads();
-  constexpr int CH = kGradThreads / 64;      // 8 chunks of 16 rows when SIZE <= 64; statistics beyond 64 loop
-  for (int k = tid & 63; k < GS::SIZE; k += 64) {
-    const int q = tid >> 6;
-    // statistic k: S0 = sum a;  R1[d] = sum a z[d];  R2[d,e] = sum a z[d] z[e];  X[d,e] = sum z[d] u[e]
-    int kind, d1 = 0, d2 = 0;
+  constexpr int CH = kGradThreads / 64;      // 8 chunks of 16 entries; statistics beyond 64 loop
+  // statistic k of a scratch block: S0 = sum a;  R1[d] = sum a z[d];  R2[d,e] = sum a z[d] z[e];  X[d,e] = sum z[d] u[e]
+  auto decode = [](int k, int& kind, int& d1, int& d2) {
+    d1 = 0; d2 = 0;
     if (k == GS::S0) kind = 0;
     else if (k < GS::R2) { kind = 1; d1 = k - GS::R1; }
     else if (k < GS::X) {
@@ -225,16 +271,24 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
       while (t >= D - d1) { t -= D - d1; ++d1; }
       d2 = d1 + t;
     } else { kind = 3; d1 = (k - GS::X) / D; d2 = (k - GS::X) % D; }
+  };
+  auto chunk_sum = [&](const double* scratch, int q, int kind, int d1, int d2) {
     double acc = 0.0;
     for (int r = q * (kGradRows / CH); r < (q + 1) * (kGradRows / CH); ++r) {
-      const double* rw = rows + r * RW;
+      const double* rw = scratch + r * RW;
       const double av = rw[0];
       if (kind == 0) acc += av;
       else if (kind == 1) acc = fma(av, rw[1 + D + d1], acc);
       else if (kind == 2) acc = fma(av * rw[1 + D + d1], rw[1 + D + d2], acc);
-      else acc = fma(rw[1 + D + d1], rw[1 + d2], acc);
+      else if (kind == 3) acc = fma(rw[1 + D + d1], rw[1 + d2], acc);
+      else acc += rw[1 + d1];                // kind 4: sum of u[d1]
     }
-    red[q * GS::SIZE + k] = acc;
+    return acc;
+  };
+  for (int k = tid & 63; k < GS::SIZE; k += 64) {
+    int kind, d1, d2;
+    decode(k, kind, d1, d2);
+    red[(tid >> 6) * GS::SIZE + k] = chunk_sum(rows, tid >> 6, kind, d1, d2);
   }
   __syncthreads();
   if (tid < GS::SIZE) {
@@ -242,6 +296,49 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
 #pragma unroll
     for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
     out[tid] = s;
+  }
+  if (diag) return;
+  // ordered pair (b, a): r1_ba = sum_i u_i (row scratch), R2_ba = sum_j a'_j z2'_j z2'_j^T (column scratch, 128 columns at a time in
+  // the per-warp column-sum buffers, free after the last fold); S0_ba and X_ba are not stored (symmetry, see k_bwd_finalize)
+  double* out2 = stats + (((size_t)n * L * L + b * L + a) * nrb + rb) * GS::SIZE;
+  double* cscr = csum;
+  static_assert(kGradCols * RW <= 2 * CF::NW * kGradCols, "column scratch fits in the column-sum buffers");
+  double acc2[(GS::SIZE + 63) / 64];
+#pragma unroll
+  for (int s = 0; s < (GS::SIZE + 63) / 64; ++s) acc2[s] = 0.0;
+  {
+    int s = 0;
+    for (int k = tid & 63; k < GS::SIZE; k += 64, ++s)
+      if (k >= GS::R1 && k < GS::R2) acc2[s] = chunk_sum(rows, tid >> 6, 4, k - GS::R1, 0);
+  }
+  for (int cbk = 0; cbk < ncb; ++cbk) {
+    __syncthreads();                         // previous block's readers are done
+    if (tid < kGradCols) {
+      const int j = cbk * kGradCols + tid;
+      double* cw = cscr + tid * RW;
+      cw[0] = colA[j];
+#pragma unroll
+      for (int d = 0; d < D; ++d) cw[1 + D + d] = j < M ? Z[((size_t)b * M + j) * D + d] - pk[PP::MU + d] : 0.0;
+    }
+    __syncthreads();
+    int s = 0;
+    for (int k = tid & 63; k < GS::SIZE; k += 64, ++s) {
+      if (k < GS::R2 || k >= GS::X) continue;
+      int kind, d1, d2;
+      decode(k, kind, d1, d2);
+      acc2[s] += chunk_sum(cscr, tid >> 6, 2, d1, d2);
+    }
+  }
+  {
+    int s = 0;
+    for (int k = tid & 63; k < GS::SIZE; k += 64, ++s) red[(tid >> 6) * GS::SIZE + k] = acc2[s];
+  }
+  __syncthreads();
+  if (tid >= GS::R1 && tid < GS::X) {        // the only statistics of (b, a) k_bwd_finalize reads
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
+    out2[tid] = s;
   }
 }
 
@@ -465,15 +562,17 @@ __global__ void __launch_bounds__(64) k_bwd_finalize(BwdFinalizeParams p) {
       for (int k = 0; k < CS; ++k) out[k] = 0.0;
       continue;
     }
+    // slot (a, b), a <= b: all statistics; slot (b, a), a < b: only r1 and R2 (S0_ba = S0_ab, X_ba = X_ab^T are not stored)
     double sab[GS::SIZE], sba[GS::SIZE];
     for (int k = 0; k < GS::SIZE; ++k) {
+      const bool mirrored = k >= GS::R1 && k < GS::X;
       double x = 0.0, y = 0.0;
       for (int rb = 0; rb < p.nrb; ++rb) {
         x += p.stats[(((size_t)n * L * L + a * L + b) * p.nrb + rb) * GS::SIZE + k];
-        y += p.stats[(((size_t)n * L * L + b * L + a) * p.nrb + rb) * GS::SIZE + k];
+        if (mirrored) y += p.stats[(((size_t)n * L * L + b * L + a) * p.nrb + rb) * GS::SIZE + k];
       }
       sab[k] = x;
-      sba[k] = y;
+      sba[k] = mirrored ? y : x;
     }
     double A1[D], A2[D];
     Mat<D> Sm, Li, G;
@@ -598,13 +697,15 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   k_bwd_prepare<<<(N + 63) / 64, 64, 0, stream>>>(bp);
   profile_begin(stream);
   {
-    const size_t smem = sizeof(double) * GradCfg<D>::TOTAL;
-    static bool configured = false;
-    if (!configured) {
+    const size_t smem = sizeof(double) * (GradCfg<D>::FIXED + (size_t)lo.nrb * kGradCols);   // nrb == number of column blocks
+    static size_t configured = 0;
+    if (smem > configured) {
+      GPP_REQUIRE(smem <= 227 * 1024, GPP_ERR_UNSUPPORTED, "gpp_mm_gp_predict_bwd: M=%d needs %zu bytes of shared memory", m->M, smem);
       GPP_CUDA_OK(cudaFuncSetAttribute(k_contract_grad<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
+      configured = smem;
     }
-    k_contract_grad<D><<<N * L * L * lo.nrb, kGradThreads, smem, stream>>>(m->Z, m->beta, m->C, packs, omega, stats, m->M, L, lo.nrb);
+    k_contract_grad<D><<<N * (L * (L + 1) / 2) * lo.nrb, kGradThreads, smem, stream>>>(m->Z, m->beta, m->C, packs, omega, stats, m->M,
+                                                                                     L, lo.nrb);
   }
   profile_end(stream);
   k_psi1_bwd<D><<<N, 128, 0, stream>>>(mu, S, N, L, m->M, m->Z, m->ell, m->var, m->beta, f1lat_bar, crosslat_bar, gm, gS);
