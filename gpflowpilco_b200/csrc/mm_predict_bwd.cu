@@ -545,11 +545,28 @@ struct BwdFinalizeParams {
 template <int D>
 __global__ void __launch_bounds__(64) k_bwd_finalize(BwdFinalizeParams p) {
   using GS = GradStats<D>;
-  constexpr int MAXP = GPP_MAX_L * (GPP_MAX_L + 1) / 2;
   constexpr int CS = D + D * D;
-  __shared__ double contrib[MAXP][CS];
+  extern __shared__ __align__(16) double fsm[];
   const int n = blockIdx.x, tid = threadIdx.x, L = p.L;
   const int npairs = L * (L + 1) / 2;
+  double (*sst)[2][GS::SIZE] = reinterpret_cast<double (*)[2][GS::SIZE]>(fsm);                            // [npairs][2][SIZE]
+  double (*contrib)[CS] = reinterpret_cast<double (*)[CS]>(fsm + (size_t)npairs * 2 * GS::SIZE);          // [npairs][CS]
+  // slot (a, b), a <= b: all statistics; slot (b, a), a < b: only r1 and R2 (S0_ba = S0_ab, X_ba = X_ab^T are not stored).
+  // The CTA sums the row blocks of every slot into shared memory first (coalesced over the statistic index).
+  for (int idx = tid; idx < npairs * 2 * GS::SIZE; idx += blockDim.x) {
+    const int k = idx % GS::SIZE, which = (idx / GS::SIZE) & 1, pr = idx / (2 * GS::SIZE);
+    int a = 0, b = pr;
+    while (b >= L - a) { b -= L - a; ++a; }
+    b += a;
+    const bool mirrored = k >= GS::R1 && k < GS::X;
+    const int slot = (which == 0 || !mirrored) ? a * L + b : b * L + a;
+    const double wgt = p.omega[((size_t)n * L + a) * L + b] + p.omega[((size_t)n * L + b) * L + a];
+    double x = 0.0;
+    if (wgt != 0.0)                          // skipped pairs were not written by k_contract_grad
+      for (int rb = 0; rb < p.nrb; ++rb) x += p.stats[(((size_t)n * L * L + slot) * p.nrb + rb) * GS::SIZE + k];
+    sst[pr][which][k] = x;
+  }
+  __syncthreads();
   for (int pr = tid; pr < npairs; pr += blockDim.x) {
     // unordered pair index -> (a <= b)
     int a = 0, rem = pr;
@@ -562,18 +579,8 @@ __global__ void __launch_bounds__(64) k_bwd_finalize(BwdFinalizeParams p) {
       for (int k = 0; k < CS; ++k) out[k] = 0.0;
       continue;
     }
-    // slot (a, b), a <= b: all statistics; slot (b, a), a < b: only r1 and R2 (S0_ba = S0_ab, X_ba = X_ab^T are not stored)
-    double sab[GS::SIZE], sba[GS::SIZE];
-    for (int k = 0; k < GS::SIZE; ++k) {
-      const bool mirrored = k >= GS::R1 && k < GS::X;
-      double x = 0.0, y = 0.0;
-      for (int rb = 0; rb < p.nrb; ++rb) {
-        x += p.stats[(((size_t)n * L * L + a * L + b) * p.nrb + rb) * GS::SIZE + k];
-        if (mirrored) y += p.stats[(((size_t)n * L * L + b * L + a) * p.nrb + rb) * GS::SIZE + k];
-      }
-      sab[k] = x;
-      sba[k] = mirrored ? y : x;
-    }
+    const double* sab = sst[pr][0];
+    const double* sba = sst[pr][1];
     double A1[D], A2[D];
     Mat<D> Sm, Li, G;
 #pragma unroll
@@ -712,7 +719,16 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   BwdFinalizeParams fp;
   fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.omega = omega; fp.gm = gm; fp.gS = gS;
   fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb;
-  k_bwd_finalize<D><<<N, 64, 0, stream>>>(fp);
+  {
+    const int npairs = L * (L + 1) / 2;
+    const size_t smem = sizeof(double) * (size_t)npairs * (2 * GradStats<D>::SIZE + D + D * D);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+      GPP_CUDA_OK(cudaFuncSetAttribute(k_bwd_finalize<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    k_bwd_finalize<D><<<N, 64, smem, stream>>>(fp);
+  }
   count_launch(6);
   GPP_CUDA_OK(cudaGetLastError());
   return GPP_OK;

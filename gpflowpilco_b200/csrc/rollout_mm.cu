@@ -358,7 +358,7 @@ static int rollout_mm_fwd_impl(const gpp_gp_model* dynamics, int N, int Dx, int 
   for (int t = 0; t < H; ++t) {
     if (saved) {   // the joint moments, Cov(x, d) and the pre-inverted cross term of every step are written where the backward reads them
       double* base = saved + (size_t)t * sv.per_step;
-      p.md = base + sv.md; p.Sd = base + sv.Sd; p.Sxd = base + sv.Sxd; p.cross = base + sv.cross;
+      p.md = base + sv.md; p.Sd = base + sv.Sd; p.Sxd = base + sv.Sxd; p.cross = base + sv.cross; p.pre = base + sv.pre;
     }
     switch (p.De) {
 #define GPP_CASE(d) case d: k_step_pre<d><<<N, 128, 0, stream>>>(p); break;

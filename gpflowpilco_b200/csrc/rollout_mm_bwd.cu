@@ -137,7 +137,15 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Dx = p.Dx;
   const int r = (p.R == 1) ? 0 : n;
-  step_pre_forward<DP>(p, n, sh);
+  if (p.pre) {   // the forward saved the stage's shared block
+    constexpr int PS = PreSharedSize<DP>::value;
+    const double* src = p.pre + (size_t)n * PS;
+    double* dst = reinterpret_cast<double*>(&sh);
+    for (int t = tid; t < PS; t += blockDim.x) dst[t] = src[t];
+    __syncthreads();
+  } else {
+    step_pre_forward<DP>(p, n, sh);
+  }
 
   if (tid == 0) {
     // ---- adjoint of the joint assembly: (md, Sd, Sxd) -> (me, See, Cxe, cpre, mu_u, vu, gain)
@@ -476,7 +484,7 @@ int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
     int rc = GPP_OK;
     if (saved) {   // step t's joint moments, Cov(x, d) and cross term as the forward stored them (read-only here)
       double* base = const_cast<double*>(saved) + (size_t)t * sv.per_step;
-      p.md = base + sv.md; p.Sd = base + sv.Sd; p.Sxd = base + sv.Sxd; p.cross = base + sv.cross;
+      p.md = base + sv.md; p.Sd = base + sv.Sd; p.Sxd = base + sv.Sxd; p.cross = base + sv.cross; p.pre = base + sv.pre;
     } else {       // recompute them: pre stage + fused forward predict
       switch (p.De) {
 #define GPP_CASE(d) case d: k_step_pre<d><<<N, 128, 0, stream>>>(p); break;

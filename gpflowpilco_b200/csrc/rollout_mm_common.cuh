@@ -18,6 +18,7 @@ struct RolloutMMParams {
   double *md, *Sd, *Sxd;     // [N,D], [N,D,D], [N,Dx,D]
   double *f1, *Sff, *cross;  // [N,L], [N,L,L], [N,D,L]
   double *traj_m, *traj_S;   // optional [H+1,N,Dx], [H+1,N,Dx,Dx]
+  double* pre;               // optional [N, sizeof(PreShared)/8]: the pre stage's shared block, saved by the forward for the backward
   int* info;
 };
 
@@ -223,6 +224,18 @@ __device__ void step_pre_write(const RolloutMMParams& p, int n, const PreShared<
   }
 }
 
+template <int DP>
+struct PreSharedSize { static constexpr int value = (int)(sizeof(PreShared<DP>) / sizeof(double)); };
+
+inline size_t pre_shared_doubles(int De) {
+  switch (De) {
+#define GPP_CASE(d) case d: return PreSharedSize<d>::value;
+    GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7)
+#undef GPP_CASE
+    default: return 0;
+  }
+}
+
 // k_step_pre: one CTA (128 threads) per rollout
 template <int DP>
 __global__ void __launch_bounds__(128) k_step_pre(RolloutMMParams p) {
@@ -230,20 +243,27 @@ __global__ void __launch_bounds__(128) k_step_pre(RolloutMMParams p) {
   const int n = blockIdx.x;
   step_pre_forward<DP>(p, n, sh);
   if (threadIdx.x == 0) step_pre_write<DP>(p, n, sh);
+  if (p.pre) {   // forward-with-save: the backward's k_bwd_pre reloads this block instead of recomputing the stage
+    constexpr int PS = PreSharedSize<DP>::value;
+    const double* src = reinterpret_cast<const double*>(&sh);
+    double* dst = p.pre + (size_t)n * PS;
+    for (int t = threadIdx.x; t < PS; t += blockDim.x) dst[t] = src[t];
+  }
 }
 
 inline size_t rollout_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // per-step block of the optional `saved` buffer of gpp_rollout_mm_fwd_save (offsets in doubles):
-//   md [N,D] | Sd [N,D,D] | Sxd [N,Dx,D] | cross [N,D,L]
+//   md [N,D] | Sd [N,D,D] | Sxd [N,Dx,D] | cross [N,D,L] | pre [N, PreShared<D-1>]
 struct RolloutSaved {
-  size_t md, Sd, Sxd, cross, per_step;
+  size_t md, Sd, Sxd, cross, pre, per_step;
   RolloutSaved(int N, int Dx, int D, int L) {
     md = 0;
     Sd = md + (size_t)N * D;
     Sxd = Sd + (size_t)N * D * D;
     cross = Sxd + (size_t)N * Dx * D;
-    per_step = cross + (size_t)N * D * L;
+    pre = cross + (size_t)N * D * L;
+    per_step = pre + (size_t)N * pre_shared_doubles(D - 1);
   }
 };
 
