@@ -4,9 +4,10 @@
 // materialises eKuffu [N,L,M,L,M] (gpflow_pilco/utils/kernel_expectation.py:217-247) and runs two batched
 // triangular solves over it (models.py:224-226, O(N L^2 M^3)); here Psi2 is never written:
 //
-//   k_pack     one thread per (input n, kernel pair ab): D x D Cholesky, coefficients of
+//   k_pack_psi1 (one launch):
+//   pack       one thread per (input n, kernel pair ab): D x D Cholesky, coefficients of
 //              log Q_ij = r_i + s_j + z1'_i^T R z2'_j  (common.cuh, PairPack)
-//   k_psi1     one warp per (n, latent): Psi1 contracted with beta -> latent mean and pre-inverted cross term
+//   psi1       one warp per (n, latent): Psi1 contracted with beta -> latent mean and pre-inverted cross term
 //   k_contract persistent CTAs pull (pair, tile, input-chunk) items; a CTA keeps one T x T tile of C_a
 //              (= beta beta^T - B, diagonal pairs) or the beta vectors (off-diagonal pairs) on chip and streams
 //              inputs through it: per 8 x 8 block of entries 2 DMMA (exponents), then per entry 8 FP64 ops (table exp)
@@ -132,7 +133,18 @@ static Plan make_plan(const gpp_gp_model* m, int N, int full_output_cov) {
   const gpp_gp_model::SlotTable& tab = m->tables[pl.tile_idx][pl.diag_only];
   // aim for ~64 items per SM (dynamic scheduling tail <= ~1.5%), but keep chunks >= 4 inputs to amortise the tile load
   long long want_items = 64LL * sms;
-  int nchunks = (int)std::max(1LL, std::min<long long>((want_items + tab.nslots - 1) / tab.nslots, (N + 3) / 4));
+  const int max_chunks = (N + 3) / 4;
+  int nchunks = (int)std::max(1LL, (want_items + tab.nslots - 1) / tab.nslots);
+  if (nchunks >= max_chunks) {
+    // small batches: too little work for 64 items per SM.  Pick the split that minimises  waves x (inputs per item + ~2 inputs'
+    // worth of per-item set-up: tile of C, table, pipeline fill)
+    long long best = -1;
+    for (int nc = 1; nc <= max_chunks; ++nc) {
+      const long long waves = ((long long)tab.nslots * nc + sms - 1) / sms;
+      const long long cost = waves * ((N + nc - 1) / nc + 2);
+      if (best < 0 || cost < best) { best = cost; nchunks = nc; }
+    }
+  }
   pl.chunk = (N + nchunks - 1) / nchunks;
   pl.nchunks = (N + pl.chunk - 1) / pl.chunk;
   const int D = m->D;
@@ -183,11 +195,12 @@ static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S,
   double* f1lat = (double*)(ws + pl.off_f1lat);
   double* crosslat = (double*)(ws + pl.off_crosslat);
   unsigned* counter = (unsigned*)(ws + pl.off_counter);
-  GPP_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
-  int total = N * tab.npairs;
-  k_pack<D><<<(total + 63) / 64, 64, 0, stream>>>(mu, S, N, m->ell, m->var, tab.d_pair_ab, tab.npairs, m->L, packs, info);
-  k_psi1<D><<<N, 128, 0, stream>>>(mu, S, N, m->L, m->M, m->Z, m->ell, m->var, m->beta, f1lat, crosslat, info);
-  count_launch(2);
+  PackPsi1Params pp;
+  pp.m = mu; pp.S = S; pp.Z = m->Z; pp.ell = m->ell; pp.var = m->var; pp.beta = m->beta; pp.pair_ab = tab.d_pair_ab;
+  pp.packs = packs; pp.f1lat = f1lat; pp.crosslat = crosslat; pp.counter = counter; pp.info = info;
+  pp.N = N; pp.L = m->L; pp.M = m->M; pp.npairs = tab.npairs;
+  launch_pack_psi1<D>(pp, stream);
+  count_launch();
   ContractParams cp;
   cp.Z = m->Z; cp.beta = m->beta; cp.C = m->C; cp.packs = packs; cp.part = part; cp.slots = tab.d_slots;
   cp.counter = counter; cp.N = N; cp.M = m->M; cp.L = m->L; cp.npairs = tab.npairs; cp.nslots = tab.nslots;

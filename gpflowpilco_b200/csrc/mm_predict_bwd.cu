@@ -14,7 +14,7 @@
 //               ds/dmu = G1 (sum w e dz) - (sum w) y,
 //               ds/dSigma = 1/2 (G1 (sum w e dz dz^T) G1 - (sum w e) G1) - 1/2 (y c^T + c y^T),  c = G1 sum w dz.
 //
-//   k_pack (ordered pairs) + k_psi1 (forward latent means)   -> k_bwd_prepare (un-mix W, Sff = f2 - f1 f1^T chain rule)
+//   k_pack_psi1 (ordered pairs + forward latent means)       -> k_bwd_prepare (un-mix W, Sff = f2 - f1 f1^T chain rule)
 //   -> k_contract_grad (DMMA exponents, warp per 8-row strip, CTA per (input, unordered pair, 128-row block)) + k_psi1_bwd (warp per (input, latent))
 //   -> k_bwd_finalize (CTA per input: D x D algebra per unordered pair, fixed-order sums).
 // Gradients w.r.t. the model parameters are not produced: the dynamics model is constant during policy optimisation
@@ -694,9 +694,11 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   double* omega = (double*)(ws + lo.omega);
   double* gm = (double*)(ws + lo.gm);
   double* gS = (double*)(ws + lo.gS);
-  const int total = N * L * L;
-  k_pack<D><<<(total + 63) / 64, 64, 0, stream>>>(mu, S, N, m->ell, m->var, nullptr, L * L, L, packs, info);
-  k_psi1<D><<<N, 128, 0, stream>>>(mu, S, N, L, m->M, m->Z, m->ell, m->var, m->beta, f1lat, crosslat, info);
+  PackPsi1Params pp;
+  pp.m = mu; pp.S = S; pp.Z = m->Z; pp.ell = m->ell; pp.var = m->var; pp.beta = m->beta; pp.pair_ab = nullptr;
+  pp.packs = packs; pp.f1lat = f1lat; pp.crosslat = crosslat; pp.counter = nullptr; pp.info = info;
+  pp.N = N; pp.L = L; pp.M = m->M; pp.npairs = L * L;
+  launch_pack_psi1<D>(pp, stream);
   BwdPrepareParams bp;
   bp.f1_bar = f1_bar; bp.Sff_bar = Sff_bar; bp.cross_bar = cross_bar; bp.f1lat = f1lat; bp.W = m->W;
   bp.f1lat_bar = f1lat_bar; bp.crosslat_bar = crosslat_bar; bp.omega = omega;
@@ -729,7 +731,7 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
     }
     k_bwd_finalize<D><<<N, 64, smem, stream>>>(fp);
   }
-  count_launch(6);
+  count_launch(5);
   GPP_CUDA_OK(cudaGetLastError());
   return GPP_OK;
 }

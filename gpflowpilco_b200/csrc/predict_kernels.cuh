@@ -1,5 +1,6 @@
-// k_pack and k_psi1: the per-input prologue kernels shared by the forward (mm_predict.cu) and backward (mm_predict_bwd.cu)
-// moment-matched GP predict.
+// k_pack_psi1: the per-input prologue shared by the forward (mm_predict.cu) and backward (mm_predict_bwd.cu) moment-matched GP
+// predict — the Psi2 coefficient packs and the Psi1 latent means are independent, so one launch does both (blocks [0, N) = Psi1 of
+// input n, the remaining blocks = 128 (input, pair) packs each) and also resets the contraction's work counter.
 #pragma once
 #include "model.cuh"
 
@@ -9,11 +10,10 @@ namespace gpp {
 // k_pack
 // ---------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(64) k_pack(const double* __restrict__ m, const double* __restrict__ S, int N,
-                                             const double* __restrict__ ell, const double* __restrict__ var,
-                                             const int* __restrict__ pair_ab, int npairs, int L,
-                                             double* __restrict__ packs, int* info) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_body(int idx, const double* __restrict__ m, const double* __restrict__ S, int N,
+                                          const double* __restrict__ ell, const double* __restrict__ var,
+                                          const int* __restrict__ pair_ab, int npairs, int L,
+                                          double* __restrict__ packs, int* info) {
   if (idx >= N * npairs) return;
   int n = idx / npairs, p = idx % npairs;
   // pair table (a <= b, forward) or, with pair_ab == nullptr, all L x L ordered pairs (backward)
@@ -41,12 +41,11 @@ __global__ void __launch_bounds__(64) k_pack(const double* __restrict__ m, const
 //         (models.py:236 and :264-277; Psi1 is GPflow's eKxz)
 // ---------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(128) k_psi1(const double* __restrict__ m, const double* __restrict__ S, int N, int L, int M,
-                                              const double* __restrict__ Z, const double* __restrict__ ell,
-                                              const double* __restrict__ var, const double* __restrict__ beta,
-                                              double* __restrict__ f1lat /*[N,L]*/, double* __restrict__ crosslat /*[N,D,L]*/,
-                                              int* info) {
-  int n = blockIdx.x;
+__device__ __forceinline__ void psi1_body(int n, const double* __restrict__ m, const double* __restrict__ S, int N, int L, int M,
+                                          const double* __restrict__ Z, const double* __restrict__ ell,
+                                          const double* __restrict__ var, const double* __restrict__ beta,
+                                          double* __restrict__ f1lat /*[N,L]*/, double* __restrict__ crosslat /*[N,D,L]*/,
+                                          int* info) {
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   double mu[D];
 #pragma unroll
@@ -112,6 +111,33 @@ __global__ void __launch_bounds__(128) k_psi1(const double* __restrict__ m, cons
       }
     }
   }
+}
+
+struct PackPsi1Params {
+  const double *m, *S;                    // [N,D], [N,D,D]
+  const double *Z, *ell, *var, *beta;     // model
+  const int* pair_ab;                     // pair table (a <= b) or nullptr = all L x L ordered pairs
+  double *packs, *f1lat, *crosslat;       // [N,npairs,PairPack], [N,L], [N,D,L]
+  unsigned* counter;                      // optional: work counter of k_contract, reset here
+  int* info;
+  int N, L, M, npairs;
+};
+
+template <int D>
+__global__ void __launch_bounds__(128) k_pack_psi1(PackPsi1Params p) {
+  if ((int)blockIdx.x < p.N) {
+    psi1_body<D>(blockIdx.x, p.m, p.S, p.N, p.L, p.M, p.Z, p.ell, p.var, p.beta, p.f1lat, p.crosslat, p.info);
+  } else {
+    const int idx = ((int)blockIdx.x - p.N) * 128 + threadIdx.x;
+    if (idx == 0 && p.counter) *p.counter = 0u;
+    pack_body<D>(idx, p.m, p.S, p.N, p.ell, p.var, p.pair_ab, p.npairs, p.L, p.packs, p.info);
+  }
+}
+
+template <int D>
+inline void launch_pack_psi1(const PackPsi1Params& p, cudaStream_t stream) {
+  const int grid = p.N + (p.N * p.npairs + 127) / 128;
+  k_pack_psi1<D><<<grid, 128, 0, stream>>>(p);
 }
 
 }  // namespace gpp
