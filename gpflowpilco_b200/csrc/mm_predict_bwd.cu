@@ -14,8 +14,8 @@
 //               ds/dmu = G1 (sum w e dz) - (sum w) y,
 //               ds/dSigma = 1/2 (G1 (sum w e dz dz^T) G1 - (sum w e) G1) - 1/2 (y c^T + c y^T),  c = G1 sum w dz.
 //
-//   k_pack_psi1 (ordered pairs + forward latent means)       -> k_bwd_prepare (un-mix W, Sff = f2 - f1 f1^T chain rule)
-//   -> k_contract_grad (DMMA exponents, warp per 8-row strip, CTA per (input, unordered pair, 128-row block)) + k_psi1_bwd (warp per (input, latent))
+//   k_pack_psi1 (coefficient packs | per input: forward latent means, un-mix W and the Sff = f2 - f1 f1^T chain rule, Psi1 adjoints)
+//   -> k_contract_grad (DMMA exponents, warp per 8-row strip, CTA per (input, unordered pair, 128-row block))
 //   -> k_bwd_finalize (CTA per input: D x D algebra per unordered pair, fixed-order sums).
 // Gradients w.r.t. the model parameters are not produced: the dynamics model is constant during policy optimisation
 // (upstream differentiates w.r.t. policy.trainable_variables only, gpflow_pilco/utils/optimizers.py:52-56).
@@ -351,9 +351,7 @@ struct BwdPrepareParams {
   int N, L, P, D, full_cov;
 };
 
-__global__ void k_bwd_prepare(BwdPrepareParams p) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= p.N) return;
+__device__ void bwd_prepare_input(const BwdPrepareParams& p, int n) {
   const int L = p.L, P = p.P, D = p.D;
   double SL[GPP_MAX_L * GPP_MAX_L];
   for (int l = 0; l < L; ++l)
@@ -420,13 +418,12 @@ __device__ __forceinline__ void gram_apply(const Mat<D>& Li, const double* x, do
 }
 
 template <int D>
-__global__ void __launch_bounds__(128) k_psi1_bwd(const double* __restrict__ m, const double* __restrict__ S, int N, int L, int M,
-                                                  const double* __restrict__ Z, const double* __restrict__ ell,
-                                                  const double* __restrict__ var, const double* __restrict__ beta,
-                                                  const double* __restrict__ f1lat_bar, const double* __restrict__ crosslat_bar,
-                                                  double* __restrict__ gm /*[N,L,D]*/, double* __restrict__ gS /*[N,L,D,D]*/) {
+__device__ __forceinline__ void psi1_bwd_body(int n, const double* __restrict__ m, const double* __restrict__ S, int L, int M,
+                                              const double* __restrict__ Z, const double* __restrict__ ell,
+                                              const double* __restrict__ var, const double* __restrict__ beta,
+                                              const double* __restrict__ f1lat_bar, const double* __restrict__ crosslat_bar,
+                                              double* __restrict__ gm /*[N,L,D]*/, double* __restrict__ gS /*[N,L,D,D]*/) {
   constexpr int TRI = D * (D + 1) / 2;
-  const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   double mu[D];
 #pragma unroll
@@ -531,6 +528,22 @@ __global__ void __launch_bounds__(128) k_psi1_bwd(const double* __restrict__ m, 
     }
   }
 }
+
+// Runs inside the prologue launch, in the Psi1 block of input n, once the block has written f1lat[n, :]: the output adjoints are
+// un-mixed to latent space (thread 0), then the Psi1 adjoints follow with a warp per latent.
+template <int D>
+struct BwdEpilogue {
+  BwdPrepareParams bp;
+  const double *m, *S, *Z, *ell, *var, *beta;
+  double *gm, *gS;
+  int M;
+  __device__ __forceinline__ void operator()(int n) const {
+    __syncthreads();
+    if (threadIdx.x == 0) bwd_prepare_input(bp, n);
+    __syncthreads();
+    psi1_bwd_body<D>(n, m, S, bp.L, M, Z, ell, var, beta, bp.f1lat_bar, bp.crosslat_bar, gm, gS);
+  }
+};
 
 struct BwdFinalizeParams {
   const double *m, *S;          // [N,D], [N,D,D]
@@ -698,12 +711,13 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   pp.m = mu; pp.S = S; pp.Z = m->Z; pp.ell = m->ell; pp.var = m->var; pp.beta = m->beta; pp.pair_ab = nullptr;
   pp.packs = packs; pp.f1lat = f1lat; pp.crosslat = crosslat; pp.counter = nullptr; pp.info = info;
   pp.N = N; pp.L = L; pp.M = m->M; pp.npairs = L * L;
-  launch_pack_psi1<D>(pp, stream);
-  BwdPrepareParams bp;
+  BwdEpilogue<D> epi;
+  epi.m = mu; epi.S = S; epi.Z = m->Z; epi.ell = m->ell; epi.var = m->var; epi.beta = m->beta; epi.gm = gm; epi.gS = gS; epi.M = m->M;
+  BwdPrepareParams& bp = epi.bp;
   bp.f1_bar = f1_bar; bp.Sff_bar = Sff_bar; bp.cross_bar = cross_bar; bp.f1lat = f1lat; bp.W = m->W;
   bp.f1lat_bar = f1lat_bar; bp.crosslat_bar = crosslat_bar; bp.omega = omega;
   bp.N = N; bp.L = L; bp.P = m->P; bp.D = D; bp.full_cov = full_output_cov;
-  k_bwd_prepare<<<(N + 63) / 64, 64, 0, stream>>>(bp);
+  launch_pack_psi1<D, BwdEpilogue<D>>(pp, stream, epi);
   profile_begin(stream);
   {
     const size_t smem = sizeof(double) * (GradCfg<D>::FIXED + (size_t)lo.nrb * kGradCols);   // nrb == number of column blocks
@@ -717,7 +731,6 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
                                                                                      L, lo.nrb);
   }
   profile_end(stream);
-  k_psi1_bwd<D><<<N, 128, 0, stream>>>(mu, S, N, L, m->M, m->Z, m->ell, m->var, m->beta, f1lat_bar, crosslat_bar, gm, gS);
   BwdFinalizeParams fp;
   fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.omega = omega; fp.gm = gm; fp.gS = gS;
   fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb;
@@ -731,7 +744,7 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
     }
     k_bwd_finalize<D><<<N, 64, smem, stream>>>(fp);
   }
-  count_launch(5);
+  count_launch(3);
   GPP_CUDA_OK(cudaGetLastError());
   return GPP_OK;
 }

@@ -123,10 +123,16 @@ struct PackPsi1Params {
   int N, L, M, npairs;
 };
 
-template <int D>
-__global__ void __launch_bounds__(128) k_pack_psi1(PackPsi1Params p) {
+// `epi(n)` runs in the Psi1 block of input n after its latent means are written (all 128 threads call it)
+struct NoEpilogue {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+
+template <int D, class Epilogue>
+__global__ void __launch_bounds__(128) k_pack_psi1(PackPsi1Params p, Epilogue epi) {
   if ((int)blockIdx.x < p.N) {
     psi1_body<D>(blockIdx.x, p.m, p.S, p.N, p.L, p.M, p.Z, p.ell, p.var, p.beta, p.f1lat, p.crosslat, p.info);
+    epi((int)blockIdx.x);
   } else {
     const int idx = ((int)blockIdx.x - p.N) * 128 + threadIdx.x;
     if (idx == 0 && p.counter) *p.counter = 0u;
@@ -134,10 +140,10 @@ __global__ void __launch_bounds__(128) k_pack_psi1(PackPsi1Params p) {
   }
 }
 
-template <int D>
-inline void launch_pack_psi1(const PackPsi1Params& p, cudaStream_t stream) {
+template <int D, class Epilogue = NoEpilogue>
+inline void launch_pack_psi1(const PackPsi1Params& p, cudaStream_t stream, Epilogue epi = Epilogue()) {
   const int grid = p.N + (p.N * p.npairs + 127) / 128;
-  k_pack_psi1<D><<<grid, 128, 0, stream>>>(p);
+  k_pack_psi1<D, Epilogue><<<grid, 128, 0, stream>>>(p, epi);
 }
 
 }  // namespace gpp
