@@ -44,8 +44,10 @@ struct FinalizeParams {
   double* cross;            // [N,D,P]
   int N, L, P, D, npairs, nslots, full_cov, model_uncertainty;
   double jitter;
+  EulerPost post;           // used by k_finalize<true> only
 };
 
+template <bool POST>
 __global__ void __launch_bounds__(128) k_finalize(FinalizeParams p) {
   __shared__ double f2[GPP_MAX_L * GPP_MAX_L];
   __shared__ double SffL[GPP_MAX_L * GPP_MAX_L];
@@ -108,6 +110,33 @@ __global__ void __launch_bounds__(128) k_finalize(FinalizeParams p) {
       v = cl[o];
     }
     p.cross[((size_t)n * p.D + d) * P + o] = v;
+  }
+  if (POST) {
+    __syncthreads();                         // this block's f1 / Sff / cross are visible to all its threads
+    const EulerPost& e = p.post;
+    const int Dx = e.Dx, D = p.D;
+    const double* Sxd = e.Sxd + (size_t)n * Dx * D;
+    const double* cr = p.cross + (size_t)n * D * P;
+    for (int t = threadIdx.x; t < Dx * Dx + Dx; t += blockDim.x) {
+      if (t < Dx * Dx) {
+        const int i = t / Dx, j = t % Dx;
+        double sij = 0.0, sji = 0.0;
+        for (int b = 0; b < D; ++b) {
+          sij = fma(Sxd[i * D + b], cr[b * P + j], sij);
+          sji = fma(Sxd[j * D + b], cr[b * P + i], sji);
+        }
+        const double v = e.S[(size_t)n * Dx * Dx + t] + sij + sji + p.Sff[(size_t)n * P * P + i * P + j];
+        e.S[(size_t)n * Dx * Dx + t] = v;
+        if (e.traj_S) e.traj_S[(size_t)n * Dx * Dx + t] = v;
+        if (e.ring_S) e.ring_S[(size_t)n * Dx * Dx + t] = v;
+      } else {
+        const int i = t - Dx * Dx;
+        const double v = e.m[(size_t)n * Dx + i] + p.f1[(size_t)n * P + i];
+        e.m[(size_t)n * Dx + i] = v;
+        if (e.traj_m) e.traj_m[(size_t)n * Dx + i] = v;
+        if (e.ring_m) e.ring_m[(size_t)n * Dx + i] = v;
+      }
+    }
   }
 }
 
@@ -187,7 +216,7 @@ static int launch_contract(const ContractParams& cp, cudaStream_t stream) {
 template <int D>
 static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S, int N, double* f1, double* Sff,
                        double* cross, int full_output_cov, double jitter, char* ws, const Plan& pl, int* info,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const EulerPost* post) {
   using PP = PairPack<D>;
   const gpp_gp_model::SlotTable& tab = m->tables[pl.tile_idx][pl.diag_only];
   double* packs = (double*)(ws + pl.off_packs);
@@ -213,7 +242,12 @@ static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S,
   fp.f1 = f1; fp.Sff = Sff; fp.cross = cross; fp.N = N; fp.L = m->L; fp.P = m->P; fp.D = D;
   fp.npairs = tab.npairs; fp.nslots = tab.nslots; fp.full_cov = full_output_cov;
   fp.model_uncertainty = m->model_uncertainty; fp.jitter = jitter;
-  k_finalize<<<N, 128, 0, stream>>>(fp);
+  if (post) {
+    fp.post = *post;
+    k_finalize<true><<<N, 128, 0, stream>>>(fp);
+  } else {
+    k_finalize<false><<<N, 128, 0, stream>>>(fp);
+  }
   count_launch();
   GPP_CUDA_OK(cudaGetLastError());
   (void)sizeof(PP);
@@ -233,16 +267,26 @@ size_t gpp_mm_gp_predict_workspace_bytes(const gpp_gp_model* model, int N) {
 int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
                           double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
                           int* info, void* stream_) {
+  return gpp::mm_predict_enqueue(model, m, S, N, f1, Sff, cross, full_output_cov, jitter, workspace, workspace_bytes, info,
+                                 (cudaStream_t)stream_, nullptr);
+}
+
+}  // extern "C"
+
+int gpp::mm_predict_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
+                            double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
+                            int* info, cudaStream_t stream, const gpp::EulerPost* post) {
   GPP_REQUIRE(model && m && S && f1 && Sff && cross && workspace, GPP_ERR_NULL, "gpp_mm_gp_predict_fwd: null argument");
   GPP_REQUIRE(N >= 1, GPP_ERR_BAD_SHAPE, "gpp_mm_gp_predict_fwd: N=%d", N);
+  GPP_REQUIRE(!post || post->Dx == model->P, GPP_ERR_BAD_SHAPE, "rollout: the dynamics model has %d outputs for a %d-dimensional state",
+              model->P, post ? post->Dx : 0);
   gpp::Plan pl = gpp::make_plan(model, N, full_output_cov);
   GPP_REQUIRE(workspace_bytes >= pl.total, GPP_ERR_WORKSPACE, "gpp_mm_gp_predict_fwd: workspace %zu < required %zu",
               workspace_bytes, pl.total);
-  cudaStream_t stream = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
   switch (model->D) {
 #define GPP_CASE(d) \
-  case d: return gpp::predict_fwd<d>(model, m, S, N, f1, Sff, cross, full_output_cov, jitter, ws, pl, info, stream);
+  case d: return gpp::predict_fwd<d>(model, m, S, N, f1, Sff, cross, full_output_cov, jitter, ws, pl, info, stream, post);
     GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
 #undef GPP_CASE
     default:
@@ -250,15 +294,3 @@ int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m, const doub
       return GPP_ERR_UNSUPPORTED;
   }
 }
-
-}  // extern "C"
-
-namespace gpp {
-// internal alias used by the rollout (same checks, typed stream)
-int mm_predict_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
-                       double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
-                       int* info, cudaStream_t stream) {
-  return gpp_mm_gp_predict_fwd(model, m, S, N, f1, Sff, cross, full_output_cov, jitter, workspace, workspace_bytes, info,
-                               (void*)stream);
-}
-}  // namespace gpp

@@ -39,3 +39,23 @@ struct gpp_gp_model {
   };
   SlotTable tables[2][2];     // [tile 64|128][full|diag-only]
 };
+
+namespace gpp {
+
+// Optional rollout epilogue of the forward predict's k_finalize (block n, after f1 / Sff / cross of input n are written):
+// the Euler step of the moment-matched state, x' = x + f with dt = 1 (upstream dynamics/solvers.py MomentMatchingEuler,
+// forward_sde.py:112-124):  m' = m + f1,  S' = S + Sxf + Sxf^T + Sff,  Sxf = Sxd cross.  Requires P == Dx.
+struct EulerPost {
+  double *m, *S;              // [N,Dx], [N,Dx,Dx]  current state, updated in place
+  const double* Sxd;          // [N,Dx,D]           Cov(x, d) of the pre stage
+  double *traj_m, *traj_S;    // optional: slice of step t+1, [N,Dx], [N,Dx,Dx]
+  double *ring_m, *ring_S;    // optional: cost-ring slot of this step, same shapes
+  int Dx;
+};
+
+// the forward predict as the rollouts call it (mm_predict.cu); gpp_mm_gp_predict_fwd is the same without an epilogue
+int mm_predict_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
+                       double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
+                       int* info, cudaStream_t stream, const EulerPost* post = nullptr);
+
+}  // namespace gpp

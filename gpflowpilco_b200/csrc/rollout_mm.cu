@@ -8,19 +8,16 @@
 // a CUDA graph — no allocation, no synchronisation):
 //   k_step_pre   one CTA per rollout: encoder rule, policy moment matching (Psi1/Psi2 of the small policy GP done by the
 //                CTA's threads), squashing link, joint moments of d = (e,u), and Sxd = Cov(x, d) rows (forward_sde.py:105-124)
-//   GP predict   the fused kernels of mm_predict.cu on the N joint states
-//   k_step_post  one thread per rollout: Sxf = Sxd cross, Euler update (solvers.py:128-129); the new state also goes into a ring
+//   GP predict   the fused kernels of mm_predict.cu on the N joint states (3 launches); its finalize kernel carries the step's
+//                epilogue (model.cuh EulerPost): Sxf = Sxd cross, Euler update (solvers.py:128-129), trajectory slice, cost ring slot
 //   k_cost_ring + k_cost_accumulate   every 32 steps: encoder rule + expected cost (components.py:30-37) of the ring's states in
 //                one parallel launch, added to the loss in step order (the cost does not feed back into the state).
-// gpp_rollout_mm_fwd_save additionally keeps each step's (md, Sd, Sxd, cross) for gpp_rollout_mm_bwd (rollout_mm_bwd.cu);
+// gpp_rollout_mm_fwd_save additionally keeps each step's (md, Sd, Sxd, cross, pre-stage block) for gpp_rollout_mm_bwd (rollout_mm_bwd.cu);
 // gpp_policy_prepare / gpp_policy_prepare_bwd map the policy's q_mu to beta = Kuu^-1 m and back.
 #include "rollout_mm_common.cuh"
 
 namespace gpp {
 
-int mm_predict_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
-                       double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
-                       int* info, cudaStream_t stream);   // mm_predict.cu
 
 // ---------------------------------------------------------------------------------------------------------
 // policy weights: beta_r = Kuu_r^-1 m_r  for R small kernel regressors (one CTA each; Cholesky in shared memory)
@@ -214,36 +211,6 @@ __global__ void __launch_bounds__(128) k_policy_prepare_bwd(int Mp, int Dp, cons
 
 constexpr int kCostRing = 32;   // steps whose costs are evaluated by one k_cost_ring launch
 
-__global__ void k_step_post(RolloutMMParams p, int step, double* __restrict__ ring_m, double* __restrict__ ring_S) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= p.N) return;
-  const int Dx = p.Dx, De = p.De, D = p.D, L = p.L;
-  double m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX], Sxf[GPP_SMALL_MAX * GPP_SMALL_MAX];
-  const double* Sxd = p.Sxd + (size_t)n * Dx * D;
-  const double* cr = p.cross + (size_t)n * D * L;
-  for (int i = 0; i < Dx; ++i)
-    for (int l = 0; l < L; ++l) {
-      double t = 0.0;
-      for (int b = 0; b < D; ++b) t = fma(Sxd[i * D + b], cr[b * L + l], t);
-      Sxf[i * L + l] = t;
-    }
-  for (int i = 0; i < Dx; ++i) m[i] = p.m[(size_t)n * Dx + i] + p.f1[(size_t)n * L + i];          // dt = 1 (pilco.py:186)
-  for (int i = 0; i < Dx; ++i)
-    for (int j = 0; j < Dx; ++j)
-      S[i * Dx + j] = p.S[(size_t)n * Dx * Dx + i * Dx + j] + Sxf[i * L + j] + Sxf[j * L + i] + p.Sff[(size_t)n * L * L + i * L + j];
-  for (int i = 0; i < Dx; ++i) p.m[(size_t)n * Dx + i] = m[i];
-  for (int i = 0; i < Dx * Dx; ++i) p.S[(size_t)n * Dx * Dx + i] = S[i];
-  if (p.traj_m) {
-    for (int i = 0; i < Dx; ++i) p.traj_m[((size_t)(step + 1) * p.N + n) * Dx + i] = m[i];
-    for (int i = 0; i < Dx * Dx; ++i) p.traj_S[((size_t)(step + 1) * p.N + n) * Dx * Dx + i] = S[i];
-  }
-  // the expected cost of the new state is evaluated later, for a whole ring of steps at once (k_cost_ring): it does not feed
-  // back into the state, so the serial LU / determinant of every step stays off the critical path of the rollout
-  const int slot = step % kCostRing;
-  for (int i = 0; i < Dx; ++i) ring_m[((size_t)slot * p.N + n) * Dx + i] = m[i];
-  for (int i = 0; i < Dx * Dx; ++i) ring_S[((size_t)slot * p.N + n) * Dx * Dx + i] = S[i];
-}
-
 // expected cost of `count` ring slots x N rollouts, one thread each  (upstream loops/pilco.py:199-205 with components.py:30-37)
 __global__ void k_cost_ring(RolloutMMParams p, const double* __restrict__ ring_m, const double* __restrict__ ring_S, int count,
                             double* __restrict__ costbuf) {
@@ -367,10 +334,17 @@ static int rollout_mm_fwd_impl(const gpp_gp_model* dynamics, int N, int Dx, int 
       default: set_error("gpp_rollout_mm_fwd: unsupported encoded dimension %d", p.De); return GPP_ERR_UNSUPPORTED;
     }
     count_launch();
-    int rc = mm_predict_enqueue(dynamics, p.md, p.Sd, N, p.f1, p.Sff, p.cross, 1, 0.0, ws + lo.predict, lo.predict_bytes, info, stream);
+    // Euler update, trajectory slice and cost-ring slot of step t ride on the predict's finalize kernel.  The expected cost of the
+    // new state is evaluated later, for a whole ring of steps at once (k_cost_ring): it does not feed back into the state, so the
+    // serial LU / determinant of every step stays off the critical path of the rollout
+    EulerPost post;
+    post.m = p.m; post.S = p.S; post.Sxd = p.Sxd; post.Dx = Dx;
+    post.traj_m = traj_m ? traj_m + (size_t)(t + 1) * N * Dx : nullptr;
+    post.traj_S = traj_S ? traj_S + (size_t)(t + 1) * N * Dx * Dx : nullptr;
+    post.ring_m = ring_m + (size_t)(t % kCostRing) * N * Dx;
+    post.ring_S = ring_S + (size_t)(t % kCostRing) * N * Dx * Dx;
+    int rc = mm_predict_enqueue(dynamics, p.md, p.Sd, N, p.f1, p.Sff, p.cross, 1, 0.0, ws + lo.predict, lo.predict_bytes, info, stream, &post);
     if (rc != GPP_OK) return rc;
-    k_step_post<<<gb, tb, 0, stream>>>(p, t, ring_m, ring_S);
-    count_launch();
     if ((t + 1) % kCostRing == 0 || t == H - 1) {
       const int count = t % kCostRing + 1;
       k_cost_ring<<<(count * N + 63) / 64, 64, 0, stream>>>(p, ring_m, ring_S, count, costbuf);

@@ -21,9 +21,6 @@
 
 namespace gpp {
 
-int mm_predict_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
-                       double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
-                       int* info, cudaStream_t stream);   // mm_predict.cu
 int mm_predict_bwd_enqueue(const gpp_gp_model* model, const double* m, const double* S, int N, const double* f1_bar,
                            const double* Sff_bar, const double* cross_bar, int full_output_cov, double* m_bar, double* S_bar,
                            void* workspace, size_t workspace_bytes, int* info, cudaStream_t stream);   // mm_predict_bwd.cu
