@@ -120,6 +120,7 @@ template <int DP>
 struct PreAdjoint {
   double me_bar[DP], See_bar[DP * DP], Cxe_bar[GPP_SMALL_MAX * DP];
   double f1b, f2b, cpre_bar[DP], y[DP];
+  double ubar[3], jac[2][3];   // (mu_u_bar, vu_bar, gain_bar); d(mu_u, vu, gain)/d f1 and /d vf of the squashing link
   double G1[DP * DP], G2[DP * DP];
   double red[4][2 * DP + DP * DP];
 };
@@ -144,6 +145,8 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
     step_pre_forward<DP>(p, n, sh);
   }
 
+  // Four independent serial pieces, one per warp (lane 0): the adjoint of the joint assembly, the two columns of the squashing
+  // link's 3 x 2 Jacobian (dual numbers), and the two Gram matrices of the policy adjoint.
   if (tid == 0) {
     // ---- adjoint of the joint assembly: (md, Sd, Sxd) -> (me, See, Cxe, cpre, mu_u, vu, gain)
     const double* md_bar = bw.md_bar + (size_t)n * D;
@@ -162,7 +165,6 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
       seu_bar[a] = Sdb[a * D + DP] + Sdb[DP * D + a];
       for (int b = 0; b < DP; ++b) ad.See_bar[a * DP + b] = Sdb[a * D + b];
     }
-    const double mu_u_bar = md_bar[DP], vu_bar = Sdb[DP * D + DP];
     for (int t = 0; t < Dx * DP; ++t) ad.Cxe_bar[t] = 0.0;
     for (int k = 0; k < na; ++k) {
       const int i = p.enc.active[k];
@@ -188,32 +190,43 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
         ad.cpre_bar[b] = fma(qb, sh.See[a * DP + b], ad.cpre_bar[b]);
       }
     }
-    // ---- squashing link: 2 x 3 Jacobian by dual numbers
+    ad.ubar[0] = md_bar[DP];
+    ad.ubar[1] = Sdb[DP * D + DP];
+    ad.ubar[2] = gain_bar;
+  } else if (tid == 32 || tid == 64) {
+    // ---- squashing link: one column of the Jacobian each (Owen's T: value from the forward, closed-form partials)
+    const int c = tid == 32 ? 0 : 1;
     Dual mu, vu, gn;
-    mm_squash_1d<Dual, true>(Dual(sh.f1, 1.0), Dual(sh.vf, 0.0), p.scale, p.shift, mu, vu, gn, sh.t0);   // Owen's T: value from the
-    double f1b = mu_u_bar * mu.d + vu_bar * vu.d + gain_bar * gn.d;                                       // forward, closed-form partials
-    mm_squash_1d<Dual, true>(Dual(sh.f1, 0.0), Dual(sh.vf, 1.0), p.scale, p.shift, mu, vu, gn, sh.t0);
-    const double vfb = mu_u_bar * mu.d + vu_bar * vu.d + gain_bar * gn.d;
-    ad.f2b = vfb;                          // vf = f2 - f1^2
-    ad.f1b = f1b - 2.0 * sh.f1 * vfb;
-    // ---- G1 = (See + Lambda)^-1, y = G1 cpre_bar, G2 = (See + Lambda/2)^-1
+    mm_squash_1d<Dual, true>(Dual(sh.f1, c == 0 ? 1.0 : 0.0), Dual(sh.vf, c == 0 ? 0.0 : 1.0), p.scale, p.shift, mu, vu, gn, sh.t0);
+    ad.jac[c][0] = mu.d;
+    ad.jac[c][1] = vu.d;
+    ad.jac[c][2] = gn.d;
+  } else if (tid == 96) {
+    // ---- G1 = (See + Lambda)^-1, G2 = (See + Lambda/2)^-1
     Mat<DP> Li, G, A2;
     for (int t = 0; t < DP * DP; ++t) Li.a[t] = sh.Li1[t];
     gram_inverse<DP>(Li, G);
     const double* ell = p.pEll + (size_t)r * DP;
-    for (int a = 0; a < DP; ++a) {
-      double t = 0.0;
+    for (int a = 0; a < DP; ++a)
       for (int b = 0; b < DP; ++b) {
         ad.G1[a * DP + b] = G(a, b);
-        t = fma(G(a, b), ad.cpre_bar[b], t);
         A2(a, b) = sh.See[a * DP + b] + (a == b ? 0.5 * ell[a] * ell[a] : 0.0);
       }
-      ad.y[a] = t;
-    }
     cholesky<DP>(A2);
     tri_inverse<DP>(A2, Li);
     gram_inverse<DP>(Li, G);
     for (int t = 0; t < DP * DP; ++t) ad.G2[t] = G.a[t];
+  }
+  __syncthreads();
+  if (tid < DP) {                            // y = G1 cpre_bar
+    double t = 0.0;
+    for (int b = 0; b < DP; ++b) t = fma(ad.G1[tid * DP + b], ad.cpre_bar[b], t);
+    ad.y[tid] = t;
+  } else if (tid == 32) {
+    const double f1b = ad.ubar[0] * ad.jac[0][0] + ad.ubar[1] * ad.jac[0][1] + ad.ubar[2] * ad.jac[0][2];
+    const double vfb = ad.ubar[0] * ad.jac[1][0] + ad.ubar[1] * ad.jac[1][1] + ad.ubar[2] * ad.jac[1][2];
+    ad.f2b = vfb;                          // vf = f2 - f1^2
+    ad.f1b = f1b - 2.0 * sh.f1 * vfb;
   }
   __syncthreads();
 

@@ -49,24 +49,31 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
     for (int i = 0; i < Dx; ++i) m[i] = p.m[(size_t)n * Dx + i];
     for (int i = 0; i < Dx * Dx; ++i) S[i] = p.S[(size_t)n * Dx * Dx + i];
     mm_encoder<double>(p.enc, m, S, sh.me, sh.See, sh.Cxe);
-    // coefficient pack of the (policy kernel, policy kernel) pair and the Psi1 factorisation
+  }
+  __syncthreads();
+  // two independent factorisations of the encoded covariance, one warp each (lane 0)
+  if (tid == 0) {
+    // coefficient pack of the (policy kernel, policy kernel) pair
     double V[DP], mu[DP], Sg[DP * DP];
-    Mat<DP> A, Li;
-    double half_log_v = 0.0;
 #pragma unroll
     for (int d = 0; d < DP; ++d) {
       V[d] = ell[d] * ell[d];
       mu[d] = sh.me[d];
+#pragma unroll
+      for (int e = 0; e < DP; ++e) Sg[d * DP + e] = sh.See[d * DP + e];
+    }
+    if (!make_pair_pack<DP>(mu, Sg, V, V, 2.0 * log(var), sh.pack)) flag_not_pd(p.info, n);
+  } else if (tid == 32) {
+    // Psi1 factorisation: inverse Cholesky factor of See + Lambda and the log normaliser
+    Mat<DP> A, Li;
+    double half_log_v = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
       half_log_v += log(ell[d]);
 #pragma unroll
-      for (int e = 0; e < DP; ++e) {
-        Sg[d * DP + e] = sh.See[d * DP + e];
-        A(d, e) = sh.See[d * DP + e] + (d == e ? V[d] : 0.0);
-      }
+      for (int e = 0; e < DP; ++e) A(d, e) = sh.See[d * DP + e] + (d == e ? ell[d] * ell[d] : 0.0);
     }
-    bool ok = make_pair_pack<DP>(mu, Sg, V, V, 2.0 * log(var), sh.pack);
-    ok = cholesky<DP>(A) && ok;
-    if (!ok) flag_not_pd(p.info, n);
+    if (!cholesky<DP>(A)) flag_not_pd(p.info, n);
     double log_det = 0.0;
 #pragma unroll
     for (int d = 0; d < DP; ++d) log_det += log(A(d, d));
@@ -192,35 +199,48 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
   __syncthreads();
 }
 
-// thread 0: write md, Sd and Sxd of rollout n
+// all threads of the CTA: write md, Sd and Sxd of rollout n (one entry per thread)
 template <int DP>
 __device__ void step_pre_write(const RolloutMMParams& p, int n, const PreShared<DP>& sh) {
   const int Dx = p.Dx, De = p.De, D = p.D;
   double* md = p.md + (size_t)n * D;
   double* Sd = p.Sd + (size_t)n * D * D;
-  for (int a = 0; a < De; ++a) {
-    md[a] = sh.me[a];
-    for (int b = 0; b < De; ++b) Sd[a * D + b] = sh.See[a * De + b];
-    Sd[a * D + De] = sh.seu[a];
-    Sd[De * D + a] = sh.seu[a];
-  }
-  md[De] = sh.mu_u;
-  Sd[De * D + De] = sh.vu;
-  // Sxd = Cov(x, d): active rows through the encoder linearisation, inactive rows copied from S_d (forward_sde.py:112-124)
   double* Sxd = p.Sxd + (size_t)n * Dx * D;
   const int na = p.enc.na, nb = p.enc.nb();
-  for (int k = 0; k < na; ++k) {
-    int i = p.enc.active[k];
-    double sau = 0.0;
-    for (int b = 0; b < De; ++b) {
-      Sxd[i * D + b] = sh.Cxe[i * De + b];
-      sau = fma(sh.Cxe[i * De + b], sh.cpre[b], sau);
+  // joint covariance of d = (e, u): [[See, seu], [seu^T, vu]]
+  auto sd_entry = [&](int a, int b) {
+    if (a < De && b < De) return sh.See[a * De + b];
+    if (a < De) return sh.seu[a];
+    if (b < De) return sh.seu[b];
+    return sh.vu;
+  };
+  for (int t = threadIdx.x; t < D + D * D + Dx * D; t += blockDim.x) {
+    if (t < D) {
+      md[t] = t < De ? sh.me[t] : sh.mu_u;
+    } else if (t < D + D * D) {
+      const int a = (t - D) / D, b = (t - D) % D;
+      Sd[a * D + b] = sd_entry(a, b);
+    } else {
+      // Sxd = Cov(x, d): active rows through the encoder linearisation, inactive rows copied from S_d (forward_sde.py:112-124)
+      const int i = (t - D - D * D) / D, b = (t - D - D * D) % D;
+      bool active = false;
+      for (int k = 0; k < na; ++k) active = active || p.enc.active[k] == i;
+      double v;
+      if (active) {
+        if (b < De) {
+          v = sh.Cxe[i * De + b];
+        } else {
+          double sau = 0.0;
+          for (int c = 0; c < De; ++c) sau = fma(sh.Cxe[i * De + c], sh.cpre[c], sau);
+          v = sau * sh.gain;
+        }
+      } else {
+        int j = 0;
+        for (int q = 0; q < nb; ++q) j = p.enc.inactive(q) == i ? q : j;
+        v = sd_entry(2 * na + j, b);
+      }
+      Sxd[i * D + b] = v;
     }
-    Sxd[i * D + De] = sau * sh.gain;
-  }
-  for (int j = 0; j < nb; ++j) {
-    int i = p.enc.inactive(j);
-    for (int b = 0; b < D; ++b) Sxd[i * D + b] = Sd[(2 * na + j) * D + b];
   }
 }
 
@@ -242,7 +262,7 @@ __global__ void __launch_bounds__(128) k_step_pre(RolloutMMParams p) {
   __shared__ PreShared<DP> sh;
   const int n = blockIdx.x;
   step_pre_forward<DP>(p, n, sh);
-  if (threadIdx.x == 0) step_pre_write<DP>(p, n, sh);
+  step_pre_write<DP>(p, n, sh);
   if (p.pre) {   // forward-with-save: the backward's k_bwd_pre reloads this block instead of recomputing the stage
     constexpr int PS = PreSharedSize<DP>::value;
     const double* src = reinterpret_cast<const double*>(&sh);
