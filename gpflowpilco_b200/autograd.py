@@ -42,32 +42,35 @@ def mm_predict(handle: GPModelHandle, m: torch.Tensor, S: torch.Tensor, full_out
 
 class _RolloutMM(torch.autograd.Function):
   @staticmethod
-  def forward(ctx, Z, lengthscales, q_mu, m0, S0, dynamics, variance, whiten, jitter, scale, shift, horizon, active_dims, target, W):
+  def forward(ctx, Z, lengthscales, q_mu, m0, S0, dynamics, variance, whiten, jitter, scale, shift, horizon, active_dims, target, W,
+              check):
     pol = PolicyParams(Z.detach(), lengthscales.detach(), variance, q_mu.detach(), whiten=whiten, jitter=jitter, squash_scale=scale,
                        squash_shift=shift)
-    beta = pol.beta()                                                                      # gpp_policy_prepare
-    res = rollout_mm(dynamics, pol, m0.detach(), S0.detach(), horizon, active_dims, target, W, beta=beta, save_for_backward=True)
+    beta = pol.beta(check=check)                                                           # gpp_policy_prepare
+    res = rollout_mm(dynamics, pol, m0.detach(), S0.detach(), horizon, active_dims, target, W, beta=beta, save_for_backward=True,
+                     check=check)
     ctx.save_for_backward(beta, res.traj_m, res.traj_S, res.saved)
-    ctx.pol, ctx.dynamics, ctx.active_dims, ctx.target, ctx.W = pol, dynamics, tuple(active_dims), target, W
+    ctx.pol, ctx.dynamics, ctx.active_dims, ctx.target, ctx.W, ctx.check = pol, dynamics, tuple(active_dims), target, W, check
     return res.loss
 
   @staticmethod
   def backward(ctx, loss_bar):
     beta, traj_m, traj_S, saved = ctx.saved_tensors
     Zb, eb, bb, m0b, S0b = rollout_mm_bwd(ctx.dynamics, ctx.pol, beta, traj_m, traj_S, ctx.active_dims, ctx.target, ctx.W,
-                                          loss_bar=loss_bar.contiguous(), saved=saved)
+                                          loss_bar=loss_bar.contiguous(), saved=saved, check=ctx.check)
     qb = policy_beta_bwd(ctx.pol, beta, bb, Zb, eb)                                         # gpp_policy_prepare_bwd
-    return Zb, eb, qb, m0b, S0b, None, None, None, None, None, None, None, None, None, None
+    return Zb, eb, qb, m0b, S0b, None, None, None, None, None, None, None, None, None, None, None
 
 
 def rollout_mm_loss(dynamics: GPModelHandle, Z: torch.Tensor, lengthscales: torch.Tensor, variance: torch.Tensor, q_mu: torch.Tensor,
                     m0: torch.Tensor, S0: torch.Tensor, horizon: int, active_dims: Sequence[int], cost_target: torch.Tensor,
                     cost_W: torch.Tensor, squash_scale: float = 1.0, squash_shift: float = -0.5, whiten: bool = True,
-                    jitter: float = 1e-6) -> torch.Tensor:
+                    jitter: float = 1e-6, check: bool = True) -> torch.Tensor:
   """loss[N] of the moment-matched rollout (upstream MomentMatchingPILCO closure, loops/pilco.py:192-220), differentiable
-  w.r.t. the policy parameters Z [R,Mp,De], lengthscales [R,De], q_mu [R,Mp] and the initial moments (m0, S0)."""
+  w.r.t. the policy parameters Z [R,Mp,De], lengthscales [R,De], q_mu [R,Mp] and the initial moments (m0, S0).
+  `check=False` skips the synchronising reads of the not-positive-definite flags (timed loops, CUDA-graph capture)."""
   return _RolloutMM.apply(Z, lengthscales, q_mu, m0, S0, dynamics, variance, bool(whiten), float(jitter), float(squash_scale),
-                          float(squash_shift), int(horizon), tuple(active_dims), cost_target, cost_W)
+                          float(squash_shift), int(horizon), tuple(active_dims), cost_target, cost_W, bool(check))
 
 
 class _RolloutPathwise(torch.autograd.Function):

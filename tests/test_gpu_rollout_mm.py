@@ -125,3 +125,28 @@ def test_rollout_is_capturable_in_a_cuda_graph():
   graph.replay()
   torch.cuda.synchronize()
   assert torch.equal(out, eager)
+
+
+def test_graphed_policy_gradient_replays_the_eager_result():
+  """Forward rollout + reverse sweep + policy-weight adjoint captured once (gpflowpilco_b200/graphs.py) and replayed with new
+  parameter values: bit-identical to the eager autograd path, for the captured values and for perturbed ones."""
+  from gpflowpilco_b200.autograd import rollout_mm_loss
+  from gpflowpilco_b200.graphs import GraphedMMPolicyGradient
+  cfg = synthetic.config1_cartpole(M=48, Mp=10)
+  h = cuda_handle(cfg["dynamics"])
+  p = cfg["policy"]
+  Z, ell, var, q = _dev(p["Z"]), _dev(p["lengthscales"]), _dev(p["variance"]), _dev(p["q_mu"][:, 0][None])
+  m0, S0, tgt, W = _dev(cfg["m0"]), _dev(cfg["S0"]), _dev(cfg["target"]), _dev(cfg["W"])
+  kw = dict(squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  g = GraphedMMPolicyGradient(h, Z, ell, var, q, m0, S0, 6, cfg["active_dims"], tgt, W, **kw)
+  gen = torch.Generator().manual_seed(3)
+  for trial in range(2):
+    Zt = (Z + 0.05 * trial * torch.randn(Z.shape, dtype=torch.float64, generator=gen).to(Z.device)).requires_grad_(True)
+    et = (ell * (1.0 + 0.1 * trial)).requires_grad_(True)
+    qt = (q + 0.01 * trial).requires_grad_(True)
+    loss = rollout_mm_loss(h, Zt, et, var, qt, m0, S0, 6, cfg["active_dims"], tgt, W, **kw)
+    ref = torch.autograd.grad(loss.sum(), (Zt, et, qt))
+    gl, gg = g(Zt.detach(), et.detach(), qt.detach())
+    assert torch.equal(gl, loss.detach())
+    for a, b in zip(gg, ref):
+      assert torch.equal(a, b)
