@@ -420,12 +420,34 @@ def policy_opt_section(dev, lib, world):
              "rollout_steps_per_s_forward": H1 / float(np.mean(c1["fwd_ms"])) * 1e3, "loss": float(l1.detach()[0])}
   if world == 1 and not args.no_cpu_baseline:
     config1["cpu"] = time_cpu_rollout(cfg, H1)
+  # the same evaluations replayed from a captured CUDA graph (gpflowpilco_b200/graphs.py): forward + backward + policy adjoint
+  from gpflowpilco_b200.graphs import GraphedMMPolicyGradient
+  def graph_ms(Zg, eg, vg, qg, m0g, S0g, Hg):
+    gr = GraphedMMPolicyGradient(handle, Zg, eg, vg, qg, m0g, S0g, Hg, cfg["active_dims"], T(cfg["target"]), T(cfg["W"]),
+                                 squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+    ts = []
+    for _ in range(4):
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      gl, _ = gr(Zg, eg, qg, check=False)
+      e1.record()
+      e1.synchronize()
+      ts.append(e0.elapsed_time(e1))
+    return float(np.mean(ts[1:])), gl.clone()
+  g1_ms, g1_loss = graph_ms(Z1.detach(), e1_.detach(), T(p["variance"]), q1.detach(), T(cfg["m0"]), T(cfg["S0"]), H1)
+  config1["graph_forward_backward_ms"] = g1_ms
+  config1["graph_loss_equal"] = bool(torch.equal(g1_loss, l1.detach()))
+  lo, Rl = gd.shard_range(Rt, int(os.environ.get("RANK", "0")), world)
+  hi = lo + Rl
+  g5_ms, _ = graph_ms(Z[lo:hi].contiguous(), ell[lo:hi].contiguous(), var[lo:hi].contiguous(), q[lo:hi].contiguous(),
+                      T(cfg["m0"]).expand(Rl, -1).contiguous(), T(cfg["S0"]).expand(Rl, -1, -1).contiguous(), H)
   M, L, D = d["Z"].shape[1], 4, 6
   flop_per_step = 4 * (L * (L + 1) // 2) * M * M * (2 * D + 26)      # fwd + bwd counted as 4 x forward
   return {"metric": "mm_policy_opt_rollout_steps_per_s", "value": Rt * H / sec, "unit": "rollout_steps/s (forward+backward)",
           "config": {"workload": "config#5 policy-optimisation step", "restarts_per_gpu": R, "horizon": H, "dynamics_inducing": M,
                      "policy_centres": int(p["Z"].shape[1]), "collective": "all-gather of loss[R] (uneven-safe), gradients stay sharded"},
-          "ms_per_opt_step": 1e3 * sec, "gpu_launches_per_opt_step": int(launches), "mean_loss": float(losses.mean()),
+          "ms_per_opt_step": 1e3 * sec, "graph_ms_per_opt_step_local_share": g5_ms,
+          "gpu_launches_per_opt_step": int(launches), "mean_loss": float(losses.mean()),
           "config1_rollout": config1,
           "grad_norm": float(grads[0].norm()),
           "roofline": {"bound": "fp64", "achieved": Rt * H * flop_per_step / sec / 1e12 / world, "unit": "TFLOP/s per GPU",
