@@ -187,6 +187,18 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
   const int csoff = warp * kGradCols + (b2 ? 8 : 0) + (b3 ? 4 : 0) + c4;    // this lane's column after the transpose-reduce
   auto main_loop = [&](auto diag_tag) {
     constexpr bool DIAG = decltype(diag_tag)::value;
+    // diagonal pairs read their weights C_a[row][j] from global memory (L2): the 4 values of an iteration are fetched one iteration
+    // ahead so that the load latency hides behind the DMMA + exp chain
+    auto load_weights = [&](int cbk, int cg, double (&w)[4]) {
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) {
+        const int j = cbk * kGradCols + (cg + uu) * 8 + c4;
+        w[2 * uu] = j < M ? Crow[j] : 0.0;
+        w[2 * uu + 1] = j + 4 < M ? Crow[j + 4] : 0.0;
+      }
+    };
+    double wn[4] = {0.0, 0.0, 0.0, 0.0};
+    if (DIAG) load_weights(0, 0, wn);
     for (int cbk = 0; cbk < ncb; ++cbk) {
       const int buf = cbk & 1;
       if (cbk + 1 < ncb) prepare_columns(cbk + 1, buf ^ 1);
@@ -195,6 +207,14 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
       double* cs = csum + buf * CF::NW * kGradCols + csoff;
 #pragma unroll 1
       for (int cg = 0; cg < kGradCols / 8; cg += 2) {
+        double w[4];
+        if (DIAG) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w[k] = wn[k];
+          // next iteration's weights (the index past the last block is masked by j < M)
+          const int cgn = cg + 2 < kGradCols / 8 ? cg + 2 : 0, cbn = cg + 2 < kGradCols / 8 ? cbk : cbk + 1;
+          load_weights(cbn, cgn, wn);
+        }
         double t[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
@@ -205,17 +225,13 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
         double A[4];
 #pragma unroll
         for (int uu = 0; uu < 2; ++uu) {
-          const int jl = (cg + uu) * 8 + c4, j = cbk * kGradCols + jl;      // this lane's columns: j and j + 4
-          double w0, w1;
-          if (DIAG) {
-            w0 = j < M ? Crow[j] : 0.0;
-            w1 = j + 4 < M ? Crow[j + 4] : 0.0;
-          } else {
-            w0 = colW[buf * kGradCols + jl] * rs;
-            w1 = colW[buf * kGradCols + jl + 4] * rs;
+          const int jl = (cg + uu) * 8 + c4;                               // this lane's columns: jl and jl + 4 of the block
+          if (!DIAG) {
+            w[2 * uu] = colW[buf * kGradCols + jl] * rs;
+            w[2 * uu + 1] = colW[buf * kGradCols + jl + 4] * rs;
           }
-          A[2 * uu] = t[2 * uu] * w0;                                      // A[row][j], A[row][j + 4]
-          A[2 * uu + 1] = t[2 * uu + 1] * w1;
+          A[2 * uu] = t[2 * uu] * w[2 * uu];                               // A[row][j], A[row][j + 4]
+          A[2 * uu + 1] = t[2 * uu + 1] * w[2 * uu + 1];
           if (!ROWSUM_IN_U) ai += A[2 * uu] + A[2 * uu + 1];
           const double* zb = cb + jl * 4 + zoff;                           // Z2'[column 8 (cg+uu) + k][dimension n], k = c4
           dmma_m8n8k4(u0, u1, A[2 * uu], zb[0]);
