@@ -7,7 +7,7 @@
 namespace gpp {
 
 // ---------------------------------------------------------------------------------------------------------
-// k_pack
+// pack_body: coefficients of one (input, kernel pair)
 // ---------------------------------------------------------------------------------------------------------
 template <int D>
 __device__ __forceinline__ void pack_body(int idx, const double* __restrict__ m, const double* __restrict__ S, int N,
@@ -37,7 +37,7 @@ __device__ __forceinline__ void pack_body(int idx, const double* __restrict__ m,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_psi1: latent mean  f1[n,l] = sum_m beta_l[m] Psi1[n,m,l]  and  cross[n,:,l] = (S_n+Lambda_l)^-1 sum_m beta Psi1 (z_m - mu)
+// psi1_body: latent mean  f1[n,l] = sum_m beta_l[m] Psi1[n,m,l]  and  cross[n,:,l] = (S_n+Lambda_l)^-1 sum_m beta Psi1 (z_m - mu)
 //         (models.py:236 and :264-277; Psi1 is GPflow's eKxz)
 // ---------------------------------------------------------------------------------------------------------
 template <int D>

@@ -2,7 +2,7 @@
 //
 // Upstream differentiates the closure of MomentMatchingPILCO (gpflow_pilco/loops/pilco.py:192-220) with tape.gradient
 // w.r.t. policy.trainable_variables (gpflow_pilco/utils/optimizers.py:52-56).  Here, for t = H-1 .. 0, from the stored
-// trajectory (m_t, S_t) and the per-step (md, Sd, Sxd, cross) kept by gpp_rollout_mm_fwd_save — or, without them:
+// trajectory (m_t, S_t) and the per-step (md, Sd, Sxd, cross, pre-stage block) kept by gpp_rollout_mm_fwd_save — or, without them:
 //   k_step_pre            recompute the pre stage of step t (md, Sd, Sxd)                       [rollout_mm_common.cuh]
 //   mm_predict_enqueue    recompute (f1, Sff, cross) of step t with the fused forward kernels   [mm_predict.cu]
 // then
@@ -11,8 +11,8 @@
 //   k_bwd_post            adjoint of (m_{t+1}, S_{t+1}) += loss_bar * that gradient, then the adjoint of the Euler moment update
 //                         (dynamics/solvers.py:128-129) and of Sxf = Sxd cross  (forward_sde.py:126)
 //   mm_predict_bwd        closed-form adjoint of the GP dynamics prediction                     [mm_predict_bwd.cu]
-//   k_bwd_pre             adjoint of the joint assembly (forward_sde.py:105-124, gaussian.py:53-63), of the squashing link
-//                         (2x2 Jacobian by dual numbers), closed-form adjoint of the policy's Psi1/Psi2 sums w.r.t. the
+//   k_bwd_pre             reload (or recompute) the pre stage's shared block; adjoint of the joint assembly (forward_sde.py:105-124,
+//                         gaussian.py:53-63), of the squashing link (3x2 Jacobian by dual numbers), closed-form adjoint of the policy's Psi1/Psi2 sums w.r.t. the
 //                         encoded moments AND the policy parameters (centres Z, weights beta = Kuu^-1 m, lengthscales),
 //                         then the encoder adjoint (dual numbers, one direction per thread).
 // Matrix adjoints follow one convention throughout: S_bar is symmetric and dLoss = sum_ij S_bar_ij dS_ij for symmetric dS.
