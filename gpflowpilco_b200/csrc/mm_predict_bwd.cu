@@ -275,86 +275,143 @@ __global__ void __launch_bounds__(kGradThreads, 2) k_contract_grad(const double*
   }
   if (!diag) fold_column_sums(ncb - 1);
   __syncthreads();
-  constexpr int CH = kGradThreads / 64;      // 8 chunks of 16 entries; statistics beyond 64 loop
-  // statistic k of a scratch block: S0 = sum a;  R1[d] = sum a z[d];  R2[d,e] = sum a z[d] z[e];  X[d,e] = sum z[d] u[e]
-  auto decode = [](int k, int& kind, int& d1, int& d2) {
-    d1 = 0; d2 = 0;
-    if (k == GS::S0) kind = 0;
-    else if (k < GS::R2) { kind = 1; d1 = k - GS::R1; }
-    else if (k < GS::X) {
-      kind = 2;
-      int t = k - GS::R2;
-      while (t >= D - d1) { t -= D - d1; ++d1; }
-      d2 = d1 + t;
-    } else { kind = 3; d1 = (k - GS::X) / D; d2 = (k - GS::X) % D; }
-  };
-  auto chunk_sum = [&](const double* scratch, int q, int kind, int d1, int d2) {
-    double acc = 0.0;
-    for (int r = q * (kGradRows / CH); r < (q + 1) * (kGradRows / CH); ++r) {
-      const double* rw = scratch + r * RW;
+  double* out2 = stats + (((size_t)n * L * L + b * L + a) * nrb + rb) * GS::SIZE;   // ordered pair (b, a), a < b
+  if constexpr (D <= 7) {
+    // Every statistic is an entry of the Gram product  G = sum_rows F^T H  with  F = [z1' (D), 1],  H = [a z1' (D), u (D), a]:
+    //   G[m][n]     (m, n < D)   = R2[m][n]        G[m][D + e] = X[m][e]        G[m][2D] = r1[m]
+    //   G[D][D + e]              = sum_i u_i[e] = r1_ba[e]                       G[D][2D] = S0
+    // and, for a < b, R2_ba = sum_cols z2'^T (a' z2').  Each warp forms the product of its own 8 rows (2 k-steps x 2 column tiles)
+    // and of 8 columns of every column block (2 k-steps) on the tensor path; the 16 partial 8 x 24 matrices are summed in warp order.
+    constexpr int GW = 24;
+    const int q = lane >> 2;                                  // A operand: feature q of row k; B operand: feature q (+8) of row k
+    double g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0, h0 = 0.0, h1 = 0.0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const double* rw = rows + (warp * 8 + c4 + 4 * s) * RW;
       const double av = rw[0];
-      if (kind == 0) acc += av;
-      else if (kind == 1) acc = fma(av, rw[1 + D + d1], acc);
-      else if (kind == 2) acc = fma(av * rw[1 + D + d1], rw[1 + D + d2], acc);
-      else if (kind == 3) acc = fma(rw[1 + D + d1], rw[1 + d2], acc);
-      else acc += rw[1 + d1];                // kind 4: sum of u[d1]
+      const double fa = q < D ? rw[1 + D + q] : (q == D ? 1.0 : 0.0);
+      auto hval = [&](int nh) -> double {                     // H[row][nh] = a z[nh] | u[nh - D] | a | 0
+        if (nh < D) return av * rw[1 + D + nh];
+        if (nh < 2 * D) return rw[1 + (nh - D)];
+        return nh == 2 * D ? av : 0.0;
+      };
+      dmma_m8n8k4(g00, g01, fa, hval(q));
+      dmma_m8n8k4(g10, g11, fa, hval(q + 8));
     }
-    return acc;
-  };
-  for (int k = tid & 63; k < GS::SIZE; k += 64) {
-    int kind, d1, d2;
-    decode(k, kind, d1, d2);
-    red[(tid >> 6) * GS::SIZE + k] = chunk_sum(rows, tid >> 6, kind, d1, d2);
-  }
-  __syncthreads();
-  if (tid < GS::SIZE) {
-    double s = 0.0;
+    if (!diag) {
+      for (int cbk = 0; cbk < ncb; ++cbk)
 #pragma unroll
-    for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
-    out[tid] = s;
-  }
-  if (diag) return;
-  // ordered pair (b, a): r1_ba = sum_i u_i (row scratch), R2_ba = sum_j a'_j z2'_j z2'_j^T (column scratch, 128 columns at a time in
-  // the per-warp column-sum buffers, free after the last fold); S0_ba and X_ba are not stored (symmetry, see k_bwd_finalize)
-  double* out2 = stats + (((size_t)n * L * L + b * L + a) * nrb + rb) * GS::SIZE;
-  double* cscr = csum;
-  static_assert(kGradCols * RW <= 2 * CF::NW * kGradCols, "column scratch fits in the column-sum buffers");
-  double acc2[(GS::SIZE + 63) / 64];
-#pragma unroll
-  for (int s = 0; s < (GS::SIZE + 63) / 64; ++s) acc2[s] = 0.0;
-  {
-    int s = 0;
-    for (int k = tid & 63; k < GS::SIZE; k += 64, ++s)
-      if (k >= GS::R1 && k < GS::R2) acc2[s] = chunk_sum(rows, tid >> 6, 4, k - GS::R1, 0);
-  }
-  for (int cbk = 0; cbk < ncb; ++cbk) {
-    __syncthreads();                         // previous block's readers are done
-    if (tid < kGradCols) {
-      const int j = cbk * kGradCols + tid;
-      double* cw = cscr + tid * RW;
-      cw[0] = colA[j];
-#pragma unroll
-      for (int d = 0; d < D; ++d) cw[1 + D + d] = j < M ? Z[((size_t)b * M + j) * D + d] - pk[PP::MU + d] : 0.0;
+        for (int s = 0; s < 2; ++s) {
+          const int j = cbk * kGradCols + warp * 8 + c4 + 4 * s;
+          const double zq = (q < D && j < M) ? Z[((size_t)b * M + j) * D + q] - pk[PP::MU + q] : 0.0;
+          dmma_m8n8k4(h0, h1, zq, colA[j] * zq);
+        }
     }
+    static_assert(CF::NW * 8 * GW <= 2 * CF::NW * kGradCols, "partial Gram matrices fit in the column-sum buffers");
+    double* gw = csum + warp * (8 * GW) + q * GW + 2 * c4;      // the per-warp column sums are folded: their buffers are free
+    gw[0] = g00; gw[1] = g01; gw[8] = g10; gw[9] = g11; gw[16] = h0; gw[17] = h1;
     __syncthreads();
-    int s = 0;
-    for (int k = tid & 63; k < GS::SIZE; k += 64, ++s) {
-      if (k < GS::R2 || k >= GS::X) continue;
+    if (tid < 8 * GW) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < CF::NW; ++w) sum += csum[w * (8 * GW) + tid];
+      const int m = tid / GW, nn2 = tid % GW;
+      if (nn2 < 16) {
+        if (m < D) {
+          if (nn2 < D) { if (nn2 >= m) out[GS::R2 + m * D - m * (m - 1) / 2 + (nn2 - m)] = sum; }
+          else if (nn2 < 2 * D) out[GS::X + m * D + (nn2 - D)] = sum;
+          else if (nn2 == 2 * D) out[GS::R1 + m] = sum;
+        } else if (m == D) {
+          if (nn2 == 2 * D) out[GS::S0] = sum;
+          else if (!diag && nn2 >= D && nn2 < 2 * D) out2[GS::R1 + (nn2 - D)] = sum;
+        }
+      } else if (!diag) {
+        const int e = nn2 - 16;
+        if (m < D && e < D && e >= m) out2[GS::R2 + m * D - m * (m - 1) / 2 + (e - m)] = sum;
+      }
+    }
+  } else {
+    // D = 8: [z, 1] does not fit one 8-row tile; one thread per (statistic, 16-row chunk) forms the products, fixed-order sums
+    constexpr int CH = kGradThreads / 64;      // 8 chunks of 16 entries; statistics beyond 64 loop
+    // statistic k of a scratch block: S0 = sum a;  R1[d] = sum a z[d];  R2[d,e] = sum a z[d] z[e];  X[d,e] = sum z[d] u[e]
+    auto decode = [](int k, int& kind, int& d1, int& d2) {
+      d1 = 0; d2 = 0;
+      if (k == GS::S0) kind = 0;
+      else if (k < GS::R2) { kind = 1; d1 = k - GS::R1; }
+      else if (k < GS::X) {
+        kind = 2;
+        int t = k - GS::R2;
+        while (t >= D - d1) { t -= D - d1; ++d1; }
+        d2 = d1 + t;
+      } else { kind = 3; d1 = (k - GS::X) / D; d2 = (k - GS::X) % D; }
+    };
+    auto chunk_sum = [&](const double* scratch, int q, int kind, int d1, int d2) {
+      double acc = 0.0;
+      for (int r = q * (kGradRows / CH); r < (q + 1) * (kGradRows / CH); ++r) {
+        const double* rw = scratch + r * RW;
+        const double av = rw[0];
+        if (kind == 0) acc += av;
+        else if (kind == 1) acc = fma(av, rw[1 + D + d1], acc);
+        else if (kind == 2) acc = fma(av * rw[1 + D + d1], rw[1 + D + d2], acc);
+        else if (kind == 3) acc = fma(rw[1 + D + d1], rw[1 + d2], acc);
+        else acc += rw[1 + d1];                // kind 4: sum of u[d1]
+      }
+      return acc;
+    };
+    for (int k = tid & 63; k < GS::SIZE; k += 64) {
       int kind, d1, d2;
       decode(k, kind, d1, d2);
-      acc2[s] += chunk_sum(cscr, tid >> 6, 2, d1, d2);
+      red[(tid >> 6) * GS::SIZE + k] = chunk_sum(rows, tid >> 6, kind, d1, d2);
     }
-  }
-  {
-    int s = 0;
-    for (int k = tid & 63; k < GS::SIZE; k += 64, ++s) red[(tid >> 6) * GS::SIZE + k] = acc2[s];
-  }
-  __syncthreads();
-  if (tid >= GS::R1 && tid < GS::X) {        // the only statistics of (b, a) k_bwd_finalize reads
-    double s = 0.0;
+    __syncthreads();
+    if (tid < GS::SIZE) {
+      double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
-    out2[tid] = s;
+      for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
+      out[tid] = s;
+    }
+    if (diag) return;
+    // ordered pair (b, a): r1_ba = sum_i u_i (row scratch), R2_ba = sum_j a'_j z2'_j z2'_j^T (column scratch, 128 columns at a time
+    // in the per-warp column-sum buffers, free after the last fold); S0_ba and X_ba are not stored (symmetry, see k_bwd_finalize)
+    double* cscr = csum;
+    static_assert(kGradCols * RW <= 2 * CF::NW * kGradCols, "column scratch fits in the column-sum buffers");
+    double acc2[(GS::SIZE + 63) / 64];
+#pragma unroll
+    for (int s = 0; s < (GS::SIZE + 63) / 64; ++s) acc2[s] = 0.0;
+    {
+      int s = 0;
+      for (int k = tid & 63; k < GS::SIZE; k += 64, ++s)
+        if (k >= GS::R1 && k < GS::R2) acc2[s] = chunk_sum(rows, tid >> 6, 4, k - GS::R1, 0);
+    }
+    for (int cbk = 0; cbk < ncb; ++cbk) {
+      __syncthreads();                         // previous block's readers are done
+      if (tid < kGradCols) {
+        const int j = cbk * kGradCols + tid;
+        double* cw = cscr + tid * RW;
+        cw[0] = colA[j];
+#pragma unroll
+        for (int d = 0; d < D; ++d) cw[1 + D + d] = j < M ? Z[((size_t)b * M + j) * D + d] - pk[PP::MU + d] : 0.0;
+      }
+      __syncthreads();
+      int s = 0;
+      for (int k = tid & 63; k < GS::SIZE; k += 64, ++s) {
+        if (k < GS::R2 || k >= GS::X) continue;
+        int kind, d1, d2;
+        decode(k, kind, d1, d2);
+        acc2[s] += chunk_sum(cscr, tid >> 6, 2, d1, d2);
+      }
+    }
+    {
+      int s = 0;
+      for (int k = tid & 63; k < GS::SIZE; k += 64, ++s) red[(tid >> 6) * GS::SIZE + k] = acc2[s];
+    }
+    __syncthreads();
+    if (tid >= GS::R1 && tid < GS::X) {        // the only statistics of (b, a) k_bwd_finalize reads
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
+      out2[tid] = s;
+    }
   }
 }
 
