@@ -87,7 +87,7 @@ struct PairPack {
 
 template <int D>
 GPP_HD bool make_pair_pack(const double* mu, const double* Sigma, const double* V1, const double* V2,
-                           double log_amp, double* out) {
+                           double log_amp, double* out, double* G_out = nullptr /* optional (Sigma + V)^-1, [D][D] */) {
   using PP = PairPack<D>;
   Mat<D> S, Li, G;
   double A1[D], A2[D], dg[D];
@@ -109,6 +109,10 @@ GPP_HD bool make_pair_pack(const double* mu, const double* Sigma, const double* 
   for (int d = 0; d < D; ++d) log_det += log(S(d, d));
   tri_inverse<D>(S, Li);
   gram_inverse<D>(Li, G);
+  if (G_out) {
+#pragma unroll
+    for (int d = 0; d < D * D; ++d) G_out[d] = G.a[d];
+  }
 #pragma unroll
   for (int d = 0; d < D; ++d)
 #pragma unroll

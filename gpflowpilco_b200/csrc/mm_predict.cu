@@ -226,7 +226,7 @@ static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S,
   unsigned* counter = (unsigned*)(ws + pl.off_counter);
   PackPsi1Params pp;
   pp.m = mu; pp.S = S; pp.Z = m->Z; pp.ell = m->ell; pp.var = m->var; pp.beta = m->beta; pp.pair_ab = tab.d_pair_ab;
-  pp.packs = packs; pp.f1lat = f1lat; pp.crosslat = crosslat; pp.counter = counter; pp.info = info;
+  pp.packs = packs; pp.f1lat = f1lat; pp.crosslat = crosslat; pp.Gs = nullptr; pp.counter = counter; pp.info = info;
   pp.N = N; pp.L = m->L; pp.M = m->M; pp.npairs = tab.npairs;
   launch_pack_psi1<D>(pp, stream);
   count_launch();

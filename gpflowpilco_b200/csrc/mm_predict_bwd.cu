@@ -623,111 +623,122 @@ struct BwdFinalizeParams {
   const double* ell;            // [L,D]
   const double* stats;          // [N,L*L,nrb,GS::SIZE]
   const double* omega;          // [N,L,L]
+  const double* Gs;             // [N,L*L,D,D]  (Sigma_n + V_ab)^-1 from the prologue
   const double *gm, *gS;        // psi1 contributions [N,L,D], [N,L,D,D]
   double *m_bar, *S_bar;        // [N,D], [N,D,D]
   int N, L, nrb;
 };
 
 template <int D>
-__global__ void __launch_bounds__(64) k_bwd_finalize(BwdFinalizeParams p) {
+struct FinalizeSmem {
   using GS = GradStats<D>;
-  constexpr int CS = D + D * D;
+  static constexpr int CS = D + D * D, DD = D * D;
+  static constexpr int PER_PAIR = 2 * GS::SIZE + 2 * CS + 2 * DD + 4;   // statistics (ab, ba), E1|E2, contribution, G, G E2, (a, b, weight, pad)
+};
+
+// CTA per input.  d f2_ab / d mu = G E1,  d f2_ab / d Sigma = 1/2 (G E2 G - S0 G)  with E1 = A1 r1_ab + A2 r1_ba and
+// E2 = A1 R2_ab A1 + A2 R2_ba A2 + A1 X A2 + (A1 X A2)^T per unordered pair; every phase is spread over the CTA's threads
+// (one matrix entry each) with the operands in shared memory, pairs and Psi1 terms are summed in a fixed order at the end.
+template <int D>
+__global__ void __launch_bounds__(128) k_bwd_finalize(BwdFinalizeParams p) {
+  using GS = GradStats<D>;
+  using FS = FinalizeSmem<D>;
+  constexpr int CS = FS::CS, DD = FS::DD;
   extern __shared__ __align__(16) double fsm[];
-  const int n = blockIdx.x, tid = threadIdx.x, L = p.L;
+  const int n = blockIdx.x, tid = threadIdx.x, L = p.L, nt = blockDim.x;
   const int npairs = L * (L + 1) / 2;
-  double (*sst)[2][GS::SIZE] = reinterpret_cast<double (*)[2][GS::SIZE]>(fsm);                            // [npairs][2][SIZE]
-  double (*contrib)[CS] = reinterpret_cast<double (*)[CS]>(fsm + (size_t)npairs * 2 * GS::SIZE);          // [npairs][CS]
-  // slot (a, b), a <= b: all statistics; slot (b, a), a < b: only r1 and R2 (S0_ba = S0_ab, X_ba = X_ab^T are not stored).
-  // The CTA sums the row blocks of every slot into shared memory first (coalesced over the statistic index).
-  for (int idx = tid; idx < npairs * 2 * GS::SIZE; idx += blockDim.x) {
-    const int k = idx % GS::SIZE, which = (idx / GS::SIZE) & 1, pr = idx / (2 * GS::SIZE);
+  double* sst = fsm;                                   // [npairs][2][SIZE]
+  double* e12 = sst + (size_t)npairs * 2 * GS::SIZE;   // [npairs][CS]
+  double* contrib = e12 + (size_t)npairs * CS;         // [npairs][CS]
+  double* gmat = contrib + (size_t)npairs * CS;        // [npairs][DD]
+  double* gt = gmat + (size_t)npairs * DD;             // [npairs][DD]
+  double* meta = gt + (size_t)npairs * DD;             // [npairs][4]: a, b, weight
+  for (int pr = tid; pr < npairs; pr += nt) {          // unordered pair index -> (a <= b)
     int a = 0, b = pr;
     while (b >= L - a) { b -= L - a; ++a; }
     b += a;
+    meta[pr * 4] = a;
+    meta[pr * 4 + 1] = b;
+    meta[pr * 4 + 2] = (a == b) ? p.omega[((size_t)n * L + a) * L + a]
+                                : p.omega[((size_t)n * L + a) * L + b] + p.omega[((size_t)n * L + b) * L + a];
+  }
+  __syncthreads();
+  // slot (a, b), a <= b: all statistics; slot (b, a), a < b: only r1 and R2 (S0_ba = S0_ab, X_ba = X_ab^T are not stored)
+  for (int idx = tid; idx < npairs * 2 * GS::SIZE; idx += nt) {
+    const int k = idx % GS::SIZE, which = (idx / GS::SIZE) & 1, pr = idx / (2 * GS::SIZE);
+    const int a = (int)meta[pr * 4], b = (int)meta[pr * 4 + 1];
     const bool mirrored = k >= GS::R1 && k < GS::X;
     const int slot = (which == 0 || !mirrored) ? a * L + b : b * L + a;
-    const double wgt = p.omega[((size_t)n * L + a) * L + b] + p.omega[((size_t)n * L + b) * L + a];
     double x = 0.0;
-    if (wgt != 0.0)                          // skipped pairs were not written by k_contract_grad
+    if (meta[pr * 4 + 2] != 0.0)             // skipped pairs were not written by k_contract_grad
       for (int rb = 0; rb < p.nrb; ++rb) x += p.stats[(((size_t)n * L * L + slot) * p.nrb + rb) * GS::SIZE + k];
-    sst[pr][which][k] = x;
+    sst[idx] = x;
+  }
+  for (int idx = tid; idx < npairs * DD; idx += nt) {
+    const int pr = idx / DD, k = idx % DD;
+    const int a = (int)meta[pr * 4], b = (int)meta[pr * 4 + 1];
+    gmat[idx] = p.Gs[((size_t)n * L * L + a * L + b) * DD + k];
   }
   __syncthreads();
-  for (int pr = tid; pr < npairs; pr += blockDim.x) {
-    // unordered pair index -> (a <= b)
-    int a = 0, rem = pr;
-    while (rem >= L - a) { rem -= L - a; ++a; }
-    const int b = a + rem;
-    double* out = contrib[pr];
-    const double wgt = (a == b) ? p.omega[((size_t)n * L + a) * L + a]
-                                : p.omega[((size_t)n * L + a) * L + b] + p.omega[((size_t)n * L + b) * L + a];
-    if (wgt == 0.0) {
-      for (int k = 0; k < CS; ++k) out[k] = 0.0;
-      continue;
-    }
-    const double* sab = sst[pr][0];
-    const double* sba = sst[pr][1];
-    double A1[D], A2[D];
-    Mat<D> Sm, Li, G;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
+  for (int idx = tid; idx < npairs * CS; idx += nt) {  // E1 [D] | E2 [D][D]
+    const int pr = idx / CS, k = idx % CS;
+    const int a = (int)meta[pr * 4], b = (int)meta[pr * 4 + 1];
+    const double* sab = sst + (size_t)pr * 2 * GS::SIZE;
+    const double* sba = sab + GS::SIZE;
+    auto mix = [&](int d, double& A1, double& A2) {
       const double v1 = p.ell[a * D + d] * p.ell[a * D + d], v2 = p.ell[b * D + d] * p.ell[b * D + d];
-      A1[d] = v2 / (v1 + v2);
-      A2[d] = v1 / (v1 + v2);
-#pragma unroll
-      for (int e = 0; e < D; ++e) Sm(d, e) = p.S[(size_t)n * D * D + d * D + e] + (d == e ? v1 * A1[d] : 0.0);
+      A1 = v2 / (v1 + v2);
+      A2 = v1 / (v1 + v2);
+    };
+    double v;
+    if (k < D) {
+      double A1, A2;
+      mix(k, A1, A2);
+      v = A1 * sab[GS::R1 + k] + A2 * sba[GS::R1 + k];
+    } else {
+      const int d = (k - D) / D, e = (k - D) % D;
+      double A1d, A2d, A1e, A2e;
+      mix(d, A1d, A2d);
+      mix(e, A1e, A2e);
+      const int lo = d < e ? d : e, hi = d < e ? e : d;
+      const int t = lo * D - lo * (lo - 1) / 2 + (hi - lo);
+      v = A1d * sab[GS::R2 + t] * A1e + A2d * sba[GS::R2 + t] * A2e + A1d * sab[GS::X + d * D + e] * A2e + A2d * sab[GS::X + e * D + d] * A1e;
     }
-    cholesky<D>(Sm);
-    tri_inverse<D>(Sm, Li);
-    gram_inverse<D>(Li, G);
-    double E1[D], E2[D * D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) E1[d] = A1[d] * sab[GS::R1 + d] + A2[d] * sba[GS::R1 + d];
-    {
-      double R2ab[D * D], R2ba[D * D];
-      int t = 0;
-#pragma unroll
-      for (int d = 0; d < D; ++d)
-#pragma unroll
-        for (int e = d; e < D; ++e, ++t) {
-          R2ab[d * D + e] = R2ab[e * D + d] = sab[GS::R2 + t];
-          R2ba[d * D + e] = R2ba[e * D + d] = sba[GS::R2 + t];
-        }
-#pragma unroll
-      for (int d = 0; d < D; ++d)
-#pragma unroll
-        for (int e = 0; e < D; ++e)
-          E2[d * D + e] = A1[d] * R2ab[d * D + e] * A1[e] + A2[d] * R2ba[d * D + e] * A2[e] +
-                          A1[d] * sab[GS::X + d * D + e] * A2[e] + A2[d] * sab[GS::X + e * D + d] * A1[e];
-    }
-    double dmu[D];
-    gram_apply<D>(Li, E1, dmu);
-#pragma unroll
-    for (int d = 0; d < D; ++d) out[d] = wgt * dmu[d];
-    double GT[D * D];
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) t = fma(G(i, k), E2[k * D + j], t);
-        GT[i * D + j] = t;
-      }
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) t = fma(GT[i * D + k], G(k, j), t);
-        out[D + i * D + j] = wgt * 0.5 * (t - sab[GS::S0] * G(i, j));
-      }
+    e12[idx] = v;
   }
   __syncthreads();
-  for (int k = tid; k < CS; k += blockDim.x) {
+  for (int idx = tid; idx < npairs * CS; idx += nt) {  // G E1 -> mean contribution; G E2 -> gt
+    const int pr = idx / CS, k = idx % CS;
+    const double* G = gmat + (size_t)pr * DD;
+    const double* E = e12 + (size_t)pr * CS;
+    if (k < D) {
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) t = fma(G[k * D + c], E[c], t);
+      contrib[idx] = meta[pr * 4 + 2] != 0.0 ? meta[pr * 4 + 2] * t : 0.0;
+    } else {
+      const int i = (k - D) / D, j = (k - D) % D;
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) t = fma(G[i * D + c], E[D + c * D + j], t);
+      gt[(size_t)pr * DD + (k - D)] = t;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < npairs * DD; idx += nt) {  // (G E2) G - S0 G -> covariance contribution
+    const int pr = idx / DD, k = idx % DD, i = k / D, j = k % D;
+    const double* G = gmat + (size_t)pr * DD;
+    const double* T = gt + (size_t)pr * DD;
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) t = fma(T[i * D + c], G[c * D + j], t);
+    const double wgt = meta[pr * 4 + 2];
+    contrib[(size_t)pr * CS + D + k] = wgt != 0.0 ? wgt * 0.5 * (t - sst[(size_t)pr * 2 * GS::SIZE + GS::S0] * G[k]) : 0.0;
+  }
+  __syncthreads();
+  for (int k = tid; k < CS; k += nt) {
     double s = 0.0;
-    for (int pr = 0; pr < npairs; ++pr) s += contrib[pr][k];
+    for (int pr = 0; pr < npairs; ++pr) s += contrib[(size_t)pr * CS + k];
     for (int l = 0; l < L; ++l) s += (k < D) ? p.gm[((size_t)n * L + l) * D + k] : p.gS[((size_t)n * L + l) * D * D + (k - D)];
     if (k < D) p.m_bar[(size_t)n * D + k] = s;
     else p.S_bar[(size_t)n * D * D + (k - D)] = s;
@@ -737,7 +748,7 @@ __global__ void __launch_bounds__(64) k_bwd_finalize(BwdFinalizeParams p) {
 static size_t bwd_align(size_t x) { return (x + 255) / 256 * 256; }
 
 struct BwdLayout {
-  size_t packs, stats, f1lat, crosslat, f1lat_bar, crosslat_bar, omega, gm, gS, total;
+  size_t packs, Gs, stats, f1lat, crosslat, f1lat_bar, crosslat_bar, omega, gm, gS, total;
   int nrb;
 };
 
@@ -754,6 +765,7 @@ static BwdLayout bwd_layout(const gpp_gp_model* m, int N) {
   size_t off = 0;
   auto take = [&](size_t doubles) { size_t o = off; off = bwd_align(off + doubles * sizeof(double)); return o; };
   lo.packs = take(pack_doubles * L * L * N);
+  lo.Gs = take((size_t)D * D * L * L * N);
   lo.stats = take(stat_doubles * L * L * lo.nrb * N);
   lo.f1lat = take((size_t)L * N);
   lo.crosslat = take((size_t)L * D * N);
@@ -772,6 +784,7 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
                        int* info, cudaStream_t stream) {
   const int L = m->L;
   double* packs = (double*)(ws + lo.packs);
+  double* Gs = (double*)(ws + lo.Gs);
   double* stats = (double*)(ws + lo.stats);
   double* f1lat = (double*)(ws + lo.f1lat);
   double* crosslat = (double*)(ws + lo.crosslat);
@@ -782,7 +795,7 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   double* gS = (double*)(ws + lo.gS);
   PackPsi1Params pp;
   pp.m = mu; pp.S = S; pp.Z = m->Z; pp.ell = m->ell; pp.var = m->var; pp.beta = m->beta; pp.pair_ab = nullptr;
-  pp.packs = packs; pp.f1lat = f1lat; pp.crosslat = crosslat; pp.counter = nullptr; pp.info = info;
+  pp.packs = packs; pp.f1lat = f1lat; pp.crosslat = crosslat; pp.Gs = Gs; pp.counter = nullptr; pp.info = info;
   pp.N = N; pp.L = L; pp.M = m->M; pp.npairs = L * L;
   BwdEpilogue<D> epi;
   epi.m = mu; epi.S = S; epi.Z = m->Z; epi.ell = m->ell; epi.var = m->var; epi.beta = m->beta; epi.gm = gm; epi.gS = gS; epi.M = m->M;
@@ -805,17 +818,17 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   }
   profile_end(stream);
   BwdFinalizeParams fp;
-  fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.omega = omega; fp.gm = gm; fp.gS = gS;
+  fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.omega = omega; fp.Gs = Gs; fp.gm = gm; fp.gS = gS;
   fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb;
   {
     const int npairs = L * (L + 1) / 2;
-    const size_t smem = sizeof(double) * (size_t)npairs * (2 * GradStats<D>::SIZE + D + D * D);
+    const size_t smem = sizeof(double) * (size_t)npairs * FinalizeSmem<D>::PER_PAIR;
     static size_t configured = 48 * 1024;
     if (smem > configured) {
       GPP_CUDA_OK(cudaFuncSetAttribute(k_bwd_finalize<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    k_bwd_finalize<D><<<N, 64, smem, stream>>>(fp);
+    k_bwd_finalize<D><<<N, 128, smem, stream>>>(fp);
   }
   count_launch(3);
   GPP_CUDA_OK(cudaGetLastError());

@@ -13,7 +13,7 @@ template <int D>
 __device__ __forceinline__ void pack_body(int idx, const double* __restrict__ m, const double* __restrict__ S, int N,
                                           const double* __restrict__ ell, const double* __restrict__ var,
                                           const int* __restrict__ pair_ab, int npairs, int L,
-                                          double* __restrict__ packs, int* info) {
+                                          double* __restrict__ packs, double* __restrict__ Gs, int* info) {
   if (idx >= N * npairs) return;
   int n = idx / npairs, p = idx % npairs;
   // pair table (a <= b, forward) or, with pair_ab == nullptr, all L x L ordered pairs (backward)
@@ -29,7 +29,7 @@ __device__ __forceinline__ void pack_body(int idx, const double* __restrict__ m,
 #pragma unroll
   for (int d = 0; d < D * D; ++d) Sg[d] = S[(size_t)n * D * D + d];
   double out[PairPack<D>::SIZE];
-  bool ok = make_pair_pack<D>(mu, Sg, V1, V2, log(var[a] * var[b]), out);
+  bool ok = make_pair_pack<D>(mu, Sg, V1, V2, log(var[a] * var[b]), out, Gs ? Gs + (size_t)idx * D * D : nullptr);
   if (!ok) flag_not_pd(info, n);
   double* dst = packs + (size_t)idx * PairPack<D>::SIZE;
 #pragma unroll
@@ -118,6 +118,7 @@ struct PackPsi1Params {
   const double *Z, *ell, *var, *beta;     // model
   const int* pair_ab;                     // pair table (a <= b) or nullptr = all L x L ordered pairs
   double *packs, *f1lat, *crosslat;       // [N,npairs,PairPack], [N,L], [N,D,L]
+  double* Gs;                             // optional [N,npairs,D,D]: (Sigma_n + V_ab)^-1 of every pair (the backward's finalize needs it)
   unsigned* counter;                      // optional: work counter of k_contract, reset here
   int* info;
   int N, L, M, npairs;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(128) k_pack_psi1(PackPsi1Params p, Epilogue ep
   } else {
     const int idx = ((int)blockIdx.x - p.N) * 128 + threadIdx.x;
     if (idx == 0 && p.counter) *p.counter = 0u;
-    pack_body<D>(idx, p.m, p.S, p.N, p.ell, p.var, p.pair_ab, p.npairs, p.L, p.packs, p.info);
+    pack_body<D>(idx, p.m, p.S, p.N, p.ell, p.var, p.pair_ab, p.npairs, p.L, p.packs, p.Gs, p.info);
   }
 }
 
