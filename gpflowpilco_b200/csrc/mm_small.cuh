@@ -74,12 +74,17 @@ __device__ S ndtr(S x) { return s_erfc(x * (-0.70710678118654752440)) * 0.5; }
 template <typename S>
 __device__ void mm_encoder(const EncoderSpec& es, const S* m, const S* Sx /*[Dx][Dx]*/, S* me, S* See, S* Cxe) {
   const int Dx = es.Dx, na = es.na, De = es.De(), nb = es.nb();
-  S s1[4], c1[4];
+  // One exp, one sin and one cos per active dimension (plus one exp per off-diagonal pair); the moments of the pairs follow from
+  // the angle-addition formulas and exp(-(v_i + v_j)/2 -+ c_ij) = ev_i ev_j exp(-+c_ij)  (this runs on a single thread of the
+  // rollout's pre stage, where every transcendental is ~0.3 us of serial latency).
+  S s1[4], c1[4], sn[4], cs[4], ev[4];
   for (int k = 0; k < na; ++k) {
     int i = es.active[k];
-    S ev = s_exp(Sx[i * Dx + i] * (-0.5));
-    s1[k] = ev * s_sin(m[i]);
-    c1[k] = ev * s_cos(m[i]);
+    ev[k] = s_exp(Sx[i * Dx + i] * (-0.5));
+    sn[k] = s_sin(m[i]);
+    cs[k] = s_cos(m[i]);
+    s1[k] = ev[k] * sn[k];
+    c1[k] = ev[k] * cs[k];
     me[k] = s1[k];
     me[na + k] = c1[k];
   }
@@ -88,12 +93,21 @@ __device__ void mm_encoder(const EncoderSpec& es, const S* m, const S* Sx /*[Dx]
   for (int k = 0; k < na; ++k)
     for (int l = 0; l < na; ++l) {
       int i = es.active[k], j = es.active[l];
-      S vsum = Sx[i * Dx + i] + Sx[j * Dx + j];
-      S ssum = Sx[i * Dx + j] + Sx[j * Dx + i];
-      S A = s_exp((vsum + ssum) * (-0.5)), B = s_exp((vsum - ssum) * (-0.5));
-      S ca = A * s_cos(m[i] + m[j]), cs = B * s_cos(m[i] - m[j]);
-      S sx_cx = s_sin(m[i]) * s_cos(m[j]), cx_sx = s_cos(m[i]) * s_sin(m[j]);
-      S ss = (cs - ca) * 0.5, cc = (cs + ca) * 0.5;
+      S A, B;                                   // exp(-(v_i + v_j + 2 c_ij)/2), exp(-(v_i + v_j - 2 c_ij)/2)
+      if (k == l) {
+        S e2 = ev[k] * ev[k];
+        A = e2 * e2;
+        B = S(1.0);
+      } else {
+        S E = ev[k] * ev[l];
+        S t = s_exp((Sx[i * Dx + j] + Sx[j * Dx + i]) * (-0.5));
+        A = E * t;
+        B = E / t;
+      }
+      S cc0 = cs[k] * cs[l], ss0 = sn[k] * sn[l];
+      S ca = A * (cc0 - ss0), cd = B * (cc0 + ss0);          // A cos(m_i + m_j), B cos(m_i - m_j)
+      S sx_cx = sn[k] * cs[l], cx_sx = cs[k] * sn[l];
+      S ss = (cd - ca) * 0.5, cc = (cd + ca) * 0.5;
       S sc = (sx_cx * (B + A) - cx_sx * (B - A)) * 0.5;      // E[sin x_k cos x_l]
       See[k * De + l] = ss - s1[k] * s1[l];
       See[(na + k) * De + na + l] = cc - c1[k] * c1[l];
@@ -118,6 +132,82 @@ __device__ void mm_encoder(const EncoderSpec& es, const S* m, const S* Sx /*[Dx]
     }
     for (int l = 0; l < nb; ++l) See[(2 * na + j) * De + 2 * na + l] = Sx[bj * Dx + es.inactive(l)];
   }
+}
+
+// ---- the same rule, one output entry at a time (for the rollout's pre stage, where the CTA's threads share the work) ------------
+// per active dimension k: exp(-v_k / 2), sin(m_k), cos(m_k)
+template <typename S>
+struct EncTrig {
+  S ev[4], sn[4], cs[4];
+};
+
+template <typename S, class MeanAt, class CovAt>
+__device__ __forceinline__ void enc_trig_one(const EncoderSpec& es, int k, MeanAt m, CovAt Sx, EncTrig<S>& t) {
+  const int i = es.active[k];
+  t.ev[k] = s_exp(Sx(i, i) * (-0.5));
+  t.sn[k] = s_sin(m(i));
+  t.cs[k] = s_cos(m(i));
+}
+
+// position a of the encoded vector e = [sin (na), cos (na), inactive (nb)]: kind 0 / 1 / 2 and the index inside its group
+__device__ __forceinline__ void enc_slot(const EncoderSpec& es, int a, int& kind, int& idx) {
+  if (a < es.na) { kind = 0; idx = a; }
+  else if (a < 2 * es.na) { kind = 1; idx = a - es.na; }
+  else { kind = 2; idx = es.inactive(a - 2 * es.na); }      // idx = state dimension
+}
+
+template <typename S, class MeanAt>
+__device__ __forceinline__ S enc_mean_at(const EncoderSpec& es, int a, MeanAt m, const EncTrig<S>& t) {
+  int kind, idx;
+  enc_slot(es, a, kind, idx);
+  if (kind == 0) return t.ev[idx] * t.sn[idx];
+  if (kind == 1) return t.ev[idx] * t.cs[idx];
+  return m(idx);
+}
+
+// Cxe[i][a] = Cov(x_i, e_a), pre-inverted form (maths.py:173)
+template <typename S, class CovAt>
+__device__ __forceinline__ S enc_cross_at(const EncoderSpec& es, int i, int a, CovAt Sx, const EncTrig<S>& t) {
+  int kind, idx;
+  enc_slot(es, a, kind, idx);
+  if (kind == 0) return Sx(i, es.active[idx]) * (t.ev[idx] * t.cs[idx]);
+  if (kind == 1) return Sx(i, es.active[idx]) * (t.ev[idx] * t.sn[idx]) * (-1.0);
+  return Sx(i, idx);
+}
+
+// See[a][b]
+template <typename S, class CovAt>
+__device__ __forceinline__ S enc_cov_at(const EncoderSpec& es, int a, int b, CovAt Sx, const EncTrig<S>& t) {
+  int ka, ia, kb, ib;
+  enc_slot(es, a, ka, ia);
+  enc_slot(es, b, kb, ib);
+  if (ka == 2 && kb == 2) return Sx(ia, ib);
+  if (ka == 2) return enc_cross_at<S>(es, ia, b, Sx, t);      // blocks involving the inactive dims (components.py:44-52)
+  if (kb == 2) return enc_cross_at<S>(es, ib, a, Sx, t);
+  // both trigonometric: uncentred moments (maths.py:147-170) minus the outer product of the means.  (sin_k, cos_l) and
+  // (cos_l, sin_k) share one value: order the pair as (k = the sine's dimension, l = the cosine's) when the kinds differ
+  const int k = (ka == 1 && kb == 0) ? ib : ia, l = (ka == 1 && kb == 0) ? ia : ib;
+  const int i = es.active[k], j = es.active[l];
+  S A, B;                                     // exp(-(v_i + v_j + 2 c_ij)/2), exp(-(v_i + v_j - 2 c_ij)/2)
+  if (k == l) {
+    S e2 = t.ev[k] * t.ev[k];
+    A = e2 * e2;
+    B = S(1.0);
+  } else {
+    S E = t.ev[k] * t.ev[l];
+    S x = s_exp((Sx(i, j) + Sx(j, i)) * (-0.5));
+    A = E * x;
+    B = E / x;
+  }
+  const S s1k = t.ev[k] * t.sn[k], c1k = t.ev[k] * t.cs[k], s1l = t.ev[l] * t.sn[l], c1l = t.ev[l] * t.cs[l];
+  if (ka != kb) {                             // E[sin x_k cos x_l] - E sin E cos
+    S sx_cx = t.sn[k] * t.cs[l], cx_sx = t.cs[k] * t.sn[l];
+    return (sx_cx * (B + A) - cx_sx * (B - A)) * 0.5 - s1k * c1l;
+  }
+  S cc0 = t.cs[k] * t.cs[l], ss0 = t.sn[k] * t.sn[l];
+  S ca = A * (cc0 - ss0), cd = B * (cc0 + ss0);            // A cos(m_i + m_j), B cos(m_i - m_j)
+  if (ka == 0) return (cd - ca) * 0.5 - s1k * s1l;
+  return (cd + ca) * 0.5 - c1k * c1l;
 }
 
 // Owen's T evaluated by the 32 lanes of a warp (one Gauss-Legendre node each); every lane returns the sum

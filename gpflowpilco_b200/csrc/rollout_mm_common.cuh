@@ -44,11 +44,25 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
   const int r = (p.R == 1) ? 0 : n;
   const double* ell = p.pEll + (size_t)r * DP;
   const double var = p.pVar[r];
-  if (tid == 0) {
-    double m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
-    for (int i = 0; i < Dx; ++i) m[i] = p.m[(size_t)n * Dx + i];
-    for (int i = 0; i < Dx * Dx; ++i) S[i] = p.S[(size_t)n * Dx * Dx + i];
-    mm_encoder<double>(p.enc, m, S, sh.me, sh.See, sh.Cxe);
+  // encoder rule, one output entry per thread (the serial form costs ~8 us of single-thread latency per step)
+  __shared__ double xm[GPP_SMALL_MAX], xS[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  __shared__ EncTrig<double> trig;
+  for (int t = tid; t < Dx + Dx * Dx; t += blockDim.x) {
+    if (t < Dx) xm[t] = p.m[(size_t)n * Dx + t];
+    else xS[t - Dx] = p.S[(size_t)n * Dx * Dx + (t - Dx)];
+  }
+  __syncthreads();
+  auto mean_at = [&](int i) { return xm[i]; };
+  auto cov_at = [&](int i, int j) { return xS[i * Dx + j]; };
+  if (tid < p.enc.na) enc_trig_one<double>(p.enc, tid, mean_at, cov_at, trig);
+  __syncthreads();
+  {
+    const int De = DP;
+    for (int t = tid; t < De + De * De + Dx * De; t += blockDim.x) {
+      if (t < De) sh.me[t] = enc_mean_at<double>(p.enc, t, mean_at, trig);
+      else if (t < De + De * De) sh.See[t - De] = enc_cov_at<double>(p.enc, (t - De) / De, (t - De) % De, cov_at, trig);
+      else sh.Cxe[t - De - De * De] = enc_cross_at<double>(p.enc, (t - De - De * De) / De, (t - De - De * De) % De, cov_at, trig);
+    }
   }
   __syncthreads();
   // two independent factorisations of the encoded covariance, one warp each (lane 0)
