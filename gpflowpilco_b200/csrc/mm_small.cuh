@@ -24,11 +24,20 @@ struct EncoderSpec {
     for (int k = 0; k < na; ++k) if (active[k] == i) return true;
     return false;
   }
+  int inact[GPP_SMALL_MAX];   // table of the inactive dims, filled by finish()
+  int ready;                  // finish() was called
   // j-th inactive dim in increasing order (upstream components.py:58-67 builds tuple(set(...)), i.e. sorted)
   __host__ __device__ int inactive(int j) const {
+    if (ready) return inact[j];
     int c = 0;
     for (int i = 0; i < Dx; ++i) if (!is_active(i)) { if (c == j) return i; ++c; }
     return -1;
+  }
+  // call on the host once Dx, na and active[] are set: the rules look the inactive dims up many times per state
+  void finish() {
+    ready = 0;
+    for (int j = 0; j < Dx - na; ++j) inact[j] = inactive(j);
+    ready = 1;
   }
 };
 
@@ -208,6 +217,128 @@ __device__ __forceinline__ S enc_cov_at(const EncoderSpec& es, int a, int b, Cov
   S ca = A * (cc0 - ss0), cd = B * (cc0 + ss0);            // A cos(m_i + m_j), B cos(m_i - m_j)
   if (ka == 0) return (cd - ca) * 0.5 - s1k * s1l;
   return (cd + ca) * 0.5 - c1k * c1l;
+}
+
+// ---- reverse mode of the encoder rule (closed form; replaces one dual-number evaluation of the rule per input direction on the
+// rollout's critical path).  Given the adjoints of (me, See, Cxe) — every matrix entry an independent output, as mm_encoder writes
+// them — returns the adjoints of m[Dx] and of every entry of Sx[Dx][Dx] (entries treated as independent inputs; the caller
+// symmetrises).  All pointers may be shared memory.
+// Shared by the threads of a CTA (all of them must call it; >= Dx*Dx + Dx threads): the linear parts are gathered
+// one input entry per thread, the small trigonometric block stays on thread 0.  `tr` is shared scratch of 8 * 4 doubles.
+// m_bar / Sx_bar are OVERWRITTEN.  Ends with a CTA barrier.
+__device__ inline void mm_encoder_bwd_cta(const EncoderSpec& es, const double* m, const double* Sx, const double* me_bar,
+                                          const double* See_bar, const double* Cxe_bar, double* m_bar, double* Sx_bar, double* tr) {
+  const int Dx = es.Dx, na = es.na, De = es.De(), nb = es.nb(), tid = threadIdx.x;
+  double *ev = tr, *sn = tr + 4, *cs = tr + 8, *s1 = tr + 12, *c1 = tr + 16, *s1b = tr + 20, *c1b = tr + 24;
+  auto pos_inactive = [&](int i) {              // position of state dim i among the inactive dims, or -1
+    int ji = -1;
+    for (int j = 0; j < nb; ++j) ji = es.inactive(j) == i ? j : ji;
+    return ji;
+  };
+  // adjoints of Cxe[i][k] (cosine-weighted) and Cxe[i][na + k] (sine-weighted) including the See blocks that copy them
+  auto bar_c = [&](int i, int ji, int k) {
+    double v = Cxe_bar[i * De + k];
+    if (ji >= 0) v += See_bar[(2 * na + ji) * De + k] + See_bar[k * De + 2 * na + ji];
+    return v;
+  };
+  auto bar_s = [&](int i, int ji, int k) {
+    double v = Cxe_bar[i * De + na + k];
+    if (ji >= 0) v += See_bar[(2 * na + ji) * De + na + k] + See_bar[(na + k) * De + 2 * na + ji];
+    return v;
+  };
+  if (tid < na) {
+    const int i = es.active[tid];
+    double s, c;
+    const double e = exp(-0.5 * Sx[i * Dx + i]);
+    sincos(m[i], &s, &c);
+    ev[tid] = e; sn[tid] = s; cs[tid] = c; s1[tid] = e * s; c1[tid] = e * c;
+  }
+  __syncthreads();
+  if (tid < Dx * Dx) {                          // linear part of d/dSx[i][j]
+    const int i = tid / Dx, j = tid % Dx, ji = pos_inactive(i);
+    double v = 0.0;
+    int kj = -1;
+    for (int k = 0; k < na; ++k) kj = es.active[k] == j ? k : kj;
+    if (kj >= 0) {
+      v = bar_c(i, ji, kj) * c1[kj] - bar_s(i, ji, kj) * s1[kj];        // Cxe[i][k] = Sx[i][a_k] c1_k,  Cxe[i][na+k] = -Sx[i][a_k] s1_k
+    } else {
+      const int jj = pos_inactive(j);
+      v = Cxe_bar[i * De + 2 * na + jj];                                   // Cxe[i][2na+jj] = Sx[i][b_jj]
+      if (ji >= 0) v += See_bar[(2 * na + ji) * De + 2 * na + jj];         // See[2na+ji][2na+jj] = Sx[b_ji][b_jj]
+    }
+    Sx_bar[tid] = v;
+  } else if (tid < Dx * Dx + Dx) {              // d/dm[i] of the inactive dims; adjoints of s1_k, c1_k from me and Cxe
+    const int i = tid - Dx * Dx, ji = pos_inactive(i);
+    m_bar[i] = ji >= 0 ? me_bar[2 * na + ji] : 0.0;
+    int k = -1;
+    for (int q = 0; q < na; ++q) k = es.active[q] == i ? q : k;
+    if (k >= 0) {
+      double sb = me_bar[k], cb = me_bar[na + k];
+      for (int r = 0; r < Dx; ++r) {
+        const int jr = pos_inactive(r);
+        const double sxa = Sx[r * Dx + i];
+        cb += bar_c(r, jr, k) * sxa;
+        sb -= bar_s(r, jr, k) * sxa;
+      }
+      s1b[k] = sb;
+      c1b[k] = cb;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double evb[4] = {0.0, 0.0, 0.0, 0.0}, snb[4] = {0.0, 0.0, 0.0, 0.0}, csb[4] = {0.0, 0.0, 0.0, 0.0};
+    // trigonometric block of See, ordered pairs (k, l)
+    for (int k = 0; k < na; ++k)
+      for (int l = 0; l < na; ++l) {
+        const int i = es.active[k], j = es.active[l];
+        double A, B, x = 1.0;
+        if (k == l) {
+          const double e2 = ev[k] * ev[k];
+          A = e2 * e2;
+          B = 1.0;
+        } else {
+          x = exp(-0.5 * (Sx[i * Dx + j] + Sx[j * Dx + i]));
+          A = ev[k] * ev[l] * x;
+          B = ev[k] * ev[l] / x;
+        }
+        const double P = cs[k] * cs[l], Q = sn[k] * sn[l], U = sn[k] * cs[l], V = cs[k] * sn[l];
+        const double bs = See_bar[k * De + l], bc = See_bar[(na + k) * De + na + l];
+        const double bx = See_bar[k * De + na + l] + See_bar[(na + l) * De + k];
+        // ss = (B (P + Q) - A (P - Q)) / 2 - s1_k s1_l;  cc = (B (P + Q) + A (P - Q)) / 2 - c1_k c1_l;
+        // sc = (U (B + A) - V (B - A)) / 2 - s1_k c1_l
+        const double Bb = 0.5 * ((bs + bc) * (P + Q) + bx * (U - V));
+        const double Ab = 0.5 * ((bc - bs) * (P - Q) + bx * (U + V));
+        const double Pb = 0.5 * (bs * (B - A) + bc * (B + A));
+        const double Qb = 0.5 * (bs * (B + A) + bc * (B - A));
+        const double Ub = 0.5 * bx * (B + A), Vb = -0.5 * bx * (B - A);
+        s1b[k] -= bs * s1[l] + bx * c1[l];
+        s1b[l] -= bs * s1[k];
+        c1b[k] -= bc * c1[l];
+        c1b[l] -= bc * c1[k] + bx * s1[k];
+        csb[k] += Pb * cs[l] + Vb * sn[l];
+        csb[l] += Pb * cs[k] + Ub * sn[k];
+        snb[k] += Qb * sn[l] + Ub * cs[l];
+        snb[l] += Qb * sn[k] + Vb * cs[k];
+        if (k == l) {
+          evb[k] += Ab * 4.0 * ev[k] * ev[k] * ev[k];
+        } else {
+          evb[k] += (Ab * x + Bb / x) * ev[l];
+          evb[l] += (Ab * x + Bb / x) * ev[k];
+          const double xb = (Ab - Bb / (x * x)) * ev[k] * ev[l];
+          Sx_bar[i * Dx + j] -= 0.5 * x * xb;
+          Sx_bar[j * Dx + i] -= 0.5 * x * xb;
+        }
+      }
+    for (int k = 0; k < na; ++k) {
+      const int i = es.active[k];
+      evb[k] += s1b[k] * sn[k] + c1b[k] * cs[k];
+      snb[k] += s1b[k] * ev[k];
+      csb[k] += c1b[k] * ev[k];
+      m_bar[i] += snb[k] * cs[k] - csb[k] * sn[k];
+      Sx_bar[i * Dx + i] -= 0.5 * ev[k] * evb[k];
+    }
+  }
+  __syncthreads();
 }
 
 // Owen's T evaluated by the 32 lanes of a warp (one Gauss-Legendre node each); every lane returns the sum

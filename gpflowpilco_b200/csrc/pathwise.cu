@@ -440,6 +440,7 @@ static int pathwise_fwd_impl(int S, int ldS, int H, int L, int F, int Mpad, int 
   PathwiseParams p{};
   p.enc.Dx = Dx; p.enc.na = num_active;
   for (int k = 0; k < num_active; ++k) p.enc.active[k] = active_dims[k];
+  p.enc.finish();
   p.S = S; p.ldS = ldS; p.H = H; p.L = L; p.F = F; p.Mpad = Mpad; p.Dx = Dx; p.De = Dx + num_active; p.Mp = Mp;
   p.basis = basis; p.zbasis = zbasis; p.w = w; p.v = v; p.amp = amp; p.var = variance; p.inv_ell = inv_lengthscales; p.mean = mean_const;
   p.pZs = policy_Zs; p.pInvEll = policy_inv_lengthscales; p.pAlpha = policy_alpha; p.scale = squash_scale; p.shift = squash_shift;

@@ -204,6 +204,7 @@ int gpp_rollout_pathwise_bwd(int S, int ldS, int H, int L, int D, int Dx, int nu
   PathwiseBwdParams p{};
   p.enc.Dx = Dx; p.enc.na = num_active;
   for (int k = 0; k < num_active; ++k) p.enc.active[k] = active_dims[k];
+  p.enc.finish();
   p.S = S; p.ldS = ldS; p.H = H; p.L = L; p.D = D; p.Dx = Dx; p.De = Dx + num_active; p.Mp = Mp;
   p.pZ = policy_Z; p.pEll = policy_lengthscales; p.pBeta = policy_beta; p.pVar = policy_variance; p.scale = squash_scale;
   p.target = cost_target; p.W = cost_W; p.traj = traj; p.jac = jac; p.loss_bar = loss_bar; p.x0_bar = x0_bar;

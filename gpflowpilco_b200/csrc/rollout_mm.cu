@@ -299,6 +299,7 @@ static int rollout_mm_fwd_impl(const gpp_gp_model* dynamics, int N, int Dx, int 
     GPP_REQUIRE(active_dims[k] >= 0 && active_dims[k] < Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_fwd: active dim %d out of range", active_dims[k]);
     p.enc.active[k] = active_dims[k];
   }
+  p.enc.finish();
   p.N = N; p.Dx = Dx; p.De = Dx + num_active; p.D = p.De + 1; p.L = dynamics->P;
   GPP_REQUIRE(p.De <= GPP_SMALL_MAX - 1, GPP_ERR_UNSUPPORTED, "gpp_rollout_mm_fwd: encoded dimension %d too large", p.De);
   GPP_REQUIRE(dynamics->D == p.D, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_fwd: dynamics input dim %d != encoded state + action = %d", dynamics->D, p.D);

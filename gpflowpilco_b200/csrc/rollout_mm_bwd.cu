@@ -348,33 +348,22 @@ __global__ void __launch_bounds__(128) k_bwd_pre(RolloutMMParams p, RolloutBwdBu
   }
   __syncthreads();
 
-  // ---- encoder adjoint: directional derivatives of <(me_bar, See_bar, Cxe_bar), encoder(m, S)>, one direction per thread
-  const int ndir = Dx + Dx * (Dx + 1) / 2;
-  if (tid < ndir) {
-    Dual m[GPP_SMALL_MAX], S[GPP_SMALL_MAX * GPP_SMALL_MAX];
-    for (int i = 0; i < Dx; ++i) m[i] = Dual(p.m[(size_t)n * Dx + i]);
-    for (int i = 0; i < Dx * Dx; ++i) S[i] = Dual(p.S[(size_t)n * Dx * Dx + i]);
-    int di = 0, dj = 0;
-    if (tid < Dx) {
-      m[tid].d = 1.0;
+  // ---- encoder adjoint (closed-form reverse mode shared by the CTA, mm_small.cuh; the state's symmetric covariance receives the
+  //      symmetrised adjoint)
+  __shared__ double xm[GPP_SMALL_MAX], xS[GPP_SMALL_MAX * GPP_SMALL_MAX], xmb[GPP_SMALL_MAX], xSb[GPP_SMALL_MAX * GPP_SMALL_MAX];
+  __shared__ double enc_scratch[32];
+  for (int t = tid; t < Dx + Dx * Dx; t += blockDim.x) {
+    if (t < Dx) xm[t] = p.m[(size_t)n * Dx + t];
+    else xS[t - Dx] = p.S[(size_t)n * Dx * Dx + (t - Dx)];
+  }
+  __syncthreads();
+  mm_encoder_bwd_cta(p.enc, xm, xS, ad.me_bar, ad.See_bar, ad.Cxe_bar, xmb, xSb, enc_scratch);
+  for (int t = tid; t < Dx + Dx * Dx; t += blockDim.x) {
+    if (t < Dx) {
+      bw.mb[(size_t)n * Dx + t] += xmb[t];
     } else {
-      direction_to_entry(tid, Dx, di, dj);
-      S[di * Dx + dj].d = 1.0;
-      S[dj * Dx + di].d = 1.0;
-    }
-    Dual me[GPP_SMALL_MAX], See[GPP_SMALL_MAX * GPP_SMALL_MAX], Cxe[GPP_SMALL_MAX * GPP_SMALL_MAX];
-    mm_encoder<Dual>(p.enc, m, S, me, See, Cxe);
-    double g = 0.0;
-    for (int a = 0; a < DP; ++a) g = fma(ad.me_bar[a], me[a].d, g);
-    for (int t = 0; t < DP * DP; ++t) g = fma(ad.See_bar[t], See[t].d, g);
-    for (int t = 0; t < Dx * DP; ++t) g = fma(ad.Cxe_bar[t], Cxe[t].d, g);
-    if (tid < Dx) {
-      bw.mb[(size_t)n * Dx + tid] += g;
-    } else if (di == dj) {
-      bw.Sb[(size_t)n * Dx * Dx + di * Dx + di] += g;
-    } else {
-      bw.Sb[(size_t)n * Dx * Dx + di * Dx + dj] += 0.5 * g;
-      bw.Sb[(size_t)n * Dx * Dx + dj * Dx + di] += 0.5 * g;
+      const int i = (t - Dx) / Dx, j = (t - Dx) % Dx;
+      bw.Sb[(size_t)n * Dx * Dx + i * Dx + j] += 0.5 * (xSb[i * Dx + j] + xSb[j * Dx + i]);
     }
   }
 }
@@ -457,6 +446,7 @@ int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
     GPP_REQUIRE(active_dims[k] >= 0 && active_dims[k] < Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_bwd: active dim %d out of range", active_dims[k]);
     p.enc.active[k] = active_dims[k];
   }
+  p.enc.finish();
   p.N = N; p.Dx = Dx; p.De = Dx + num_active; p.D = p.De + 1; p.L = dynamics->P;
   GPP_REQUIRE(p.De <= GPP_SMALL_MAX - 1, GPP_ERR_UNSUPPORTED, "gpp_rollout_mm_bwd: encoded dimension %d too large", p.De);
   GPP_REQUIRE(dynamics->D == p.D && dynamics->P == Dx, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_bwd: dynamics dims (%d in, %d out) do not match the state (%d, %d)",

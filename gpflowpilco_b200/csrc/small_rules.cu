@@ -87,6 +87,7 @@ int gpp_mm_encoder(int N, int Dx, int num_active, const int* active_dims, const 
     GPP_REQUIRE(active_dims[k] >= 0 && active_dims[k] < Dx, GPP_ERR_BAD_SHAPE, "gpp_mm_encoder: active dim out of range");
     es.active[k] = active_dims[k];
   }
+  es.finish();
   gpp::k_mm_encoder<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(es, N, m, S, me, See, Cxe);
   gpp::count_launch();
   GPP_CUDA_OK(cudaGetLastError());

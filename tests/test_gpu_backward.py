@@ -148,6 +148,43 @@ def test_rollout_mm_gradients_match_autograd(shared_policy, whiten):
   scaled_close(q.grad, torch.stack([t[2][:, 0] for t in trip]), 1e-6, "policy q_mu gradient")
 
 
+@pytest.mark.parametrize("active_dims", [(0, 2), (), (3, 1, 0)])
+def test_rollout_mm_gradients_other_encodings(active_dims):
+  """Several / no sincos-encoded dimensions: exercises the pair terms exp(-(v_k + v_l)/2 -+ c_kl) of the encoder rule and of its
+  closed-form adjoint (mm_small.cuh), which the cart-pole encoding (one angle) never reaches."""
+  from gpflowpilco_b200.autograd import rollout_mm_loss
+  N, H, Dx = 2, 3, 4
+  na = len(active_dims)
+  De = Dx + na
+  g = torch.Generator().manual_seed(17)
+  rng = np.random.default_rng(4)
+  dynp = synthetic.random_svgp(L=Dx, M=24, D=De + 1, seed=31, whiten=True, z_scale=1.5)
+  dynp["q_mu"] = 0.2 * dynp["q_mu"]
+  dynp["mean_const"] = np.zeros(Dx)
+  pp = synthetic.random_svgp(L=1, M=8, D=De, seed=71, whiten=True)
+  pp["mean_const"] = np.zeros(1)
+  m0 = torch.tensor([0.3, 2.0, -0.4, 0.6], dtype=DTYPE) + 0.3 * torch.randn(N, Dx, dtype=DTYPE, generator=g)
+  S0 = generate_covariance(Dx, [N], 0.2, g)
+  A = rng.standard_normal((De, De))
+  cfg = dict(active_dims=tuple(active_dims), target=rng.standard_normal(De), W=A @ A.T / De, squash_scale=2.0, squash_shift=-0.5)
+  loss_bar = torch.randn(N, dtype=DTYPE, generator=g)
+  loss_ref, trip, gm0, gS0 = _oracle_rollout_grads(cfg, dynp, [pp], m0, S0, H, loss_bar)
+  Z = _dev(pp["Z"][0][None]).requires_grad_(True)
+  ell = _dev(pp["lengthscales"][0][None]).requires_grad_(True)
+  q = _dev(pp["q_mu"][:, 0][None]).requires_grad_(True)
+  var = _dev(np.array([pp["variance"][0]]))
+  m0d, S0d = _dev(m0).requires_grad_(True), _dev(S0).requires_grad_(True)
+  loss = rollout_mm_loss(cuda_handle(dynp), Z, ell, var, q, m0d, S0d, H, cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]),
+                         squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"], whiten=True)
+  scaled_close(loss, loss_ref, 1e-6, "loss")
+  (loss * _dev(loss_bar)).sum().backward()
+  scaled_close(m0d.grad, gm0, 1e-6, "m0 gradient")
+  scaled_close(0.5 * (S0d.grad + S0d.grad.transpose(-1, -2)), gS0, 1e-6, "S0 gradient")
+  scaled_close(Z.grad, trip[0][0][None], 1e-6, "policy centre gradient")
+  scaled_close(ell.grad, trip[0][1][None], 1e-6, "policy lengthscale gradient")
+  scaled_close(q.grad, trip[0][2][:, 0][None], 1e-6, "policy q_mu gradient")
+
+
 # ---------------------------------------------------------------------------------------------------------
 # pathwise particle rollout: gradient w.r.t. the policy parameters and the initial states
 # ---------------------------------------------------------------------------------------------------------
