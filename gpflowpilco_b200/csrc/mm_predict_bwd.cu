@@ -424,38 +424,43 @@ struct BwdPrepareParams {
   int N, L, P, D, full_cov;
 };
 
+// all threads of the CTA (one output entry each); ends with a CTA barrier
 __device__ void bwd_prepare_input(const BwdPrepareParams& p, int n) {
-  const int L = p.L, P = p.P, D = p.D;
-  double SL[GPP_MAX_L * GPP_MAX_L];
-  for (int l = 0; l < L; ++l)
-    for (int k = 0; k < L; ++k) {
+  const int L = p.L, P = p.P, D = p.D, tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double SL[GPP_MAX_L * GPP_MAX_L];
+  for (int t = tid; t < L * L; t += nt) {
+    const int l = t / L, k = t % L;
+    double v = 0.0;
+    if (p.Sff_bar) {
+      const double* Sb = p.Sff_bar + (size_t)n * P * P;
+      if (p.W) {
+        for (int a = 0; a < P; ++a)
+          for (int b = 0; b < P; ++b)
+            if (p.full_cov || a == b) v = fma(p.W[a * L + l] * p.W[b * L + k], Sb[a * P + b], v);
+      } else if (p.full_cov || l == k) {
+        v = Sb[l * P + k];
+      }
+    }
+    SL[t] = v;
+    p.omega[((size_t)n * L + l) * L + k] = v;
+  }
+  __syncthreads();
+  const double* f1l = p.f1lat + (size_t)n * L;
+  for (int t = tid; t < L + D * L; t += nt) {
+    if (t < L) {
+      const int l = t;
       double v = 0.0;
-      if (p.Sff_bar) {
-        const double* Sb = p.Sff_bar + (size_t)n * P * P;
+      if (p.f1_bar) {
         if (p.W) {
-          for (int a = 0; a < P; ++a)
-            for (int b = 0; b < P; ++b)
-              if (p.full_cov || a == b) v = fma(p.W[a * L + l] * p.W[b * L + k], Sb[a * P + b], v);
-        } else if (p.full_cov || l == k) {
-          v = Sb[l * P + k];
+          for (int o = 0; o < P; ++o) v = fma(p.W[o * L + l], p.f1_bar[(size_t)n * P + o], v);
+        } else {
+          v = p.f1_bar[(size_t)n * P + l];
         }
       }
-      SL[l * L + k] = v;
-      p.omega[((size_t)n * L + l) * L + k] = v;
-    }
-  const double* f1l = p.f1lat + (size_t)n * L;
-  for (int l = 0; l < L; ++l) {
-    double v = 0.0;
-    if (p.f1_bar) {
-      if (p.W) {
-        for (int o = 0; o < P; ++o) v = fma(p.W[o * L + l], p.f1_bar[(size_t)n * P + o], v);
-      } else {
-        v = p.f1_bar[(size_t)n * P + l];
-      }
-    }
-    for (int k = 0; k < L; ++k) v -= (SL[l * L + k] + SL[k * L + l]) * f1l[k];
-    p.f1lat_bar[(size_t)n * L + l] = v;
-    for (int d = 0; d < D; ++d) {
+      for (int k = 0; k < L; ++k) v -= (SL[l * L + k] + SL[k * L + l]) * f1l[k];
+      p.f1lat_bar[(size_t)n * L + l] = v;
+    } else {
+      const int d = (t - L) / L, l = (t - L) % L;
       double c = 0.0;
       if (p.cross_bar) {
         const double* cb = p.cross_bar + ((size_t)n * D + d) * P;
@@ -468,6 +473,7 @@ __device__ void bwd_prepare_input(const BwdPrepareParams& p, int n) {
       p.crosslat_bar[((size_t)n * D + d) * L + l] = c;
     }
   }
+  __syncthreads();
 }
 
 // G x for symmetric G = Li^T Li given the lower-triangular Li
@@ -612,8 +618,7 @@ struct BwdEpilogue {
   int M;
   __device__ __forceinline__ void operator()(int n) const {
     __syncthreads();
-    if (threadIdx.x == 0) bwd_prepare_input(bp, n);
-    __syncthreads();
+    bwd_prepare_input(bp, n);
     psi1_bwd_body<D>(n, m, S, bp.L, M, Z, ell, var, beta, bp.f1lat_bar, bp.crosslat_bar, gm, gS);
   }
 };
