@@ -62,3 +62,16 @@ def test_dispatcher_and_episode_spec():
   assert d(B(), 1) == "B" and d(B(), 1.0) == "A" and d(A(), 2) == "A"
   with pytest.raises(NotImplementedError):
     d(A(), "s")
+
+
+def test_graphed_policy_gradient_refuses_cpu_tensors():
+  """The CUDA-graph wrapper is part of the product path: no CPU fallback, it fails loudly on host tensors."""
+  import pytest
+  import torch
+  from gpflowpilco_b200.graphs import GraphedMMPolicyGradient
+  z = torch.zeros(1, 4, 5, dtype=torch.float64)
+  with pytest.raises(ValueError, match="CUDA"):
+    GraphedMMPolicyGradient(None, z, torch.ones(1, 5, dtype=torch.float64), torch.ones(1, dtype=torch.float64),
+                            torch.zeros(1, 4, dtype=torch.float64), torch.zeros(1, 4, dtype=torch.float64),
+                            torch.eye(4, dtype=torch.float64)[None], 3, (1,), torch.zeros(5, dtype=torch.float64),
+                            torch.eye(5, dtype=torch.float64))
