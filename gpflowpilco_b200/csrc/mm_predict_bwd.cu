@@ -501,29 +501,20 @@ __device__ __forceinline__ void psi1_bwd_body(int n, const double* __restrict__ 
                                               const double* __restrict__ Z, const double* __restrict__ ell,
                                               const double* __restrict__ var, const double* __restrict__ beta,
                                               const double* __restrict__ f1lat_bar, const double* __restrict__ crosslat_bar,
-                                              double* __restrict__ gm /*[N,L,D]*/, double* __restrict__ gS /*[N,L,D,D]*/) {
+                                              double* __restrict__ gm /*[N,L,D]*/, double* __restrict__ gS /*[N,L,D,D]*/,
+                                              const double* li_in /* shared [L][D*D + 1] from psi1_body */) {
   constexpr int TRI = D * (D + 1) / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   double mu[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) mu[d] = m[(size_t)n * D + d];
   for (int l = warp; l < L; l += nwarps) {
-    Mat<D> A, Li, G;
-    double half_log_v = 0.0;
+    // the forward half of this block factorised S + Lambda_l a moment ago: reuse its inverse Cholesky factor and log normaliser
+    Mat<D> Li, G;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      double e = ell[l * D + d];
-      half_log_v += log(e);
-#pragma unroll
-      for (int e2 = 0; e2 < D; ++e2) A(d, e2) = S[(size_t)n * D * D + d * D + e2] + (d == e2 ? e * e : 0.0);
-    }
-    cholesky<D>(A);
-    double log_det = 0.0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) log_det += log(A(d, d));
-    tri_inverse<D>(A, Li);
+    for (int t = 0; t < D * D; ++t) Li.a[t] = li_in[l * (D * D + 1) + t];
+    const double c0 = li_in[l * (D * D + 1) + D * D];
     gram_inverse<D>(Li, G);
-    const double c0 = log(var[l]) + half_log_v - log_det;
     const double fb = f1lat_bar[(size_t)n * L + l];
     double cb[D], y[D];
 #pragma unroll
@@ -616,10 +607,11 @@ struct BwdEpilogue {
   const double *m, *S, *Z, *ell, *var, *beta;
   double *gm, *gS;
   int M;
-  __device__ __forceinline__ void operator()(int n) const {
+  static constexpr bool kNeedsFactors = true;
+  __device__ __forceinline__ void operator()(int n, const double* li) const {
     __syncthreads();
     bwd_prepare_input(bp, n);
-    psi1_bwd_body<D>(n, m, S, bp.L, M, Z, ell, var, beta, bp.f1lat_bar, bp.crosslat_bar, gm, gS);
+    psi1_bwd_body<D>(n, m, S, bp.L, M, Z, ell, var, beta, bp.f1lat_bar, bp.crosslat_bar, gm, gS, li);
   }
 };
 
