@@ -80,21 +80,21 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
   } else if (tid == 32) {
     // Psi1 factorisation: inverse Cholesky factor of See + Lambda and the log normaliser
     Mat<DP> A, Li;
-    double half_log_v = 0.0;
+    double ell_prod = 1.0;                   // one log of a ratio of products instead of 2 DP logs
 #pragma unroll
     for (int d = 0; d < DP; ++d) {
-      half_log_v += log(ell[d]);
+      ell_prod *= ell[d];
 #pragma unroll
       for (int e = 0; e < DP; ++e) A(d, e) = sh.See[d * DP + e] + (d == e ? ell[d] * ell[d] : 0.0);
     }
     if (!cholesky<DP>(A)) flag_not_pd(p.info, n);
-    double log_det = 0.0;
+    double diag_prod = 1.0;
 #pragma unroll
-    for (int d = 0; d < DP; ++d) log_det += log(A(d, d));
+    for (int d = 0; d < DP; ++d) diag_prod *= A(d, d);
     tri_inverse<DP>(A, Li);
 #pragma unroll
     for (int d = 0; d < DP * DP; ++d) sh.Li1[d] = Li.a[d];
-    sh.c01 = log(var) + half_log_v - log_det;
+    sh.c01 = log(var * ell_prod / diag_prod);
   }
   __syncthreads();
   // ---- policy Psi1 terms: f1 = sum_i beta_i psi1_i, vec = sum_i beta_i psi1_i (z_i - me)
