@@ -222,6 +222,11 @@ GPP_HD bool cholesky(Mat<D>& A) {
 // Li = L^{-1} (lower), from lower-triangular L.
 template <int D>
 GPP_HD void tri_inverse(const Mat<D>& L, Mat<D>& Li) {
+  // D reciprocals up front (independent, so they pipeline) instead of one dependent FP64 division per entry: these factorisations
+  // sit on single-thread critical paths of the rollout stages, where a division is ~100 cycles of latency
+  double rd[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) rd[i] = 1.0 / L(i, i);
 #pragma unroll
   for (int j = 0; j < D; ++j) {
 #pragma unroll
@@ -230,7 +235,7 @@ GPP_HD void tri_inverse(const Mat<D>& L, Mat<D>& Li) {
       double v = (i == j) ? 1.0 : 0.0;
 #pragma unroll
       for (int k = j; k < i; ++k) v = fma_(-L(i, k), Li(k, j), v);
-      Li(i, j) = v / L(i, i);
+      Li(i, j) = v * rd[i];
     }
   }
 }
