@@ -35,7 +35,9 @@ SIGNATURES = {
     "gpp_rollout_mm_workspace_bytes": (c_size_t, [_P, c_int, c_int]),
     "gpp_rollout_mm_fwd": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_double, c_double,
                                    _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
-    "gpp_rollout_mm_bwd_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int]),
+    "gpp_rollout_mm_bwd_workspace_bytes": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
+    "gpp_rollout_mm_set_mode": (c_int, [c_int]),
+    "gpp_rollout_mm_get_mode": (c_int, []),
     "gpp_rollout_mm_bwd": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), c_int, c_int, _P, _P, _P, _P, c_double, c_double,
                                    _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "gpp_rollout_mm_saved_doubles": (c_size_t, [_P, c_int, c_int, c_int]),

@@ -56,6 +56,13 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// The per-rollout ("scalar") stages of the rollouts are written for a GROUP of 128 threads = warps 0..3 of the CTA: threadIdx.x is
+// the index inside the group and the group synchronises on named barrier 6.  In the stand-alone kernels the CTA is exactly one
+// group (bar.sync 6, 128 == __syncthreads()); in the persistent rollout kernels (rollout_persist.cu) the same code runs on the
+// scalar warps of a warp-specialised CTA while the other warps contract, so it must never use a CTA-wide barrier.
+constexpr int kGroupThreads = 128;
+__device__ __forceinline__ void group_sync() { asm volatile("bar.sync 6, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void flag_not_pd(int* info, int index) {
   if (info) atomicCAS(info, 0, index + 1);   // first writer wins; 0 means "all fine"
 }

@@ -22,6 +22,7 @@
 //   Ct[i][j] with row stride T + 8 doubles      8 rows x 4 column pairs per 128-bit load: quarter-warps hit disjoint banks
 #pragma once
 #include "mma_exp.cuh"
+#include "model.cuh"
 
 namespace gpp {
 

@@ -225,7 +225,7 @@ __device__ __forceinline__ S enc_cov_at(const EncoderSpec& es, int a, int b, Cov
 // symmetrises).  All pointers may be shared memory.
 // Shared by the threads of a CTA (all of them must call it; >= Dx*Dx + Dx threads): the linear parts are gathered
 // one input entry per thread, the small trigonometric block stays on thread 0.  `tr` is shared scratch of 8 * 4 doubles.
-// m_bar / Sx_bar are OVERWRITTEN.  Ends with a CTA barrier.
+// m_bar / Sx_bar are OVERWRITTEN.  Ends with a group barrier (common.cuh group_sync: the 128 threads of warps 0..3).
 __device__ inline void mm_encoder_bwd_cta(const EncoderSpec& es, const double* m, const double* Sx, const double* me_bar,
                                           const double* See_bar, const double* Cxe_bar, double* m_bar, double* Sx_bar, double* tr) {
   const int Dx = es.Dx, na = es.na, De = es.De(), nb = es.nb(), tid = threadIdx.x;
@@ -253,7 +253,7 @@ __device__ inline void mm_encoder_bwd_cta(const EncoderSpec& es, const double* m
     sincos(m[i], &s, &c);
     ev[tid] = e; sn[tid] = s; cs[tid] = c; s1[tid] = e * s; c1[tid] = e * c;
   }
-  __syncthreads();
+  group_sync();
   if (tid < Dx * Dx) {                          // linear part of d/dSx[i][j]
     const int i = tid / Dx, j = tid % Dx, ji = pos_inactive(i);
     double v = 0.0;
@@ -284,7 +284,7 @@ __device__ inline void mm_encoder_bwd_cta(const EncoderSpec& es, const double* m
       c1b[k] = cb;
     }
   }
-  __syncthreads();
+  group_sync();
   if (tid == 0) {
     double evb[4] = {0.0, 0.0, 0.0, 0.0}, snb[4] = {0.0, 0.0, 0.0, 0.0}, csb[4] = {0.0, 0.0, 0.0, 0.0};
     // trigonometric block of See, ordered pairs (k, l)
@@ -338,7 +338,7 @@ __device__ inline void mm_encoder_bwd_cta(const EncoderSpec& es, const double* m
       Sx_bar[i * Dx + i] -= 0.5 * ev[k] * evb[k];
     }
   }
-  __syncthreads();
+  group_sync();
 }
 
 // Owen's T evaluated by the 32 lanes of a warp (one Gauss-Legendre node each); every lane returns the sum

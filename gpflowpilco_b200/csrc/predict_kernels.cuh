@@ -46,7 +46,7 @@ __device__ __forceinline__ void psi1_body(int n, const double* __restrict__ m, c
                                           const double* __restrict__ var, const double* __restrict__ beta,
                                           double* __restrict__ f1lat /*[N,L]*/, double* __restrict__ crosslat /*[N,D,L]*/,
                                           int* info, double* li_out /* shared [L][D*D + 1]: Li and c0 per latent, for the backward */) {
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kGroupThreads >> 5;   // a group of 128 threads (common.cuh)
   double mu[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) mu[d] = m[(size_t)n * D + d];

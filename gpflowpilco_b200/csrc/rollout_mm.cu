@@ -15,6 +15,7 @@
 // gpp_rollout_mm_fwd_save additionally keeps each step's (md, Sd, Sxd, cross, pre-stage block) for gpp_rollout_mm_bwd (rollout_mm_bwd.cu);
 // gpp_policy_prepare / gpp_policy_prepare_bwd map the policy's q_mu to beta = Kuu^-1 m and back.
 #include "rollout_mm_common.cuh"
+#include "rollout_persist.h"
 
 namespace gpp {
 
@@ -254,7 +255,7 @@ __global__ void k_rollout_init(RolloutMMParams p, const double* m0, const double
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct RolloutLayout {
-  size_t m, S, md, Sd, Sxd, f1, Sff, cross, ring_m, ring_S, costbuf, predict, total, predict_bytes;
+  size_t m, S, md, Sd, Sxd, f1, Sff, cross, ring_m, ring_S, costbuf, predict, persist, total, predict_bytes;
 };
 
 static RolloutLayout rollout_layout(const gpp_gp_model* dyn, int N, int Dx) {
@@ -275,7 +276,10 @@ static RolloutLayout rollout_layout(const gpp_gp_model* dyn, int N, int Dx) {
   lo.costbuf = take((size_t)kCostRing * N);
   lo.predict = off;
   lo.predict_bytes = gpp_mm_gp_predict_workspace_bytes(dyn, N);
-  lo.total = off + align_up(lo.predict_bytes, 256);
+  off += align_up(lo.predict_bytes, 256);
+  lo.persist = off;                         // region of the persistent kernel (packs, tile partials, counters)
+  if (persist_fwd_supported(dyn, N, Dx)) off += align_up(persist_fwd_layout(dyn, N).total, 256);
+  lo.total = off;
   return lo;
 }
 
@@ -315,6 +319,15 @@ static int rollout_mm_fwd_impl(const gpp_gp_model* dynamics, int N, int Dx, int 
   p.f1 = (double*)(ws + lo.f1); p.Sff = (double*)(ws + lo.Sff); p.cross = (double*)(ws + lo.cross);
   p.traj_m = traj_m; p.traj_S = traj_S; p.info = info;
   GPP_REQUIRE((traj_m == nullptr) == (traj_S == nullptr), GPP_ERR_NULL, "gpp_rollout_mm_fwd: traj_m and traj_S go together");
+
+  // the H-loop on the device: one persistent cooperative launch for the whole sweep (rollout_persist.cu)
+  const int mode = rollout_mode();
+  const bool can_persist = persist_fwd_supported(dynamics, N, Dx);
+  GPP_REQUIRE(mode != GPP_ROLLOUT_PERSIST || can_persist, GPP_ERR_UNSUPPORTED,
+              "gpp_rollout_mm_fwd: the persistent kernel does not support this model (D=%d, %d tiles of 64 x 64)", dynamics->D,
+              dynamics->tables[0][0].nslots);
+  if (mode != GPP_ROLLOUT_LEGACY && can_persist)
+    return rollout_mm_fwd_persist(dynamics, p, H, m0, S0, m_final, S_final, saved, ws + lo.persist, stream);
 
   const int tb = 64, gb = (N + tb - 1) / tb;
   k_rollout_init<<<gb, tb, 0, stream>>>(p, m0, S0);

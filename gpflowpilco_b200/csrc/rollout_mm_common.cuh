@@ -35,36 +35,45 @@ struct PreShared {
   double vec[DP], cpre[DP], seu[DP]; // sum beta psi1 (z - me), (See+Lambda)^-1 vec, Cov(e, u)
 };
 
-// all 128 threads of the CTA call this; on return (after a CTA barrier) `sh` is complete
+// all 128 threads of the group call this: encoder rule on the current state (p.m, p.S) of rollout n -> sh.me, sh.See, sh.Cxe
+// (one output entry per thread: the serial form costs ~8 us of single-thread latency per step).  Ends with a group barrier.
 template <int DP>
-__device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>& sh) {
-  using PP = PairPack<DP>;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ void step_pre_encode(const RolloutMMParams& p, int n, PreShared<DP>& sh) {
+  const int tid = threadIdx.x;
   const int Dx = p.Dx;
-  const int r = (p.R == 1) ? 0 : n;
-  const double* ell = p.pEll + (size_t)r * DP;
-  const double var = p.pVar[r];
-  // encoder rule, one output entry per thread (the serial form costs ~8 us of single-thread latency per step)
   __shared__ double xm[GPP_SMALL_MAX], xS[GPP_SMALL_MAX * GPP_SMALL_MAX];
   __shared__ EncTrig<double> trig;
-  for (int t = tid; t < Dx + Dx * Dx; t += blockDim.x) {
+  for (int t = tid; t < Dx + Dx * Dx; t += kGroupThreads) {
     if (t < Dx) xm[t] = p.m[(size_t)n * Dx + t];
     else xS[t - Dx] = p.S[(size_t)n * Dx * Dx + (t - Dx)];
   }
-  __syncthreads();
+  group_sync();
   auto mean_at = [&](int i) { return xm[i]; };
   auto cov_at = [&](int i, int j) { return xS[i * Dx + j]; };
   if (tid < p.enc.na) enc_trig_one<double>(p.enc, tid, mean_at, cov_at, trig);
-  __syncthreads();
+  group_sync();
   {
     const int De = DP;
-    for (int t = tid; t < De + De * De + Dx * De; t += blockDim.x) {
+    for (int t = tid; t < De + De * De + Dx * De; t += kGroupThreads) {
       if (t < De) sh.me[t] = enc_mean_at<double>(p.enc, t, mean_at, trig);
       else if (t < De + De * De) sh.See[t - De] = enc_cov_at<double>(p.enc, (t - De) / De, (t - De) % De, cov_at, trig);
       else sh.Cxe[t - De - De * De] = enc_cross_at<double>(p.enc, (t - De - De * De) / De, (t - De - De * De) % De, cov_at, trig);
     }
   }
-  __syncthreads();
+  group_sync();
+}
+
+// all 128 threads of the group call this; on return (after a group barrier) `sh` is complete.  With `cost_out` the expected cost of
+// the current state (upstream components.py:30-37 on the encoded moments, loops/pilco.py:199-205) is evaluated by an otherwise idle
+// warp next to the two factorisations.
+template <int DP>
+__device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>& sh, double* cost_out = nullptr) {
+  using PP = PairPack<DP>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = (p.R == 1) ? 0 : n;
+  const double* ell = p.pEll + (size_t)r * DP;
+  const double var = p.pVar[r];
+  step_pre_encode<DP>(p, n, sh);
   // two independent factorisations of the encoded covariance, one warp each (lane 0)
   if (tid == 0) {
     // coefficient pack of the (policy kernel, policy kernel) pair
@@ -95,15 +104,17 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
 #pragma unroll
     for (int d = 0; d < DP * DP; ++d) sh.Li1[d] = Li.a[d];
     sh.c01 = log(var * ell_prod / diag_prod);
+  } else if (tid == 64 && cost_out) {
+    *cost_out = expected_cost<double>(DP, sh.me, sh.See, p.target, p.W);
   }
-  __syncthreads();
+  group_sync();
   // ---- policy Psi1 terms: f1 = sum_i beta_i psi1_i, vec = sum_i beta_i psi1_i (z_i - me)
   const double* Zp = p.pZ + (size_t)r * p.Mp * DP;
   const double* beta = p.pBeta + (size_t)r * p.Mp;
   double acc = 0.0, vec[DP];
 #pragma unroll
   for (int d = 0; d < DP; ++d) vec[d] = 0.0;
-  for (int i = tid; i < p.Mp; i += blockDim.x) {
+  for (int i = tid; i < p.Mp; i += kGroupThreads) {
     double dz[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) dz[d] = Zp[i * DP + d] - sh.me[d];
@@ -123,7 +134,7 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
   // ---- policy Psi2 contraction: f2 = sum_ij beta_i beta_j Q_ij  (KernelRegressor: no model uncertainty, models.py:34-41)
   //      thread = (row i, quarter c of the columns): 4 threads share a row so that all 128 threads work at Mp = 30
   double f2 = 0.0;
-  for (int idx = tid; idx < 4 * p.Mp; idx += blockDim.x) {
+  for (int idx = tid; idx < 4 * p.Mp; idx += kGroupThreads) {
     const int i = idx >> 2, c = idx & 3;
     double zr[DP], g[DP];
 #pragma unroll
@@ -158,7 +169,7 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
 #pragma unroll
     for (int d = 0; d < DP; ++d) sh.red[warp][2 + d] = vec[d];
   }
-  __syncthreads();
+  group_sync();
   if (warp == 0) {
     double f1 = 0.0, f2s = 0.0;
     for (int w = 0; w < 4; ++w) {
@@ -210,7 +221,7 @@ __device__ void step_pre_forward(const RolloutMMParams& p, int n, PreShared<DP>&
       }
     }
   }
-  __syncthreads();
+  group_sync();
 }
 
 // all threads of the CTA: write md, Sd and Sxd of rollout n (one entry per thread)
@@ -228,7 +239,7 @@ __device__ void step_pre_write(const RolloutMMParams& p, int n, const PreShared<
     if (b < De) return sh.seu[b];
     return sh.vu;
   };
-  for (int t = threadIdx.x; t < D + D * D + Dx * D; t += blockDim.x) {
+  for (int t = threadIdx.x; t < D + D * D + Dx * D; t += kGroupThreads) {
     if (t < D) {
       md[t] = t < De ? sh.me[t] : sh.mu_u;
     } else if (t < D + D * D) {
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(128) k_step_pre(RolloutMMParams p) {
     constexpr int PS = PreSharedSize<DP>::value;
     const double* src = reinterpret_cast<const double*>(&sh);
     double* dst = p.pre + (size_t)n * PS;
-    for (int t = threadIdx.x; t < PS; t += blockDim.x) dst[t] = src[t];
+    for (int t = threadIdx.x; t < PS; t += kGroupThreads) dst[t] = src[t];
   }
 }
 

@@ -1,0 +1,712 @@
+// Persistent moment-matched rollout: the whole H-step sweep of gpp_rollout_mm_fwd / gpp_rollout_mm_bwd in ONE cooperative launch
+// per direction — the device-side counterpart of upstream's compiled scan (gpflow_pilco/dynamics/solvers.py:84-105 driven by
+// gpflow_pilco/loops/pilco.py:207-217; reverse sweep = tape.gradient through it, utils/optimizers.py:52-56).
+//
+// Every CTA (one per SM) is warp specialised:
+//   warps 0..3   "scalar group": the per-rollout stages of a step (rollout_mm_common.cuh, predict_kernels.cuh, finalize.cuh,
+//                rollout_mm_bwd_common.cuh, predict_bwd_kernels.cuh — the very code the one-launch-per-stage path runs)
+//   other warps  the Psi2 contraction: forward = the DMMA producer/consumer pipeline of contract_kernel.cuh on a 64 x 64 tile of C
+//                that stays in shared memory for the whole sweep when the model has no more tiles than the GPU has SMs (M = 256,
+//                L = 4: 136 tiles); backward = contract_grad_item work items pulled from a ticket counter.
+// Rollout n's step t is a chain  scalar(n,t) -> contraction(n,t; all tiles) -> scalar(n,t+1) ...; the two roles of all CTAs meet
+// only through per-rollout release/acquire counters (persist_common.cuh), never through a grid-wide barrier, so with many rollouts
+// in flight the serial stages of one rollout hide behind the contractions of the others: N independent rollouts advance as a
+// skewed pipeline and the FP64 pipe stays busy.
+#include <algorithm>
+#include <cstdlib>
+
+#include "contract_kernel.cuh"
+#include "finalize.cuh"
+#include "persist_common.cuh"
+#include "predict_bwd_kernels.cuh"
+#include "predict_kernels.cuh"
+#include "rollout_mm_bwd_common.cuh"
+#include "rollout_persist.h"
+
+namespace gpp {
+
+constexpr int kPersistTile = 64;        // tile edge of the forward contraction
+constexpr int kFwdThreads = 512;        // 4 scalar + 2 producer (+ 2 idle) + 8 consumer warps
+constexpr int kFwdBatch = 8;            // inputs whose packs a producer waits for at once
+
+struct PersistSaved {                   // the per-step block of gpp_rollout_mm_fwd_save (RolloutSaved offsets), or base == nullptr
+  double* base;
+  size_t per_step, md, Sd, Sxd, cross, pre;
+};
+
+struct PersistFwdParams {
+  RolloutMMParams r;                    // r.md / r.Sd / r.Sxd / r.cross: workspace buffers used when nothing is saved
+  PersistSaved sv;
+  int H;
+  const double *m0, *S0;
+  double *m_final, *S_final;
+  // dynamics model
+  const double *Z, *ell, *var, *beta, *C, *mean, *W;
+  int M, Lm, Pm, model_uncertainty;
+  const gpp_slot* slots;
+  const int* pair_start;
+  const int* pair_ab;
+  int npairs, nslots;
+  // workspace
+  double *packs, *part, *f1lat, *crosslat;
+  unsigned *pack_ready, *part_done;     // [N] each, zero at launch
+};
+
+__device__ __forceinline__ void persist_step_pointers(RolloutMMParams& p, const PersistSaved& sv, const RolloutMMParams& base, int t) {
+  if (sv.base) {
+    double* b = sv.base + (size_t)t * sv.per_step;
+    p.md = b + sv.md; p.Sd = b + sv.Sd; p.Sxd = b + sv.Sxd; p.cross = b + sv.cross; p.pre = b + sv.pre;
+  } else {
+    p.md = base.md; p.Sd = base.Sd; p.Sxd = base.Sxd; p.cross = base.cross; p.pre = nullptr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward: scalar group
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__device__ void persist_fwd_scalar(const PersistFwdParams& P) {
+  constexpr int DP = D - 1;
+  __shared__ PreShared<DP> sh;
+  const int tid = threadIdx.x, G = gridDim.x;
+  RolloutMMParams p = P.r;
+  const int N = p.N, Dx = p.Dx;
+  const int n0 = G - 1 - (int)blockIdx.x;       // rollouts are dealt from the last CTA down: CTAs without a tile take them first
+  for (int n = n0; n < N; n += G) {
+    for (int i = tid; i < Dx + Dx * Dx; i += kGroupThreads) {
+      if (i < Dx) {
+        const double v = P.m0[(size_t)n * Dx + i];
+        p.m[(size_t)n * Dx + i] = v;
+        if (p.traj_m) p.traj_m[(size_t)n * Dx + i] = v;
+      } else {
+        const double v = P.S0[(size_t)n * Dx * Dx + (i - Dx)];
+        p.S[(size_t)n * Dx * Dx + (i - Dx)] = v;
+        if (p.traj_S) p.traj_S[(size_t)n * Dx * Dx + (i - Dx)] = v;
+      }
+    }
+    if (tid == 0) p.loss[n] = 0.0;
+  }
+  group_sync();
+  FinalizeParams fp;
+  fp.part = P.part; fp.slots = P.slots; fp.pair_start = P.pair_start; fp.pair_ab = P.pair_ab;
+  fp.f1lat = P.f1lat; fp.crosslat = P.crosslat; fp.var = P.var; fp.mean = P.mean; fp.W = P.W;
+  fp.f1 = p.f1; fp.Sff = p.Sff; fp.cross = nullptr;
+  fp.N = N; fp.L = P.Lm; fp.P = P.Pm; fp.D = D; fp.npairs = P.npairs; fp.nslots = P.nslots; fp.full_cov = 1;
+  fp.model_uncertainty = P.model_uncertainty; fp.jitter = 0.0;
+  fp.post.m = p.m; fp.post.S = p.S; fp.post.Dx = Dx; fp.post.ring_m = nullptr; fp.post.ring_S = nullptr;
+  for (int t = 0; t <= P.H; ++t) {
+    for (int n = n0; n < N; n += G) {
+      if (t > 0) {
+        // step t-1 of rollout n: all tile partials are in -> outputs of the GP predict, Euler update, trajectory slice t
+        if (tid == 0) spin_wait_ge(P.part_done + n, (unsigned)t * (unsigned)P.nslots);
+        group_sync();
+        persist_step_pointers(p, P.sv, P.r, t - 1);
+        fp.cross = p.cross;
+        fp.post.Sxd = p.Sxd;
+        fp.post.traj_m = p.traj_m ? p.traj_m + (size_t)t * N * Dx : nullptr;
+        fp.post.traj_S = p.traj_S ? p.traj_S + (size_t)t * N * Dx * Dx : nullptr;
+        finalize_body<true>(fp, n);
+        group_sync();
+      }
+      if (t == P.H) {
+        if (P.H > 0) {                         // cost of the final state (the loss callback runs after every step)
+          step_pre_encode<DP>(p, n, sh);
+          if (tid == 64) p.loss[n] += expected_cost<double>(DP, sh.me, sh.See, p.target, p.W);
+        }
+        for (int i = tid; i < Dx + Dx * Dx; i += kGroupThreads) {
+          if (i < Dx) { if (P.m_final) P.m_final[(size_t)n * Dx + i] = p.m[(size_t)n * Dx + i]; }
+          else if (P.S_final) P.S_final[(size_t)n * Dx * Dx + (i - Dx)] = p.S[(size_t)n * Dx * Dx + (i - Dx)];
+        }
+        group_sync();
+        continue;
+      }
+      persist_step_pointers(p, P.sv, P.r, t);
+      double cost = 0.0;
+      step_pre_forward<DP>(p, n, sh, t > 0 ? &cost : nullptr);
+      if (t > 0 && tid == 64) p.loss[n] += cost;            // thread 64 is the only writer of loss[n]: step order, fixed
+      step_pre_write<DP>(p, n, sh);
+      if (p.pre) {
+        constexpr int PS = PreSharedSize<DP>::value;
+        const double* src = reinterpret_cast<const double*>(&sh);
+        double* dst = p.pre + (size_t)n * PS;
+        for (int i = tid; i < PS; i += kGroupThreads) dst[i] = src[i];
+      }
+      group_sync();                                          // md / Sd of rollout n are visible to the group
+      {
+        // Psi2 coefficient packs of the kernel pairs: pair pp on lane pp / 4 of warp pp % 4 (same code path on every live lane)
+        const int pp = (tid & 31) * 4 + (tid >> 5);
+        if (pp < P.npairs)
+          pack_body<D>(n * P.npairs + pp, p.md, p.Sd, N, P.ell, P.var, P.pair_ab, P.npairs, P.Lm, P.packs, nullptr, p.info);
+      }
+      psi1_body<D>(n, p.md, p.Sd, N, P.Lm, P.M, P.Z, P.ell, P.var, P.beta, P.f1lat, P.crosslat, p.info, nullptr);
+      __threadfence();
+      group_sync();
+      if (tid == 0) st_release_u32(P.pack_ready + n, (unsigned)(t + 1));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward: contraction warps (the k_contract pipeline with the item loop replaced by a static (step, tile, input) order)
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+struct PersistFwdCfg {
+  static constexpr int T = kPersistTile, NP = 2, NC = 8;
+  using CF = ContractCfg<D, T, NP, NC>;
+  static constexpr int PT = 32 * NP, CT = 32 * NC, NTC = PT + CT;      // producer / consumer / contraction threads
+  static constexpr int KS = CF::KS, LDC = CF::LDC;
+  static constexpr int FBUF = KS * T * 4, WBUF = 2 * T, DBUF = NC * 32;
+  static constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_PROD = 5, BAR_TILE = 7;   // 6 is the scalar group's barrier
+};
+
+// both contraction roles: (re)load the C tile of a diagonal pair; `ctid` = index among the NTC contraction threads
+template <int D>
+__device__ __forceinline__ void persist_load_tile(const PersistFwdParams& P, const gpp_slot& sl, double* Ct, int ctid) {
+  using F = PersistFwdCfg<D>;
+  role_bar_sync<F::BAR_TILE, F::NTC>();
+  const double* Ca = P.C + (size_t)sl.a * P.M * P.M;
+  for (int idx = ctid; idx < F::T * F::T; idx += F::NTC) {
+    const int ii = idx / F::T, jj = idx % F::T;
+    const int ig = sl.ti * F::T + ii, jg = sl.tj * F::T + jj;
+    Ct[ii * F::LDC + jj] = (jg < P.M && ig < P.M) ? Ca[(size_t)ig * P.M + jg] : 0.0;
+  }
+  role_bar_sync<F::BAR_TILE, F::NTC>();
+}
+
+template <int D>
+__device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
+  using F = PersistFwdCfg<D>;
+  using CF = typename F::CF;
+  using PP = PairPack<D>;
+  constexpr int T = F::T, PT = F::PT, KS = F::KS, NTC = F::NTC;
+  constexpr int NPV = (PP::SIZE + PT - 1) / PT;
+  double* Ct = smem + CF::CT;
+  double* colB = smem + CF::COL;
+  double* rowA = smem + CF::ROW;
+  double* wgt = smem + CF::WGT;
+  double* red = smem + CF::RED;
+  double* pkbuf = smem + CF::PKBUF;
+  const int ptid = threadIdx.x - kGroupThreads, lane = ptid & 31, pwarp = ptid >> 5;
+  const int N = P.r.N, G = gridDim.x;
+  const size_t pk_stride = (size_t)P.npairs * PP::SIZE;
+  int resident = -1;
+  for (int t = 0; t < P.H; ++t) {
+    for (int slot = blockIdx.x; slot < P.nslots; slot += G) {
+      const gpp_slot sl = P.slots[slot];
+      const bool diag = sl.a == sl.b;
+      if (slot != resident) {
+        if (diag) persist_load_tile<D>(P, sl, Ct, ptid);
+        resident = slot;
+      }
+      const int ig = sl.ti * T + ptid, jg = sl.tj * T + ptid;
+      double zrow[D], zcol[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        zrow[d] = ig < P.M ? P.Z[((size_t)sl.a * P.M + ig) * D + d] : 0.0;
+        zcol[d] = jg < P.M ? P.Z[((size_t)sl.b * P.M + jg) * D + d] : 0.0;
+      }
+      const double brow = (!diag && ig < P.M) ? P.beta[(size_t)sl.a * P.M + ig] : 0.0;
+      const double bcol = (!diag && jg < P.M) ? P.beta[(size_t)sl.b * P.M + jg] : 0.0;
+      const double* pk0 = P.packs + (size_t)sl.pair * PP::SIZE;
+      double pv[NPV];
+      for (int k = 0; k < N + 2; ++k) {
+        const int b = k & 1;
+        if (k >= 2) {                        // consumers are done with input k-2 (buffer b): publish its tile partial
+          named_bar_sync<F::BAR_EMPTY>(b, NTC);
+          if (pwarp == 0) {
+            const double* rp = red + b * F::DBUF + lane;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < F::NC; ++w) s += rp[w * 32];
+            s = warp_sum(s);
+            if (lane == 0) {
+              P.part[(size_t)(k - 2) * P.nslots + slot] = s;
+              __threadfence();
+              red_release_add_u32(P.part_done + (k - 2), 1u);
+            }
+          }
+        }
+        if (k >= N) continue;
+        if (k % kFwdBatch == 0) {            // the scalar groups of the next batch of rollouts have published step t's packs?
+          if (ptid < kFwdBatch && k + ptid < N) spin_wait_ge(P.pack_ready + k + ptid, (unsigned)(t + 1));
+          named_bar_sync_imm<F::BAR_PROD>(PT);
+#pragma unroll
+          for (int q = 0; q < NPV; ++q) pv[q] = ptid + q * PT < PP::SIZE ? __ldcg(pk0 + (size_t)k * pk_stride + ptid + q * PT) : 0.0;
+        }
+        double* pk = pkbuf + b * PP::SIZE;
+#pragma unroll
+        for (int q = 0; q < NPV; ++q)
+          if (ptid + q * PT < PP::SIZE) pk[ptid + q * PT] = pv[q];
+        named_bar_sync_imm<F::BAR_PROD>(PT);   // pack k visible to the producers; pack k-2 (same buffer) no longer read
+        if ((k + 1) % kFwdBatch != 0 && k + 1 < N) {
+#pragma unroll
+          for (int q = 0; q < NPV; ++q)
+            if (ptid + q * PT < PP::SIZE) pv[q] = __ldcg(pk0 + (size_t)(k + 1) * pk_stride + ptid + q * PT);
+        }
+        double ext[4 * KS];
+        {
+          double zc[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) zc[d] = zrow[d] - pk[PP::MU + d];
+#pragma unroll
+          for (int e = 0; e < D; ++e) {
+            double tt = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) tt = fma(zc[d], pk[PP::R + d * D + e], tt);
+            ext[e] = tt;
+          }
+          ext[D] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
+          ext[D + 1] = 1.0;
+#pragma unroll
+          for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
+          double* ra = rowA + b * F::FBUF + ptid * 4;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int q = 0; q < 4; q += 2)
+              *reinterpret_cast<double2*>(ra + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
+          wgt[b * F::WBUF + ptid] = brow;
+        }
+        {
+#pragma unroll
+          for (int d = 0; d < D; ++d) ext[d] = zcol[d] - pk[PP::MU + d];
+          ext[D + 1] = packed_quad<D>(pk + PP::P2, ext);
+          ext[D] = 1.0;
+          double* cb = colB + b * F::FBUF + ptid * 4;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int q = 0; q < 4; q += 2)
+              *reinterpret_cast<double2*>(cb + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
+          wgt[b * F::WBUF + T + ptid] = bcol;
+        }
+        __threadfence_block();
+        named_bar_arrive<F::BAR_FULL>(b, NTC);
+      }
+    }
+  }
+}
+
+template <int D>
+__device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
+  using F = PersistFwdCfg<D>;
+  using CF = typename F::CF;
+  constexpr int T = F::T, KS = F::KS, LDC = F::LDC, NTC = F::NTC;
+  double* Ct = smem + CF::CT;
+  double* colB = smem + CF::COL;
+  double* rowA = smem + CF::ROW;
+  double* wgt = smem + CF::WGT;
+  double* red = smem + CF::RED;
+  double* etab = smem + CF::ETAB;
+  const int ctid = threadIdx.x - 2 * kGroupThreads, lane = ctid & 31, strip = ctid >> 5;
+  const int row = strip * 8 + (lane >> 2);
+  const int cpair = 2 * (lane & 3);
+  const double* ct = Ct + row * LDC + cpair;
+  const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (CF::REP - 1)));
+  const int N = P.r.N, G = gridDim.x;
+  int resident = -1;
+  for (int t = 0; t < P.H; ++t) {
+    for (int slot = blockIdx.x; slot < P.nslots; slot += G) {
+      const gpp_slot sl = P.slots[slot];
+      const bool diag = sl.a == sl.b;
+      if (slot != resident) {
+        if (diag) persist_load_tile<D>(P, sl, Ct, F::PT + ctid);
+        resident = slot;
+      }
+      for (int k = 0; k < N; ++k) {
+        const int b = k & 1;
+        named_bar_sync<F::BAR_FULL>(b, NTC);
+        const double* ra = rowA + b * F::FBUF + strip * 32 + lane;
+        const double* cb = colB + b * F::FBUF + lane;
+        const double* wsrc = diag ? ct : wgt + b * F::WBUF + T + cpair;
+        double a[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) a[ks] = ra[ks * T * 4];
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 2
+        for (int cg = 0; cg < T / 8; cg += 2) {
+          double tt[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            dmma_m8n8k4(tt[0], tt[1], a[ks], cb[ks * T * 4 + cg * 32]);
+            dmma_m8n8k4(tt[2], tt[3], a[ks], cb[ks * T * 4 + cg * 32 + 32]);
+          }
+          exp_tab_contract<4, CF::REP>(tt, etab_lane);
+          const double2 w0 = *reinterpret_cast<const double2*>(wsrc + cg * 8);
+          const double2 w1 = *reinterpret_cast<const double2*>(wsrc + cg * 8 + 8);
+          acc0 = fma(tt[0], w0.x, acc0);
+          acc1 = fma(tt[2], w1.x, acc1);
+          acc0 = fma(tt[1], w0.y, acc0);
+          acc1 = fma(tt[3], w1.y, acc1);
+        }
+        double total = acc0 + acc1;
+        if (!diag) total *= wgt[b * F::WBUF + row];
+        red[b * F::DBUF + strip * 32 + lane] = total;
+        __threadfence_block();
+        named_bar_arrive<F::BAR_EMPTY>(b, NTC);
+      }
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kFwdThreads, 1) k_rollout_fwd_persist(const PersistFwdParams P) {
+  using CF = typename PersistFwdCfg<D>::CF;
+  extern __shared__ __align__(16) double smem[];
+  double* etab = smem + CF::ETAB;
+  for (int i = threadIdx.x; i < kContractTab * CF::REP; i += kFwdThreads) etab[i] = kExp2Tab256[i / CF::REP];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  if (warp < 4) {
+    warpgroup_reg_inc<224>();
+    persist_fwd_scalar<D>(P);
+  } else if (warp < 8) {
+    warpgroup_reg_dec<96>();
+    if (warp < 4 + PersistFwdCfg<D>::NP) persist_fwd_producer<D>(P, smem);
+  } else {
+    warpgroup_reg_dec<96>();
+    persist_fwd_consumer<D>(P, smem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward: the reverse sweep.  Per step t = H-1 .. 0 and rollout n (same order as gpp_rollout_mm_bwd's one-launch-per-stage path):
+//   scalar group   bwd_post (cost gradient of state t+1, adjoint of the Euler update)  ->  prologue of the predict's adjoint
+//                  (coefficient packs of the unordered kernel pairs, Psi1 forward + adjoint, un-mixing)  ->  publish ready[n]
+//   contraction    L (L+1)/2 x nrb work items (contract_grad_item) per (step, rollout), drawn from one ticket counter in
+//                  (step, rollout) order by the 16 contraction warps of every CTA  ->  stat_done[n]
+//   scalar group   bwd_finalize (D x D algebra per pair) -> bwd_pre (joint assembly, squashing link, policy, encoder adjoints)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = kGroupThreads + kGradThreads;    // 4 scalar + 16 contraction warps
+
+struct PersistBwdParams {
+  RolloutMMParams r;
+  RolloutBwdBuffers bw;
+  PersistSaved sv;
+  int H;
+  const double *traj_m, *traj_S, *loss_bar;
+  const double* cg;                     // [H,N,ndir] cost gradients of the states 1..H (k_cost_grad_ring, one launch)
+  // dynamics model
+  const double *Z, *ell, *var, *beta, *C, *W;
+  int M, Lm, Pm;
+  // workspace of the predict's adjoint
+  double *packs, *Gs, *stats, *f1lat, *crosslat, *f1lat_bar, *crosslat_bar, *omega, *gm, *gS;
+  int nrb;
+  unsigned *ready, *stat_done, *ticket; // [N], [N], [1]; zero at launch
+};
+
+template <int D>
+__device__ void persist_bwd_scalar(const PersistBwdParams& P, double* fsm) {
+  constexpr int DP = D - 1;
+  const int tid = threadIdx.x, G = gridDim.x;
+  RolloutMMParams p = P.r;
+  const RolloutBwdBuffers& bw = P.bw;
+  const int N = p.N, Dx = p.Dx, Lm = P.Lm;
+  const int ndir = Dx + Dx * (Dx + 1) / 2;
+  const int items = Lm * (Lm + 1) / 2 * P.nrb;
+  const size_t sm = (size_t)N * Dx, sS = (size_t)N * Dx * Dx;
+  const int n0 = G - 1 - (int)blockIdx.x;
+  __shared__ double li_sm[GPP_MAX_L * (D * D + 1)];
+  BwdPrepareParams bp;
+  bp.f1_bar = bw.f1_bar; bp.Sff_bar = bw.Sff_bar; bp.cross_bar = bw.cross_bar; bp.f1lat = P.f1lat; bp.W = P.W;
+  bp.f1lat_bar = P.f1lat_bar; bp.crosslat_bar = P.crosslat_bar; bp.omega = P.omega;
+  bp.N = N; bp.L = Lm; bp.P = P.Pm; bp.D = D; bp.full_cov = 1;
+  BwdFinalizeParams fp;
+  fp.m = nullptr; fp.S = nullptr; fp.ell = P.ell; fp.stats = P.stats; fp.omega = P.omega; fp.Gs = P.Gs; fp.gm = P.gm; fp.gS = P.gS;
+  fp.m_bar = bw.md_bar; fp.S_bar = bw.Sd_bar; fp.N = N; fp.L = Lm; fp.nrb = P.nrb;
+  auto set_step = [&](int t) {
+    p.m = const_cast<double*>(P.traj_m) + (size_t)t * sm;       // read-only
+    p.S = const_cast<double*>(P.traj_S) + (size_t)t * sS;
+    persist_step_pointers(p, P.sv, P.r, t);
+  };
+  for (int t = P.H - 1; t >= -1; --t) {
+    for (int n = n0; n < N; n += G) {
+      if (t < P.H - 1) {
+        // step t+1 of rollout n: its statistics are in -> adjoint of the joint moments, then of the pre stage
+        if (tid == 0) spin_wait_ge(P.stat_done + n, (unsigned)(P.H - 1 - t) * (unsigned)items);
+        group_sync();
+        set_step(t + 1);
+        bwd_finalize_body<D>(fp, n, fsm);
+        group_sync();
+        bwd_pre_body<DP>(p, bw, n);
+        group_sync();
+      }
+      if (t < 0) continue;
+      set_step(t);
+      if (tid < 32) bwd_post_body(p, n, P.cg + ((size_t)t * N) * ndir, P.loss_bar, bw);
+      group_sync();
+      {
+        // coefficient packs (and (Sigma + V_ab)^-1) of the unordered kernel pairs: pair u on lane u / 4 of warp u % 4
+        const int u = (tid & 31) * 4 + (tid >> 5);
+        if (u < Lm * (Lm + 1) / 2) {
+          int a = 0, b = u;
+          while (b >= Lm - a) { b -= Lm - a; ++a; }
+          b += a;
+          pack_body<D>(n * Lm * Lm + a * Lm + b, p.md, p.Sd, N, P.ell, P.var, nullptr, Lm * Lm, Lm, P.packs, P.Gs, p.info);
+        }
+      }
+      psi1_body<D>(n, p.md, p.Sd, N, Lm, P.M, P.Z, P.ell, P.var, P.beta, P.f1lat, P.crosslat, p.info, li_sm);
+      group_sync();
+      bwd_prepare_input(bp, n);
+      psi1_bwd_body<D>(n, p.md, p.Sd, Lm, P.M, P.Z, P.ell, P.var, P.beta, P.f1lat_bar, P.crosslat_bar, P.gm, P.gS, li_sm);
+      __threadfence();
+      group_sync();
+      if (tid == 0) st_release_u32(P.ready + n, (unsigned)(P.H - t));
+    }
+  }
+}
+
+template <int D>
+__device__ void persist_bwd_contract(const PersistBwdParams& P, double* smem) {
+  __shared__ unsigned s_ticket;
+  const int gtid = threadIdx.x - kGroupThreads;
+  const int N = P.r.N, Lm = P.Lm;
+  const int items = Lm * (Lm + 1) / 2 * P.nrb;
+  const unsigned per_step = (unsigned)N * (unsigned)items, total = per_step * (unsigned)P.H;
+  for (;;) {
+    if (gtid == 0) {
+      const unsigned k = atomicAdd(P.ticket, 1u);
+      if (k < total) spin_wait_ge(P.ready + (k % per_step) / items, k / per_step + 1u);
+      s_ticket = k;
+    }
+    grad_sync<true>();
+    const unsigned k = s_ticket;
+    if (k >= total) break;
+    const int rem = (int)(k % per_step);
+    const int n = rem / items, it = rem % items;
+    contract_grad_item<D, true>(smem, gtid, n, it / P.nrb, it % P.nrb, P.Z, P.beta, P.C, P.packs, P.omega, P.stats, P.M, Lm, P.nrb, false);
+    grad_sync<true>();                     // all statistics of the item are written (and s_ticket may be overwritten)
+    if (gtid == 0) {
+      __threadfence();
+      red_release_add_u32(P.stat_done + n, 1u);
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBwdThreads, 1) k_rollout_bwd_persist(const PersistBwdParams P, const int fsm_offset) {
+  using CF = GradCfg<D>;
+  extern __shared__ __align__(16) double smem[];
+  double* etab = smem + CF::ETAB;
+  for (int i = threadIdx.x; i < 256 * CF::REP; i += kBwdThreads) etab[i] = kExp2Tab256[i / CF::REP];
+  __syncthreads();
+  if (threadIdx.x < kGroupThreads) {
+    warpgroup_reg_inc<224>();
+    persist_bwd_scalar<D>(P, smem + fsm_offset);
+  } else {
+    warpgroup_reg_dec<64>();
+    persist_bwd_contract<D>(P, smem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int g_rollout_mode = -1;   // -1: not read yet; GPP_ROLLOUT_AUTO / _LEGACY / _PERSIST
+
+int rollout_mode() {
+  if (g_rollout_mode < 0) {
+    const char* e = std::getenv("GPP_ROLLOUT_MODE");
+    g_rollout_mode = e ? std::atoi(e) : GPP_ROLLOUT_AUTO;
+    if (g_rollout_mode < GPP_ROLLOUT_AUTO || g_rollout_mode > GPP_ROLLOUT_PERSIST) g_rollout_mode = GPP_ROLLOUT_AUTO;
+  }
+  return g_rollout_mode;
+}
+
+static bool cooperative_ok() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+    ok = v ? 1 : 0;
+  }
+  return ok == 1;
+}
+
+static size_t pack_doubles(int D) {
+  switch (D) {
+#define GPP_CASE(d) case d: return PairPack<d>::SIZE;
+    GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+    default: return 0;
+  }
+}
+
+bool persist_fwd_supported(const gpp_gp_model* dyn, int N, int Dx) {
+  (void)N; (void)Dx;
+  if (!dyn || dyn->D < 2 || dyn->D > 8 || !cooperative_ok()) return false;
+  const gpp_gp_model::SlotTable& tab = dyn->tables[0][0];
+  // a CTA re-loads its C tile whenever it owns more than one: fine for a few, the multi-launch path amortises better beyond that
+  return tab.nslots <= 2 * num_sms();
+}
+
+PersistFwdLayout persist_fwd_layout(const gpp_gp_model* dyn, int N) {
+  PersistFwdLayout lo{};
+  const gpp_gp_model::SlotTable& tab = dyn->tables[0][0];
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  lo.packs = take(sizeof(double) * pack_doubles(dyn->D) * tab.npairs * N);
+  lo.part = take(sizeof(double) * (size_t)tab.nslots * N);
+  lo.f1lat = take(sizeof(double) * (size_t)dyn->L * N);
+  lo.crosslat = take(sizeof(double) * (size_t)dyn->L * dyn->D * N);
+  lo.flags = take(sizeof(unsigned) * 2 * (size_t)N);
+  lo.total = off;
+  return lo;
+}
+
+template <int D>
+static int launch_fwd_persist(PersistFwdParams& P, int grid, cudaStream_t stream) {
+  using CF = typename PersistFwdCfg<D>::CF;
+  const size_t smem = sizeof(double) * CF::TOTAL;
+  GPP_CUDA_OK(cudaFuncSetAttribute(k_rollout_fwd_persist<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {(void*)&P};
+  GPP_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_rollout_fwd_persist<D>, dim3(grid), dim3(kFwdThreads), args, smem, stream));
+  count_launch();
+  return GPP_OK;
+}
+
+int rollout_mm_fwd_persist(const gpp_gp_model* dyn, const RolloutMMParams& r, int H, const double* m0, const double* S0, double* m_final,
+                           double* S_final, double* saved, char* ws_persist, cudaStream_t stream) {
+  const int N = r.N;
+  const gpp_gp_model::SlotTable& tab = dyn->tables[0][0];
+  const PersistFwdLayout lo = persist_fwd_layout(dyn, N);
+  PersistFwdParams P{};
+  P.r = r;
+  P.sv.base = saved;
+  if (saved) {
+    const RolloutSaved sv(N, r.Dx, r.D, r.L);
+    P.sv.per_step = sv.per_step; P.sv.md = sv.md; P.sv.Sd = sv.Sd; P.sv.Sxd = sv.Sxd; P.sv.cross = sv.cross; P.sv.pre = sv.pre;
+  }
+  P.H = H; P.m0 = m0; P.S0 = S0; P.m_final = m_final; P.S_final = S_final;
+  P.Z = dyn->Z; P.ell = dyn->ell; P.var = dyn->var; P.beta = dyn->beta; P.C = dyn->C; P.mean = dyn->mean; P.W = dyn->W;
+  P.M = dyn->M; P.Lm = dyn->L; P.Pm = dyn->P; P.model_uncertainty = dyn->model_uncertainty;
+  P.slots = tab.d_slots; P.pair_start = tab.d_pair_start; P.pair_ab = tab.d_pair_ab; P.npairs = tab.npairs; P.nslots = tab.nslots;
+  P.packs = (double*)(ws_persist + lo.packs); P.part = (double*)(ws_persist + lo.part);
+  P.f1lat = (double*)(ws_persist + lo.f1lat); P.crosslat = (double*)(ws_persist + lo.crosslat);
+  P.pack_ready = (unsigned*)(ws_persist + lo.flags); P.part_done = P.pack_ready + N;
+  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * 2 * (size_t)N, stream));
+  const int grid = std::min(num_sms(), tab.nslots + N);
+  switch (dyn->D) {
+#define GPP_CASE(d) case d: return launch_fwd_persist<d>(P, grid, stream);
+    GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+    default:
+      set_error("persistent rollout: unsupported dynamics input dimension %d", dyn->D);
+      return GPP_ERR_UNSUPPORTED;
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------------
+bool persist_bwd_supported(const gpp_gp_model* dyn, int N, int Dx) {
+  (void)N;
+  if (!dyn || dyn->D < 2 || dyn->D > 8 || !cooperative_ok()) return false;
+  if (Dx + Dx * (Dx + 1) / 2 > 128) return false;
+  const int ncb = (dyn->M + kGradCols - 1) / kGradCols;
+  const int npairs = dyn->L * (dyn->L + 1) / 2;
+  size_t fin = 0, fixed = 0;
+  switch (dyn->D) {
+#define GPP_CASE(d) case d: fin = (size_t)npairs * FinalizeSmem<d>::PER_PAIR; fixed = GradCfg<d>::FIXED; break;
+    GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+  }
+  return sizeof(double) * (fixed + (size_t)ncb * kGradCols + fin) + 16 * 1024 <= 227 * 1024;   // + the scalar stages' static arrays
+}
+
+PersistBwdLayout persist_bwd_layout(const gpp_gp_model* dyn, int N, int Dx, int H) {
+  PersistBwdLayout lo{};
+  const int D = dyn->D, L = dyn->L;
+  size_t stat_doubles = 0;
+  switch (D) {
+#define GPP_CASE(d) case d: stat_doubles = GradStats<d>::SIZE; break;
+    GPP_CASE(1) GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+  }
+  lo.nrb = (dyn->M + kGradRows - 1) / kGradRows;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  lo.packs = take(sizeof(double) * pack_doubles(D) * L * L * N);
+  lo.Gs = take(sizeof(double) * (size_t)D * D * L * L * N);
+  lo.stats = take(sizeof(double) * stat_doubles * L * L * lo.nrb * N);
+  lo.f1lat = take(sizeof(double) * (size_t)L * N);
+  lo.crosslat = take(sizeof(double) * (size_t)L * D * N);
+  lo.f1lat_bar = take(sizeof(double) * (size_t)L * N);
+  lo.crosslat_bar = take(sizeof(double) * (size_t)L * D * N);
+  lo.omega = take(sizeof(double) * (size_t)L * L * N);
+  lo.gm = take(sizeof(double) * (size_t)L * D * N);
+  lo.gS = take(sizeof(double) * (size_t)L * D * D * N);
+  lo.cg = take(sizeof(double) * (size_t)std::max(H, 1) * N * (Dx + Dx * (Dx + 1) / 2));
+  lo.flags = take(sizeof(unsigned) * (2 * (size_t)N + 8));
+  lo.total = off;
+  return lo;
+}
+
+template <int D>
+static int launch_bwd_persist(PersistBwdParams& P, int grid, cudaStream_t stream) {
+  const int ncb = (P.M + kGradCols - 1) / kGradCols;
+  const int npairs = P.Lm * (P.Lm + 1) / 2;
+  int fsm_offset = GradCfg<D>::FIXED + ncb * kGradCols;
+  fsm_offset = (fsm_offset + 1) & ~1;
+  const size_t smem = sizeof(double) * ((size_t)fsm_offset + (size_t)npairs * FinalizeSmem<D>::PER_PAIR);
+  GPP_CUDA_OK(cudaFuncSetAttribute(k_rollout_bwd_persist<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {(void*)&P, (void*)&fsm_offset};
+  GPP_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_rollout_bwd_persist<D>, dim3(grid), dim3(kBwdThreads), args, smem, stream));
+  count_launch();
+  return GPP_OK;
+}
+
+int rollout_mm_bwd_persist(const gpp_gp_model* dyn, const RolloutMMParams& r, const RolloutBwdBuffers& bw, int H, const double* traj_m,
+                           const double* traj_S, const double* saved, const double* loss_bar, char* ws_persist, cudaStream_t stream) {
+  if (H <= 0) return GPP_OK;
+  const int N = r.N, Dx = r.Dx;
+  const PersistBwdLayout lo = persist_bwd_layout(dyn, N, Dx, H);
+  auto D_ = [&](size_t off) { return (double*)(ws_persist + off); };
+  PersistBwdParams P{};
+  P.r = r; P.bw = bw;
+  const RolloutSaved sv(N, Dx, r.D, r.L);
+  P.sv.base = const_cast<double*>(saved);
+  P.sv.per_step = sv.per_step; P.sv.md = sv.md; P.sv.Sd = sv.Sd; P.sv.Sxd = sv.Sxd; P.sv.cross = sv.cross; P.sv.pre = sv.pre;
+  P.H = H; P.traj_m = traj_m; P.traj_S = traj_S; P.loss_bar = loss_bar;
+  P.Z = dyn->Z; P.ell = dyn->ell; P.var = dyn->var; P.beta = dyn->beta; P.C = dyn->C; P.W = dyn->W;
+  P.M = dyn->M; P.Lm = dyn->L; P.Pm = dyn->P;
+  P.packs = D_(lo.packs); P.Gs = D_(lo.Gs); P.stats = D_(lo.stats); P.f1lat = D_(lo.f1lat); P.crosslat = D_(lo.crosslat);
+  P.f1lat_bar = D_(lo.f1lat_bar); P.crosslat_bar = D_(lo.crosslat_bar); P.omega = D_(lo.omega); P.gm = D_(lo.gm); P.gS = D_(lo.gS);
+  P.nrb = lo.nrb;
+  P.ready = (unsigned*)(ws_persist + lo.flags); P.stat_done = P.ready + N; P.ticket = P.ready + 2 * N;
+  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * (2 * (size_t)N + 8), stream));
+  // cost gradients of all H trajectory states in one launch (dual numbers through the encoder and expected-cost rules)
+  const int ndir = Dx + Dx * (Dx + 1) / 2;
+  double* cg = D_(lo.cg);
+  {
+    const long long total = (long long)H * N * ndir;
+    k_cost_grad_ring<<<(unsigned)((total + 63) / 64), 64, 0, stream>>>(r, traj_m + (size_t)N * Dx, traj_S + (size_t)N * Dx * Dx, H, ndir, cg);
+    count_launch();
+  }
+  P.cg = cg;
+  const int items = P.Lm * (P.Lm + 1) / 2 * lo.nrb;
+  const int grid = (int)std::min<long long>(num_sms(), (long long)N * items + N);
+  switch (dyn->D) {
+#define GPP_CASE(d) case d: return launch_bwd_persist<d>(P, grid, stream);
+    GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
+#undef GPP_CASE
+    default:
+      set_error("persistent rollout: unsupported dynamics input dimension %d", dyn->D);
+      return GPP_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace gpp
+
+extern "C" {
+
+int gpp_rollout_mm_set_mode(int mode) {
+  GPP_REQUIRE(mode >= GPP_ROLLOUT_AUTO && mode <= GPP_ROLLOUT_PERSIST, GPP_ERR_BAD_SHAPE, "gpp_rollout_mm_set_mode: unknown mode %d", mode);
+  gpp::g_rollout_mode = mode;
+  return GPP_OK;
+}
+
+int gpp_rollout_mm_get_mode(void) { return gpp::rollout_mode(); }
+
+}  // extern "C"

@@ -62,6 +62,18 @@ def policy_beta_bwd(policy: PolicyParams, beta: torch.Tensor, beta_bar: torch.Te
   return q_bar
 
 
+ROLLOUT_AUTO, ROLLOUT_LEGACY, ROLLOUT_PERSIST = 0, 1, 2
+
+
+def set_rollout_mode(mode: int) -> int:
+  """Select how the moment-matched rollouts run: ROLLOUT_AUTO (default) = the persistent on-device H-loop whenever the model
+  fits, ROLLOUT_LEGACY = one launch per stage and step, ROLLOUT_PERSIST = persistent or error.  Returns the previous mode."""
+  lib = _lib.load()
+  prev = lib.gpp_rollout_mm_get_mode()
+  _lib.check(lib.gpp_rollout_mm_set_mode(int(mode)))
+  return prev
+
+
 @dataclass
 class MMRolloutResult:
   loss: torch.Tensor                      # [N]
@@ -141,7 +153,7 @@ def rollout_mm_bwd(dynamics: GPModelHandle, policy: PolicyParams, beta: torch.Te
   lib = _lib.load()
   if saved is not None and (not saved.is_cuda or saved.numel() != lib.gpp_rollout_mm_saved_doubles(dynamics._h, N, Dx, H1 - 1)):
     raise ValueError("rollout_mm_bwd: `saved` does not match this rollout")
-  need = lib.gpp_rollout_mm_bwd_workspace_bytes(dynamics._h, N, Dx, Mp)
+  need = lib.gpp_rollout_mm_bwd_workspace_bytes(dynamics._h, N, Dx, Mp, H1 - 1)
   ws = torch.empty(need, dtype=torch.uint8, device=dev)
   Zb = torch.empty(R, Mp, De, dtype=F64, device=dev)
   eb = torch.empty(R, De, dtype=F64, device=dev)

@@ -143,7 +143,18 @@ int gpp_policy_prepare_bwd(int R, int Mp, int Dp, const double* Z, const double*
  *   policy_*      R = 1 (shared) or R = N parameter sets; action dimension 1; beta from gpp_policy_prepare
  *   cost_target [De], cost_W [De,De] with De = Dx + num_active
  *   m0 [N,Dx], S0 [N,Dx,Dx] -> loss [N]; optional traj_m [H+1,N,Dx], traj_S [H+1,N,Dx,Dx], m_final, S_final.
- * All launches go to `stream` without synchronisation (capturable in a CUDA graph). */
+ * All launches go to `stream` without synchronisation (capturable in a CUDA graph).
+ *
+ * Execution mode.  By default (GPP_ROLLOUT_AUTO) the H-loop runs ON THE DEVICE: one persistent, warp-specialised cooperative
+ * kernel per sweep direction (csrc/rollout_persist.cu) — upstream's loop is a compiled tf.foldl / tf.scan
+ * (dynamics/solvers.py:84-105) — whenever the model's Psi2 tiles fit the GPU (<= 2 tiles of 64 x 64 per SM) and, for the backward,
+ * the forward kept its per-step block (`saved`).  GPP_ROLLOUT_LEGACY forces one launch per stage and step, GPP_ROLLOUT_PERSIST
+ * makes an unsupported shape an error instead of a fallback.  Initial value: environment variable GPP_ROLLOUT_MODE (0/1/2). */
+#define GPP_ROLLOUT_AUTO 0
+#define GPP_ROLLOUT_LEGACY 1
+#define GPP_ROLLOUT_PERSIST 2
+int gpp_rollout_mm_set_mode(int mode);
+int gpp_rollout_mm_get_mode(void);
 size_t gpp_rollout_mm_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx);
 int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_active, const int* active_dims,
                        int R, int Mp, const double* policy_Z, const double* policy_lengthscales,
@@ -159,7 +170,7 @@ int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
  *      beta_bar [R,Mp]: gradient w.r.t. beta = Kuu^-1 m (the caller chains beta to (Z, lengthscales, q_mu); the policy
  *      variance is frozen upstream, loops/pilco.py:99-103), m0_bar [N,Dx], S0_bar [N,Dx,Dx] (symmetric; either may be NULL).
  *   R = 1 sums the gradient over the N rollouts in a fixed order; R = N returns one gradient per restart. */
-size_t gpp_rollout_mm_bwd_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx, int Mp);
+size_t gpp_rollout_mm_bwd_workspace_bytes(const gpp_gp_model* dynamics, int N, int Dx, int Mp, int H);
 /* Forward that also keeps, for every step, what the backward would otherwise recompute (joint moments of (e, u), Cov(x, d),
  * pre-inverted cross term): saved [gpp_rollout_mm_saved_doubles(dynamics, N, Dx, H)] doubles; traj_m / traj_S are required.
  * Pass the buffer to gpp_rollout_mm_bwd (`saved`; NULL there = recompute from the trajectory). */
