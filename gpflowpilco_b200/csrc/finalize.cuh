@@ -4,11 +4,14 @@
 // Shared by k_finalize (mm_predict.cu) and the persistent rollout kernel (rollout_persist.cu).
 #pragma once
 #include "model.cuh"
+#include "persist_common.cuh"
 
 namespace gpp {
 
 struct FinalizeParams {
   const double* part;
+  const unsigned long long* part_ll;   // persistent rollout: the partials arrive as tagged words (persist_common.cuh), tag = ll_tag
+  unsigned ll_tag;                      // 0: plain doubles in `part`
   const gpp_slot* slots;
   const int* pair_start;
   const int* pair_ab;
@@ -25,8 +28,8 @@ struct FinalizeParams {
   EulerPost post;           // used by k_finalize<true> only
 };
 
-// all 128 threads of the group call this for input n.  The tile partials may have been written by other CTAs of the same launch
-// (persistent rollout): they are read past L1 (__ldcg).
+// all 128 threads of the group call this for input n.  In the persistent rollout the tile partials are written by other CTAs of the
+// same launch and arrive as tagged words: every thread waits for exactly the entries it sums.
 template <bool POST>
 __device__ void finalize_body(const FinalizeParams& p, int n) {
   __shared__ double f2[GPP_MAX_L * GPP_MAX_L];
@@ -38,7 +41,10 @@ __device__ void finalize_body(const FinalizeParams& p, int n) {
   for (int pr = warp; pr < p.npairs; pr += 4) {
     double s = 0.0;
     for (int k = p.pair_start[pr] + lane; k < p.pair_start[pr + 1]; k += 32)
-      s = fma(p.slots[k].weight, __ldcg(p.part + (size_t)n * p.nslots + k), s);
+      {
+      const double v = p.ll_tag ? ll_load(p.part_ll + 2 * ((size_t)n * p.nslots + k), p.ll_tag) : p.part[(size_t)n * p.nslots + k];
+      s = fma(p.slots[k].weight, v, s);
+    }
     s = warp_sum(s);
     if (lane == 0) {
       int a = p.pair_ab[2 * pr], b = p.pair_ab[2 * pr + 1];

@@ -124,7 +124,7 @@ static int predict_fwd(const gpp_gp_model* m, const double* mu, const double* S,
   int rc = pl.tile_idx ? launch_contract<D, 128, 4, 16>(cp, stream) : launch_contract<D, 64, 2, 8>(cp, stream);
   if (rc != GPP_OK) return rc;
   FinalizeParams fp;
-  fp.part = part; fp.slots = tab.d_slots; fp.pair_start = tab.d_pair_start; fp.pair_ab = tab.d_pair_ab;
+  fp.part = part; fp.part_ll = nullptr; fp.ll_tag = 0; fp.slots = tab.d_slots; fp.pair_start = tab.d_pair_start; fp.pair_ab = tab.d_pair_ab;
   fp.f1lat = f1lat; fp.crosslat = crosslat; fp.var = m->var; fp.mean = m->mean; fp.W = m->W;
   fp.f1 = f1; fp.Sff = Sff; fp.cross = cross; fp.N = N; fp.L = m->L; fp.P = m->P; fp.D = D;
   fp.npairs = tab.npairs; fp.nslots = tab.nslots; fp.full_cov = full_output_cov;

@@ -99,7 +99,7 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   }
   profile_end(stream);
   BwdFinalizeParams fp;
-  fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.omega = omega; fp.Gs = Gs; fp.gm = gm; fp.gS = gS;
+  fp.m = mu; fp.S = S; fp.ell = m->ell; fp.stats = stats; fp.ll_tag = 0; fp.omega = omega; fp.Gs = Gs; fp.gm = gm; fp.gS = gS;
   fp.m_bar = m_bar; fp.S_bar = S_bar; fp.N = N; fp.L = L; fp.nrb = lo.nrb;
   {
     const int npairs = L * (L + 1) / 2;

@@ -27,6 +27,32 @@ __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Flag-in-data publication of one double (the "LL" protocol of collective libraries): the value travels as two 8-byte words
+// {32 data bits, 32-bit tag}; an aligned 8-byte store is single-copy atomic, so a reader that sees the expected tag in both words
+// has the data — no fence on either side.  Tags are the (1-based) step number; buffers start zeroed.
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned tag) {
+  const unsigned long long w0 = ((unsigned long long)tag << 32) | (unsigned)__double2loint(v);
+  const unsigned long long w1 = ((unsigned long long)tag << 32) | (unsigned)__double2hiint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slot), "l"(w0) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_load(const unsigned long long* slot, unsigned tag) {
+  long long t0 = 0;
+  for (;;) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w0) : "l"(slot) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w1) : "l"(slot + 1) : "memory");
+    if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) return __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
+    if (t0 == 0) t0 = clock64();
+    __nanosleep(40);
+    if (clock64() - t0 > kSpinLimit) {
+      printf("gpp persistent rollout: CTA %d thread %d waited too long for value %p (tag %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+             (const void*)slot, tag);
+      asm volatile("trap;");
+    }
+  }
+}
+
 // spin until *flag >= target (one thread; callers follow with their role's barrier)
 __device__ __forceinline__ void spin_wait_ge(const unsigned* flag, unsigned target) {
   if (ld_acquire_u32(flag) >= target) return;

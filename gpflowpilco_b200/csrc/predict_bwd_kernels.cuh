@@ -7,6 +7,7 @@
 
 #include "mma_exp.cuh"
 #include "model.cuh"
+#include "persist_common.cuh"
 #include "predict_kernels.cuh"
 
 namespace gpp {
@@ -53,12 +54,13 @@ template <bool PERSIST>
 __device__ __forceinline__ double grad_ld(const double* p) { return PERSIST ? __ldcg(p) : *p; }   // written by another CTA of the launch?
 
 // `tid` = index among the 512 contraction threads (16 warps); `smem` = GradCfg<D> layout (+ ncb * 128 doubles).  With `fill_table`
-// the exp table is (re)written first (once per CTA in the persistent kernel, once per item in k_contract_grad).
+// the exp table is (re)written first (once per CTA in the persistent kernel, once per item in k_contract_grad).  With ll_tag != 0
+// (persistent sweep) `stats` is an array of tagged words, two per statistic, read by bwd_finalize_body without any fence.
 template <int D, bool PERSIST>
 __device__ void contract_grad_item(double* __restrict__ smem, const int tid, const int n, const int pr, const int rb,
                                    const double* __restrict__ Z, const double* __restrict__ beta, const double* __restrict__ C,
                                    const double* __restrict__ packs, const double* __restrict__ omega, double* __restrict__ stats,
-                                   const int M, const int L, const int nrb, const bool fill_table) {
+                                   const int M, const int L, const int nrb, const bool fill_table, const unsigned ll_tag = 0u) {
   using PP = PairPack<D>;
   using GS = GradStats<D>;
   using CF = GradCfg<D>;
@@ -77,7 +79,11 @@ __device__ void contract_grad_item(double* __restrict__ smem, const int tid, con
   b += a;
   const bool diag = a == b;
   const int p = a * L + b;
-  double* out = stats + (((size_t)n * L * L + p) * nrb + rb) * GS::SIZE;
+  double* out = stats + (((size_t)n * L * L + p) * nrb + rb) * GS::SIZE * (ll_tag ? 2 : 1);
+  auto put = [&](double* base, int k, double v) {
+    if (ll_tag) ll_store(reinterpret_cast<unsigned long long*>(base) + 2 * k, v, ll_tag);
+    else base[k] = v;
+  };
   // pairs whose output adjoint is zero (e.g. diagonal-only covariance) are skipped; k_bwd_finalize skips them too
   const double wgt = grad_ld<PERSIST>(omega + ((size_t)n * L + a) * L + b) + grad_ld<PERSIST>(omega + ((size_t)n * L + b) * L + a);
   if (wgt == 0.0) return;
@@ -265,7 +271,7 @@ __device__ void contract_grad_item(double* __restrict__ smem, const int tid, con
   }
   if (!diag) fold_column_sums(ncb - 1);
   grad_sync<PERSIST>();
-  double* out2 = stats + (((size_t)n * L * L + b * L + a) * nrb + rb) * GS::SIZE;   // ordered pair (b, a), a < b
+  double* out2 = stats + (((size_t)n * L * L + b * L + a) * nrb + rb) * GS::SIZE * (ll_tag ? 2 : 1);   // ordered pair (b, a), a < b
   if constexpr (D <= 7) {
     // Every statistic is an entry of the Gram product  G = sum_rows F^T H  with  F = [z1' (D), 1],  H = [a z1' (D), u (D), a]:
     //   G[m][n]     (m, n < D)   = R2[m][n]        G[m][D + e] = X[m][e]        G[m][2D] = r1[m]
@@ -308,16 +314,16 @@ __device__ void contract_grad_item(double* __restrict__ smem, const int tid, con
       const int m = tid / GW, nn2 = tid % GW;
       if (nn2 < 16) {
         if (m < D) {
-          if (nn2 < D) { if (nn2 >= m) out[GS::R2 + m * D - m * (m - 1) / 2 + (nn2 - m)] = sum; }
-          else if (nn2 < 2 * D) out[GS::X + m * D + (nn2 - D)] = sum;
-          else if (nn2 == 2 * D) out[GS::R1 + m] = sum;
+          if (nn2 < D) { if (nn2 >= m) put(out, GS::R2 + m * D - m * (m - 1) / 2 + (nn2 - m), sum); }
+          else if (nn2 < 2 * D) put(out, GS::X + m * D + (nn2 - D), sum);
+          else if (nn2 == 2 * D) put(out, GS::R1 + m, sum);
         } else if (m == D) {
-          if (nn2 == 2 * D) out[GS::S0] = sum;
-          else if (!diag && nn2 >= D && nn2 < 2 * D) out2[GS::R1 + (nn2 - D)] = sum;
+          if (nn2 == 2 * D) put(out, GS::S0, sum);
+          else if (!diag && nn2 >= D && nn2 < 2 * D) put(out2, GS::R1 + (nn2 - D), sum);
         }
       } else if (!diag) {
         const int e = nn2 - 16;
-        if (m < D && e < D && e >= m) out2[GS::R2 + m * D - m * (m - 1) / 2 + (e - m)] = sum;
+        if (m < D && e < D && e >= m) put(out2, GS::R2 + m * D - m * (m - 1) / 2 + (e - m), sum);
       }
     }
   } else {
@@ -358,7 +364,7 @@ __device__ void contract_grad_item(double* __restrict__ smem, const int tid, con
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
-      out[tid] = s;
+      put(out, tid, s);
     }
     if (diag) return;
     // ordered pair (b, a): r1_ba = sum_i u_i (row scratch), R2_ba = sum_j a'_j z2'_j z2'_j^T (column scratch, 128 columns at a time
@@ -400,7 +406,7 @@ __device__ void contract_grad_item(double* __restrict__ smem, const int tid, con
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < CH; ++q) s += red[q * GS::SIZE + tid];
-      out2[tid] = s;
+      put(out2, tid, s);
     }
   }
 }
@@ -621,7 +627,8 @@ struct BwdEpilogue {
 struct BwdFinalizeParams {
   const double *m, *S;          // [N,D], [N,D,D]
   const double* ell;            // [L,D]
-  const double* stats;          // [N,L*L,nrb,GS::SIZE]
+  const double* stats;          // [N,L*L,nrb,GS::SIZE]  (ll_tag != 0: tagged words, two per statistic)
+  unsigned ll_tag;
   const double* omega;          // [N,L,L]
   const double* Gs;             // [N,L*L,D,D]  (Sigma_n + V_ab)^-1 from the prologue
   const double *gm, *gS;        // psi1 contributions [N,L,D], [N,L,D,D]
@@ -671,7 +678,10 @@ __device__ void bwd_finalize_body(const BwdFinalizeParams& p, const int n, doubl
     const int slot = (which == 0 || !mirrored) ? a * L + b : b * L + a;
     double x = 0.0;
     if (meta[pr * 4 + 2] != 0.0)             // skipped pairs were not written by k_contract_grad
-      for (int rb = 0; rb < p.nrb; ++rb) x += __ldcg(p.stats + (((size_t)n * L * L + slot) * p.nrb + rb) * GS::SIZE + k);
+      for (int rb = 0; rb < p.nrb; ++rb) {
+        const size_t at = (((size_t)n * L * L + slot) * p.nrb + rb) * GS::SIZE + k;
+        x += p.ll_tag ? ll_load(reinterpret_cast<const unsigned long long*>(p.stats) + 2 * at, p.ll_tag) : p.stats[at];
+      }
     sst[idx] = x;
   }
   for (int idx = tid; idx < npairs * DD; idx += nt) {

@@ -26,7 +26,7 @@
 namespace gpp {
 
 constexpr int kPersistTile = 64;        // tile edge of the forward contraction
-constexpr int kFwdThreads = 512;        // 4 scalar + 2 producer (+ 2 idle) + 8 consumer warps
+constexpr int kFwdThreads = 512;        // 4 scalar + 4 producer + 8 consumer warps
 constexpr int kFwdBatch = 8;            // inputs whose packs a producer waits for at once
 
 struct PersistSaved {                   // the per-step block of gpp_rollout_mm_fwd_save (RolloutSaved offsets), or base == nullptr
@@ -48,8 +48,9 @@ struct PersistFwdParams {
   const int* pair_ab;
   int npairs, nslots;
   // workspace
-  double *packs, *part, *f1lat, *crosslat;
-  unsigned *pack_ready, *part_done;     // [N] each, zero at launch
+  double *packs, *f1lat, *crosslat;
+  unsigned long long* part_ll;          // [N, nslots, 2] tile partials as tagged words (ll_store, tag = step + 1); zero at launch
+  unsigned* pack_ready;                 // [N] steps whose coefficient packs are published; zero at launch
 };
 
 __device__ __forceinline__ void persist_step_pointers(RolloutMMParams& p, const PersistSaved& sv, const RolloutMMParams& base, int t) {
@@ -88,7 +89,7 @@ __device__ void persist_fwd_scalar(const PersistFwdParams& P) {
   }
   group_sync();
   FinalizeParams fp;
-  fp.part = P.part; fp.slots = P.slots; fp.pair_start = P.pair_start; fp.pair_ab = P.pair_ab;
+  fp.part = nullptr; fp.part_ll = P.part_ll; fp.ll_tag = 0; fp.slots = P.slots; fp.pair_start = P.pair_start; fp.pair_ab = P.pair_ab;
   fp.f1lat = P.f1lat; fp.crosslat = P.crosslat; fp.var = P.var; fp.mean = P.mean; fp.W = P.W;
   fp.f1 = p.f1; fp.Sff = p.Sff; fp.cross = nullptr;
   fp.N = N; fp.L = P.Lm; fp.P = P.Pm; fp.D = D; fp.npairs = P.npairs; fp.nslots = P.nslots; fp.full_cov = 1;
@@ -97,10 +98,9 @@ __device__ void persist_fwd_scalar(const PersistFwdParams& P) {
   for (int t = 0; t <= P.H; ++t) {
     for (int n = n0; n < N; n += G) {
       if (t > 0) {
-        // step t-1 of rollout n: all tile partials are in -> outputs of the GP predict, Euler update, trajectory slice t
-        if (tid == 0) spin_wait_ge(P.part_done + n, (unsigned)t * (unsigned)P.nslots);
-        group_sync();
+        // step t-1 of rollout n: wait for its tile partials (tag t) -> outputs of the GP predict, Euler update, trajectory slice t
         persist_step_pointers(p, P.sv, P.r, t - 1);
+        fp.ll_tag = (unsigned)t;
         fp.cross = p.cross;
         fp.post.Sxd = p.Sxd;
         fp.post.traj_m = p.traj_m ? p.traj_m + (size_t)t * N * Dx : nullptr;
@@ -151,12 +151,21 @@ __device__ void persist_fwd_scalar(const PersistFwdParams& P) {
 // ---------------------------------------------------------------------------------------------------------
 template <int D>
 struct PersistFwdCfg {
-  static constexpr int T = kPersistTile, NP = 2, NC = 8;
-  using CF = ContractCfg<D, T, NP, NC>;
+  static constexpr int T = kPersistTile, NP = 4, NC = 8;                // producer warps 0,1: rows; 2,3: columns
   static constexpr int PT = 32 * NP, CT = 32 * NC, NTC = PT + CT;      // producer / consumer / contraction threads
-  static constexpr int KS = CF::KS, LDC = CF::LDC;
-  static constexpr int FBUF = KS * T * 4, WBUF = 2 * T, DBUF = NC * 32;
+  static constexpr int KS = ExtLayout<D>::KS, LDC = T + 8;
+  static constexpr int REP = KS <= 2 ? 16 : 8;                          // replication of the exp table
+  static constexpr int FBUF = KS * T * 4, WBUF = 2 * T, DBUF = NC * 32, NRED = 4;
   static constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_PROD = 5, BAR_TILE = 7;   // 6 is the scalar group's barrier
+  // shared memory (doubles)
+  static constexpr int S_CT = 0;                                        // [T][LDC]        tile of C_a (diagonal pairs)
+  static constexpr int S_COL = S_CT + T * LDC;                          // [2][KS][T][4]   extended column vectors B_j
+  static constexpr int S_ROW = S_COL + 2 * FBUF;                        // [2][KS][T][4]   extended row vectors A_i
+  static constexpr int S_WGT = S_ROW + 2 * FBUF;                        // [2][2][T]       beta of the rows / columns (off-diagonal pairs)
+  static constexpr int S_RED = S_WGT + 2 * WBUF;                        // [NRED][NC][32]  lane partials of the last NRED inputs
+  static constexpr int S_ETAB = S_RED + NRED * DBUF;                    // [256][REP]
+  static constexpr int S_PKBUF = S_ETAB + 256 * REP;                    // [2][PairPack<D>::SIZE]
+  static constexpr int S_TOTAL = S_PKBUF + 2 * PairPack<D>::SIZE;
 };
 
 // both contraction roles: (re)load the C tile of a diagonal pair; `ctid` = index among the NTC contraction threads
@@ -176,17 +185,18 @@ __device__ __forceinline__ void persist_load_tile(const PersistFwdParams& P, con
 template <int D>
 __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
   using F = PersistFwdCfg<D>;
-  using CF = typename F::CF;
   using PP = PairPack<D>;
   constexpr int T = F::T, PT = F::PT, KS = F::KS, NTC = F::NTC;
   constexpr int NPV = (PP::SIZE + PT - 1) / PT;
-  double* Ct = smem + CF::CT;
-  double* colB = smem + CF::COL;
-  double* rowA = smem + CF::ROW;
-  double* wgt = smem + CF::WGT;
-  double* red = smem + CF::RED;
-  double* pkbuf = smem + CF::PKBUF;
-  const int ptid = threadIdx.x - kGroupThreads, lane = ptid & 31, pwarp = ptid >> 5;
+  double* Ct = smem + F::S_CT;
+  double* colB = smem + F::S_COL;
+  double* rowA = smem + F::S_ROW;
+  double* wgt = smem + F::S_WGT;
+  const double* red = smem + F::S_RED;
+  double* pkbuf = smem + F::S_PKBUF;
+  const int ptid = threadIdx.x - kGroupThreads, lane = ptid & 31;
+  const bool is_row = ptid < T;                       // threads 0..63: row ptid of the tile; 64..127: column ptid - 64
+  const int idx = is_row ? ptid : ptid - T;
   const int N = P.r.N, G = gridDim.x;
   const size_t pk_stride = (size_t)P.npairs * PP::SIZE;
   int resident = -1;
@@ -198,32 +208,27 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
         if (diag) persist_load_tile<D>(P, sl, Ct, ptid);
         resident = slot;
       }
-      const int ig = sl.ti * T + ptid, jg = sl.tj * T + ptid;
-      double zrow[D], zcol[D];
+      // this thread's centre and weight do not change over the inputs
+      const int lat = is_row ? sl.a : sl.b;
+      const int g = (is_row ? sl.ti : sl.tj) * T + idx;
+      double z[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        zrow[d] = ig < P.M ? P.Z[((size_t)sl.a * P.M + ig) * D + d] : 0.0;
-        zcol[d] = jg < P.M ? P.Z[((size_t)sl.b * P.M + jg) * D + d] : 0.0;
-      }
-      const double brow = (!diag && ig < P.M) ? P.beta[(size_t)sl.a * P.M + ig] : 0.0;
-      const double bcol = (!diag && jg < P.M) ? P.beta[(size_t)sl.b * P.M + jg] : 0.0;
+      for (int d = 0; d < D; ++d) z[d] = g < P.M ? P.Z[((size_t)lat * P.M + g) * D + d] : 0.0;
+      const double bw = (!diag && g < P.M) ? P.beta[(size_t)lat * P.M + g] : 0.0;
       const double* pk0 = P.packs + (size_t)sl.pair * PP::SIZE;
+      unsigned long long* out = P.part_ll + 2 * (size_t)slot;
       double pv[NPV];
       for (int k = 0; k < N + 2; ++k) {
         const int b = k & 1;
-        if (k >= 2) {                        // consumers are done with input k-2 (buffer b): publish its tile partial
+        if (k >= 2) {                        // consumers are done with input k-2: its vector buffers are free, its partial is complete
           named_bar_sync<F::BAR_EMPTY>(b, NTC);
-          if (pwarp == 0) {
-            const double* rp = red + b * F::DBUF + lane;
+          if (ptid < 32) {                   // fixed-order sum of the lane partials -> tagged words (no fence: persist_common.cuh)
+            const double* rp = red + ((k - 2) & (F::NRED - 1)) * F::DBUF + lane;
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < F::NC; ++w) s += rp[w * 32];
             s = warp_sum(s);
-            if (lane == 0) {
-              P.part[(size_t)(k - 2) * P.nslots + slot] = s;
-              __threadfence();
-              red_release_add_u32(P.part_done + (k - 2), 1u);
-            }
+            if (lane == 0) ll_store(out + 2 * (size_t)(k - 2) * P.nslots, s, (unsigned)(t + 1));
           }
         }
         if (k >= N) continue;
@@ -243,11 +248,10 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
           for (int q = 0; q < NPV; ++q)
             if (ptid + q * PT < PP::SIZE) pv[q] = __ldcg(pk0 + (size_t)(k + 1) * pk_stride + ptid + q * PT);
         }
-        double ext[4 * KS];
-        {
-          double zc[D];
+        double ext[4 * KS], zc[D];
 #pragma unroll
-          for (int d = 0; d < D; ++d) zc[d] = zrow[d] - pk[PP::MU + d];
+        for (int d = 0; d < D; ++d) zc[d] = z[d] - pk[PP::MU + d];
+        if (is_row) {                        // A_i = [R^T z1' (D), c0 + z1'^T P1 z1', 1, 0..]
 #pragma unroll
           for (int e = 0; e < D; ++e) {
             double tt = 0.0;
@@ -257,29 +261,21 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
           }
           ext[D] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
           ext[D + 1] = 1.0;
+        } else {                             // B_j = [z2' (D), 1, z2'^T P2 z2', 0..]
 #pragma unroll
-          for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
-          double* ra = rowA + b * F::FBUF + ptid * 4;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-            for (int q = 0; q < 4; q += 2)
-              *reinterpret_cast<double2*>(ra + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
-          wgt[b * F::WBUF + ptid] = brow;
-        }
-        {
-#pragma unroll
-          for (int d = 0; d < D; ++d) ext[d] = zcol[d] - pk[PP::MU + d];
-          ext[D + 1] = packed_quad<D>(pk + PP::P2, ext);
+          for (int d = 0; d < D; ++d) ext[d] = zc[d];
           ext[D] = 1.0;
-          double* cb = colB + b * F::FBUF + ptid * 4;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-            for (int q = 0; q < 4; q += 2)
-              *reinterpret_cast<double2*>(cb + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
-          wgt[b * F::WBUF + T + ptid] = bcol;
+          ext[D + 1] = packed_quad<D>(pk + PP::P2, zc);
         }
+#pragma unroll
+        for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
+        double* dst = (is_row ? rowA : colB) + b * F::FBUF + idx * 4;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int q = 0; q < 4; q += 2)
+            *reinterpret_cast<double2*>(dst + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
+        wgt[b * F::WBUF + (is_row ? 0 : T) + idx] = bw;
         __threadfence_block();
         named_bar_arrive<F::BAR_FULL>(b, NTC);
       }
@@ -290,19 +286,18 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
 template <int D>
 __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
   using F = PersistFwdCfg<D>;
-  using CF = typename F::CF;
   constexpr int T = F::T, KS = F::KS, LDC = F::LDC, NTC = F::NTC;
-  double* Ct = smem + CF::CT;
-  double* colB = smem + CF::COL;
-  double* rowA = smem + CF::ROW;
-  double* wgt = smem + CF::WGT;
-  double* red = smem + CF::RED;
-  double* etab = smem + CF::ETAB;
+  double* Ct = smem + F::S_CT;
+  double* colB = smem + F::S_COL;
+  double* rowA = smem + F::S_ROW;
+  double* wgt = smem + F::S_WGT;
+  double* red = smem + F::S_RED;
+  double* etab = smem + F::S_ETAB;
   const int ctid = threadIdx.x - 2 * kGroupThreads, lane = ctid & 31, strip = ctid >> 5;
   const int row = strip * 8 + (lane >> 2);
   const int cpair = 2 * (lane & 3);
   const double* ct = Ct + row * LDC + cpair;
-  const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (CF::REP - 1)));
+  const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (F::REP - 1)));
   const int N = P.r.N, G = gridDim.x;
   int resident = -1;
   for (int t = 0; t < P.H; ++t) {
@@ -331,7 +326,7 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
             dmma_m8n8k4(tt[0], tt[1], a[ks], cb[ks * T * 4 + cg * 32]);
             dmma_m8n8k4(tt[2], tt[3], a[ks], cb[ks * T * 4 + cg * 32 + 32]);
           }
-          exp_tab_contract<4, CF::REP>(tt, etab_lane);
+          exp_tab_contract<4, F::REP>(tt, etab_lane);
           const double2 w0 = *reinterpret_cast<const double2*>(wsrc + cg * 8);
           const double2 w1 = *reinterpret_cast<const double2*>(wsrc + cg * 8 + 8);
           acc0 = fma(tt[0], w0.x, acc0);
@@ -341,7 +336,7 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
         }
         double total = acc0 + acc1;
         if (!diag) total *= wgt[b * F::WBUF + row];
-        red[b * F::DBUF + strip * 32 + lane] = total;
+        red[(k & (F::NRED - 1)) * F::DBUF + strip * 32 + lane] = total;
         __threadfence_block();
         named_bar_arrive<F::BAR_EMPTY>(b, NTC);
       }
@@ -351,10 +346,10 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
 
 template <int D>
 __global__ void __launch_bounds__(kFwdThreads, 1) k_rollout_fwd_persist(const PersistFwdParams P) {
-  using CF = typename PersistFwdCfg<D>::CF;
+  using F = PersistFwdCfg<D>;
   extern __shared__ __align__(16) double smem[];
-  double* etab = smem + CF::ETAB;
-  for (int i = threadIdx.x; i < kContractTab * CF::REP; i += kFwdThreads) etab[i] = kExp2Tab256[i / CF::REP];
+  double* etab = smem + F::S_ETAB;
+  for (int i = threadIdx.x; i < kContractTab * F::REP; i += kFwdThreads) etab[i] = kExp2Tab256[i / F::REP];
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   if (warp < 4) {
@@ -362,7 +357,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_rollout_fwd_persist(const Pe
     persist_fwd_scalar<D>(P);
   } else if (warp < 8) {
     warpgroup_reg_dec<96>();
-    if (warp < 4 + PersistFwdCfg<D>::NP) persist_fwd_producer<D>(P, smem);
+    persist_fwd_producer<D>(P, smem);
   } else {
     warpgroup_reg_dec<96>();
     persist_fwd_consumer<D>(P, smem);
@@ -374,7 +369,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_rollout_fwd_persist(const Pe
 //   scalar group   bwd_post (cost gradient of state t+1, adjoint of the Euler update)  ->  prologue of the predict's adjoint
 //                  (coefficient packs of the unordered kernel pairs, Psi1 forward + adjoint, un-mixing)  ->  publish ready[n]
 //   contraction    L (L+1)/2 x nrb work items (contract_grad_item) per (step, rollout), drawn from one ticket counter in
-//                  (step, rollout) order by the 16 contraction warps of every CTA  ->  stat_done[n]
+//                  (step, rollout) order by the 16 contraction warps of every CTA  ->  statistics as tagged words
 //   scalar group   bwd_finalize (D x D algebra per pair) -> bwd_pre (joint assembly, squashing link, policy, encoder adjoints)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = kGroupThreads + kGradThreads;    // 4 scalar + 16 contraction warps
@@ -392,7 +387,7 @@ struct PersistBwdParams {
   // workspace of the predict's adjoint
   double *packs, *Gs, *stats, *f1lat, *crosslat, *f1lat_bar, *crosslat_bar, *omega, *gm, *gS;
   int nrb;
-  unsigned *ready, *stat_done, *ticket; // [N], [N], [1]; zero at launch
+  unsigned *ready, *ticket;             // [N], [1]; zero at launch (so is `stats`: tagged words, tag = sweep index + 1)
 };
 
 template <int D>
@@ -403,7 +398,6 @@ __device__ void persist_bwd_scalar(const PersistBwdParams& P, double* fsm) {
   const RolloutBwdBuffers& bw = P.bw;
   const int N = p.N, Dx = p.Dx, Lm = P.Lm;
   const int ndir = Dx + Dx * (Dx + 1) / 2;
-  const int items = Lm * (Lm + 1) / 2 * P.nrb;
   const size_t sm = (size_t)N * Dx, sS = (size_t)N * Dx * Dx;
   const int n0 = G - 1 - (int)blockIdx.x;
   __shared__ double li_sm[GPP_MAX_L * (D * D + 1)];
@@ -422,10 +416,9 @@ __device__ void persist_bwd_scalar(const PersistBwdParams& P, double* fsm) {
   for (int t = P.H - 1; t >= -1; --t) {
     for (int n = n0; n < N; n += G) {
       if (t < P.H - 1) {
-        // step t+1 of rollout n: its statistics are in -> adjoint of the joint moments, then of the pre stage
-        if (tid == 0) spin_wait_ge(P.stat_done + n, (unsigned)(P.H - 1 - t) * (unsigned)items);
-        group_sync();
+        // step t+1 of rollout n: wait for its statistics (tagged words) -> adjoint of the joint moments, then of the pre stage
         set_step(t + 1);
+        fp.ll_tag = (unsigned)(P.H - 1 - t);
         bwd_finalize_body<D>(fp, n, fsm);
         group_sync();
         bwd_pre_body<DP>(p, bw, n);
@@ -458,28 +451,29 @@ __device__ void persist_bwd_scalar(const PersistBwdParams& P, double* fsm) {
 
 template <int D>
 __device__ void persist_bwd_contract(const PersistBwdParams& P, double* smem) {
-  __shared__ unsigned s_ticket;
+  __shared__ unsigned s_ticket[2];
   const int gtid = threadIdx.x - kGroupThreads;
   const int N = P.r.N, Lm = P.Lm;
   const int items = Lm * (Lm + 1) / 2 * P.nrb;
   const unsigned per_step = (unsigned)N * (unsigned)items, total = per_step * (unsigned)P.H;
-  for (;;) {
+  unsigned next = gtid == 0 ? atomicAdd(P.ticket, 1u) : 0u;
+  for (int iter = 0;; ++iter) {
     if (gtid == 0) {
-      const unsigned k = atomicAdd(P.ticket, 1u);
-      if (k < total) spin_wait_ge(P.ready + (k % per_step) / items, k / per_step + 1u);
-      s_ticket = k;
+      const unsigned k = next;
+      if (k < total) {
+        spin_wait_ge(P.ready + (k % per_step) / items, k / per_step + 1u);
+        next = atomicAdd(P.ticket, 1u);     // the following item's ticket: the round trip hides behind this item's contraction
+      }
+      s_ticket[iter & 1] = k;
     }
     grad_sync<true>();
-    const unsigned k = s_ticket;
+    const unsigned k = s_ticket[iter & 1];
     if (k >= total) break;
     const int rem = (int)(k % per_step);
     const int n = rem / items, it = rem % items;
-    contract_grad_item<D, true>(smem, gtid, n, it / P.nrb, it % P.nrb, P.Z, P.beta, P.C, P.packs, P.omega, P.stats, P.M, Lm, P.nrb, false);
-    grad_sync<true>();                     // all statistics of the item are written (and s_ticket may be overwritten)
-    if (gtid == 0) {
-      __threadfence();
-      red_release_add_u32(P.stat_done + n, 1u);
-    }
+    // the statistics leave as tagged words (tag = sweep index + 1): nothing to fence, nothing to count
+    contract_grad_item<D, true>(smem, gtid, n, it / P.nrb, it % P.nrb, P.Z, P.beta, P.C, P.packs, P.omega, P.stats, P.M, Lm, P.nrb, false,
+                                k / per_step + 1u);
   }
 }
 
@@ -549,18 +543,17 @@ PersistFwdLayout persist_fwd_layout(const gpp_gp_model* dyn, int N) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   lo.packs = take(sizeof(double) * pack_doubles(dyn->D) * tab.npairs * N);
-  lo.part = take(sizeof(double) * (size_t)tab.nslots * N);
+  lo.part = take(sizeof(unsigned long long) * 2 * (size_t)tab.nslots * N);
   lo.f1lat = take(sizeof(double) * (size_t)dyn->L * N);
   lo.crosslat = take(sizeof(double) * (size_t)dyn->L * dyn->D * N);
-  lo.flags = take(sizeof(unsigned) * 2 * (size_t)N);
+  lo.flags = take(sizeof(unsigned) * (size_t)N);
   lo.total = off;
   return lo;
 }
 
 template <int D>
 static int launch_fwd_persist(PersistFwdParams& P, int grid, cudaStream_t stream) {
-  using CF = typename PersistFwdCfg<D>::CF;
-  const size_t smem = sizeof(double) * CF::TOTAL;
+  const size_t smem = sizeof(double) * PersistFwdCfg<D>::S_TOTAL;
   GPP_CUDA_OK(cudaFuncSetAttribute(k_rollout_fwd_persist<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&P};
   GPP_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_rollout_fwd_persist<D>, dim3(grid), dim3(kFwdThreads), args, smem, stream));
@@ -584,10 +577,11 @@ int rollout_mm_fwd_persist(const gpp_gp_model* dyn, const RolloutMMParams& r, in
   P.Z = dyn->Z; P.ell = dyn->ell; P.var = dyn->var; P.beta = dyn->beta; P.C = dyn->C; P.mean = dyn->mean; P.W = dyn->W;
   P.M = dyn->M; P.Lm = dyn->L; P.Pm = dyn->P; P.model_uncertainty = dyn->model_uncertainty;
   P.slots = tab.d_slots; P.pair_start = tab.d_pair_start; P.pair_ab = tab.d_pair_ab; P.npairs = tab.npairs; P.nslots = tab.nslots;
-  P.packs = (double*)(ws_persist + lo.packs); P.part = (double*)(ws_persist + lo.part);
+  P.packs = (double*)(ws_persist + lo.packs); P.part_ll = (unsigned long long*)(ws_persist + lo.part);
   P.f1lat = (double*)(ws_persist + lo.f1lat); P.crosslat = (double*)(ws_persist + lo.crosslat);
-  P.pack_ready = (unsigned*)(ws_persist + lo.flags); P.part_done = P.pack_ready + N;
-  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * 2 * (size_t)N, stream));
+  P.pack_ready = (unsigned*)(ws_persist + lo.flags);
+  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * (size_t)N, stream));
+  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.part, 0, sizeof(unsigned long long) * 2 * (size_t)tab.nslots * N, stream));
   const int grid = std::min(num_sms(), tab.nslots + N);
   switch (dyn->D) {
 #define GPP_CASE(d) case d: return launch_fwd_persist<d>(P, grid, stream);
@@ -629,7 +623,7 @@ PersistBwdLayout persist_bwd_layout(const gpp_gp_model* dyn, int N, int Dx, int 
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   lo.packs = take(sizeof(double) * pack_doubles(D) * L * L * N);
   lo.Gs = take(sizeof(double) * (size_t)D * D * L * L * N);
-  lo.stats = take(sizeof(double) * stat_doubles * L * L * lo.nrb * N);
+  lo.stats = take(2 * sizeof(double) * stat_doubles * L * L * lo.nrb * N);   // tagged words
   lo.f1lat = take(sizeof(double) * (size_t)L * N);
   lo.crosslat = take(sizeof(double) * (size_t)L * D * N);
   lo.f1lat_bar = take(sizeof(double) * (size_t)L * N);
@@ -638,7 +632,7 @@ PersistBwdLayout persist_bwd_layout(const gpp_gp_model* dyn, int N, int Dx, int 
   lo.gm = take(sizeof(double) * (size_t)L * D * N);
   lo.gS = take(sizeof(double) * (size_t)L * D * D * N);
   lo.cg = take(sizeof(double) * (size_t)std::max(H, 1) * N * (Dx + Dx * (Dx + 1) / 2));
-  lo.flags = take(sizeof(unsigned) * (2 * (size_t)N + 8));
+  lo.flags = take(sizeof(unsigned) * ((size_t)N + 8));
   lo.total = off;
   return lo;
 }
@@ -674,8 +668,9 @@ int rollout_mm_bwd_persist(const gpp_gp_model* dyn, const RolloutMMParams& r, co
   P.packs = D_(lo.packs); P.Gs = D_(lo.Gs); P.stats = D_(lo.stats); P.f1lat = D_(lo.f1lat); P.crosslat = D_(lo.crosslat);
   P.f1lat_bar = D_(lo.f1lat_bar); P.crosslat_bar = D_(lo.crosslat_bar); P.omega = D_(lo.omega); P.gm = D_(lo.gm); P.gS = D_(lo.gS);
   P.nrb = lo.nrb;
-  P.ready = (unsigned*)(ws_persist + lo.flags); P.stat_done = P.ready + N; P.ticket = P.ready + 2 * N;
-  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * (2 * (size_t)N + 8), stream));
+  P.ready = (unsigned*)(ws_persist + lo.flags); P.ticket = P.ready + N;
+  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * ((size_t)N + 8), stream));
+  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.stats, 0, lo.f1lat - lo.stats, stream));
   // cost gradients of all H trajectory states in one launch (dual numbers through the encoder and expected-cost rules)
   const int ndir = Dx + Dx * (Dx + 1) / 2;
   double* cg = D_(lo.cg);
