@@ -4,7 +4,9 @@
 Workload (BASELINE.json configs[1]): batched exact moment-matched GP prediction — N Gaussian input states per GPU
 pushed through E=4 independent exact SE-ARD GPs on 1000 training points (D=6), full 4x4 output covariance and
 input-output cross-covariance, FP64.  One "step" = one pass of the hot path over the N inputs of every rank;
-metric = Gaussian states moment-matched per second (MM rollout steps/s), whole job.
+metric = Gaussian states moment-matched through the GP per second, whole job.  The rollout proper (config #1 / #5: encoder ->
+policy -> GP dynamics -> Euler -> cost over a horizon, forward + backward) is reported under "policy_opt_step", the pathwise half of
+BASELINE's metric under "pathwise"; at N > 1 rank 0 also checks the sharded closures against single-process results ("multirank_check").
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--inputs N_per_gpu]
 
@@ -28,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "mm_rollout_steps_per_s"
+METRIC = "mm_gp_predict_states_per_s"
 UNIT = "gaussian_states/s"
 M_TRAIN, D_IN, E_OUT = 1000, 6, 4
 FLOP_PER_ENTRY = 2 * D_IN + 26          # D FMAs + 2 adds + exp(=20) + 2 contraction FMAs
@@ -52,7 +54,8 @@ def parse_args():
                   help="skip the run of all 2^20 particles of config #4 (about 4 s on one GPU, split over the ranks)")
   ap.add_argument("--no-policy-opt", action="store_true")
   ap.add_argument("--no-psi2", action="store_true")
-  ap.add_argument("--restarts", type=int, default=64, help="policy restarts per GPU (config #5: 512 over 8 GPUs)")
+  ap.add_argument("--restarts-total", type=int, default=512,
+                  help="policy restarts of config #5, FIXED TOTAL sharded over the ranks (strong scaling: 512 on 1 GPU, 64 per GPU on 8)")
   ap.add_argument("--restart-horizon", type=int, default=100)
   return ap.parse_args()
 
@@ -293,6 +296,31 @@ def pathwise_section(dev, lib, pk, world):
       dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
     full = {"particles": total_particles, "horizon": H, "seconds": float(tf_[0]), "particle_steps_per_s": total_particles * H / float(tf_[0]),
             "mean_loss": float(acc_loss) / total_particles, "includes": "device-side path generation of every chunk + rollouts + cost all-reduce"}
+    if world > 1:
+      # 1 -> N curve of this collective-bearing path: rank 0 repeats ITS share alone (the others wait at the barrier); one GPU needs
+      # `world` such shares for the whole job, so efficiency = T(share, alone) / T(sharded job, all ranks + all-reduce)
+      dist.barrier()
+      alone = None
+      if rank == 0:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        done = 0
+        while done < per_rank:
+          n = min(S, per_rank - done)
+          pth = generate_paths(handle, n, F, seed=0, first_particle=done, out=paths) if n == S else generate_paths(handle, n, F, seed=0, first_particle=done)
+          pth = paths if n == S else pth
+          xs = draw_initial_states(T(cfg["m0"][0]), T(cfg["S0"][0]), 0, done, n)
+          l_, _, _ = rollout_pathwise(pth, policy, xs, H, cfg["active_dims"], target, W, beta=beta)
+          done += n
+        torch.cuda.synchronize()
+        alone = time.perf_counter() - t0
+      dist.barrier()
+      if rank == 0:
+        full["share_alone_seconds"] = alone
+        full["efficiency_vs_n1"] = alone / float(tf_[0])
+        full["efficiency_note"] = "T(one rank's share of the particles, run alone on rank 0) / T(sharded job incl. all-reduce); 1-GPU job time = world x share"
+    else:
+      full["efficiency_vs_n1"] = 1.0
   t = torch.tensor([float(np.mean(times)), float(np.mean(gtimes))], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -353,7 +381,7 @@ def psi2_section(dev, lib, pk):
                        "kernel": "k_ekzxkxz", "kernel_ms": 1e3 * ks, "call_ms": 1e3 * ts, "algorithmic": "8 B written per entry"}}
 
 
-def policy_opt_section(dev, lib, world):
+def policy_opt_section(dev, lib, world, fp64_peak):
   """BASELINE config #5 (full PILCO policy-optimisation step): R policy restarts per GPU, cart-pole models of config #1
   (M=256 dynamics, 30 policy centres), horizon H, forward + backward of the moment-matched rollout; restarts are sharded over
   ranks, every rank receives loss[R_total] by all-gather.  Reports rollout-steps/s (forward + backward), whole job."""
@@ -362,13 +390,15 @@ def policy_opt_section(dev, lib, world):
   from gpflowpilco_b200 import distributed as gd
   from gpflowpilco_b200 import ops, synthetic
   args = ARGS
-  R, H = args.restarts, args.restart_horizon
+  Rt, H = args.restarts_total, args.restart_horizon
+  if Rt % world:
+    raise ValueError("--restarts-total must be a multiple of the number of GPUs")
+  R = Rt // world
   cfg = synthetic.config1_cartpole()
   T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
   d, p = cfg["dynamics"], cfg["policy"]
   handle = ops.GPModelHandle(T(d["Z"]), T(d["lengthscales"]), T(d["variance"]), T(d["q_mu"]), T(d["q_sqrt"]), whiten=True,
                              mean_const=T(d["mean_const"]))
-  Rt = R * world
   g = torch.Generator().manual_seed(5)
   Z = T(p["Z"]).repeat(Rt, 1, 1) + 0.3 * torch.randn(Rt, *p["Z"].shape[1:], dtype=torch.float64, generator=g).to(dev)
   ell = T(p["lengthscales"]).repeat(Rt, 1) * torch.exp(torch.empty(Rt, 1, dtype=torch.float64).uniform_(-0.7, 0.7, generator=g)).to(dev)
@@ -402,7 +432,9 @@ def policy_opt_section(dev, lib, world):
   q1 = T(p["q_mu"][:, 0][None]).clone().requires_grad_(True)
   e1_ = T(p["lengthscales"]).clone().requires_grad_(True)
   c1 = {"fwd_ms": [], "fwd_bwd_ms": []}
+  launches1 = 0
   for it in range(4):
+    l0_ = lib.gpp_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
     l1 = rollout_mm_loss(handle, Z1, e1_, T(p["variance"]), q1, T(cfg["m0"]), T(cfg["S0"]), H1, cfg["active_dims"], T(cfg["target"]), T(cfg["W"]),
@@ -411,6 +443,7 @@ def policy_opt_section(dev, lib, world):
     l1.sum().backward()
     ev[2].record()
     torch.cuda.synchronize()
+    launches1 = lib.gpp_launch_count() - l0_
     if it:
       c1["fwd_ms"].append(ev[0].elapsed_time(ev[1]))
       c1["fwd_bwd_ms"].append(ev[0].elapsed_time(ev[2]))
@@ -443,15 +476,71 @@ def policy_opt_section(dev, lib, world):
                       T(cfg["m0"]).expand(Rl, -1).contiguous(), T(cfg["S0"]).expand(Rl, -1, -1).contiguous(), H)
   M, L, D = d["Z"].shape[1], 4, 6
   flop_per_step = 4 * (L * (L + 1) // 2) * M * M * (2 * D + 26)      # fwd + bwd counted as 4 x forward
+  ach5 = Rt * H * flop_per_step / sec / 1e12 / world
+  ach1 = H1 * flop_per_step / (config1["forward_backward_ms"] * 1e-3) / 1e12
+  config1["roofline"] = {"bound": "fp64 (latency-bound at one rollout: a chain of serial D x D stages per step)", "achieved": ach1, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": ach1 / fp64_peak}
+  config1["gpu_launches_forward_backward"] = int(launches1)
   return {"metric": "mm_policy_opt_rollout_steps_per_s", "value": Rt * H / sec, "unit": "rollout_steps/s (forward+backward)",
-          "config": {"workload": "config#5 policy-optimisation step", "restarts_per_gpu": R, "horizon": H, "dynamics_inducing": M,
-                     "policy_centres": int(p["Z"].shape[1]), "collective": "all-gather of loss[R] (uneven-safe), gradients stay sharded"},
+          "config": {"workload": "config#5 policy-optimisation step", "restarts_total": Rt, "restarts_per_gpu": R, "scaling": "strong (fixed total)",
+                     "horizon": H, "dynamics_inducing": M, "policy_centres": int(p["Z"].shape[1]),
+                     "collective": "all-gather of loss[R] (uneven-safe) inside the timed region, gradients stay sharded",
+                     "h_loop": "on the device: one persistent cooperative kernel per sweep direction (csrc/rollout_persist.cu)"},
           "ms_per_opt_step": 1e3 * sec, "graph_ms_per_opt_step_local_share": g5_ms,
           "gpu_launches_per_opt_step": int(launches), "mean_loss": float(losses.mean()),
           "config1_rollout": config1,
           "grad_norm": float(grads[0].norm()),
-          "roofline": {"bound": "fp64", "achieved": Rt * H * flop_per_step / sec / 1e12 / world, "unit": "TFLOP/s per GPU",
-                       "algorithmic": f"{flop_per_step} flop per rollout-step (4 x forward, SURVEY 8d)"}}
+          "roofline": {"bound": "fp64", "achieved": ach5, "peak": fp64_peak, "unit": "TFLOP/s per GPU", "frac": ach5 / fp64_peak,
+                       "algorithmic": f"{flop_per_step} flop per rollout-step (4 x forward, SURVEY 8d)",
+                       "kernels": "k_rollout_fwd_persist + k_rollout_bwd_persist (all of a sweep in one launch each)"}}
+
+
+def multirank_check(dev, world):
+  """N > 1 only: the sharded closures (particles by global index + cost/gradient all-reduce; policy restarts + loss all-gather)
+  against the same closures evaluated by rank 0 alone, on small cases.  What tests/test_gpu_multirank.py asserts on a 2-GPU box,
+  executed here on whatever the driver launched; rank 0 reports the worst relative differences."""
+  import torch
+  import torch.distributed as dist
+  from gpflowpilco_b200 import distributed as gd
+  from gpflowpilco_b200 import ops, synthetic
+  rank = dist.get_rank()
+  cfg = synthetic.config1_cartpole(M=32, Mp=8)
+  cfg["policy"]["q_mu"] = 100.0 * cfg["policy"]["q_mu"]
+  T = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+  d, p = cfg["dynamics"], cfg["policy"]
+  handle = ops.GPModelHandle(T(d["Z"]), T(d["lengthscales"]), T(d["variance"]), T(d["q_mu"]), T(d["q_sqrt"]), whiten=True, mean_const=T(d["mean_const"]))
+  pw_args = (handle, T(p["Z"]), T(p["lengthscales"]), T(p["variance"]), T(p["q_mu"][:, 0][None]), T(cfg["m0"][0]), T(cfg["S0"][0]))
+  pw_kw = dict(total_particles=1000, num_bases=64, seed=4, horizon=3, active_dims=cfg["active_dims"], cost_target=T(cfg["target"]),
+               cost_W=T(cfg["W"]), squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  R = 2 * world + 1                                           # uneven shards on purpose
+  g = torch.Generator().manual_seed(0)
+  Z = T(p["Z"]).repeat(R, 1, 1) + 0.1 * torch.randn(R, *p["Z"].shape[1:], dtype=torch.float64, generator=g).to(dev)
+  ell, q, var = T(p["lengthscales"]).repeat(R, 1), T(p["q_mu"][:, 0][None]).repeat(R, 1), T(p["variance"]).repeat(R)
+  mm_args = (handle, Z, ell, var, q, T(cfg["m0"]), T(cfg["S0"]), 4, cfg["active_dims"], T(cfg["target"]), T(cfg["W"]), cfg["squash_scale"],
+             cfg["squash_shift"])
+  # sharded over all ranks
+  loss, grads = gd.pathwise_policy_loss_and_grad(*pw_args, **pw_kw)
+  losses, (start, count), rg = gd.mm_restart_losses_and_grads(*mm_args)
+  # gradients of every rank's restart block, gathered in global order for the comparison
+  rg_all = [gd.allgather_concat(x, R) for x in rg]
+  out = None
+  # rank 0 alone: a one-member group makes the helpers take their single-process path
+  g0 = dist.new_group([0])
+  if rank == 0:
+    loss1, grads1 = gd.pathwise_policy_loss_and_grad(*pw_args, **pw_kw, group=g0)
+    losses1, _, rg1 = gd.mm_restart_losses_and_grads(*mm_args, group=g0)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+    out = {"pathwise_mean_loss_rel": abs(float(loss) - float(loss1)) / abs(float(loss1)),
+           "pathwise_grad_rel": max(rel(a, b) for a, b in zip(grads, grads1)),
+           "mm_restart_loss_rel": rel(losses, losses1),
+           "mm_restart_grad_rel": max(rel(a, b) for a, b in zip(rg_all, rg1)),
+           "cases": f"pathwise: 1000 particles, 64 bases, H=3, one all-reduce of [1+P]; MM: {R} restarts (uneven shards), H=4, all-gather of loss"}
+    out["ok"] = bool(out["pathwise_mean_loss_rel"] < 1e-12 and out["pathwise_grad_rel"] < 1e-9 and out["mm_restart_loss_rel"] < 1e-12
+                     and out["mm_restart_grad_rel"] < 1e-9)
+    if not out["ok"]:
+      raise RuntimeError(f"sharded closures disagree with the single-process result: {out}")
+  dist.barrier()
+  return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -590,8 +679,9 @@ def run_b200(args):
 
   # second half of the metric; every rank takes part (its particles are sharded by global index)
   pathwise = None if args.no_pathwise else pathwise_section(dev, lib, pk, world)
-  policy_opt = None if args.no_policy_opt else policy_opt_section(dev, lib, world)
+  policy_opt = None if args.no_policy_opt else policy_opt_section(dev, lib, world, fp64_peak)
   psi2 = psi2_section(dev, lib, pk) if (rank == 0 and not args.no_psi2) else None
+  mr_check = multirank_check(dev, world) if world > 1 else None
 
   if rank == 0:
     kern_s = float(np.mean(kern_ms)) * 1e-3
@@ -621,6 +711,8 @@ def run_b200(args):
       line["policy_opt_step"] = policy_opt
     if psi2 is not None:
       line["psi2"] = psi2
+    if mr_check is not None:
+      line["multirank_check"] = mr_check
     if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (rank 0), on a bounded sample
       small = {k: (v[:64] if k in ("mu", "cov") else v) for k, v in cfg.items()}
       rate, sample, _ = time_cpu(small, args.cpu_baseline_seconds, reference_form=True)

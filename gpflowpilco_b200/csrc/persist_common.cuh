@@ -13,7 +13,7 @@
 
 namespace gpp {
 
-constexpr long long kSpinLimit = 60LL * 2000000000LL;   // ~60 s at 2 GHz
+constexpr long long kSpinLimit = 10LL * 2000000000LL;   // ~10 s at 2 GHz
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -44,12 +44,60 @@ __device__ __forceinline__ double ll_load(const unsigned long long* slot, unsign
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w1) : "l"(slot + 1) : "memory");
     if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) return __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
     if (t0 == 0) t0 = clock64();
-    __nanosleep(40);
+    __nanosleep(200);
     if (clock64() - t0 > kSpinLimit) {
       printf("gpp persistent rollout: CTA %d thread %d waited too long for value %p (tag %u)\n", (int)blockIdx.x, (int)threadIdx.x,
              (const void*)slot, tag);
       asm volatile("trap;");
     }
+  }
+}
+
+// raw halves of a tagged value, for readers that issue the loads early and test the tags later
+__device__ __forceinline__ void ll_load_raw(const unsigned long long* slot, unsigned long long& w0, unsigned long long& w1) {
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w0) : "l"(slot) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w1) : "l"(slot + 1) : "memory");
+}
+__device__ __forceinline__ void ll_load_raw_cg(const unsigned long long* slot, unsigned long long& w0, unsigned long long& w1) {
+  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");   // one 16-byte L2 load
+}
+__device__ __forceinline__ bool ll_ready(unsigned long long w0, unsigned long long w1, unsigned tag) {
+  return (unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag;
+}
+__device__ __forceinline__ double ll_value(unsigned long long w0, unsigned long long w1) {
+  return __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
+}
+
+// barrier among COUNT threads that also AND-reduces a predicate (everybody learns whether everybody's words had arrived)
+template <int ID, int COUNT>
+__device__ __forceinline__ bool role_bar_and(bool pred) {
+  unsigned out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.and.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(out)
+      : "r"((unsigned)pred), "n"(ID), "n"(COUNT)
+      : "memory");
+  return out != 0;
+}
+
+// HINT counters.  Thousands of threads spinning on tagged words would load the L2 with polling traffic (measured: the finalize
+// stage's 128 threads x 64 groups polling 16-byte entries every ~0.1 us cost the contraction ~15 %).  Writers therefore also bump
+// a per-rollout counter with a relaxed, fire-and-forget reduction (no fence: it orders nothing), ONE thread of the reader polls
+// that counter with back-off, and only then does the group read the tagged words — which still carry the correctness: a word
+// that has not landed when the counter says "all published" is simply polled a little longer.
+__device__ __forceinline__ void hint_add(unsigned* counter) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void hint_wait_ge(const unsigned* counter, unsigned target) {
+  unsigned ns = 64;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= target) return;
+    __nanosleep(ns);
+    if (ns < 512) ns += 64;
+    if (clock64() - t0 > kSpinLimit) return;        // only a hint: the tagged-word reads that follow carry their own time-out
   }
 }
 

@@ -3,6 +3,7 @@
 // input n, the remaining blocks = 128 (input, pair) packs each) and also resets the contraction's work counter.
 #pragma once
 #include "model.cuh"
+#include "persist_common.cuh"
 
 namespace gpp {
 
@@ -13,7 +14,8 @@ template <int D>
 __device__ __forceinline__ void pack_body(int idx, const double* __restrict__ m, const double* __restrict__ S, int N,
                                           const double* __restrict__ ell, const double* __restrict__ var,
                                           const int* __restrict__ pair_ab, int npairs, int L,
-                                          double* __restrict__ packs, double* __restrict__ Gs, int* info) {
+                                          double* __restrict__ packs, double* __restrict__ Gs, int* info,
+                                          unsigned ll_tag = 0u /* != 0: `packs` holds tagged words, two per coefficient */) {
   if (idx >= N * npairs) return;
   int n = idx / npairs, p = idx % npairs;
   // pair table (a <= b, forward) or, with pair_ab == nullptr, all L x L ordered pairs (backward)
@@ -31,6 +33,12 @@ __device__ __forceinline__ void pack_body(int idx, const double* __restrict__ m,
   double out[PairPack<D>::SIZE];
   bool ok = make_pair_pack<D>(mu, Sg, V1, V2, log(var[a] * var[b]), out, Gs ? Gs + (size_t)idx * D * D : nullptr);
   if (!ok) flag_not_pd(info, n);
+  if (ll_tag) {   // persistent rollout: the contraction CTAs poll the tags (persist_common.cuh), no fence and no flag
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(packs) + 2 * (size_t)idx * PairPack<D>::SIZE;
+#pragma unroll
+    for (int t = 0; t < PairPack<D>::SIZE; ++t) ll_store(dst + 2 * t, out[t], ll_tag);
+    return;
+  }
   double* dst = packs + (size_t)idx * PairPack<D>::SIZE;
 #pragma unroll
   for (int t = 0; t < PairPack<D>::SIZE; ++t) dst[t] = out[t];

@@ -27,7 +27,6 @@ namespace gpp {
 
 constexpr int kPersistTile = 64;        // tile edge of the forward contraction
 constexpr int kFwdThreads = 512;        // 4 scalar + 4 producer + 8 consumer warps
-constexpr int kFwdBatch = 8;            // inputs whose packs a producer waits for at once
 
 struct PersistSaved {                   // the per-step block of gpp_rollout_mm_fwd_save (RolloutSaved offsets), or base == nullptr
   double* base;
@@ -48,9 +47,11 @@ struct PersistFwdParams {
   const int* pair_ab;
   int npairs, nslots;
   // workspace
-  double *packs, *f1lat, *crosslat;
-  unsigned long long* part_ll;          // [N, nslots, 2] tile partials as tagged words (ll_store, tag = step + 1); zero at launch
-  unsigned* pack_ready;                 // [N] steps whose coefficient packs are published; zero at launch
+  double *f1lat, *crosslat;
+  unsigned long long* packs_ll;         // [N, npairs, PairPack::SIZE, 2] coefficient packs as tagged words (tag = step + 1); zero at launch
+  unsigned long long* part_ll;          // [N, nslots, 2] tile partials, same protocol
+  unsigned* part_hint;                  // [N] number of tile partials published so far (hint counter, persist_common.cuh)
+  int debug;                            // developer switch (env GPP_PERSIST_DEBUG): 1 = drain the pipeline every step
 };
 
 __device__ __forceinline__ void persist_step_pointers(RolloutMMParams& p, const PersistSaved& sv, const RolloutMMParams& base, int t) {
@@ -99,6 +100,8 @@ __device__ void persist_fwd_scalar(const PersistFwdParams& P) {
     for (int n = n0; n < N; n += G) {
       if (t > 0) {
         // step t-1 of rollout n: wait for its tile partials (tag t) -> outputs of the GP predict, Euler update, trajectory slice t
+        if (tid == 0 && !(P.debug & 2)) hint_wait_ge(P.part_hint + n, (unsigned)t * (unsigned)P.nslots);
+        group_sync();
         persist_step_pointers(p, P.sv, P.r, t - 1);
         fp.ll_tag = (unsigned)t;
         fp.cross = p.cross;
@@ -136,12 +139,11 @@ __device__ void persist_fwd_scalar(const PersistFwdParams& P) {
         // Psi2 coefficient packs of the kernel pairs: pair pp on lane pp / 4 of warp pp % 4 (same code path on every live lane)
         const int pp = (tid & 31) * 4 + (tid >> 5);
         if (pp < P.npairs)
-          pack_body<D>(n * P.npairs + pp, p.md, p.Sd, N, P.ell, P.var, P.pair_ab, P.npairs, P.Lm, P.packs, nullptr, p.info);
+          pack_body<D>(n * P.npairs + pp, p.md, p.Sd, N, P.ell, P.var, P.pair_ab, P.npairs, P.Lm, reinterpret_cast<double*>(P.packs_ll), nullptr,
+                       p.info, (unsigned)(t + 1));   // tagged words: the contraction CTAs pick them up as they arrive
       }
       psi1_body<D>(n, p.md, p.Sd, N, P.Lm, P.M, P.Z, P.ell, P.var, P.beta, P.f1lat, P.crosslat, p.info, nullptr);
-      __threadfence();
       group_sync();
-      if (tid == 0) st_release_u32(P.pack_ready + n, (unsigned)(t + 1));
     }
   }
 }
@@ -165,7 +167,10 @@ struct PersistFwdCfg {
   static constexpr int S_RED = S_WGT + 2 * WBUF;                        // [NRED][NC][32]  lane partials of the last NRED inputs
   static constexpr int S_ETAB = S_RED + NRED * DBUF;                    // [256][REP]
   static constexpr int S_PKBUF = S_ETAB + 256 * REP;                    // [2][PairPack<D>::SIZE]
-  static constexpr int S_TOTAL = S_PKBUF + 2 * PairPack<D>::SIZE;
+  static constexpr int NSTAGE = 3;                                      // tagged words of the packs in flight (cp.async landing zone)
+  static constexpr int S_STAGE = S_PKBUF + 2 * PairPack<D>::SIZE;       // [NSTAGE][PairPack<D>::SIZE][2] 64-bit words, 16-byte aligned
+  static constexpr int S_TOTAL = S_STAGE + NSTAGE * 2 * PairPack<D>::SIZE;
+  static_assert(S_STAGE % 2 == 0, "staging area must be 16-byte aligned");
 };
 
 // both contraction roles: (re)load the C tile of a diagonal pair; `ctid` = index among the NTC contraction threads
@@ -182,6 +187,26 @@ __device__ __forceinline__ void persist_load_tile(const PersistFwdParams& P, con
   role_bar_sync<F::BAR_TILE, F::NTC>();
 }
 
+// The contraction warps walk their work as SEGMENTS of inputs that share a C tile: a CTA that owns one tile (the usual case: no more
+// tiles than SMs) has a single segment of H * N (step, rollout) items and its pipeline never drains; a CTA that owns several tiles
+// has one segment of N items per (step, tile) and re-loads the tile in between.
+struct PersistSegments {
+  int nmy, nseg, seg_items;
+  bool cont;
+  __device__ PersistSegments(int nslots, int N, int H, int debug = 0) {
+    const int G = gridDim.x, c = blockIdx.x;
+    nmy = nslots > c ? (nslots - 1 - c) / G + 1 : 0;
+    // Item j's pack needs the partial of item j - N (same rollout, previous step), and the pipeline publishes item j - 2 before it
+    // waits for pack j: continuous operation needs N >= 2.  A single rollout drains every step instead.
+    cont = nmy == 1 && N >= 2 && !(debug & 1);
+    nseg = cont ? 1 : H * nmy;
+    seg_items = cont ? H * N : N;
+    if (H == 0) nseg = 0;
+  }
+  __device__ int slot(int seg) const { return blockIdx.x + (cont ? 0 : seg % nmy) * gridDim.x; }
+  __device__ int first_step(int seg) const { return cont ? 0 : seg / nmy; }
+};
+
 template <int D>
 __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
   using F = PersistFwdCfg<D>;
@@ -197,88 +222,110 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
   const int ptid = threadIdx.x - kGroupThreads, lane = ptid & 31;
   const bool is_row = ptid < T;                       // threads 0..63: row ptid of the tile; 64..127: column ptid - 64
   const int idx = is_row ? ptid : ptid - T;
-  const int N = P.r.N, G = gridDim.x;
+  const int N = P.r.N;
   const size_t pk_stride = (size_t)P.npairs * PP::SIZE;
+  const PersistSegments segs(P.nslots, N, P.H, P.debug);
   int resident = -1;
-  for (int t = 0; t < P.H; ++t) {
-    for (int slot = blockIdx.x; slot < P.nslots; slot += G) {
-      const gpp_slot sl = P.slots[slot];
-      const bool diag = sl.a == sl.b;
-      if (slot != resident) {
-        if (diag) persist_load_tile<D>(P, sl, Ct, ptid);
-        resident = slot;
-      }
-      // this thread's centre and weight do not change over the inputs
-      const int lat = is_row ? sl.a : sl.b;
-      const int g = (is_row ? sl.ti : sl.tj) * T + idx;
-      double z[D];
+  for (int seg = 0; seg < segs.nseg; ++seg) {
+    const int slot = segs.slot(seg), t0 = segs.first_step(seg);
+    const gpp_slot sl = P.slots[slot];
+    const bool diag = sl.a == sl.b;
+    if (slot != resident) {
+      if (diag) persist_load_tile<D>(P, sl, Ct, ptid);
+      resident = slot;
+    }
+    // this thread's centre and weight do not change over the segment
+    const int lat = is_row ? sl.a : sl.b;
+    const int g = (is_row ? sl.ti : sl.tj) * T + idx;
+    double z[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) z[d] = g < P.M ? P.Z[((size_t)lat * P.M + g) * D + d] : 0.0;
-      const double bw = (!diag && g < P.M) ? P.beta[(size_t)lat * P.M + g] : 0.0;
-      const double* pk0 = P.packs + (size_t)sl.pair * PP::SIZE;
-      unsigned long long* out = P.part_ll + 2 * (size_t)slot;
-      double pv[NPV];
-      for (int k = 0; k < N + 2; ++k) {
-        const int b = k & 1;
-        if (k >= 2) {                        // consumers are done with input k-2: its vector buffers are free, its partial is complete
-          named_bar_sync<F::BAR_EMPTY>(b, NTC);
-          if (ptid < 32) {                   // fixed-order sum of the lane partials -> tagged words (no fence: persist_common.cuh)
-            const double* rp = red + ((k - 2) & (F::NRED - 1)) * F::DBUF + lane;
-            double s = 0.0;
+    for (int d = 0; d < D; ++d) z[d] = g < P.M ? P.Z[((size_t)lat * P.M + g) * D + d] : 0.0;
+    const double bw = (!diag && g < P.M) ? P.beta[(size_t)lat * P.M + g] : 0.0;
+    const unsigned long long* pk0 = P.packs_ll + 2 * (size_t)sl.pair * PP::SIZE;
+    unsigned long long* out = P.part_ll + 2 * (size_t)slot;
+    // coefficient pack of item j = tagged words written by rollout (j % N)'s scalar group for step t0 + j / N.  They are fetched TWO
+    // items ahead with cp.async into a shared-memory landing zone (16 bytes = one tagged value per thread): a register prefetch
+    // would hold a scoreboard slot across iterations and make every shared-memory read of the loop wait for the ~1 us L2 round trip
+    // (measured: +0.2 us per item).  Speculative: the words may not have arrived yet; tags are tested when the item's turn comes.
+    unsigned long long* stage = reinterpret_cast<unsigned long long*>(smem + F::S_STAGE);
+    auto issue = [&](int j) {
+      const unsigned long long* src = pk0 + 2 * (size_t)(j % N) * pk_stride;
+      unsigned long long* dst = stage + (size_t)(j % F::NSTAGE) * 2 * PP::SIZE;
 #pragma unroll
-            for (int w = 0; w < F::NC; ++w) s += rp[w * 32];
-            s = warp_sum(s);
-            if (lane == 0) ll_store(out + 2 * (size_t)(k - 2) * P.nslots, s, (unsigned)(t + 1));
+      for (int q = 0; q < NPV; ++q)
+        if (ptid + q * PT < PP::SIZE) cp_async16(dst + 2 * (ptid + q * PT), src + 2 * (ptid + q * PT));
+      cp_async_commit();
+    };
+    cp_async_wait<0>();                      // nothing of a previous segment is still landing
+    issue(0);
+    issue(1);                                // (an item index past the segment only fetches an existing pack a second time)
+    for (int j = 0; j < segs.seg_items + 2; ++j) {
+      const int b = j & 1;
+      if (j >= 2) {                          // consumers are done with item j-2: its vector buffers are free, its partial is complete
+        named_bar_sync<F::BAR_EMPTY>(b, NTC);
+        if (ptid < 32) {                     // fixed-order sum of the lane partials -> tagged words (no fence: persist_common.cuh)
+          const double* rp = red + ((j - 2) & (F::NRED - 1)) * F::DBUF + lane;
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < F::NC; ++w) s += rp[w * 32];
+          s = warp_sum(s);
+          if (lane == 0) {
+            const int n = (j - 2) % N;
+            ll_store(out + 2 * (size_t)n * P.nslots, s, (unsigned)(t0 + (j - 2) / N + 1));
+            if (!(P.debug & 2)) hint_add(P.part_hint + n);
           }
         }
-        if (k >= N) continue;
-        if (k % kFwdBatch == 0) {            // the scalar groups of the next batch of rollouts have published step t's packs?
-          if (ptid < kFwdBatch && k + ptid < N) spin_wait_ge(P.pack_ready + k + ptid, (unsigned)(t + 1));
-          named_bar_sync_imm<F::BAR_PROD>(PT);
-#pragma unroll
-          for (int q = 0; q < NPV; ++q) pv[q] = ptid + q * PT < PP::SIZE ? __ldcg(pk0 + (size_t)k * pk_stride + ptid + q * PT) : 0.0;
-        }
-        double* pk = pkbuf + b * PP::SIZE;
-#pragma unroll
-        for (int q = 0; q < NPV; ++q)
-          if (ptid + q * PT < PP::SIZE) pk[ptid + q * PT] = pv[q];
-        named_bar_sync_imm<F::BAR_PROD>(PT);   // pack k visible to the producers; pack k-2 (same buffer) no longer read
-        if ((k + 1) % kFwdBatch != 0 && k + 1 < N) {
-#pragma unroll
-          for (int q = 0; q < NPV; ++q)
-            if (ptid + q * PT < PP::SIZE) pv[q] = __ldcg(pk0 + (size_t)(k + 1) * pk_stride + ptid + q * PT);
-        }
-        double ext[4 * KS], zc[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) zc[d] = z[d] - pk[PP::MU + d];
-        if (is_row) {                        // A_i = [R^T z1' (D), c0 + z1'^T P1 z1', 1, 0..]
-#pragma unroll
-          for (int e = 0; e < D; ++e) {
-            double tt = 0.0;
-#pragma unroll
-            for (int d = 0; d < D; ++d) tt = fma(zc[d], pk[PP::R + d * D + e], tt);
-            ext[e] = tt;
-          }
-          ext[D] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
-          ext[D + 1] = 1.0;
-        } else {                             // B_j = [z2' (D), 1, z2'^T P2 z2', 0..]
-#pragma unroll
-          for (int d = 0; d < D; ++d) ext[d] = zc[d];
-          ext[D] = 1.0;
-          ext[D + 1] = packed_quad<D>(pk + PP::P2, zc);
-        }
-#pragma unroll
-        for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
-        double* dst = (is_row ? rowA : colB) + b * F::FBUF + idx * 4;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-          for (int q = 0; q < 4; q += 2)
-            *reinterpret_cast<double2*>(dst + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
-        wgt[b * F::WBUF + (is_row ? 0 : T) + idx] = bw;
-        __threadfence_block();
-        named_bar_arrive<F::BAR_FULL>(b, NTC);
       }
+      if (j >= segs.seg_items) continue;
+      double* pk = pkbuf + b * PP::SIZE;
+      {
+        // every thread waits for ITS words only (they go to the pack buffer next; the barrier after that store is the only one needed)
+        const unsigned tag = (unsigned)(t0 + j / N + 1);
+        cp_async_wait<1>();                  // the group of item j has landed (item j + 1's may still be in flight)
+        const unsigned long long* mine = stage + (size_t)(j % F::NSTAGE) * 2 * PP::SIZE;
+        const unsigned long long* src = pk0 + 2 * (size_t)(j % N) * pk_stride;
+#pragma unroll
+        for (int q = 0; q < NPV; ++q) {
+          const int e = ptid + q * PT;
+          if (e < PP::SIZE) {
+            unsigned long long w0 = mine[2 * e], w1 = mine[2 * e + 1];
+            if (!ll_ready(w0, w1, tag)) pk[e] = ll_load(src + 2 * e, tag);     // not there yet: the rollout's scalar stage is still running
+            else pk[e] = ll_value(w0, w1);
+          }
+        }
+      }
+      named_bar_sync_imm<F::BAR_PROD>(PT);   // pack j visible to the producers; pack j-2 (same buffer) no longer read
+      issue(j + 2);                          // (lands in the slot item j - 1 used; always committed so that the group count stays in step)
+      double ext[4 * KS], zc[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) zc[d] = z[d] - pk[PP::MU + d];
+      if (is_row) {                          // A_i = [R^T z1' (D), c0 + z1'^T P1 z1', 1, 0..]
+#pragma unroll
+        for (int e = 0; e < D; ++e) {
+          double tt = 0.0;
+#pragma unroll
+          for (int d = 0; d < D; ++d) tt = fma(zc[d], pk[PP::R + d * D + e], tt);
+          ext[e] = tt;
+        }
+        ext[D] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
+        ext[D + 1] = 1.0;
+      } else {                               // B_j = [z2' (D), 1, z2'^T P2 z2', 0..]
+#pragma unroll
+        for (int d = 0; d < D; ++d) ext[d] = zc[d];
+        ext[D] = 1.0;
+        ext[D + 1] = packed_quad<D>(pk + PP::P2, zc);
+      }
+#pragma unroll
+      for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
+      double* dst = (is_row ? rowA : colB) + b * F::FBUF + idx * 4;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int q = 0; q < 4; q += 2)
+          *reinterpret_cast<double2*>(dst + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
+      wgt[b * F::WBUF + (is_row ? 0 : T) + idx] = bw;
+      __threadfence_block();
+      named_bar_arrive<F::BAR_FULL>(b, NTC);
     }
   }
 }
@@ -298,48 +345,47 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
   const int cpair = 2 * (lane & 3);
   const double* ct = Ct + row * LDC + cpair;
   const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (F::REP - 1)));
-  const int N = P.r.N, G = gridDim.x;
+  const PersistSegments segs(P.nslots, P.r.N, P.H, P.debug);
   int resident = -1;
-  for (int t = 0; t < P.H; ++t) {
-    for (int slot = blockIdx.x; slot < P.nslots; slot += G) {
-      const gpp_slot sl = P.slots[slot];
-      const bool diag = sl.a == sl.b;
-      if (slot != resident) {
-        if (diag) persist_load_tile<D>(P, sl, Ct, F::PT + ctid);
-        resident = slot;
-      }
-      for (int k = 0; k < N; ++k) {
-        const int b = k & 1;
-        named_bar_sync<F::BAR_FULL>(b, NTC);
-        const double* ra = rowA + b * F::FBUF + strip * 32 + lane;
-        const double* cb = colB + b * F::FBUF + lane;
-        const double* wsrc = diag ? ct : wgt + b * F::WBUF + T + cpair;
-        double a[KS];
+  for (int seg = 0; seg < segs.nseg; ++seg) {
+    const int slot = segs.slot(seg);
+    const gpp_slot sl = P.slots[slot];
+    const bool diag = sl.a == sl.b;
+    if (slot != resident) {
+      if (diag) persist_load_tile<D>(P, sl, Ct, F::PT + ctid);
+      resident = slot;
+    }
+    for (int j = 0; j < segs.seg_items; ++j) {
+      const int b = j & 1;
+      named_bar_sync<F::BAR_FULL>(b, NTC);
+      const double* ra = rowA + b * F::FBUF + strip * 32 + lane;
+      const double* cb = colB + b * F::FBUF + lane;
+      const double* wsrc = diag ? ct : wgt + b * F::WBUF + T + cpair;
+      double a[KS];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) a[ks] = ra[ks * T * 4];
-        double acc0 = 0.0, acc1 = 0.0;
+      for (int ks = 0; ks < KS; ++ks) a[ks] = ra[ks * T * 4];
+      double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 2
-        for (int cg = 0; cg < T / 8; cg += 2) {
-          double tt[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int cg = 0; cg < T / 8; cg += 2) {
+        double tt[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            dmma_m8n8k4(tt[0], tt[1], a[ks], cb[ks * T * 4 + cg * 32]);
-            dmma_m8n8k4(tt[2], tt[3], a[ks], cb[ks * T * 4 + cg * 32 + 32]);
-          }
-          exp_tab_contract<4, F::REP>(tt, etab_lane);
-          const double2 w0 = *reinterpret_cast<const double2*>(wsrc + cg * 8);
-          const double2 w1 = *reinterpret_cast<const double2*>(wsrc + cg * 8 + 8);
-          acc0 = fma(tt[0], w0.x, acc0);
-          acc1 = fma(tt[2], w1.x, acc1);
-          acc0 = fma(tt[1], w0.y, acc0);
-          acc1 = fma(tt[3], w1.y, acc1);
+        for (int ks = 0; ks < KS; ++ks) {
+          dmma_m8n8k4(tt[0], tt[1], a[ks], cb[ks * T * 4 + cg * 32]);
+          dmma_m8n8k4(tt[2], tt[3], a[ks], cb[ks * T * 4 + cg * 32 + 32]);
         }
-        double total = acc0 + acc1;
-        if (!diag) total *= wgt[b * F::WBUF + row];
-        red[(k & (F::NRED - 1)) * F::DBUF + strip * 32 + lane] = total;
-        __threadfence_block();
-        named_bar_arrive<F::BAR_EMPTY>(b, NTC);
+        exp_tab_contract<4, F::REP>(tt, etab_lane);
+        const double2 w0 = *reinterpret_cast<const double2*>(wsrc + cg * 8);
+        const double2 w1 = *reinterpret_cast<const double2*>(wsrc + cg * 8 + 8);
+        acc0 = fma(tt[0], w0.x, acc0);
+        acc1 = fma(tt[2], w1.x, acc1);
+        acc0 = fma(tt[1], w0.y, acc0);
+        acc1 = fma(tt[3], w1.y, acc1);
       }
+      double total = acc0 + acc1;
+      if (!diag) total *= wgt[b * F::WBUF + row];
+      red[(j & (F::NRED - 1)) * F::DBUF + strip * 32 + lane] = total;
+      __threadfence_block();
+      named_bar_arrive<F::BAR_EMPTY>(b, NTC);
     }
   }
 }
@@ -388,6 +434,7 @@ struct PersistBwdParams {
   double *packs, *Gs, *stats, *f1lat, *crosslat, *f1lat_bar, *crosslat_bar, *omega, *gm, *gS;
   int nrb;
   unsigned *ready, *ticket;             // [N], [1]; zero at launch (so is `stats`: tagged words, tag = sweep index + 1)
+  unsigned* stat_hint;                  // [N] work items finished so far (hint counter, persist_common.cuh)
 };
 
 template <int D>
@@ -399,6 +446,7 @@ __device__ void persist_bwd_scalar(const PersistBwdParams& P, double* fsm) {
   const int N = p.N, Dx = p.Dx, Lm = P.Lm;
   const int ndir = Dx + Dx * (Dx + 1) / 2;
   const size_t sm = (size_t)N * Dx, sS = (size_t)N * Dx * Dx;
+  const int items = Lm * (Lm + 1) / 2 * P.nrb;
   const int n0 = G - 1 - (int)blockIdx.x;
   __shared__ double li_sm[GPP_MAX_L * (D * D + 1)];
   BwdPrepareParams bp;
@@ -417,6 +465,8 @@ __device__ void persist_bwd_scalar(const PersistBwdParams& P, double* fsm) {
     for (int n = n0; n < N; n += G) {
       if (t < P.H - 1) {
         // step t+1 of rollout n: wait for its statistics (tagged words) -> adjoint of the joint moments, then of the pre stage
+        if (tid == 0) hint_wait_ge(P.stat_hint + n, (unsigned)(P.H - 1 - t) * (unsigned)items);
+        group_sync();
         set_step(t + 1);
         fp.ll_tag = (unsigned)(P.H - 1 - t);
         bwd_finalize_body<D>(fp, n, fsm);
@@ -474,6 +524,7 @@ __device__ void persist_bwd_contract(const PersistBwdParams& P, double* smem) {
     // the statistics leave as tagged words (tag = sweep index + 1): nothing to fence, nothing to count
     contract_grad_item<D, true>(smem, gtid, n, it / P.nrb, it % P.nrb, P.Z, P.beta, P.C, P.packs, P.omega, P.stats, P.M, Lm, P.nrb, false,
                                 k / per_step + 1u);
+    if (gtid == 0) hint_add(P.stat_hint + n);        // issued by one thread, possibly before the other warps' words: only a hint
   }
 }
 
@@ -542,7 +593,7 @@ PersistFwdLayout persist_fwd_layout(const gpp_gp_model* dyn, int N) {
   const gpp_gp_model::SlotTable& tab = dyn->tables[0][0];
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  lo.packs = take(sizeof(double) * pack_doubles(dyn->D) * tab.npairs * N);
+  lo.packs = take(sizeof(unsigned long long) * 2 * pack_doubles(dyn->D) * tab.npairs * N);
   lo.part = take(sizeof(unsigned long long) * 2 * (size_t)tab.nslots * N);
   lo.f1lat = take(sizeof(double) * (size_t)dyn->L * N);
   lo.crosslat = take(sizeof(double) * (size_t)dyn->L * dyn->D * N);
@@ -577,11 +628,15 @@ int rollout_mm_fwd_persist(const gpp_gp_model* dyn, const RolloutMMParams& r, in
   P.Z = dyn->Z; P.ell = dyn->ell; P.var = dyn->var; P.beta = dyn->beta; P.C = dyn->C; P.mean = dyn->mean; P.W = dyn->W;
   P.M = dyn->M; P.Lm = dyn->L; P.Pm = dyn->P; P.model_uncertainty = dyn->model_uncertainty;
   P.slots = tab.d_slots; P.pair_start = tab.d_pair_start; P.pair_ab = tab.d_pair_ab; P.npairs = tab.npairs; P.nslots = tab.nslots;
-  P.packs = (double*)(ws_persist + lo.packs); P.part_ll = (unsigned long long*)(ws_persist + lo.part);
+  {
+    const char* e = std::getenv("GPP_PERSIST_DEBUG");
+    P.debug = e ? std::atoi(e) : 0;
+  }
+  P.packs_ll = (unsigned long long*)(ws_persist + lo.packs); P.part_ll = (unsigned long long*)(ws_persist + lo.part);
   P.f1lat = (double*)(ws_persist + lo.f1lat); P.crosslat = (double*)(ws_persist + lo.crosslat);
-  P.pack_ready = (unsigned*)(ws_persist + lo.flags);
+  P.part_hint = (unsigned*)(ws_persist + lo.flags);
+  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.packs, 0, lo.f1lat - lo.packs, stream));   // tags of the packs and the partials
   GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * (size_t)N, stream));
-  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.part, 0, sizeof(unsigned long long) * 2 * (size_t)tab.nslots * N, stream));
   const int grid = std::min(num_sms(), tab.nslots + N);
   switch (dyn->D) {
 #define GPP_CASE(d) case d: return launch_fwd_persist<d>(P, grid, stream);
@@ -632,7 +687,7 @@ PersistBwdLayout persist_bwd_layout(const gpp_gp_model* dyn, int N, int Dx, int 
   lo.gm = take(sizeof(double) * (size_t)L * D * N);
   lo.gS = take(sizeof(double) * (size_t)L * D * D * N);
   lo.cg = take(sizeof(double) * (size_t)std::max(H, 1) * N * (Dx + Dx * (Dx + 1) / 2));
-  lo.flags = take(sizeof(unsigned) * ((size_t)N + 8));
+  lo.flags = take(sizeof(unsigned) * (2 * (size_t)N + 8));
   lo.total = off;
   return lo;
 }
@@ -668,8 +723,8 @@ int rollout_mm_bwd_persist(const gpp_gp_model* dyn, const RolloutMMParams& r, co
   P.packs = D_(lo.packs); P.Gs = D_(lo.Gs); P.stats = D_(lo.stats); P.f1lat = D_(lo.f1lat); P.crosslat = D_(lo.crosslat);
   P.f1lat_bar = D_(lo.f1lat_bar); P.crosslat_bar = D_(lo.crosslat_bar); P.omega = D_(lo.omega); P.gm = D_(lo.gm); P.gS = D_(lo.gS);
   P.nrb = lo.nrb;
-  P.ready = (unsigned*)(ws_persist + lo.flags); P.ticket = P.ready + N;
-  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * ((size_t)N + 8), stream));
+  P.ready = (unsigned*)(ws_persist + lo.flags); P.stat_hint = P.ready + N; P.ticket = P.ready + 2 * N;
+  GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.flags, 0, sizeof(unsigned) * (2 * (size_t)N + 8), stream));
   GPP_CUDA_OK(cudaMemsetAsync(ws_persist + lo.stats, 0, lo.f1lat - lo.stats, stream));
   // cost gradients of all H trajectory states in one launch (dual numbers through the encoder and expected-cost rules)
   const int ndir = Dx + Dx * (Dx + 1) / 2;

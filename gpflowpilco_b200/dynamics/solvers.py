@@ -20,12 +20,20 @@ def foldl(fn, elems, initializer):
   return state
 
 
+def _stack_leaves(items):
+  """tf.scan stacks the per-step outputs leaf by leaf: a list of (nested) tuples of tensors -> the same nesting of [T, ...] tensors"""
+  first = items[0]
+  if isinstance(first, (tuple, list)):
+    return type(first)(_stack_leaves([it[k] for it in items]) for k in range(len(first)))
+  return torch.stack([torch.as_tensor(it) for it in items])
+
+
 def scan(fn, elems, initializer):
   state, out = initializer, []
   for t, dt in zip(*elems):
     state = fn(state, (t, dt))
     out.append(state)
-  return out
+  return _stack_leaves(out) if out else out
 
 
 class Euler:

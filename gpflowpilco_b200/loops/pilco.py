@@ -19,7 +19,7 @@ import torch
 from gpflowpilco_b200 import pathwise as pw
 from gpflowpilco_b200.components import GaussianObjective, TrigonometricEncoder
 from gpflowpilco_b200.dynamics import DynamicalSystem, MomentMatchingEuler, foldl
-from gpflowpilco_b200.models.core import (BijectorChain, InverseLinkWrapper, KernelRegressor, LinearCoregionalization, SVGP)
+from gpflowpilco_b200.models.core import (BijectorChain, Constant, InverseLinkWrapper, KernelRegressor, LinearCoregionalization, SVGP, Zero)
 from gpflowpilco_b200.moment_matching import GaussianMoments, moment_matching
 from gpflowpilco_b200.moment_matching.models import DEFAULT_JITTER, svgp_handle
 from gpflowpilco_b200.rollouts import PolicyParams, rollout_mm
@@ -67,6 +67,16 @@ class AbstractPILCO(DynamicalSystem):
     svgp = pol.model.model
     if not isinstance(svgp, SVGP) or len(svgp.latent_kernels()) != 1 or svgp.latent_kernels()[0].active_dims is not None:
       return None
+    # the fused kernels take a zero-mean, single-output regressor: anything else goes through the rule-by-rule path, which honours
+    # the mean function and every output column (the two closures must return the same loss for the same objects)
+    if not _has_zero_mean(svgp.mean_function) or svgp.q_mu.shape[1] != 1:
+      return None
+    jitter = DEFAULT_JITTER if svgp.kuu_jitter is None else svgp.kuu_jitter
+    if not isinstance(jitter, (int, float)):
+      jitter = [float(v) for v in jitter]
+      if len(jitter) != 1:
+        return None
+      jitter = jitter[0]
     try:
       scale, shift = pol.invlink.squash_parameters()
     except NotImplementedError:
@@ -74,7 +84,7 @@ class AbstractPILCO(DynamicalSystem):
     k, Z = svgp.latent_kernels()[0], svgp.latent_inducing()[0]
     De = Z.shape[-1]
     return PolicyParams(Z[None], k.ell(De)[None], k.variance.reshape(1), svgp.q_mu[:, 0][None], whiten=svgp.whiten,
-                        jitter=DEFAULT_JITTER, squash_scale=scale, squash_shift=shift)
+                        jitter=float(jitter), squash_scale=scale, squash_shift=shift)
 
   def _fusable(self) -> bool:
     return (isinstance(self.encoder, TrigonometricEncoder) and isinstance(self.objective, GaussianObjective) and
@@ -155,7 +165,15 @@ class PathwisePILCO(AbstractPILCO):
       if _paths is None:   # fresh sample paths with each call of the closure (upstream :281-284)
         _paths = pw.generate_paths(handle, state.shape[0], num_bases, seed + counter["calls"], first_particle)
       counter["calls"] += 1
-      loss, _, _ = pw.rollout_pathwise(_paths, self._policy_params(), state, len(solution_times), self.encoder.active_dims,
+      pp = self._policy_params()
+      if torch.is_grad_enabled() and any(t.requires_grad for t in (pp.Z, pp.lengthscales, pp.q_mu, state)):
+        # differentiable closure (upstream differentiates it with tape.gradient, utils/optimizers.py:52-56): gradient-mode forward
+        # + reverse sweep through the autograd shim, as the moment-matched closure does
+        from gpflowpilco_b200.autograd import rollout_pathwise_loss
+        return rollout_pathwise_loss(_paths, pp.Z, pp.lengthscales, pp.variance, pp.q_mu, state, len(solution_times),
+                                     self.encoder.active_dims, self.objective.target, self.objective.precis,
+                                     squash_scale=pp.squash_scale, squash_shift=pp.squash_shift, whiten=pp.whiten, jitter=pp.jitter)
+      loss, _, _ = pw.rollout_pathwise(_paths, pp, state, len(solution_times), self.encoder.active_dims,
                                        self.objective.target, self.objective.precis)
       return loss
 
@@ -165,6 +183,22 @@ class PathwisePILCO(AbstractPILCO):
     def _initializer(seed: int = 0, first_particle: int = 0):   # initial states 1-to-1 with paths (upstream :300-303)
       return pw.draw_initial_states(p.mean().to(torch.float64), p.covariance().to(torch.float64), seed, first_particle, batch_size)
     return _initializer
+
+
+def _has_zero_mean(mean_function) -> bool:
+  """Zero, or a Constant whose value is identically zero (upstream's cart-pole policy: models/svgp.py builds Constant(0)).  The
+  device read behind the second case is cached per tensor version, so a closure evaluated in a loop does not synchronise."""
+  if isinstance(mean_function, Zero):
+    return True
+  if not isinstance(mean_function, Constant):
+    return False
+  c = mean_function.c
+  key = (id(c), c._version, c.data_ptr())
+  hit = mean_function.__dict__.get("_zero_check")
+  if hit is None or hit[0] != key:
+    hit = (key, bool((c == 0).all()))
+    mean_function.__dict__["_zero_check"] = hit
+  return hit[1]
 
 
 def _takes_seed(fn) -> bool:

@@ -112,8 +112,12 @@ class _HandleCache:
   def _param_tensors(self) -> Tuple[torch.Tensor, ...]:
     raise NotImplementedError
 
+  def _settings(self) -> tuple:
+    """non-tensor attributes that are baked into a handle (jitter, whitening, kind of mean function, ...)"""
+    return ()
+
   def _signature(self, extra):
-    return tuple((id(t), t._version, t.data_ptr()) for t in self._param_tensors()) + tuple(extra)
+    return tuple((id(t), t._version, t.data_ptr()) for t in self._param_tensors()) + tuple(self._settings()) + tuple(extra)
 
   def cached_handle(self, extra, factory):
     sig = self._signature(extra)
@@ -159,6 +163,13 @@ class SVGP(_HandleCache):
     if isinstance(iv, SharedIndependentInducingVariables):
       return [iv.inducing_variable.Z] * L
     return [iv.Z] * L
+
+  def _settings(self):
+    j = self.kuu_jitter
+    j = None if j is None else (tuple(float(v) for v in j) if isinstance(j, (list, tuple)) else float(j))
+    lik = getattr(self.likelihood, "variance", None)
+    return (j, bool(self.whiten), type(self.mean_function).__name__, type(self.kernel).__name__, type(self.inducing_variable).__name__,
+            None if lik is None else float(lik))
 
   def _param_tensors(self):
     ts = [self.q_mu, self.q_sqrt]

@@ -72,8 +72,12 @@ def _predict(x: GaussianMoments, handle: ops.GPModelHandle, active_dims, full_ou
     ms, Ss = m, S
   f1, Sff, cross = handle.predict(ms, Ss, full_output_cov=full_output_cov, jitter=jitter, check=check)
   if active_dims is not None:
-    # upstream returns the cross term w.r.t. the sliced inputs as well (models.py:264-277 slices x per kernel)
-    pass
+    # GaussianMatch.x is the FULL state: rows of Sxx^-1 Cov(x, f) that belong to inactive dims are exactly zero (f does not depend
+    # on them), so the pre-inverted cross term of the sliced problem is scattered into a zero [N, D, P] block.  (Upstream returns
+    # the sliced rows, models.py:264-277, and then mis-multiplies them in cross_covariance(preinv=False) / joint().)
+    full = torch.zeros(*m.shape[:-1], m.shape[-1], cross.shape[-1], dtype=cross.dtype, device=cross.device)
+    full[..., list(active_dims), :] = cross
+    cross = full
   return GaussianMatch(x=x, y=GaussianMoments(moments=(f1, Sff), centered=True), cross=(cross, True))
 
 

@@ -81,7 +81,8 @@ if __name__ == "__main__":
 
 
 def sweep():
-  for R in (1, 4, 8, 16, 32, 64, 96, 128):
+  Rs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else (1, 4, 8, 16, 32, 64, 96, 128)
+  for R in Rs:
     args = setup(R)
     rollouts.set_rollout_mode(rollouts.ROLLOUT_PERSIST)
     best = (1e9, 1e9)

@@ -21,7 +21,7 @@ def test_reference_arm_prints_one_json_line():
   for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "cpu_baseline", "e2e"):
     assert key in line, key
-  assert line["impl"] == "reference" and line["metric"] == "mm_rollout_steps_per_s" and line["dtype"] == "f64"
+  assert line["impl"] == "reference" and line["metric"] == "mm_gp_predict_states_per_s" and line["dtype"] == "f64"
   assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
   assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
   assert "workload" in line["config"] and line["vs_baseline"] is None

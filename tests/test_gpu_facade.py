@@ -195,3 +195,92 @@ def test_gradient_descent_minimises_the_mm_policy_loss():
   hist = opt.minimize(closure, [svgp.q_mu, Zvar])
   assert len(hist) == 25 and all(math.isfinite(h) for h in hist)
   assert hist[-1] < hist[0] - 1e-6, f"loss did not decrease: {hist[0]} -> {hist[-1]}"
+
+
+def test_gradient_descent_on_the_pathwise_closure():
+  """PathwisePILCO's closure is differentiable (upstream takes tape.gradient of it, utils/optimizers.py:52-56): with trainable policy
+  tensors it goes through the gradient-mode forward + reverse sweep, and GradientDescent.minimize lowers the mean particle cost."""
+  from gpflowpilco_b200.components import GaussianObjective, TrigonometricEncoder
+  from gpflowpilco_b200.loops import EpisodeSpec, GaussianStateDistribution, PathwisePILCO
+  from gpflowpilco_b200.utils.optimizers import GradientDescent, clip_by_global_norm
+  cfg = synthetic.config1_cartpole(M=32, Mp=8)
+  cfg["policy"]["q_mu"] = 100.0 * cfg["policy"]["q_mu"]
+  drift, policy = _facade_models(cfg)
+  svgp = policy.model.model
+  svgp.q_mu = svgp.q_mu.clone().requires_grad_(True)
+  spec = EpisodeSpec(GaussianStateDistribution(_dev(cfg["m0"][0]), _dev(cfg["S0"][0])), horizon=0.5, step_size=0.1)
+  loop = PathwisePILCO(spec, GaussianObjective(_dev(cfg["target"]), _dev(cfg["W"])), drift, policy, TrigonometricEncoder(cfg["active_dims"]))
+  from gpflowpilco_b200 import pathwise as pw
+  from gpflowpilco_b200.moment_matching.models import svgp_handle
+  paths = pw.generate_paths(svgp_handle(drift, True), 256, 64, seed=3)        # fixed paths: a deterministic objective
+  closure = loop.policy_loss_closure(batch_size=256, num_bases=64, seed=3, paths=paths)
+  loss = closure()
+  assert loss.shape == (256,) and loss.requires_grad
+  mean_closure = lambda: closure().mean()[None]
+  opt = GradientDescent(step_limit=15, optimizer_factory=lambda vs: torch.optim.Adam(vs, lr=5e-2), transform=clip_by_global_norm(1.0))
+  hist = opt.minimize(mean_closure, [svgp.q_mu])
+  assert len(hist) == 15 and all(math.isfinite(h) for h in hist)
+  assert hist[-1] < hist[0] - 1e-7, f"loss did not decrease: {hist[0]} -> {hist[-1]}"
+
+
+def test_fused_and_rule_by_rule_closures_agree_when_the_policy_has_a_mean_or_jitter():
+  """A policy SVGP with a Constant mean is not what the fused kernels compute: the closure must fall back (and give the same loss as
+  fused=False); a non-default kuu_jitter is honoured by the fused path."""
+  from gpflowpilco_b200 import models as M
+  from gpflowpilco_b200.components import GaussianObjective, TrigonometricEncoder
+  from gpflowpilco_b200.loops import EpisodeSpec, GaussianStateDistribution, MomentMatchingPILCO
+  cfg = synthetic.config1_cartpole(M=32, Mp=8)
+  cfg["policy"]["q_mu"] = 100.0 * cfg["policy"]["q_mu"]
+  spec = EpisodeSpec(GaussianStateDistribution(_dev(cfg["m0"][0]), _dev(cfg["S0"][0])), horizon=0.4, step_size=0.1)
+  obj = GaussianObjective(_dev(cfg["target"]), _dev(cfg["W"]))
+  enc = TrigonometricEncoder(cfg["active_dims"])
+  # (a) constant mean
+  drift, policy = _facade_models(cfg)
+  policy.model.model.mean_function = M.Constant(_dev(np.array([0.3])))
+  loop = MomentMatchingPILCO(spec, obj, drift, policy, enc)
+  assert loop._policy_params() is None and not loop._fusable()
+  a, b = loop.policy_loss_closure()(), loop.policy_loss_closure(fused=False)()
+  assert torch.equal(a, b)
+  drift0, policy0 = _facade_models(cfg)
+  base = MomentMatchingPILCO(spec, obj, drift0, policy0, enc).policy_loss_closure()()
+  assert float((a - base).abs().max()) > 1e-9          # the mean is not silently dropped
+  # (b) non-default jitter
+  drift, policy = _facade_models(cfg)
+  policy.model.model.kuu_jitter = 1e-3
+  loop = MomentMatchingPILCO(spec, obj, drift, policy, enc)
+  assert loop._fusable() and loop._policy_params().jitter == 1e-3
+  scaled_close(loop.policy_loss_closure()(), loop.policy_loss_closure(fused=False)(), 1e-9, "fused vs rule-by-rule with kuu_jitter = 1e-3")
+  assert float((loop.policy_loss_closure()() - base).abs().max()) > 1e-12
+
+
+def test_active_dims_cross_term_lives_in_the_full_state_and_handle_cache_sees_settings():
+  from gpflowpilco_b200 import models as M
+  from gpflowpilco_b200.moment_matching import GaussianMoments, moment_matching
+  g = torch.Generator().manual_seed(4)
+  D, Mi, N = 5, 12, 3
+  act = (0, 2, 3)
+  Z = torch.randn(Mi, D, dtype=DTYPE, generator=g)
+  kern = M.SquaredExponential(_dev(np.array(0.8)), _dev(np.array([0.9, 1.1, 1.3])), active_dims=act)
+  model = M.SVGP(kern, M.InducingPoints(_dev(Z)), _dev(torch.randn(Mi, 1, dtype=DTYPE, generator=g)), None, whiten=True)
+  mu = torch.randn(N, D, dtype=DTYPE, generator=g)
+  A = torch.randn(N, D, D, dtype=DTYPE, generator=g)
+  cov = 0.1 * A @ A.transpose(-1, -2) + 0.05 * torch.eye(D, dtype=DTYPE)
+  x = GaussianMoments((_dev(mu), _dev(cov)), True)
+  mm = moment_matching(x, model)
+  assert mm.cross[0].shape == (N, D, 1)
+  inactive = [d for d in range(D) if d not in act]
+  assert float(mm.cross[0][:, inactive].abs().max()) == 0.0
+  # Cov(x, f) = Sxx (Sxx^-1 Cov(x, f)) through the full state: compare with Monte Carlo-free identity on the active block
+  sub = GaussianMoments((_dev(mu[:, list(act)]), _dev(cov[:, list(act)][:, :, list(act)])), True)
+  kern_sub = M.SquaredExponential(_dev(np.array(0.8)), _dev(np.array([0.9, 1.1, 1.3])))
+  model_sub = M.SVGP(kern_sub, M.InducingPoints(_dev(Z[:, list(act)])), model.q_mu, None, whiten=True)
+  ref = moment_matching(sub, model_sub)
+  scaled_close(mm.y.mean(), ref.y.mean().cpu(), 1e-12, "mean through active dims")
+  scaled_close(mm.cross_covariance()[:, list(act)], ref.cross_covariance().cpu(), 1e-10, "Cov(x_active, f)")
+  joint = mm.joint()
+  assert joint.mean().shape == (N, D + 1)
+  # handle cache: a changed setting (jitter) must rebuild the handle
+  f_before = mm.y.covariance().clone()
+  model.kuu_jitter = 1e-2
+  f_after = moment_matching(x, model).y.covariance()
+  assert float((f_after - f_before).abs().max()) > 1e-9

@@ -118,3 +118,90 @@ def test_config4_particles_are_sharding_invariant():
   assert torch.equal(x0_whole, torch.cat([s[2] for s in shards], 0))      # initial states likewise
   scaled_close(torch.cat([s[0] for s in shards]), whole, 1e-9, "per-particle losses, sharded vs one launch")
   assert torch.isfinite(whole).all() and float(whole.std()) > 0
+
+
+def _config5_problem(R, seed=5):
+  from gpflowpilco_b200 import ops
+  cfg = synthetic.config1_cartpole()                     # M = 256 dynamics, 30 policy centres
+  d, p = cfg["dynamics"], cfg["policy"]
+  handle = ops.GPModelHandle(_dev(d["Z"]), _dev(d["lengthscales"]), _dev(d["variance"]), _dev(d["q_mu"]), _dev(d["q_sqrt"]), whiten=True,
+                             mean_const=_dev(d["mean_const"]))
+  g = torch.Generator().manual_seed(seed)
+  Z = _dev(p["Z"]).repeat(R, 1, 1) + 0.3 * torch.randn(R, *p["Z"].shape[1:], dtype=DTYPE, generator=g).cuda()
+  ell = _dev(p["lengthscales"]).repeat(R, 1) * torch.exp(torch.empty(R, 1, dtype=DTYPE).uniform_(-0.5, 0.5, generator=g)).cuda()
+  q = 0.3 * torch.randn(R, p["Z"].shape[1], dtype=DTYPE, generator=g).cuda()      # large enough for the policy to act
+  var = _dev(p["variance"]).repeat(R)
+  m0, S0 = _dev(cfg["m0"]).expand(R, -1).contiguous(), _dev(cfg["S0"]).expand(R, -1, -1).contiguous()
+  return cfg, handle, Z, ell, var, q, m0, S0
+
+
+def test_config5_shape_backward_persistent_vs_per_stage_and_directional_differences():
+  """BASELINE config #5's per-GPU shape (M = 256, H = 100, 30 policy centres; 4 of the 64 restarts): gpp_rollout_mm_fwd_save +
+  gpp_rollout_mm_bwd.  (i) the persistent on-device sweep and the one-launch-per-stage sweep agree; (ii) the gradient agrees with
+  central differences of the forward loss along random directions in (Z, lengthscales, q_mu) space — the forward itself is pinned to
+  upstream's vectors at H = 30 (tests/test_gpu_golden.py), the backward to upstream's finite differences at H = 5."""
+  from gpflowpilco_b200 import rollouts
+  from gpflowpilco_b200.autograd import rollout_mm_loss
+  R, H = 4, 100
+  cfg, handle, Z, ell, var, q, m0, S0 = _config5_problem(R)
+  kw = dict(squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  args = (H, cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]))
+
+  def loss_and_grads(mode):
+    prev = rollouts.set_rollout_mode(mode)
+    try:
+      leaves = [t.clone().requires_grad_(True) for t in (Z, ell, q)]
+      loss = rollout_mm_loss(handle, leaves[0], leaves[1], var, leaves[2], m0, S0, *args, **kw)
+      loss.sum().backward()
+      return loss.detach(), [t.grad for t in leaves]
+    finally:
+      rollouts.set_rollout_mode(prev)
+
+  loss_p, g_p = loss_and_grads(rollouts.ROLLOUT_PERSIST)
+  loss_l, g_l = loss_and_grads(rollouts.ROLLOUT_LEGACY)
+  assert torch.isfinite(loss_p).all() and all(torch.isfinite(g).all() for g in g_p)
+  scaled_close(loss_p, loss_l, 1e-9, "loss, persistent vs per-stage")
+  for name, a, b in zip(("Z", "lengthscales", "q_mu"), g_p, g_l):
+    scaled_close(a, b, 1e-7, f"{name} gradient, persistent vs per-stage")
+  gen = torch.Generator().manual_seed(3)
+  for trial in range(2):
+    v = [torch.randn(t.shape, dtype=DTYPE, generator=gen).cuda() * s for t, s in ((Z, 1.0), (ell, 0.2), (q, 0.3))]
+    h = 1e-5
+    lp = rollout_mm_loss(handle, Z + h * v[0], ell + h * v[1], var, q + h * v[2], m0, S0, *args, **kw)
+    lm = rollout_mm_loss(handle, Z - h * v[0], ell - h * v[1], var, q - h * v[2], m0, S0, *args, **kw)
+    fd = (lp - lm) / (2 * h)                                                     # [R]: the restarts are independent
+    an = sum((g * d).reshape(R, -1).sum(-1) for g, d in zip(g_p, v))
+    scaled_close(an, fd, 2e-5, f"directional derivative {trial} (H = 100)")
+
+
+def test_config5_shape_backward_vs_oracle_autograd():
+  """Same models at M = 256 with a shorter horizon (H = 12, 2 restarts) against torch.autograd on the oracle (CUDA's O(M^2) association,
+  oracle/gp_models.py mm_sparse_reassociated): full-size Psi2 tiles, all 10 kernel pairs, both row blocks of the gradient contraction."""
+  from gpflowpilco_b200.autograd import rollout_mm_loss
+  from oracle import gp_models as gm
+  from oracle import moments as mo
+  from oracle import rollout as ro
+  R, H = 2, 12
+  cfg, handle, Z, ell, var, q, m0, S0 = _config5_problem(R, seed=9)
+  d, p = cfg["dynamics"], cfg["policy"]
+  dyn = gm.SVGPModel([ps.SEKernel(float(d["variance"][l]), torch.as_tensor(d["lengthscales"][l])) for l in range(4)],
+                     [torch.as_tensor(d["Z"][l]) for l in range(4)], torch.as_tensor(d["q_mu"]), torch.as_tensor(d["q_sqrt"]), whiten=True,
+                     mean_const=torch.as_tensor(d["mean_const"]))
+  enc = mo.TrigonometricEncoder(tuple(cfg["active_dims"]))
+  obj = mo.GaussianObjective(torch.as_tensor(cfg["target"]), torch.as_tensor(cfg["W"]))
+  ref_loss, ref_g = [], []
+  for r in range(R):
+    Zr, er, qr = (t[r].cpu().clone().requires_grad_(True) for t in (Z, ell, q))
+    pol = gm.SVGPModel([ps.SEKernel(float(var[r]), er)], [Zr], qr[:, None], torch.as_tensor(p["q_sqrt"]), whiten=True,
+                       mean_const=torch.zeros(1, dtype=DTYPE))
+    loss = ro.mm_rollout(m0[r:r + 1].cpu(), S0[r:r + 1].cpu(), H, lambda s: gm.mm_sparse_reassociated(s, dyn),
+                         lambda s: gm.mm_policy(s, pol, cfg["squash_scale"], cfg["squash_shift"]), enc, obj)
+    ref_loss.append(loss.detach()[0])
+    ref_g.append(torch.autograd.grad(loss.sum(), [Zr, er, qr]))
+  leaves = [t.clone().requires_grad_(True) for t in (Z, ell, q)]
+  loss = rollout_mm_loss(handle, leaves[0], leaves[1], var, leaves[2], m0, S0, H, cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]),
+                         squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  loss.sum().backward()
+  scaled_close(loss, torch.stack(ref_loss), 1e-6, "loss")
+  for k, name in enumerate(("Z", "lengthscales", "q_mu")):
+    scaled_close(leaves[k].grad, torch.stack([g[k] for g in ref_g]), 1e-6, f"{name} gradient")

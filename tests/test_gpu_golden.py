@@ -123,3 +123,96 @@ def test_squash_nd_golden():
     scaled_close(mm.y.mean(), torch.as_tensor(g[f"{tag}_mean"]), 1e-9, f"{tag} mean")
     scaled_close(mm.y.covariance(), torch.as_tensor(g[f"{tag}_cov"]), 1e-9, f"{tag} cov")
     scaled_close(mm.cross_covariance(preinv=True), torch.as_tensor(g[f"{tag}_cross_pre"]), 1e-9, f"{tag} cross (pre-inverted)")
+
+
+def _cartpole_handle_and_policy(d, p, scale, shift):
+  from gpflowpilco_b200 import ops
+  from gpflowpilco_b200.rollouts import PolicyParams
+  h = ops.GPModelHandle(_dev(d["Z"]), _dev(d["lengthscales"]), _dev(d["variance"]), _dev(d["q_mu"]), _dev(d["q_sqrt"]), whiten=True,
+                        mean_const=_dev(d["mean_const"]))
+  P = PolicyParams(_dev(p["Z"]), _dev(p["lengthscales"]), _dev(p["variance"]), _dev(np.asarray(p["q_mu"])[:, 0][None]), whiten=True,
+                   squash_scale=float(scale), squash_shift=float(shift))
+  return h, P
+
+
+@pytest.mark.parametrize("mode", ["persistent", "per_stage"])
+def test_rollout_config1_full_size_golden(mode):
+  """BASELINE config #1 at full size (M = 256 dynamics, 30 policy centres, H = 30): the fused device rollout — the persistent
+  on-device H-loop and the one-launch-per-stage path — against upstream's own forward_sde / MomentMatchingEuler / loss callback
+  (tests/golden/rollout_cfg1.npz).  Upstream forms Luu^-1 Q Luu^-T by triangular solves, the kernels contract Q with Kuu^-1-derived
+  weights; at cond(Kuu) ~ 1e7 the two float64 forms differ by ~1e-8 (SURVEY §7 hard part 1), the north-star tolerance is 1e-6."""
+  from gpflowpilco_b200 import rollouts, synthetic
+  g = load("rollout_cfg1.npz")
+  cfg = synthetic.config1_cartpole()
+  h, P = _cartpole_handle_and_policy(cfg["dynamics"], cfg["policy"], cfg["squash_scale"], cfg["squash_shift"])
+  prev = rollouts.set_rollout_mode(rollouts.ROLLOUT_PERSIST if mode == "persistent" else rollouts.ROLLOUT_LEGACY)
+  try:
+    res = rollouts.rollout_mm(h, P, _dev(cfg["m0"]), _dev(cfg["S0"]), int(g["horizon"]), cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]),
+                              return_trajectory=True)
+  finally:
+    rollouts.set_rollout_mode(prev)
+  scaled_close(res.traj_m, torch.as_tensor(g["traj_m"]), 1e-6, "trajectory means")
+  scaled_close(res.traj_S, torch.as_tensor(g["traj_S"]), 1e-6, "trajectory covariances")
+  scaled_close(res.loss, torch.as_tensor(g["loss"]), 1e-6, "loss")
+  # element-wise worst case, reported once (scaled_close is relative to the largest entry of a tensor)
+  ref = torch.as_tensor(g["traj_S"])
+  big = ref.abs() > 1e-6 * ref.abs().max()
+  worst = float(((res.traj_S.cpu() - ref).abs() / ref.abs())[big].max())
+  print(f"config #1 {mode}: worst element-wise relative error of the covariance trajectory (entries above 1e-6 of the largest) {worst:.2e}")
+  assert worst < 1e-4
+
+
+def test_rollout_gradients_golden():
+  """gpp_rollout_mm_bwd (through the autograd shim that stands where upstream's tape.gradient does, utils/optimizers.py:52-56) against
+  Richardson-extrapolated central differences of UPSTREAM's own closure value (tests/golden/rollout_grads.npz, H = 5)."""
+  from gpflowpilco_b200 import ops
+  from gpflowpilco_b200.autograd import rollout_mm_loss
+  g = load("rollout_grads.npz")
+  h = ops.GPModelHandle(_dev(g["dyn_Z"]), _dev(g["dyn_ell"]), _dev(g["dyn_var"]), _dev(g["dyn_q_mu"]), _dev(g["dyn_q_sqrt"]), whiten=True,
+                        mean_const=_dev(g["dyn_c"]))
+  Z = _dev(g["pol_Z"]).requires_grad_(True)
+  ell = _dev(g["pol_ell"]).requires_grad_(True)
+  q = _dev(g["pol_q_mu"][:, 0][None]).requires_grad_(True)
+  m0, S0 = _dev(g["m0"]).requires_grad_(True), _dev(g["S0"]).requires_grad_(True)
+  loss = rollout_mm_loss(h, Z, ell, _dev(g["pol_var"]), q, m0, S0, int(g["horizon"]), tuple(int(a) for a in g["active_dims"]),
+                         _dev(g["target"]), _dev(g["W"]), squash_scale=float(g["scale"]), squash_shift=float(g["shift"]))
+  scaled_close(loss, torch.as_tensor(np.atleast_1d(g["loss"])), 1e-7, "loss")
+  loss.sum().backward()
+  scaled_close(Z.grad, torch.as_tensor(g["g_Z"]), 2e-6, "d loss / d Z")
+  scaled_close(q.grad[0], torch.as_tensor(g["g_q_mu"][:, 0]), 2e-6, "d loss / d q_mu")
+  scaled_close(ell.grad, torch.as_tensor(g["g_ell"]), 2e-6, "d loss / d lengthscales")
+  scaled_close(m0.grad, torch.as_tensor(g["g_m0"]), 2e-6, "d loss / d m0")
+  scaled_close(0.5 * (S0.grad + S0.grad.transpose(-1, -2)), torch.as_tensor(g["g_S0"]), 2e-6, "d loss / d S0")
+
+
+def test_forward_sde_without_policy_golden():
+  """forward_sde's registrations without a policy (upstream dynamics/forward_sde.py:34-46 and :72-92) and MomentMatchingEuler on them,
+  through the reference-facing objects, against upstream's outputs (tests/golden/forward_sde_variants.npz)."""
+  from gpflowpilco_b200 import models as M
+  from gpflowpilco_b200.components import TrigonometricEncoder
+  from gpflowpilco_b200.dynamics import DynamicalSystem, MomentMatchingEuler, forward_sde
+  from gpflowpilco_b200.moment_matching import GaussianMoments
+  g = load("forward_sde_variants.npz")
+  x = GaussianMoments((_dev(g["m"]), _dev(g["S"])), True)
+  for tag, enc in (("plain", None), ("enc", TrigonometricEncoder((1,)))):
+    L = g[f"{tag}_Z"].shape[0]
+    drift = M.SVGP(M.SeparateIndependent([M.SquaredExponential(_dev(g[f"{tag}_var"][l]), _dev(g[f"{tag}_ell"][l])) for l in range(L)]),
+                   M.SeparateIndependentInducingVariables([M.InducingPoints(_dev(g[f"{tag}_Z"][l])) for l in range(L)]), _dev(g[f"{tag}_q_mu"]),
+                   _dev(g[f"{tag}_q_sqrt"]), whiten=True, mean_function=M.Constant(_dev(g[f"{tag}_c"])))
+    match, noise = forward_sde(x, drift, None, None, enc)
+    assert noise is None
+    scaled_close(match.y.mean(), torch.as_tensor(g[f"{tag}_mean"]), 1e-8, f"{tag} mean")
+    scaled_close(match.y.covariance(), torch.as_tensor(g[f"{tag}_cov"]), 1e-6, f"{tag} cov")
+    scaled_close(match.cross_covariance(), torch.as_tensor(g[f"{tag}_cross"]), 1e-7, f"{tag} Cov(x, f)")
+    system = DynamicalSystem(drift=drift, policy=None, encoder=enc, solver=MomentMatchingEuler())
+    states = system.solve_forward(initial_time=0.0, initial_state=(x.mean(), x.covariance()), solution_times=[1.0, 2.0])
+    ms, Ss = _stack_states(states)
+    scaled_close(ms, torch.as_tensor(g[f"{tag}_euler_m"]), 1e-7, f"{tag} Euler means")
+    scaled_close(Ss, torch.as_tensor(g[f"{tag}_euler_S"]), 1e-6, f"{tag} Euler covariances")
+
+
+def _stack_states(states):
+  """solve_forward returns upstream's tf.scan structure: a (means [T,...], covariances [T,...]) pair (or a list of per-step pairs)."""
+  if isinstance(states, (tuple, list)) and len(states) == 2 and torch.is_tensor(states[0]):
+    return states[0], states[1]
+  return torch.stack([s[0] for s in states]), torch.stack([s[1] for s in states])
