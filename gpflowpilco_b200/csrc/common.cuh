@@ -61,7 +61,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // group (bar.sync 6, 128 == __syncthreads()); in the persistent rollout kernels (rollout_persist.cu) the same code runs on the
 // scalar warps of a warp-specialised CTA while the other warps contract, so it must never use a CTA-wide barrier.
 constexpr int kGroupThreads = 128;
-__device__ __forceinline__ void group_sync() { asm volatile("bar.sync 6, 128;" ::: "memory"); }
+// (bar.sync is warp-ALIGNED: every thread of a warp must execute it together.  The compiler reconverges a warp before
+// __syncthreads(), but an inline-asm barrier is opaque to it — after a divergent section such as `if (tid == 0) spin();` nothing
+// guarantees reconvergence, and a partially arrived warp hangs the barrier.  Every asm barrier in this library is therefore
+// preceded by __syncwarp().)
+__device__ __forceinline__ void group_sync() {
+  __syncwarp();
+  asm volatile("bar.sync 6, 128;" ::: "memory");
+}
 
 __device__ __forceinline__ void flag_not_pd(int* info, int index) {
   if (info) atomicCAS(info, 0, index + 1);   // first writer wins; 0 means "all fine"
@@ -69,11 +76,11 @@ __device__ __forceinline__ void flag_not_pd(int* info, int index) {
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
 
 // ---- per-(input, kernel pair) coefficients of  log Q_ij = r_i + s_j + z1'_i^T R z2'_j  ------------------

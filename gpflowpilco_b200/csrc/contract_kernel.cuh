@@ -58,10 +58,12 @@ struct ContractCfg {
 // barrier ids are immediates (a register id would make ptxas reserve all 16 hardware barriers for the CTA)
 template <int ID>
 __device__ __forceinline__ void named_bar_sync_imm(int count) {
+  __syncwarp();                                // inline-asm barriers do not make the compiler reconverge the warp (common.cuh)
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(count) : "memory");
 }
 template <int ID>
 __device__ __forceinline__ void named_bar_arrive_imm(int count) {
+  __syncwarp();
   asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(count) : "memory");
 }
 template <int BASE>

@@ -13,7 +13,7 @@
 
 namespace gpp {
 
-constexpr long long kSpinLimit = 10LL * 2000000000LL;   // ~10 s at 2 GHz
+constexpr long long kSpinLimit = 4LL * 2000000000LL;    // ~4 s at 2 GHz
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -72,6 +72,7 @@ __device__ __forceinline__ double ll_value(unsigned long long w0, unsigned long 
 template <int ID, int COUNT>
 __device__ __forceinline__ bool role_bar_and(bool pred) {
   unsigned out;
+  __syncwarp();
   asm volatile(
       "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.and.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(out)
@@ -137,6 +138,7 @@ __device__ __forceinline__ void warpgroup_reg_dec() {
 
 template <int ID, int COUNT>
 __device__ __forceinline__ void role_bar_sync() {
+  __syncwarp();
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
 }
 

@@ -47,8 +47,12 @@ struct GradCfg {
 // column into shared memory, summed over the 16 strips in a fixed order.  The exponentials of (b, a) are never evaluated.
 template <bool PERSIST>
 __device__ __forceinline__ void grad_sync() {
-  if (PERSIST) asm volatile("bar.sync 7, 512;" ::: "memory");   // the 16 contraction warps of a persistent CTA (rollout_persist.cu)
-  else __syncthreads();
+  if (PERSIST) {                               // the 16 contraction warps of a persistent CTA (rollout_persist.cu)
+    __syncwarp();
+    asm volatile("bar.sync 7, 512;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
 }
 template <bool PERSIST>
 __device__ __forceinline__ double grad_ld(const double* p) { return PERSIST ? __ldcg(p) : *p; }   // written by another CTA of the launch?
@@ -56,11 +60,14 @@ __device__ __forceinline__ double grad_ld(const double* p) { return PERSIST ? __
 // `tid` = index among the 512 contraction threads (16 warps); `smem` = GradCfg<D> layout (+ ncb * 128 doubles).  With `fill_table`
 // the exp table is (re)written first (once per CTA in the persistent kernel, once per item in k_contract_grad).  With ll_tag != 0
 // (persistent sweep) `stats` is an array of tagged words, two per statistic, read by bwd_finalize_body without any fence.
+// With `pack_given` the caller has already fetched the pair's coefficient pack (thread tid holds element tid in `pack_value`), checked
+// that the pair's weight is not zero and synchronised the 512 threads once since the previous item.
 template <int D, bool PERSIST>
 __device__ void contract_grad_item(double* __restrict__ smem, const int tid, const int n, const int pr, const int rb,
                                    const double* __restrict__ Z, const double* __restrict__ beta, const double* __restrict__ C,
                                    const double* __restrict__ packs, const double* __restrict__ omega, double* __restrict__ stats,
-                                   const int M, const int L, const int nrb, const bool fill_table, const unsigned ll_tag = 0u) {
+                                   const int M, const int L, const int nrb, const bool fill_table, const unsigned ll_tag = 0u,
+                                   const bool pack_given = false, const double pack_value = 0.0) {
   using PP = PairPack<D>;
   using GS = GradStats<D>;
   using CF = GradCfg<D>;
@@ -85,10 +92,15 @@ __device__ void contract_grad_item(double* __restrict__ smem, const int tid, con
     else base[k] = v;
   };
   // pairs whose output adjoint is zero (e.g. diagonal-only covariance) are skipped; k_bwd_finalize skips them too
-  const double wgt = grad_ld<PERSIST>(omega + ((size_t)n * L + a) * L + b) + grad_ld<PERSIST>(omega + ((size_t)n * L + b) * L + a);
-  if (wgt == 0.0) return;
-  if (PERSIST) grad_sync<PERSIST>();           // the previous item's readers of this scratch are done
-  for (int t = tid; t < PP::SIZE; t += kGradThreads) pk[t] = grad_ld<PERSIST>(packs + ((size_t)n * L * L + p) * PP::SIZE + t);
+  if (pack_given) {
+    static_assert(PP::SIZE <= kGradThreads, "one pack element per thread");
+    if (tid < PP::SIZE) pk[tid] = pack_value;
+  } else {
+    const double wgt = grad_ld<PERSIST>(omega + ((size_t)n * L + a) * L + b) + grad_ld<PERSIST>(omega + ((size_t)n * L + b) * L + a);
+    if (wgt == 0.0) return;
+    if (PERSIST) grad_sync<PERSIST>();         // the previous item's readers of this scratch are done
+    for (int t = tid; t < PP::SIZE; t += kGradThreads) pk[t] = grad_ld<PERSIST>(packs + ((size_t)n * L * L + p) * PP::SIZE + t);
+  }
   if (fill_table)
     for (int t = tid; t < 256 * CF::REP; t += kGradThreads) etab[t] = kExp2Tab256[t / CF::REP];
   grad_sync<PERSIST>();

@@ -45,6 +45,48 @@ __device__ __forceinline__ void pack_body(int idx, const double* __restrict__ m,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// publish_packs_tagged: the coefficient packs of one input as TAGGED words (persist_common.cuh) for the persistent rollout kernels.
+// All 128 threads of the group call it.  Pairs are processed in rounds of 12 (lanes 0..2 of the 4 warps run make_pair_pack side by
+// side, writing straight into shared memory — no 86-double register array), then the whole group publishes the round's words with
+// coalesced strong stores (7 per thread instead of 172 on one lane).  pair_of(q, a, b, dst): latent indices and pack index of pair q.
+// ---------------------------------------------------------------------------------------------------------
+template <int D, class PairFn>
+__device__ void publish_packs_tagged(const double* __restrict__ m, const double* __restrict__ S, const int n, const int npairs, PairFn pair_of,
+                                     const double* __restrict__ ell, const double* __restrict__ var, unsigned long long* __restrict__ packs_ll,
+                                     double* __restrict__ Gs, const unsigned tag, int* info) {
+  using PP = PairPack<D>;
+  constexpr int ROUND = 12;
+  __shared__ double s_pack[ROUND][PP::SIZE];
+  __shared__ int s_dst[ROUND];
+  const int tid = threadIdx.x, lane = tid & 31, q_local = lane * 4 + (tid >> 5);
+  for (int q0 = 0; q0 < npairs; q0 += ROUND) {
+    if (lane < 3 && q0 + q_local < npairs) {
+      int a, b, dst;
+      pair_of(q0 + q_local, a, b, dst);
+      double V1[D], V2[D], mu[D], Sg[D * D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double e1 = ell[a * D + d], e2 = ell[b * D + d];
+        V1[d] = e1 * e1;
+        V2[d] = e2 * e2;
+        mu[d] = m[(size_t)n * D + d];
+      }
+#pragma unroll
+      for (int d = 0; d < D * D; ++d) Sg[d] = S[(size_t)n * D * D + d];
+      if (!make_pair_pack<D>(mu, Sg, V1, V2, log(var[a] * var[b]), s_pack[q_local], Gs ? Gs + (size_t)dst * D * D : nullptr)) flag_not_pd(info, n);
+      s_dst[q_local] = dst;
+    }
+    group_sync();
+    const int cnt = min(ROUND, npairs - q0);
+    for (int e = tid; e < cnt * PP::SIZE; e += kGroupThreads) {
+      const int q = e / PP::SIZE, t = e % PP::SIZE;
+      ll_store(packs_ll + 2 * ((size_t)s_dst[q] * PP::SIZE + t), s_pack[q][t], tag);
+    }
+    group_sync();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // psi1_body: latent mean  f1[n,l] = sum_m beta_l[m] Psi1[n,m,l]  and  cross[n,:,l] = (S_n+Lambda_l)^-1 sum_m beta Psi1 (z_m - mu)
 //         (models.py:236 and :264-277; Psi1 is GPflow's eKxz)
 // ---------------------------------------------------------------------------------------------------------

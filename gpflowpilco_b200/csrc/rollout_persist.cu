@@ -135,13 +135,10 @@ __device__ void persist_fwd_scalar(const PersistFwdParams& P) {
         for (int i = tid; i < PS; i += kGroupThreads) dst[i] = src[i];
       }
       group_sync();                                          // md / Sd of rollout n are visible to the group
-      {
-        // Psi2 coefficient packs of the kernel pairs: pair pp on lane pp / 4 of warp pp % 4 (same code path on every live lane)
-        const int pp = (tid & 31) * 4 + (tid >> 5);
-        if (pp < P.npairs)
-          pack_body<D>(n * P.npairs + pp, p.md, p.Sd, N, P.ell, P.var, P.pair_ab, P.npairs, P.Lm, reinterpret_cast<double*>(P.packs_ll), nullptr,
-                       p.info, (unsigned)(t + 1));   // tagged words: the contraction CTAs pick them up as they arrive
-      }
+      // Psi2 coefficient packs of the kernel pairs, as tagged words: the contraction CTAs pick them up as they arrive
+      publish_packs_tagged<D>(p.md, p.Sd, n, P.npairs,
+                              [&](int q, int& a, int& b, int& dst) { a = P.pair_ab[2 * q]; b = P.pair_ab[2 * q + 1]; dst = n * P.npairs + q; },
+                              P.ell, P.var, P.packs_ll, nullptr, (unsigned)(t + 1), p.info);
       psi1_body<D>(n, p.md, p.Sd, N, P.Lm, P.M, P.Z, P.ell, P.var, P.beta, P.f1lat, P.crosslat, p.info, nullptr);
       group_sync();
     }
@@ -398,14 +395,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_rollout_fwd_persist(const Pe
   for (int i = threadIdx.x; i < kContractTab * F::REP; i += kFwdThreads) etab[i] = kExp2Tab256[i / F::REP];
   __syncthreads();
   const int warp = threadIdx.x >> 5;
+  // Register reallocation, then a CTA-wide barrier BEFORE any role starts: contraction warps of a CTA that owns no tile return at
+  // once, and a warp that exits while the registers it released are still unclaimed in the CTA pool takes them with it — the scalar
+  // warps' allocation then never completes (observed as a hard hang, no time-out involved, only when the exit wins the race).
+  // (The barrier is repeated inside each branch: ptxas budgets registers for the code DOMINATED by a setmaxnreg, so each role must
+  //  stay in the branch of its own setmaxnreg — behind a common merge point every role would be compiled for the launch count.)
   if (warp < 4) {
     warpgroup_reg_inc<224>();
+    role_bar_sync<8, kFwdThreads>();
     persist_fwd_scalar<D>(P);
   } else if (warp < 8) {
     warpgroup_reg_dec<96>();
+    role_bar_sync<8, kFwdThreads>();
     persist_fwd_producer<D>(P, smem);
   } else {
     warpgroup_reg_dec<96>();
+    role_bar_sync<8, kFwdThreads>();
     persist_fwd_consumer<D>(P, smem);
   }
 }
@@ -535,11 +540,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_rollout_bwd_persist(const Pe
   double* etab = smem + CF::ETAB;
   for (int i = threadIdx.x; i < 256 * CF::REP; i += kBwdThreads) etab[i] = kExp2Tab256[i / CF::REP];
   __syncthreads();
+  // (reallocate, then synchronise the CTA before any warp can return: see k_rollout_fwd_persist)
   if (threadIdx.x < kGroupThreads) {
     warpgroup_reg_inc<224>();
+    role_bar_sync<8, kBwdThreads>();
     persist_bwd_scalar<D>(P, smem + fsm_offset);
   } else {
     warpgroup_reg_dec<64>();
+    role_bar_sync<8, kBwdThreads>();
     persist_bwd_contract<D>(P, smem);
   }
 }
