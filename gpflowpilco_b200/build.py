@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC,
 ]
-LINK_LIBS = ["-lcusolver", "-lcublas"]
+LINK_LIBS = ["-lcusolver", "-lcublas", "-ldl"]
 
 
 def _nvcc() -> str:

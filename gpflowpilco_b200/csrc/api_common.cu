@@ -56,6 +56,7 @@ int gpp_profile_last_ms(float* ms) {
 }
 
 int gpp_microbench_fp64(int blocks, int threads, int iters, double* sink, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(sink && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0, GPP_ERR_BAD_SHAPE, "gpp_microbench_fp64: bad arguments");
   gpp::k_microbench_fp64<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
   gpp::count_launch();

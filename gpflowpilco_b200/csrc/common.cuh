@@ -1,6 +1,7 @@
 // Internal helpers shared by the translation units of libgpp_b200.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdarg>
@@ -32,6 +33,16 @@ inline void count_launch(unsigned long long n = 1) { g_launches.fetch_add(n, std
       return (code);                      \
     }                                     \
   } while (0)
+
+// NVTX range around every compute entry point of the C ABI (visible in Nsight Systems / ncu --nvtx as gpp_* ranges); header-only
+// nvtx3: a no-op costing one indirect call when no tool is attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define GPP_NVTX_RANGE() gpp::NvtxRange gpp_nvtx_range__(__func__)
 
 // profiling hooks (api_common.cu)
 void profile_begin(cudaStream_t stream);

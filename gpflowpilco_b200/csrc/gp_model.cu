@@ -114,6 +114,7 @@ int gpp_gp_model_create(gpp_gp_model** out, int L, int M, int D, const double* Z
                         const double* variance, const double* q_mu, const double* q_sqrt, int whiten,
                         const double* mean_const, const double* W, int P, const double* kuu_jitter,
                         int model_uncertainty, void* stream_) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(out && Z && lengthscales && variance && q_mu && kuu_jitter, GPP_ERR_NULL, "gpp_gp_model_create: null argument");
   GPP_REQUIRE(L >= 1 && L <= GPP_MAX_L && M >= 1 && D >= 1, GPP_ERR_BAD_SHAPE, "gpp_gp_model_create: bad sizes L=%d M=%d D=%d", L, M, D);
   GPP_REQUIRE(D <= GPP_MAX_D, GPP_ERR_UNSUPPORTED, "gpp_gp_model_create: D=%d exceeds GPP_MAX_D=%d", D, GPP_MAX_D);
@@ -248,6 +249,7 @@ int gpp_gp_model_destroy(gpp_gp_model* m) {
 }
 
 int gpp_gp_model_weights(const gpp_gp_model* m, double* beta, double* C, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(m, GPP_ERR_NULL, "gpp_gp_model_weights: null model");
   if (beta) GPP_CUDA_OK(cudaMemcpyAsync(beta, m->beta, sizeof(double) * m->L * m->M, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (C) GPP_CUDA_OK(cudaMemcpyAsync(C, m->C, sizeof(double) * m->L * m->M * m->M, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

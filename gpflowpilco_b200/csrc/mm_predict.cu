@@ -154,6 +154,7 @@ size_t gpp_mm_gp_predict_workspace_bytes(const gpp_gp_model* model, int N) {
 int gpp_mm_gp_predict_fwd(const gpp_gp_model* model, const double* m, const double* S, int N, double* f1, double* Sff,
                           double* cross, int full_output_cov, double jitter, void* workspace, size_t workspace_bytes,
                           int* info, void* stream_) {
+  GPP_NVTX_RANGE();
   return gpp::mm_predict_enqueue(model, m, S, N, f1, Sff, cross, full_output_cov, jitter, workspace, workspace_bytes, info,
                                  (cudaStream_t)stream_, nullptr);
 }

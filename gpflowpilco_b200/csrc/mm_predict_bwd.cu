@@ -136,6 +136,7 @@ size_t gpp_mm_gp_predict_bwd_workspace_bytes(const gpp_gp_model* model, int N) {
 int gpp_mm_gp_predict_bwd(const gpp_gp_model* model, const double* m, const double* S, int N, const double* f1_bar,
                           const double* Sff_bar, const double* cross_bar, int full_output_cov, double* m_bar, double* S_bar,
                           void* workspace, size_t workspace_bytes, int* info, void* stream_) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(model && m && S && m_bar && S_bar && workspace, GPP_ERR_NULL, "gpp_mm_gp_predict_bwd: null argument");
   GPP_REQUIRE(N >= 1, GPP_ERR_BAD_SHAPE, "gpp_mm_gp_predict_bwd: N=%d", N);
   gpp::BwdLayout lo = gpp::bwd_layout(model, N);

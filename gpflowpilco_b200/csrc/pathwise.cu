@@ -461,6 +461,7 @@ int gpp_pathwise_particles_per_cta(void) { return gpp::kPathP; }
 
 int gpp_pathwise_pack_basis(int L, int F, int M, int Mpad, int D, const double* omega, const double* phase, const double* Z,
                             const double* lengthscales, double* basis, double* zbasis, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(omega && phase && Z && lengthscales && basis && zbasis, GPP_ERR_NULL, "gpp_pathwise_pack_basis: null argument");
   GPP_REQUIRE(D >= 1 && D <= GPP_MAX_D && Mpad >= M, GPP_ERR_BAD_SHAPE, "gpp_pathwise_pack_basis: bad sizes");
   int BS = (D + 2) & ~1;
@@ -477,6 +478,7 @@ int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int 
                              int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
                              double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
                              const double* x0, double* loss, double* x_final, double* traj, void* stream) {
+  GPP_NVTX_RANGE();
   return pathwise_fwd_impl(S, ldS, H, L, F, Mpad, D, Dx, num_active, active_dims, basis, zbasis, w, v, amp, variance, inv_lengthscales,
                            mean_const, Mp, policy_Zs, policy_inv_lengthscales, policy_alpha, squash_scale, squash_shift, cost_target,
                            cost_W, x0, loss, x_final, traj, nullptr, stream);
@@ -488,6 +490,7 @@ int gpp_rollout_pathwise_fwd_grad(int S, int ldS, int H, int L, int F, int Mpad,
                                   int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
                                   double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
                                   const double* x0, double* loss, double* x_final, double* traj, double* jac, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(traj && jac, GPP_ERR_NULL, "gpp_rollout_pathwise_fwd_grad: traj and jac are required (they are what the backward reads)");
   return pathwise_fwd_impl(S, ldS, H, L, F, Mpad, D, Dx, num_active, active_dims, basis, zbasis, w, v, amp, variance, inv_lengthscales,
                            mean_const, Mp, policy_Zs, policy_inv_lengthscales, policy_alpha, squash_scale, squash_shift, cost_target,

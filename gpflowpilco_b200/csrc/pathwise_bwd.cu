@@ -193,6 +193,7 @@ int gpp_rollout_pathwise_bwd(int S, int ldS, int H, int L, int D, int Dx, int nu
                              const double* traj, const double* jac, const double* loss_bar,
                              double* Z_bar, double* lengthscales_bar, double* beta_bar, double* x0_bar,
                              void* workspace, size_t workspace_bytes, void* stream_) {
+  GPP_NVTX_RANGE();
   using namespace gpp;
   GPP_REQUIRE(policy_Z && policy_lengthscales && policy_beta && cost_target && cost_W && traj && jac && Z_bar && lengthscales_bar && beta_bar &&
                   workspace, GPP_ERR_NULL, "gpp_rollout_pathwise_bwd: null argument");

@@ -79,6 +79,7 @@ __global__ void k_phi_z(int M, int F, int D, const double* Z, const double* ell,
 extern "C" {
 
 int gpp_philox_raw(unsigned long long first_index, int count, unsigned stream_id, unsigned long long seed, unsigned* out, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(out && count >= 0, GPP_ERR_NULL, "gpp_philox_raw: bad arguments");
   if (count == 0) return GPP_OK;
   gpp::k_philox_raw<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(first_index, count, stream_id, seed, out);
@@ -88,6 +89,7 @@ int gpp_philox_raw(unsigned long long first_index, int count, unsigned stream_id
 }
 
 int gpp_pathwise_draw_basis(int L, int F, int D, unsigned long long seed, double* omega, double* phase, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(omega && phase, GPP_ERR_NULL, "gpp_pathwise_draw_basis: null argument");
   int n = L * F * D;
   gpp::k_draw_basis<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(L, F, D, seed, omega, phase);
@@ -98,6 +100,7 @@ int gpp_pathwise_draw_basis(int L, int F, int D, unsigned long long seed, double
 
 int gpp_pathwise_draw_x0(int S, unsigned long long first_particle, int Dx, const double* m0, const double* chol0,
                          unsigned long long seed, double* x0, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(m0 && chol0 && x0, GPP_ERR_NULL, "gpp_pathwise_draw_x0: null argument");
   GPP_REQUIRE(S >= 1 && Dx >= 1 && Dx <= 8, GPP_ERR_BAD_SHAPE, "gpp_pathwise_draw_x0: bad sizes");
   gpp::k_draw_x0<<<(S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, first_particle, Dx, m0, chol0, seed, x0);
@@ -114,6 +117,7 @@ size_t gpp_pathwise_generate_workspace_bytes(const gpp_gp_model* model, int ldS,
 int gpp_pathwise_generate(gpp_gp_model* model, int S, int ldS, unsigned long long first_particle, int F, int Mpad,
                           unsigned long long seed, const double* omega, const double* phase, double* w, double* v,
                           void* workspace, size_t workspace_bytes, void* stream_) {
+  GPP_NVTX_RANGE();
   using namespace gpp;
   GPP_REQUIRE(model && omega && phase && w && v && workspace, GPP_ERR_NULL, "gpp_pathwise_generate: null argument");
   const int L = model->L, M = model->M, D = model->D;

@@ -289,6 +289,7 @@ extern "C" {
 
 int gpp_ekxz(const double* mu, const double* cov, int N, int D, const double* Z, int M, const double* lengthscales,
              double variance, double* out, int* info, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(N >= 0 && M >= 0 && D >= 1, GPP_ERR_BAD_SHAPE, "gpp_ekxz: bad sizes N=%d M=%d D=%d", N, M, D);
   GPP_REQUIRE(N <= 65535, GPP_ERR_UNSUPPORTED, "gpp_ekxz: N=%d > 65535 inputs per call", N);
   if (N == 0 || M == 0) return GPP_OK;      // empty batch: nothing to do (the array pointers may be null)
@@ -304,6 +305,7 @@ int gpp_ekxz(const double* mu, const double* cov, int N, int D, const double* Z,
 int gpp_ekzxkxz(const double* mu, const double* cov, int N, int D, const double* Z1, int M1, const double* lengthscales1,
                 double variance1, const double* Z2, int M2, const double* lengthscales2, double variance2, double* out,
                 int* info, void* stream) {
+  GPP_NVTX_RANGE();
   if (!Z2) { Z2 = Z1; M2 = M1; }
   if (!lengthscales2) { lengthscales2 = lengthscales1; variance2 = variance1; }
   GPP_REQUIRE(N >= 0 && M1 >= 0 && M2 >= 0 && D >= 1, GPP_ERR_BAD_SHAPE, "gpp_ekzxkxz: bad sizes N=%d M1=%d M2=%d D=%d", N, M1, M2, D);

@@ -377,6 +377,7 @@ extern "C" {
 
 int gpp_policy_prepare(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance,
                        const double* q_mu, int whiten, double jitter, double* beta, int* info, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(Z && lengthscales && variance && q_mu && beta, GPP_ERR_NULL, "gpp_policy_prepare: null argument");
   GPP_REQUIRE(R >= 1 && Mp >= 1 && Dp >= 1, GPP_ERR_BAD_SHAPE, "gpp_policy_prepare: bad sizes R=%d Mp=%d Dp=%d", R, Mp, Dp);
   size_t smem = sizeof(double) * ((size_t)Mp * (Mp + 1) + Mp);
@@ -391,6 +392,7 @@ int gpp_policy_prepare(int R, int Mp, int Dp, const double* Z, const double* len
 int gpp_policy_prepare_bwd(int R, int Mp, int Dp, const double* Z, const double* lengthscales, const double* variance, const double* beta,
                            const double* beta_bar, int whiten, double jitter, double* Z_bar, double* lengthscales_bar, double* q_mu_bar,
                            void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(Z && lengthscales && variance && beta && beta_bar && Z_bar && lengthscales_bar && q_mu_bar, GPP_ERR_NULL,
               "gpp_policy_prepare_bwd: null argument");
   GPP_REQUIRE(R >= 1 && Mp >= 1 && Dp >= 1, GPP_ERR_BAD_SHAPE, "gpp_policy_prepare_bwd: bad sizes R=%d Mp=%d Dp=%d", R, Mp, Dp);
@@ -420,6 +422,7 @@ int gpp_rollout_mm_fwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
                        const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
                        double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final,
                        void* workspace, size_t workspace_bytes, int* info, void* stream) {
+  GPP_NVTX_RANGE();
   return rollout_mm_fwd_impl(dynamics, N, Dx, num_active, active_dims, R, Mp, policy_Z, policy_lengthscales, policy_variance, policy_beta,
                              squash_scale, squash_shift, cost_target, cost_W, H, m0, S0, loss, traj_m, traj_S, m_final, S_final, nullptr,
                              workspace, workspace_bytes, info, stream);
@@ -431,6 +434,7 @@ int gpp_rollout_mm_fwd_save(const gpp_gp_model* dynamics, int N, int Dx, int num
                             const double* cost_target, const double* cost_W, int H, const double* m0, const double* S0,
                             double* loss, double* traj_m, double* traj_S, double* m_final, double* S_final, double* saved,
                             void* workspace, size_t workspace_bytes, int* info, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(traj_m && traj_S && saved, GPP_ERR_NULL, "gpp_rollout_mm_fwd_save: traj_m, traj_S and saved are required (the backward reads them)");
   return rollout_mm_fwd_impl(dynamics, N, Dx, num_active, active_dims, R, Mp, policy_Z, policy_lengthscales, policy_variance, policy_beta,
                              squash_scale, squash_shift, cost_target, cost_W, H, m0, S0, loss, traj_m, traj_S, m_final, S_final, saved,

@@ -93,6 +93,7 @@ int gpp_rollout_mm_bwd(const gpp_gp_model* dynamics, int N, int Dx, int num_acti
                        const double* cost_target, const double* cost_W, int H, const double* traj_m, const double* traj_S,
                        const double* saved, const double* loss_bar, double* Z_bar, double* lengthscales_bar, double* beta_bar,
                        double* m0_bar, double* S0_bar, void* workspace, size_t workspace_bytes, int* info, void* stream_) {
+  GPP_NVTX_RANGE();
   using namespace gpp;
   GPP_REQUIRE(dynamics && policy_Z && policy_lengthscales && policy_variance && policy_beta && cost_target && cost_W && traj_m && traj_S &&
                   Z_bar && lengthscales_bar && beta_bar && workspace, GPP_ERR_NULL, "gpp_rollout_mm_bwd: null argument");

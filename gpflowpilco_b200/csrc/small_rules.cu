@@ -77,6 +77,7 @@ extern "C" {
 
 int gpp_mm_encoder(int N, int Dx, int num_active, const int* active_dims, const double* m, const double* S, double* me, double* See,
                    double* Cxe, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(m && S && me && See && Cxe, GPP_ERR_NULL, "gpp_mm_encoder: null argument");
   GPP_REQUIRE(N >= 0 && Dx >= 1 && num_active >= 0 && num_active <= 4 && num_active <= Dx && Dx + num_active <= GPP_SMALL_MAX,
               GPP_ERR_BAD_SHAPE, "gpp_mm_encoder: bad sizes Dx=%d active=%d", Dx, num_active);
@@ -95,6 +96,7 @@ int gpp_mm_encoder(int N, int Dx, int num_active, const int* active_dims, const 
 }
 
 int gpp_mm_squash(int N, const double* mf, const double* vf, double scale, double shift, double* mu, double* vu, double* gain, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(mf && vf && mu && vu && gain, GPP_ERR_NULL, "gpp_mm_squash: null argument");
   if (N <= 0) return GPP_OK;
   gpp::k_mm_squash<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(N, mf, vf, scale, shift, mu, vu, gain);
@@ -105,6 +107,7 @@ int gpp_mm_squash(int N, const double* mf, const double* vf, double scale, doubl
 
 int gpp_mm_squash_nd(int N, int A, const double* mf, const double* Sf, double scale, double shift, double* mu, double* Su, double* gain,
                      void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(mf && Sf && mu && Su && gain, GPP_ERR_NULL, "gpp_mm_squash_nd: null argument");
   GPP_REQUIRE(A >= 1 && A <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE, "gpp_mm_squash_nd: A=%d", A);
   if (N <= 0) return GPP_OK;
@@ -116,6 +119,7 @@ int gpp_mm_squash_nd(int N, int A, const double* mf, const double* Sf, double sc
 }
 
 int gpp_cost_gaussian(int N, int De, const double* me, const double* See, const double* target, const double* W, double* out, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(me && See && target && W && out, GPP_ERR_NULL, "gpp_cost_gaussian: null argument");
   GPP_REQUIRE(De >= 1 && De <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE, "gpp_cost_gaussian: De=%d", De);
   if (N <= 0) return GPP_OK;
@@ -126,6 +130,7 @@ int gpp_cost_gaussian(int N, int De, const double* me, const double* See, const 
 }
 
 int gpp_cost_samples(int N, int De, const double* e, const double* target, const double* W, double* out, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(e && target && W && out, GPP_ERR_NULL, "gpp_cost_samples: null argument");
   GPP_REQUIRE(De >= 1 && De <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE, "gpp_cost_samples: De=%d", De);
   if (N <= 0) return GPP_OK;
@@ -136,6 +141,7 @@ int gpp_cost_samples(int N, int De, const double* e, const double* target, const
 }
 
 int gpp_owens_t(int N, const double* h, const double* a, double* out, void* stream) {
+  GPP_NVTX_RANGE();
   GPP_REQUIRE(h && a && out, GPP_ERR_NULL, "gpp_owens_t: null argument");
   if (N <= 0) return GPP_OK;
   gpp::k_owens_t<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, h, a, out);
