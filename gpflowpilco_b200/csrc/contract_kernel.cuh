@@ -55,6 +55,11 @@ struct ContractCfg {
   static constexpr int TOTAL = PKBUF + 2 * PairPack<D>::SIZE;   // doubles
 };
 
+// Hand-over fence before bar.arrive: the producer/consumer pattern of the PTX ISA (st.shared; bar.arrive / bar.sync; ld.shared) relies on
+// the barrier's own ordering at CTA scope, so an acquire-release CTA fence is already more than required; __threadfence_block() is a
+// sequentially consistent fence (SASS MEMBAR.SC.CTA) and cost every consumer warp a round trip per input.
+__device__ __forceinline__ void handover_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
 // barrier ids are immediates (a register id would make ptxas reserve all 16 hardware barriers for the CTA)
 template <int ID>
 __device__ __forceinline__ void named_bar_sync_imm(int count) {
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
               *reinterpret_cast<double2*>(cb + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
           wgt[b * WBUF + T + tid] = bcol;
         }
-        __threadfence_block();
+        handover_fence();
         named_bar_arrive<BAR_FULL>(b, NT);
       }
     }
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
       double total = acc0 + acc1;
       if (!diag) total *= wgt[b * WBUF + row];
       red[b * DBUF + strip * 32 + lane] = total;
-      __threadfence_block();
+      handover_fence();
       named_bar_arrive<BAR_EMPTY>(b, NT);
     }
   }

@@ -26,7 +26,7 @@
 namespace gpp {
 
 constexpr int kPersistTile = 64;        // tile edge of the forward contraction
-constexpr int kFwdThreads = 512;        // 4 scalar + 4 producer + 8 consumer warps
+// forward CTA = 4 scalar + 4 producer + NC consumer warps; NC = 8 (512 threads, scalar warps at 224 registers) is what runs.
 
 struct PersistSaved {                   // the per-step block of gpp_rollout_mm_fwd_save (RolloutSaved offsets), or base == nullptr
   double* base;
@@ -148,9 +148,13 @@ __device__ void persist_fwd_scalar(const PersistFwdParams& P) {
 // ---------------------------------------------------------------------------------------------------------
 // forward: contraction warps (the k_contract pipeline with the item loop replaced by a static (step, tile, input) order)
 // ---------------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int NC_>
 struct PersistFwdCfg {
-  static constexpr int T = kPersistTile, NP = 4, NC = 8;                // producer warps 0,1: rows; 2,3: columns
+  static constexpr int T = kPersistTile, NP = 4, NC = NC_;              // producer warps 0,1: rows; 2,3: columns
+  static_assert(NC == 8 || NC == 16, "one or two consumer warps per 8-row strip");
+  static constexpr int HALVES = NC / 8, COLS = T / HALVES;             // columns of the tile a consumer warp covers
+  static constexpr int THREADS = kGroupThreads + 32 * (NP + NC);
+  static constexpr int REGS_SCALAR = NC == 8 ? 224 : 112, REGS_CONTRACT = NC == 8 ? 96 : 72;
   static constexpr int PT = 32 * NP, CT = 32 * NC, NTC = PT + CT;      // producer / consumer / contraction threads
   static constexpr int KS = ExtLayout<D>::KS, LDC = T + 8;
   static constexpr int REP = KS <= 2 ? 16 : 8;                          // replication of the exp table
@@ -171,9 +175,9 @@ struct PersistFwdCfg {
 };
 
 // both contraction roles: (re)load the C tile of a diagonal pair; `ctid` = index among the NTC contraction threads
-template <int D>
+template <int D, int NC>
 __device__ __forceinline__ void persist_load_tile(const PersistFwdParams& P, const gpp_slot& sl, double* Ct, int ctid) {
-  using F = PersistFwdCfg<D>;
+  using F = PersistFwdCfg<D, NC>;
   role_bar_sync<F::BAR_TILE, F::NTC>();
   const double* Ca = P.C + (size_t)sl.a * P.M * P.M;
   for (int idx = ctid; idx < F::T * F::T; idx += F::NTC) {
@@ -204,9 +208,9 @@ struct PersistSegments {
   __device__ int first_step(int seg) const { return cont ? 0 : seg / nmy; }
 };
 
-template <int D>
+template <int D, int NC>
 __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
-  using F = PersistFwdCfg<D>;
+  using F = PersistFwdCfg<D, NC>;
   using PP = PairPack<D>;
   constexpr int T = F::T, PT = F::PT, KS = F::KS, NTC = F::NTC;
   constexpr int NPV = (PP::SIZE + PT - 1) / PT;
@@ -228,7 +232,7 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
     const gpp_slot sl = P.slots[slot];
     const bool diag = sl.a == sl.b;
     if (slot != resident) {
-      if (diag) persist_load_tile<D>(P, sl, Ct, ptid);
+      if (diag) persist_load_tile<D, NC>(P, sl, Ct, ptid);
       resident = slot;
     }
     // this thread's centre and weight do not change over the segment
@@ -321,15 +325,15 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
         for (int q = 0; q < 4; q += 2)
           *reinterpret_cast<double2*>(dst + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
       wgt[b * F::WBUF + (is_row ? 0 : T) + idx] = bw;
-      __threadfence_block();
+      handover_fence();
       named_bar_arrive<F::BAR_FULL>(b, NTC);
     }
   }
 }
 
-template <int D>
+template <int D, int NC>
 __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
-  using F = PersistFwdCfg<D>;
+  using F = PersistFwdCfg<D, NC>;
   constexpr int T = F::T, KS = F::KS, LDC = F::LDC, NTC = F::NTC;
   double* Ct = smem + F::S_CT;
   double* colB = smem + F::S_COL;
@@ -337,10 +341,11 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
   double* wgt = smem + F::S_WGT;
   double* red = smem + F::S_RED;
   double* etab = smem + F::S_ETAB;
-  const int ctid = threadIdx.x - 2 * kGroupThreads, lane = ctid & 31, strip = ctid >> 5;
+  const int ctid = threadIdx.x - 2 * kGroupThreads, lane = ctid & 31, cwarp = ctid >> 5;
+  const int strip = cwarp & 7, col0 = (cwarp >> 3) * F::COLS;       // 8-row strip and first column of this warp's part of the tile
   const int row = strip * 8 + (lane >> 2);
   const int cpair = 2 * (lane & 3);
-  const double* ct = Ct + row * LDC + cpair;
+  const double* ct = Ct + row * LDC + col0 + cpair;
   const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (F::REP - 1)));
   const PersistSegments segs(P.nslots, P.r.N, P.H, P.debug);
   int resident = -1;
@@ -349,21 +354,21 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
     const gpp_slot sl = P.slots[slot];
     const bool diag = sl.a == sl.b;
     if (slot != resident) {
-      if (diag) persist_load_tile<D>(P, sl, Ct, F::PT + ctid);
+      if (diag) persist_load_tile<D, NC>(P, sl, Ct, F::PT + ctid);
       resident = slot;
     }
     for (int j = 0; j < segs.seg_items; ++j) {
       const int b = j & 1;
       named_bar_sync<F::BAR_FULL>(b, NTC);
       const double* ra = rowA + b * F::FBUF + strip * 32 + lane;
-      const double* cb = colB + b * F::FBUF + lane;
-      const double* wsrc = diag ? ct : wgt + b * F::WBUF + T + cpair;
+      const double* cb = colB + b * F::FBUF + col0 * 4 + lane;
+      const double* wsrc = diag ? ct : wgt + b * F::WBUF + T + col0 + cpair;
       double a[KS];
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) a[ks] = ra[ks * T * 4];
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 2
-      for (int cg = 0; cg < T / 8; cg += 2) {
+      for (int cg = 0; cg < F::COLS / 8; cg += 2) {
         double tt[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
@@ -380,16 +385,17 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
       }
       double total = acc0 + acc1;
       if (!diag) total *= wgt[b * F::WBUF + row];
-      red[(j & (F::NRED - 1)) * F::DBUF + strip * 32 + lane] = total;
-      __threadfence_block();
+      red[(j & (F::NRED - 1)) * F::DBUF + cwarp * 32 + lane] = total;
+      handover_fence();
       named_bar_arrive<F::BAR_EMPTY>(b, NTC);
     }
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(kFwdThreads, 1) k_rollout_fwd_persist(const PersistFwdParams P) {
-  using F = PersistFwdCfg<D>;
+template <int D, int NC>
+__global__ void __launch_bounds__(PersistFwdCfg<D, NC>::THREADS, 1) k_rollout_fwd_persist(const PersistFwdParams P) {
+  using F = PersistFwdCfg<D, NC>;
+  constexpr int kFwdThreads = F::THREADS;
   extern __shared__ __align__(16) double smem[];
   double* etab = smem + F::S_ETAB;
   for (int i = threadIdx.x; i < kContractTab * F::REP; i += kFwdThreads) etab[i] = kExp2Tab256[i / F::REP];
@@ -401,17 +407,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_rollout_fwd_persist(const Pe
   // (The barrier is repeated inside each branch: ptxas budgets registers for the code DOMINATED by a setmaxnreg, so each role must
   //  stay in the branch of its own setmaxnreg — behind a common merge point every role would be compiled for the launch count.)
   if (warp < 4) {
-    warpgroup_reg_inc<224>();
+    warpgroup_reg_inc<F::REGS_SCALAR>();
     role_bar_sync<8, kFwdThreads>();
     persist_fwd_scalar<D>(P);
   } else if (warp < 8) {
-    warpgroup_reg_dec<96>();
+    warpgroup_reg_dec<F::REGS_CONTRACT>();
     role_bar_sync<8, kFwdThreads>();
-    persist_fwd_producer<D>(P, smem);
+    persist_fwd_producer<D, NC>(P, smem);
   } else {
-    warpgroup_reg_dec<96>();
+    warpgroup_reg_dec<F::REGS_CONTRACT>();
     role_bar_sync<8, kFwdThreads>();
-    persist_fwd_consumer<D>(P, smem);
+    persist_fwd_consumer<D, NC>(P, smem);
   }
 }
 
@@ -610,14 +616,22 @@ PersistFwdLayout persist_fwd_layout(const gpp_gp_model* dyn, int N) {
   return lo;
 }
 
-template <int D>
-static int launch_fwd_persist(PersistFwdParams& P, int grid, cudaStream_t stream) {
-  const size_t smem = sizeof(double) * PersistFwdCfg<D>::S_TOTAL;
-  GPP_CUDA_OK(cudaFuncSetAttribute(k_rollout_fwd_persist<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int D, int NC>
+static int launch_fwd_persist_nc(PersistFwdParams& P, int grid, cudaStream_t stream) {
+  using F = PersistFwdCfg<D, NC>;
+  const size_t smem = sizeof(double) * F::S_TOTAL;
+  GPP_CUDA_OK(cudaFuncSetAttribute(k_rollout_fwd_persist<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&P};
-  GPP_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_rollout_fwd_persist<D>, dim3(grid), dim3(kFwdThreads), args, smem, stream));
+  GPP_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_rollout_fwd_persist<D, NC>, dim3(grid), dim3(F::THREADS), args, smem, stream));
   count_launch();
   return GPP_OK;
+}
+
+template <int D>
+static int launch_fwd_persist(PersistFwdParams& P, int grid, cudaStream_t stream) {
+  // NC = 16 (two consumer warps per strip, scalar group squeezed to 112 registers) was measured and is SLOWER (64 restarts: 110 vs 87 us
+  // per step): with half the columns per warp the per-input hand-over dominates.  It stays a template parameter, not an instantiation.
+  return launch_fwd_persist_nc<D, 8>(P, grid, stream);
 }
 
 int rollout_mm_fwd_persist(const gpp_gp_model* dyn, const RolloutMMParams& r, int H, const double* m0, const double* S0, double* m_final,
