@@ -213,7 +213,7 @@ def pathwise_section(dev, lib, pk, world):
   import torch
   import torch.distributed as dist
   from gpflowpilco_b200 import ops, synthetic
-  from gpflowpilco_b200.pathwise import draw_initial_states, generate_paths, rollout_pathwise
+  from gpflowpilco_b200.pathwise import draw_initial_states, generate_paths, rollout_pathwise, rollout_pathwise_chunked
   from gpflowpilco_b200.rollouts import PolicyParams
   args = ARGS
   rank = int(os.environ.get("RANK", "0"))
@@ -276,18 +276,9 @@ def pathwise_section(dev, lib, pk, world):
       dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    done, acc_loss = 0, torch.zeros((), dtype=torch.float64, device=dev)
-    while done < per_rank:
-      n = min(S, per_rank - done)
-      if n == S:
-        generate_paths(handle, n, F, seed=0, first_particle=first + done, out=paths)
-        pth = paths
-      else:
-        pth = generate_paths(handle, n, F, seed=0, first_particle=first + done)
-      xs = draw_initial_states(T(cfg["m0"][0]), T(cfg["S0"][0]), 0, first + done, n)
-      l_, _, _ = rollout_pathwise(pth, policy, xs, H, cfg["active_dims"], target, W, beta=beta)
-      acc_loss = acc_loss + l_.sum()
-      done += n
+    # chunks of one wave of CTAs; the generation of chunk k+1 overlaps the rollout of chunk k on a second stream (pathwise.py)
+    acc_loss = rollout_pathwise_chunked(handle, policy, T(cfg["m0"][0]), T(cfg["S0"][0]), per_rank, F, 0, H, cfg["active_dims"], target, W,
+                                        first_particle=first, particles_per_launch=S, beta=beta)
     if world > 1:
       dist.all_reduce(acc_loss)                       # the one collective of the pathwise closure: the summed cost
     torch.cuda.synchronize()
@@ -295,7 +286,7 @@ def pathwise_section(dev, lib, pk, world):
     if world > 1:
       dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
     full = {"particles": total_particles, "horizon": H, "seconds": float(tf_[0]), "particle_steps_per_s": total_particles * H / float(tf_[0]),
-            "mean_loss": float(acc_loss) / total_particles, "includes": "device-side path generation of every chunk + rollouts + cost all-reduce"}
+            "mean_loss": float(acc_loss) / total_particles, "includes": "device-side path generation of every chunk (overlapped with the previous chunk's rollout on a second stream) + rollouts + cost all-reduce"}
     if world > 1:
       # 1 -> N curve of this collective-bearing path: rank 0 repeats ITS share alone (the others wait at the barrier); one GPU needs
       # `world` such shares for the whole job, so efficiency = T(share, alone) / T(sharded job, all ranks + all-reduce)
@@ -304,14 +295,8 @@ def pathwise_section(dev, lib, pk, world):
       if rank == 0:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        done = 0
-        while done < per_rank:
-          n = min(S, per_rank - done)
-          pth = generate_paths(handle, n, F, seed=0, first_particle=done, out=paths) if n == S else generate_paths(handle, n, F, seed=0, first_particle=done)
-          pth = paths if n == S else pth
-          xs = draw_initial_states(T(cfg["m0"][0]), T(cfg["S0"][0]), 0, done, n)
-          l_, _, _ = rollout_pathwise(pth, policy, xs, H, cfg["active_dims"], target, W, beta=beta)
-          done += n
+        rollout_pathwise_chunked(handle, policy, T(cfg["m0"][0]), T(cfg["S0"][0]), per_rank, F, 0, H, cfg["active_dims"], target, W,
+                                 first_particle=0, particles_per_launch=S, beta=beta)
         torch.cuda.synchronize()
         alone = time.perf_counter() - t0
       dist.barrier()
@@ -699,6 +684,10 @@ def run_b200(args):
                      "kernel_share_of_step": kern_s / (total_s / args.steps),
                      "algorithmic": f"{FLOP_PER_ENTRY} flop/entry x {ENTRIES_PER_INPUT} entries/input x {N} inputs",
                      "peak_source": "in-run DFMA microbenchmark (gpp_microbench_fp64); MEASURED_PEAKS.json has no FP64 figure",
+                     "peak_nominal": 148 * 64 * 2 * 1.965e-3, "frac_of_nominal": achieved / (148 * 64 * 2 * 1.965e-3),
+                     "entries_evaluated_per_input": (E_OUT * (M_TRAIN // 128 + (1 if M_TRAIN % 128 else 0)) * ((M_TRAIN // 128 + (1 if M_TRAIN % 128 else 0)) + 1) // 2
+                                                     + E_OUT * (E_OUT - 1) // 2 * (M_TRAIN // 128 + (1 if M_TRAIN % 128 else 0)) ** 2) * 128 * 128,
+                     "entries_note": "algorithmic count (SURVEY 8d) = E(E+1)/2 M^2 = 1.0e7 per input; the kernel evaluates 128 x 128 tiles, upper tiles only for the E diagonal pairs",
                      "hbm_peak_gbs": pk.get("hbm_gbs"), "hbm_peak_source": peak_src},
         "e2e": {"value": world * N * args.steps / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": int(mu_h.numel() * 8 + cov_h.numel() * 8), "d2h_bytes_per_step": int(sum(o.numel() * 8 for o in out_h))},

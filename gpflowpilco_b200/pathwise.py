@@ -189,3 +189,53 @@ def rollout_pathwise_bwd(policy: PolicyParams, beta: torch.Tensor, traj: torch.T
                                           _ptr(cost_W), _ptr(traj), _ptr(jac), _ptr(loss_bar), _ptr(Zb), _ptr(eb), _ptr(bb), _ptr(x0b),
                                           _ptr(ws), ws.numel(), _stream()))
   return Zb, eb, bb, x0b
+
+
+def rollout_pathwise_chunked(handle, policy: PolicyParams, m0: torch.Tensor, S0: torch.Tensor, total_particles: int, num_bases: int, seed: int,
+                             horizon: int, active_dims: Sequence[int], cost_target: torch.Tensor, cost_W: torch.Tensor,
+                             first_particle: int = 0, particles_per_launch: Optional[int] = None, overlap: bool = True,
+                             beta: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """Sum of the particle losses of `total_particles` particles (global indices first_particle ...), processed in chunks of one launch
+  each: fresh function draws per chunk (upstream loops/pilco.py:281-284), initial states 1-to-1 with the draws (:300-303).
+  The weights of all particles would not fit (139 KB per particle at L=4, F=4096, M=256), so a chunk's paths are generated on the
+  device right before its rollout; with `overlap` the generation of chunk k+1 (Philox draws + the update-weight solve) runs on a
+  second stream while chunk k rolls out — two path buffers, events in both directions, no host synchronisation."""
+  lib = _lib.load()
+  S = particles_per_launch or lib.gpp_pathwise_particles_per_cta() * 148
+  dev = handle.device
+  if beta is None:
+    beta = policy.beta()
+  main = torch.cuda.current_stream(dev)
+  side = torch.cuda.Stream(dev) if overlap else main
+  chunks = [(first_particle + o, min(S, total_particles - o)) for o in range(0, total_particles, S)]
+  bufs = [None, None]
+  ev_gen = [torch.cuda.Event(), torch.cuda.Event()]
+  ev_roll = [None, None]
+  total = torch.zeros((), dtype=F64, device=dev)
+
+  def generate(k):
+    first, n = chunks[k]
+    b = k % 2
+    with torch.cuda.stream(side):
+      if ev_roll[b] is not None:
+        side.wait_event(ev_roll[b])                 # the rollout that read this buffer two chunks ago has finished
+      if n == S and bufs[b] is not None:
+        generate_paths(handle, n, num_bases, seed, first_particle=first, out=bufs[b])
+      else:
+        bufs[b] = generate_paths(handle, n, num_bases, seed, first_particle=first)
+      ev_gen[b].record(side)
+
+  side.wait_stream(main)
+  generate(0)
+  for k, (first, n) in enumerate(chunks):
+    if k + 1 < len(chunks):
+      generate(k + 1)
+    b = k % 2
+    main.wait_event(ev_gen[b])
+    x0 = draw_initial_states(m0, S0, seed, first, n)
+    loss, _, _ = rollout_pathwise(bufs[b], policy, x0, horizon, active_dims, cost_target, cost_W, beta=beta)
+    total = total + loss.sum()
+    ev_roll[b] = torch.cuda.Event()
+    ev_roll[b].record(main)
+  main.wait_stream(side)
+  return total

@@ -64,3 +64,30 @@ def test_pathwise_mean_loss_close_to_moment_matching():
                    squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
   mm = rollout_mm(cuda_handle(cfg["dynamics"]), P, _dev(cfg["m0"]), _dev(cfg["S0"]), H, cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]))
   assert abs(float(loss.mean()) - float(mm.loss[0])) < 0.05 * max(abs(float(mm.loss[0])), 1e-3) + 5.0 / np.sqrt(S) * float(loss.std())
+
+
+def test_chunked_rollout_with_overlapped_generation_matches_serial():
+  """rollout_pathwise_chunked (path generation of chunk k+1 on a second stream while chunk k rolls out) returns bit for bit what the
+  serial generate -> rollout loop returns: same Philox streams by global particle index, same chunking, same summation order."""
+  from gpflowpilco_b200.pathwise import draw_initial_states, generate_paths, rollout_pathwise, rollout_pathwise_chunked
+  from gpflowpilco_b200.rollouts import PolicyParams
+  from tests.helpers import cuda_handle
+  cfg = synthetic.config1_cartpole(M=32, Mp=8)
+  p = cfg["policy"]
+  handle = cuda_handle(cfg["dynamics"])
+  P = PolicyParams(_dev(p["Z"]), _dev(p["lengthscales"]), _dev(p["variance"]), _dev(p["q_mu"][:, 0][None]), whiten=True,
+                   squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  m0, S0 = _dev(cfg["m0"][0]), _dev(cfg["S0"][0])
+  total, per, F, H, seed, first = 1000, 256, 64, 3, 9, 12345
+  args = (H, cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]))
+  ref = torch.zeros((), dtype=DTYPE, device="cuda")
+  for o in range(0, total, per):
+    n = min(per, total - o)
+    paths = generate_paths(handle, n, F, seed, first_particle=first + o)
+    x0 = draw_initial_states(m0, S0, seed, first + o, n)
+    loss, _, _ = rollout_pathwise(paths, P, x0, *args)
+    ref = ref + loss.sum()
+  for overlap in (True, False):
+    got = rollout_pathwise_chunked(handle, P, m0, S0, total, F, seed, *args, first_particle=first, particles_per_launch=per, overlap=overlap)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref), (overlap, float(got), float(ref))
