@@ -17,6 +17,7 @@
 #include <cublas_v2.h>
 
 #include "mm_small.cuh"
+#include "mma_exp.cuh"
 #include "model.cuh"
 #include "philox.cuh"
 
@@ -146,10 +147,17 @@ struct PathwiseParams {
 template <int D, int P, int TF, int NS>
 struct PathwiseCfg {
   static constexpr int BS = (D + 1 + 1) & ~1;
-  static constexpr int STAGE_DOUBLES = TF * BS + TF * P;
+  // weight rows are padded by 2 doubles: in the tensor-core form of the phase (below) the lanes of a quad read 4 different feature rows
+  // at the same particle; a row stride of 2 (mod 8) doubles spreads a half-warp's 64-bit loads over all 32 banks
+  static constexpr int PS = P + 2;
+  static constexpr int STAGE_DOUBLES = TF * BS + TF * PS;
   static constexpr int NWARPS = P / 32 + 1;
+  static_assert((NS & (NS - 1)) == 0, "the 32-bit tile counter may wrap: stage = it % NS and parity = (it / NS) & 1 need a power-of-two NS");
+  // phases on the FP64 tensor path: [d, 1] (D + 1 <= 8 entries = 2 k-steps of mma.m8n8k4) times the basis tile; needs TF == 8
+  static constexpr bool MMA_PHASE = (D + 1 <= 8) && TF == 8;
+  static constexpr int DSTAGE = MMA_PHASE ? P * 8 : 0;            // per-particle inputs [P][8] = [d (D), 1, 0..] for the A fragments
   static constexpr size_t SMEM = sizeof(double) * NS * STAGE_DOUBLES + 2 * NS * sizeof(uint64_t) +
-                                 sizeof(double) * (64 * (GPP_SMALL_MAX + 1) + 8 * GPP_SMALL_MAX * GPP_SMALL_MAX);
+                                 sizeof(double) * (64 * (GPP_SMALL_MAX + 1) + 8 * GPP_SMALL_MAX * GPP_SMALL_MAX) + sizeof(double) * DSTAGE;
 };
 
 template <int D, int P, int TF, int NS, bool GRAD>
@@ -162,6 +170,7 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
   uint64_t* empty = full + NS;
   double* pol = reinterpret_cast<double*>(empty + NS);          // policy centres [Mp][De] + alpha [Mp]  (Mp <= 64)
   double* cst = pol + 64 * (GPP_SMALL_MAX + 1);                  // target, W, inv_ell, amp, var, mean
+  double* dstage = cst + 8 * GPP_SMALL_MAX * GPP_SMALL_MAX;      // [P][8] (tensor-core phase form only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s0 = blockIdx.x * P;
@@ -201,8 +210,9 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
     // ------------------------------------------------------------------ producer warp (one elected lane)
     if (lane == 0) {
       const int pcount = min(P, p.ldS - s0);        // particles this CTA really has columns for (last CTA of a launch)
+      constexpr int PS = CF::PS;
       const unsigned bytes = (unsigned)(sizeof(double) * (TF * BS + TF * pcount));
-      long it = 0;
+      unsigned it = 0;
       for (int t = 0; t < p.H; ++t)
         for (int l = 0; l < p.L; ++l)
           for (int tile = 0; tile < tiles_f + tiles_m; ++tile, ++it) {
@@ -218,13 +228,15 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
             bulk_g2s(sb, bsrc, (unsigned)(sizeof(double) * TF * BS), &full[st]);
 #pragma unroll 1
             for (int f = 0; f < TF; ++f)
-              bulk_g2s(sb + TF * BS + f * P, wsrc + (size_t)f * p.ldS, (unsigned)(sizeof(double) * pcount), &full[st]);
+              bulk_g2s(sb + TF * BS + f * PS, wsrc + (size_t)f * p.ldS, (unsigned)(sizeof(double) * pcount), &full[st]);
           }
     }
     return;
   }
 
   // -------------------------------------------------------------------- consumers: one particle per thread
+  constexpr int PS = CF::PS;
+  constexpr bool MMA = CF::MMA_PHASE && !GRAD;
   const int s = s0 + tid;
   const bool valid = s < p.S;
   const int Dx = p.Dx, De = p.De;
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
   for (int i = 0; i < Dx; ++i) x[i] = valid ? p.x0[(size_t)s * Dx + i] : 0.0;
   if (p.traj && valid)
     for (int i = 0; i < Dx; ++i) p.traj[(size_t)s * Dx + i] = x[i];
-  long it = 0;
+  unsigned it = 0;   // 32-bit: H * L * tiles stays far below 2^32 and keeps the stage / parity arithmetic to two ALU ops
   for (int t = 0; t < p.H; ++t) {
     // e = [sin, cos, inactive]; u = scale (Phi(policy mean) + shift); d = (e, u)
     double dd[D];
@@ -265,7 +277,65 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
 #pragma unroll
         for (int d = 0; d < D; ++d) { jw[d] = 0.0; jv[d] = 0.0; }
       }
-      for (int tile = 0; tile < tiles_f; ++tile, ++it) {
+      if (MMA) {
+        // Random-Fourier part on the FP64 tensor path.  The phase of (particle s, feature i) is the length-(D+1) inner product
+        // [d_s, 1] . [4 omega_i / (2 pi ell), 4 b_i / (2 pi)]: per warp and 8-feature tile that is a [32 x 8] . [8 x 8] product = 4 row
+        // groups x 2 k-steps of mma.sync.m8n8k4.f64 (SASS DMMA) instead of 8 x D three-register DFMAs and as many broadcast loads per
+        // thread.  DMMA gives lane (r, c) = (lane >> 2, lane & 3) the phases of particle 8 g + r at features 2 c, 2 c + 1: the lane
+        // then does the cosines and the weight FMAs for those 8 (particle, feature) pairs; the per-particle sums are put back
+        // together across the 4 lanes of a quad and handed to the particle's own thread at the end of the latent.
+        const int r = lane >> 2, c = lane & 3;
+        double afr[4][2];
+        if (l == 0) {                            // this step's inputs -> A fragments (same for every latent)
+          double* mine = dstage + (size_t)tid * 8;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) mine[d] = d < D ? dd[d] : (d == D ? 1.0 : 0.0);
+          __syncwarp();
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) afr[g][ks] = dstage[(size_t)(warp * 32 + 8 * g + r) * 8 + c + 4 * ks];
+        double acc[4][2];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[g][0] = acc[g][1] = 0.0;
+        for (int tile = 0; tile < tiles_f; ++tile, ++it) {
+          const int st = (int)(it % NS);
+          mbar_wait(&full[st], (unsigned)((it / NS) & 1));
+          const double* bs = stages + st * CF::STAGE_DOUBLES;
+          const double* ws = bs + TF * BS + warp * 32 + r;
+          // B fragment: lane (n, k) = (lane >> 2, lane & 3) holds entry k + 4 ks of feature n's basis row (rows are BS wide, zero padded)
+          const double b0 = bs[r * BS + c];
+          const double b1 = (c + 4 < BS) ? bs[r * BS + c + 4] : 0.0;
+          double q[8];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            q[2 * g] = 0.0; q[2 * g + 1] = 0.0;
+            dmma_m8n8k4(q[2 * g], q[2 * g + 1], afr[g][0], b0);
+            dmma_m8n8k4(q[2 * g], q[2 * g + 1], afr[g][1], b1);
+          }
+          cos_quarter_turns<8>(q);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            acc[g][0] = fma(ws[(2 * c) * PS + 8 * g], q[2 * g], acc[g][0]);
+            acc[g][1] = fma(ws[(2 * c + 1) * PS + 8 * g], q[2 * g + 1], acc[g][1]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        // particle 8 g + r: sum over the quad's 4 lanes (fixed order), then to the thread that owns the particle (lane 8 g + r)
+        double mine_sum = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          double v = acc[g][0] + acc[g][1];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          const double got = __shfl_sync(0xffffffffu, v, 4 * (lane & 7));
+          if ((lane >> 3) == g) mine_sum = got;
+        }
+        accw[0] = mine_sum;
+      }
+      for (int tile = 0; !MMA && tile < tiles_f; ++tile, ++it) {
         const int st = (int)(it % NS);
         mbar_wait(&full[st], (unsigned)((it / NS) & 1));
         const double* bs = stages + st * CF::STAGE_DOUBLES;
@@ -284,7 +354,7 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
             sincos_quarter_turns<4>(q, sn);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const double w = ws[(f0 + k) * P];
+              const double w = ws[(f0 + k) * PS];
               accw[k] = fma(w, q[k], accw[k]);
               sn[k] *= w;
             }
@@ -295,7 +365,7 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
           } else {
             cos_quarter_turns<4>(q);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) accw[k] = fma(ws[(f0 + k) * P], q[k], accw[k]);
+            for (int k = 0; k < 4; ++k) accw[k] = fma(ws[(f0 + k) * PS], q[k], accw[k]);
           }
         }
         __syncwarp();
@@ -325,7 +395,7 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
           if (GRAD) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              q[k] *= ws[(f0 + k) * P];
+              q[k] *= ws[(f0 + k) * PS];
               accv[k] += q[k];
             }
 #pragma unroll
@@ -334,7 +404,7 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
               for (int k = 0; k < 4; ++k) jv[d] = fma(q[k], bs[(f0 + k) * BS + d] - ds[d], jv[d]);
           } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) accv[k] = fma(ws[(f0 + k) * P], q[k], accv[k]);
+            for (int k = 0; k < 4; ++k) accv[k] = fma(ws[(f0 + k) * PS], q[k], accv[k]);
           }
         }
         __syncwarp();

@@ -257,6 +257,19 @@ template <int D>
 static int run_ekzxkxz(const double* mu, const double* cov, int N, const double* Z1, int M1, const double* ell1, double var1,
                        const double* Z2, int M2, const double* ell2, double var2, double* out, int* info,
                        cudaStream_t stream) {
+  // the per-call scratch (coefficient packs, column vectors: tens of MB) comes from the stream-ordered pool; with the default release
+  // threshold of 0 the pool hands everything back to the driver at every synchronisation and each call pays a real cudaMalloc
+  // (measured: 3.2 ms per call against a 1.7 ms kernel) — keep the pool's memory
+  static bool pool_configured = false;
+  if (!pool_configured) {
+    int dev = 0;
+    cudaMemPool_t pool;
+    GPP_CUDA_OK(cudaGetDevice(&dev));
+    GPP_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;
+    GPP_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    pool_configured = true;
+  }
   double* packs = nullptr;
   GPP_CUDA_OK(cudaMallocAsync(&packs, sizeof(double) * PairPack<D>::SIZE * (size_t)N, stream));
   k_pack_single<D><<<(N + 63) / 64, 64, 0, stream>>>(mu, cov, N, ell1, ell2, log(var1 * var2), packs, info);
