@@ -53,6 +53,14 @@ __device__ __forceinline__ double ll_load(const unsigned long long* slot, unsign
   }
 }
 
+// mbarrier wait with the same time-out policy as the global-memory spins (no printf here: these sit in the hot contraction roles)
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity) {
+  if (mbar_test(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test(bar, parity))
+    if (clock64() - t0 > kSpinLimit) asm volatile("trap;");
+}
+
 // raw halves of a tagged value, for readers that issue the loads early and test the tags later
 __device__ __forceinline__ void ll_load_raw(const unsigned long long* slot, unsigned long long& w0, unsigned long long& w1) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w0) : "l"(slot) : "memory");

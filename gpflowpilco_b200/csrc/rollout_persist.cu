@@ -159,7 +159,11 @@ struct PersistFwdCfg {
   static constexpr int KS = ExtLayout<D>::KS, LDC = T + 8;
   static constexpr int REP = KS <= 2 ? 16 : 8;                          // replication of the exp table
   static constexpr int FBUF = KS * T * 4, WBUF = 2 * T, DBUF = NC * 32, NRED = 4;
-  static constexpr int BAR_FULL = 1, BAR_EMPTY = 3, BAR_PROD = 5, BAR_TILE = 7;   // 6 is the scalar group's barrier
+  static constexpr int BAR_PROD = 5, BAR_TILE = 7;                      // named barriers; 6 is the scalar group's
+  // The vector buffers change hands through two pairs of mbarriers (full[b]: 4 producer warps arrive, empty[b]: NC consumer warps
+  // arrive) instead of counted named barriers: a bar.sync over producers + consumers also made every consumer warp wait for the
+  // SLOWEST consumer warp of the previous input before it could start the next one (ncu: a quarter of the consumers' samples sat at
+  // that barrier while the producers were idle too).  With mbarriers a consumer warp only waits for the producers.
   // shared memory (doubles)
   static constexpr int S_CT = 0;                                        // [T][LDC]        tile of C_a (diagonal pairs)
   static constexpr int S_COL = S_CT + T * LDC;                          // [2][KS][T][4]   extended column vectors B_j
@@ -170,7 +174,8 @@ struct PersistFwdCfg {
   static constexpr int S_PKBUF = S_ETAB + 256 * REP;                    // [2][PairPack<D>::SIZE]
   static constexpr int NSTAGE = 3;                                      // tagged words of the packs in flight (cp.async landing zone)
   static constexpr int S_STAGE = S_PKBUF + 2 * PairPack<D>::SIZE;       // [NSTAGE][PairPack<D>::SIZE][2] 64-bit words, 16-byte aligned
-  static constexpr int S_TOTAL = S_STAGE + NSTAGE * 2 * PairPack<D>::SIZE;
+  static constexpr int S_MBAR = S_STAGE + NSTAGE * 2 * PairPack<D>::SIZE;   // full[2], empty[2] (mbarriers of the vector buffers)
+  static constexpr int S_TOTAL = S_MBAR + 4;
   static_assert(S_STAGE % 2 == 0, "staging area must be 16-byte aligned");
 };
 
@@ -198,7 +203,8 @@ struct PersistSegments {
     const int G = gridDim.x, c = blockIdx.x;
     nmy = nslots > c ? (nslots - 1 - c) / G + 1 : 0;
     // Item j's pack needs the partial of item j - N (same rollout, previous step), and the pipeline publishes item j - 2 before it
-    // waits for pack j: continuous operation needs N >= 2.  A single rollout drains every step instead.
+    // waits for pack j (few rollouts; with many it publishes later in iteration j, persist_fwd_producer): continuous operation
+    // needs N >= 2.  A single rollout drains every step instead.
     cont = nmy == 1 && N >= 2 && !(debug & 1);
     nseg = cont ? 1 : H * nmy;
     seg_items = cont ? H * N : N;
@@ -226,6 +232,9 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
   const int N = P.r.N;
   const size_t pk_stride = (size_t)P.npairs * PP::SIZE;
   const PersistSegments segs(P.nslots, N, P.H, P.debug);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + F::S_MBAR);
+  uint64_t* empty = full + 2;
+  unsigned pe = 0;                                     // bit b: parity of the next phase of empty[b] (carried across segments)
   int resident = -1;
   for (int seg = 0; seg < segs.nseg; ++seg) {
     const int slot = segs.slot(seg), t0 = segs.first_step(seg);
@@ -249,84 +258,108 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
     // would hold a scoreboard slot across iterations and make every shared-memory read of the loop wait for the ~1 us L2 round trip
     // (measured: +0.2 us per item).  Speculative: the words may not have arrived yet; tags are tested when the item's turn comes.
     unsigned long long* stage = reinterpret_cast<unsigned long long*>(smem + F::S_STAGE);
-    auto issue = [&](int j) {
-      const unsigned long long* src = pk0 + 2 * (size_t)(j % N) * pk_stride;
-      unsigned long long* dst = stage + (size_t)(j % F::NSTAGE) * 2 * PP::SIZE;
+    // (rollout, step, landing slot) of items j, j - 2 and j + 2 are carried as counters: a division per use costs ~20 dependent
+    // instructions on the hand-over path
+    auto next_n = [&](int n) { return n + 1 == N ? 0 : n + 1; };
+    auto issue = [&](int n, int slot3) {
+      const unsigned long long* src = pk0 + 2 * (size_t)n * pk_stride;
+      unsigned long long* dst = stage + (size_t)slot3 * 2 * PP::SIZE;
 #pragma unroll
       for (int q = 0; q < NPV; ++q)
         if (ptid + q * PT < PP::SIZE) cp_async16(dst + 2 * (ptid + q * PT), src + 2 * (ptid + q * PT));
       cp_async_commit();
     };
     cp_async_wait<0>();                      // nothing of a previous segment is still landing
-    issue(0);
-    issue(1);                                // (an item index past the segment only fetches an existing pack a second time)
+    issue(0, 0);
+    issue(next_n(0), 1);                     // (an item index past the segment only fetches an existing pack a second time)
+    int cn = 0, ct = t0, cs = 0;             // item j:      rollout, step, landing slot
+    int rn = 0, rt = t0;                     // item j - 2:  rollout, step
+    int in2 = next_n(next_n(0));             // item j + 2:  rollout (its landing slot is (cs + 2) % 3)
+    // With many rollouts in flight the partial of item j - 2 is not urgent (its reader is the scalar stage of the NEXT step, N items
+    // away): its reduction stays off the path EMPTY -> pack -> vectors -> FULL that the consumers wait for, and the four producer
+    // warps take turns at it (ncu, before: one warp reduced ahead of the pack wait = 43 % of its time, with the other three idle at
+    // the producers' barrier).  With few rollouts the partial IS the critical path and is published first.
+    // Fixed order: over the consumer warps, then the lanes; tagged words, no fence (persist_common.cuh).
+    const bool urgent = !segs.cont || N < 16;
+    auto reduce_and_publish = [&](int item) {
+      if ((ptid >> 5) != (urgent ? 0 : (item & 3))) return;
+      const double* rp = red + (item & (F::NRED - 1)) * F::DBUF + lane;
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < F::NC; ++w) sum += rp[w * 32];
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        ll_store(out + 2 * (size_t)rn * P.nslots, sum, (unsigned)(rt + 1));
+        if (!(P.debug & 2)) hint_add(P.part_hint + rn);
+      }
+    };
     for (int j = 0; j < segs.seg_items + 2; ++j) {
       const int b = j & 1;
       if (j >= 2) {                          // consumers are done with item j-2: its vector buffers are free, its partial is complete
-        named_bar_sync<F::BAR_EMPTY>(b, NTC);
-        if (ptid < 32) {                     // fixed-order sum of the lane partials -> tagged words (no fence: persist_common.cuh)
-          const double* rp = red + ((j - 2) & (F::NRED - 1)) * F::DBUF + lane;
-          double s = 0.0;
+        mbar_wait_bounded(&empty[b], (pe >> b) & 1u);
+        pe ^= 1u << b;
+        if (urgent) reduce_and_publish(j - 2);
+      }
+      if (j < segs.seg_items) {
+        double* pk = pkbuf + b * PP::SIZE;
+        {
+          // every thread waits for ITS words only (they go to the pack buffer next; the barrier after that store is the only one needed)
+          const unsigned tag = (unsigned)(ct + 1);
+          cp_async_wait<1>();                // the group of item j has landed (item j + 1's may still be in flight)
+          const unsigned long long* mine = stage + (size_t)cs * 2 * PP::SIZE;
+          const unsigned long long* src = pk0 + 2 * (size_t)cn * pk_stride;
 #pragma unroll
-          for (int w = 0; w < F::NC; ++w) s += rp[w * 32];
-          s = warp_sum(s);
-          if (lane == 0) {
-            const int n = (j - 2) % N;
-            ll_store(out + 2 * (size_t)n * P.nslots, s, (unsigned)(t0 + (j - 2) / N + 1));
-            if (!(P.debug & 2)) hint_add(P.part_hint + n);
+          for (int q = 0; q < NPV; ++q) {
+            const int e = ptid + q * PT;
+            if (e < PP::SIZE) {
+              unsigned long long w0 = mine[2 * e], w1 = mine[2 * e + 1];
+              if (!ll_ready(w0, w1, tag)) pk[e] = ll_load(src + 2 * e, tag);   // not there yet: the rollout's scalar stage is still running
+              else pk[e] = ll_value(w0, w1);
+            }
           }
         }
-      }
-      if (j >= segs.seg_items) continue;
-      double* pk = pkbuf + b * PP::SIZE;
-      {
-        // every thread waits for ITS words only (they go to the pack buffer next; the barrier after that store is the only one needed)
-        const unsigned tag = (unsigned)(t0 + j / N + 1);
-        cp_async_wait<1>();                  // the group of item j has landed (item j + 1's may still be in flight)
-        const unsigned long long* mine = stage + (size_t)(j % F::NSTAGE) * 2 * PP::SIZE;
-        const unsigned long long* src = pk0 + 2 * (size_t)(j % N) * pk_stride;
+        named_bar_sync_imm<F::BAR_PROD>(PT);   // pack j visible to the producers; pack j-2 (same buffer) no longer read
+        issue(in2, cs == 0 ? 2 : cs - 1);      // (lands in the slot item j - 1 used; always committed so that the group count stays in step)
+        double ext[4 * KS], zc[D];
 #pragma unroll
-        for (int q = 0; q < NPV; ++q) {
-          const int e = ptid + q * PT;
-          if (e < PP::SIZE) {
-            unsigned long long w0 = mine[2 * e], w1 = mine[2 * e + 1];
-            if (!ll_ready(w0, w1, tag)) pk[e] = ll_load(src + 2 * e, tag);     // not there yet: the rollout's scalar stage is still running
-            else pk[e] = ll_value(w0, w1);
+        for (int d = 0; d < D; ++d) zc[d] = z[d] - pk[PP::MU + d];
+        if (is_row) {                          // A_i = [R^T z1' (D), c0 + z1'^T P1 z1', 1, 0..]
+#pragma unroll
+          for (int e = 0; e < D; ++e) {
+            double tt = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) tt = fma(zc[d], pk[PP::R + d * D + e], tt);
+            ext[e] = tt;
           }
+          ext[D] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
+          ext[D + 1] = 1.0;
+        } else {                               // B_j = [z2' (D), 1, z2'^T P2 z2', 0..]
+#pragma unroll
+          for (int d = 0; d < D; ++d) ext[d] = zc[d];
+          ext[D] = 1.0;
+          ext[D + 1] = packed_quad<D>(pk + PP::P2, zc);
         }
+#pragma unroll
+        for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
+        double* dst = (is_row ? rowA : colB) + b * F::FBUF + idx * 4;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int q = 0; q < 4; q += 2)
+            *reinterpret_cast<double2*>(dst + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
+        wgt[b * F::WBUF + (is_row ? 0 : T) + idx] = bw;
+        __syncwarp();                          // the warp's stores are ordered before lane 0's arrive (release at CTA scope)
+        if (lane == 0) mbar_arrive(&full[b]);
+        cn = next_n(cn);
+        if (cn == 0) ++ct;
+        cs = cs == 2 ? 0 : cs + 1;
+        in2 = next_n(in2);
       }
-      named_bar_sync_imm<F::BAR_PROD>(PT);   // pack j visible to the producers; pack j-2 (same buffer) no longer read
-      issue(j + 2);                          // (lands in the slot item j - 1 used; always committed so that the group count stays in step)
-      double ext[4 * KS], zc[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) zc[d] = z[d] - pk[PP::MU + d];
-      if (is_row) {                          // A_i = [R^T z1' (D), c0 + z1'^T P1 z1', 1, 0..]
-#pragma unroll
-        for (int e = 0; e < D; ++e) {
-          double tt = 0.0;
-#pragma unroll
-          for (int d = 0; d < D; ++d) tt = fma(zc[d], pk[PP::R + d * D + e], tt);
-          ext[e] = tt;
-        }
-        ext[D] = pk[PP::C0] + packed_quad<D>(pk + PP::P1, zc);
-        ext[D + 1] = 1.0;
-      } else {                               // B_j = [z2' (D), 1, z2'^T P2 z2', 0..]
-#pragma unroll
-        for (int d = 0; d < D; ++d) ext[d] = zc[d];
-        ext[D] = 1.0;
-        ext[D + 1] = packed_quad<D>(pk + PP::P2, zc);
+      if (j >= 2) {
+        if (!urgent) reduce_and_publish(j - 2);
+        rn = next_n(rn);
+        if (rn == 0) ++rt;
       }
-#pragma unroll
-      for (int e = D + 2; e < 4 * KS; ++e) ext[e] = 0.0;
-      double* dst = (is_row ? rowA : colB) + b * F::FBUF + idx * 4;
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-        for (int q = 0; q < 4; q += 2)
-          *reinterpret_cast<double2*>(dst + ks * T * 4 + q) = make_double2(ext[ks * 4 + q], ext[ks * 4 + q + 1]);
-      wgt[b * F::WBUF + (is_row ? 0 : T) + idx] = bw;
-      handover_fence();
-      named_bar_arrive<F::BAR_FULL>(b, NTC);
     }
   }
 }
@@ -348,6 +381,9 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
   const double* ct = Ct + row * LDC + col0 + cpair;
   const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (F::REP - 1)));
   const PersistSegments segs(P.nslots, P.r.N, P.H, P.debug);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + F::S_MBAR);
+  uint64_t* empty = full + 2;
+  unsigned pf = 0;                                     // bit b: parity of the next phase of full[b]
   int resident = -1;
   for (int seg = 0; seg < segs.nseg; ++seg) {
     const int slot = segs.slot(seg);
@@ -359,7 +395,8 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
     }
     for (int j = 0; j < segs.seg_items; ++j) {
       const int b = j & 1;
-      named_bar_sync<F::BAR_FULL>(b, NTC);
+      mbar_wait_bounded(&full[b], (pf >> b) & 1u);
+      pf ^= 1u << b;
       const double* ra = rowA + b * F::FBUF + strip * 32 + lane;
       const double* cb = colB + b * F::FBUF + col0 * 4 + lane;
       const double* wsrc = diag ? ct : wgt + b * F::WBUF + T + col0 + cpair;
@@ -386,8 +423,8 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
       double total = acc0 + acc1;
       if (!diag) total *= wgt[b * F::WBUF + row];
       red[(j & (F::NRED - 1)) * F::DBUF + cwarp * 32 + lane] = total;
-      handover_fence();
-      named_bar_arrive<F::BAR_EMPTY>(b, NTC);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[b]);
     }
   }
 }
@@ -399,6 +436,13 @@ __global__ void __launch_bounds__(PersistFwdCfg<D, NC>::THREADS, 1) k_rollout_fw
   extern __shared__ __align__(16) double smem[];
   double* etab = smem + F::S_ETAB;
   for (int i = threadIdx.x; i < kContractTab * F::REP; i += kFwdThreads) etab[i] = kExp2Tab256[i / F::REP];
+  if (threadIdx.x == 0) {
+    uint64_t* mb = reinterpret_cast<uint64_t*>(smem + F::S_MBAR);
+    mbar_init(mb + 0, F::NP);
+    mbar_init(mb + 1, F::NP);
+    mbar_init(mb + 2, F::NC);
+    mbar_init(mb + 3, F::NC);
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   // Register reallocation, then a CTA-wide barrier BEFORE any role starts: contraction warps of a CTA that owns no tile return at
