@@ -148,6 +148,8 @@ __device__ void persist_fwd_scalar(const PersistFwdParams& P) {
 // ---------------------------------------------------------------------------------------------------------
 // forward: contraction warps (the k_contract pipeline with the item loop replaced by a static (step, tile, input) order)
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kPersistFwdBuffers = 2;    // vector buffers between the producer and consumer warps (PersistFwdCfg::NBUF)
+
 template <int D, int NC_>
 struct PersistFwdCfg {
   static constexpr int T = kPersistTile, NP = 4, NC = NC_;              // producer warps 0,1: rows; 2,3: columns
@@ -159,6 +161,8 @@ struct PersistFwdCfg {
   static constexpr int KS = ExtLayout<D>::KS, LDC = T + 8;
   static constexpr int REP = KS <= 2 ? 16 : 8;                          // replication of the exp table
   static constexpr int FBUF = KS * T * 4, WBUF = 2 * T, DBUF = NC * 32, NRED = 4;
+  static constexpr int NBUF = kPersistFwdBuffers;                       // vector buffers in flight (3 measured slower than 2: 80 vs 78 us per step at 64 rollouts)
+  static_assert(NRED >= NBUF + 1, "lane partials: item j - NBUF is reduced while the consumers may already write item j");
   static constexpr int BAR_PROD = 5, BAR_TILE = 7;                      // named barriers; 6 is the scalar group's
   // The vector buffers change hands through two pairs of mbarriers (full[b]: 4 producer warps arrive, empty[b]: NC consumer warps
   // arrive) instead of counted named barriers: a bar.sync over producers + consumers also made every consumer warp wait for the
@@ -166,16 +170,16 @@ struct PersistFwdCfg {
   // that barrier while the producers were idle too).  With mbarriers a consumer warp only waits for the producers.
   // shared memory (doubles)
   static constexpr int S_CT = 0;                                        // [T][LDC]        tile of C_a (diagonal pairs)
-  static constexpr int S_COL = S_CT + T * LDC;                          // [2][KS][T][4]   extended column vectors B_j
-  static constexpr int S_ROW = S_COL + 2 * FBUF;                        // [2][KS][T][4]   extended row vectors A_i
-  static constexpr int S_WGT = S_ROW + 2 * FBUF;                        // [2][2][T]       beta of the rows / columns (off-diagonal pairs)
-  static constexpr int S_RED = S_WGT + 2 * WBUF;                        // [NRED][NC][32]  lane partials of the last NRED inputs
+  static constexpr int S_COL = S_CT + T * LDC;                          // [NBUF][KS][T][4] extended column vectors B_j
+  static constexpr int S_ROW = S_COL + NBUF * FBUF;                     // [NBUF][KS][T][4] extended row vectors A_i
+  static constexpr int S_WGT = S_ROW + NBUF * FBUF;                     // [NBUF][2][T]    beta of the rows / columns (off-diagonal pairs)
+  static constexpr int S_RED = S_WGT + NBUF * WBUF;                       // [NRED][NC][32]  lane partials of the last NRED inputs
   static constexpr int S_ETAB = S_RED + NRED * DBUF;                    // [256][REP]
-  static constexpr int S_PKBUF = S_ETAB + 256 * REP;                    // [2][PairPack<D>::SIZE]
+  static constexpr int S_PKBUF = S_ETAB + 256 * REP;                    // [NBUF][PairPack<D>::SIZE]
   static constexpr int NSTAGE = 3;                                      // tagged words of the packs in flight (cp.async landing zone)
-  static constexpr int S_STAGE = S_PKBUF + 2 * PairPack<D>::SIZE;       // [NSTAGE][PairPack<D>::SIZE][2] 64-bit words, 16-byte aligned
-  static constexpr int S_MBAR = S_STAGE + NSTAGE * 2 * PairPack<D>::SIZE;   // full[2], empty[2] (mbarriers of the vector buffers)
-  static constexpr int S_TOTAL = S_MBAR + 4;
+  static constexpr int S_STAGE = (S_PKBUF + NBUF * PairPack<D>::SIZE + 1) & ~1;     // [NSTAGE][PairPack<D>::SIZE][2] 64-bit words, 16-byte aligned
+  static constexpr int S_MBAR = S_STAGE + NSTAGE * 2 * PairPack<D>::SIZE;   // full[NBUF], empty[NBUF] (mbarriers of the vector buffers)
+  static constexpr int S_TOTAL = S_MBAR + 2 * NBUF;
   static_assert(S_STAGE % 2 == 0, "staging area must be 16-byte aligned");
 };
 
@@ -202,10 +206,10 @@ struct PersistSegments {
   __device__ PersistSegments(int nslots, int N, int H, int debug = 0) {
     const int G = gridDim.x, c = blockIdx.x;
     nmy = nslots > c ? (nslots - 1 - c) / G + 1 : 0;
-    // Item j's pack needs the partial of item j - N (same rollout, previous step), and the pipeline publishes item j - 2 before it
+    // Item j's pack needs the partial of item j - N (same rollout, previous step), and the pipeline publishes item j - NBUF before it
     // waits for pack j (few rollouts; with many it publishes later in iteration j, persist_fwd_producer): continuous operation
-    // needs N >= 2.  A single rollout drains every step instead.
-    cont = nmy == 1 && N >= 2 && !(debug & 1);
+    // needs N >= kPersistFwdBuffers.  Fewer rollouts drain every step instead.
+    cont = nmy == 1 && N >= kPersistFwdBuffers && !(debug & 1);
     nseg = cont ? 1 : H * nmy;
     seg_items = cont ? H * N : N;
     if (H == 0) nseg = 0;
@@ -233,7 +237,7 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
   const size_t pk_stride = (size_t)P.npairs * PP::SIZE;
   const PersistSegments segs(P.nslots, N, P.H, P.debug);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + F::S_MBAR);
-  uint64_t* empty = full + 2;
+  uint64_t* empty = full + F::NBUF;
   unsigned pe = 0;                                     // bit b: parity of the next phase of empty[b] (carried across segments)
   int resident = -1;
   for (int seg = 0; seg < segs.nseg; ++seg) {
@@ -273,16 +277,18 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
     issue(0, 0);
     issue(next_n(0), 1);                     // (an item index past the segment only fetches an existing pack a second time)
     int cn = 0, ct = t0, cs = 0;             // item j:      rollout, step, landing slot
-    int rn = 0, rt = t0;                     // item j - 2:  rollout, step
+    int rn = 0, rt = t0;                     // item j - NBUF:  rollout, step
+    int b = 0;                               // j % NBUF
     int in2 = next_n(next_n(0));             // item j + 2:  rollout (its landing slot is (cs + 2) % 3)
     // With many rollouts in flight the partial of item j - 2 is not urgent (its reader is the scalar stage of the NEXT step, N items
-    // away): its reduction stays off the path EMPTY -> pack -> vectors -> FULL that the consumers wait for, and the four producer
-    // warps take turns at it (ncu, before: one warp reduced ahead of the pack wait = 43 % of its time, with the other three idle at
-    // the producers' barrier).  With few rollouts the partial IS the critical path and is published first.
+    // away): its reduction stays off the path EMPTY -> pack -> vectors -> FULL that the consumers wait for, and the two COLUMN warps
+    // take turns at it — a column vector costs half the flops of a row vector (no R^T z), so those warps have the slack (ncu,
+    // before: warp 0 reduced ahead of the pack wait = 43 % of its time, with the other three idle at the producers' barrier).
+    // With few rollouts the partial IS the critical path and is published first.
     // Fixed order: over the consumer warps, then the lanes; tagged words, no fence (persist_common.cuh).
     const bool urgent = !segs.cont || N < 16;
     auto reduce_and_publish = [&](int item) {
-      if ((ptid >> 5) != (urgent ? 0 : (item & 3))) return;
+      if ((ptid >> 5) != 2 + (urgent ? 0 : (item & 1))) return;
       const double* rp = red + (item & (F::NRED - 1)) * F::DBUF + lane;
       double sum = 0.0;
 #pragma unroll
@@ -293,12 +299,11 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
         if (!(P.debug & 2)) hint_add(P.part_hint + rn);
       }
     };
-    for (int j = 0; j < segs.seg_items + 2; ++j) {
-      const int b = j & 1;
-      if (j >= 2) {                          // consumers are done with item j-2: its vector buffers are free, its partial is complete
+    for (int j = 0; j < segs.seg_items + F::NBUF; ++j) {
+      if (j >= F::NBUF) {                    // consumers are done with item j-NBUF: its vector buffers are free, its partial is complete
         mbar_wait_bounded(&empty[b], (pe >> b) & 1u);
         pe ^= 1u << b;
-        if (urgent) reduce_and_publish(j - 2);
+        if (urgent) reduce_and_publish(j - F::NBUF);
       }
       if (j < segs.seg_items) {
         double* pk = pkbuf + b * PP::SIZE;
@@ -318,7 +323,7 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
             }
           }
         }
-        named_bar_sync_imm<F::BAR_PROD>(PT);   // pack j visible to the producers; pack j-2 (same buffer) no longer read
+        named_bar_sync_imm<F::BAR_PROD>(PT);   // pack j visible to the producers; pack j-NBUF (same buffer) no longer read
         issue(in2, cs == 0 ? 2 : cs - 1);      // (lands in the slot item j - 1 used; always committed so that the group count stays in step)
         double ext[4 * KS], zc[D];
 #pragma unroll
@@ -355,11 +360,12 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
         cs = cs == 2 ? 0 : cs + 1;
         in2 = next_n(in2);
       }
-      if (j >= 2) {
-        if (!urgent) reduce_and_publish(j - 2);
+      if (j >= F::NBUF) {
+        if (!urgent) reduce_and_publish(j - F::NBUF);
         rn = next_n(rn);
         if (rn == 0) ++rt;
       }
+      b = b + 1 == F::NBUF ? 0 : b + 1;
     }
   }
 }
@@ -382,7 +388,7 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
   const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (F::REP - 1)));
   const PersistSegments segs(P.nslots, P.r.N, P.H, P.debug);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + F::S_MBAR);
-  uint64_t* empty = full + 2;
+  uint64_t* empty = full + F::NBUF;
   unsigned pf = 0;                                     // bit b: parity of the next phase of full[b]
   int resident = -1;
   for (int seg = 0; seg < segs.nseg; ++seg) {
@@ -393,8 +399,8 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
       if (diag) persist_load_tile<D, NC>(P, sl, Ct, F::PT + ctid);
       resident = slot;
     }
+    int b = 0;                               // j % NBUF
     for (int j = 0; j < segs.seg_items; ++j) {
-      const int b = j & 1;
       mbar_wait_bounded(&full[b], (pf >> b) & 1u);
       pf ^= 1u << b;
       const double* ra = rowA + b * F::FBUF + strip * 32 + lane;
@@ -425,6 +431,7 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
       red[(j & (F::NRED - 1)) * F::DBUF + cwarp * 32 + lane] = total;
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[b]);
+      b = b + 1 == F::NBUF ? 0 : b + 1;
     }
   }
 }
@@ -438,10 +445,10 @@ __global__ void __launch_bounds__(PersistFwdCfg<D, NC>::THREADS, 1) k_rollout_fw
   for (int i = threadIdx.x; i < kContractTab * F::REP; i += kFwdThreads) etab[i] = kExp2Tab256[i / F::REP];
   if (threadIdx.x == 0) {
     uint64_t* mb = reinterpret_cast<uint64_t*>(smem + F::S_MBAR);
-    mbar_init(mb + 0, F::NP);
-    mbar_init(mb + 1, F::NP);
-    mbar_init(mb + 2, F::NC);
-    mbar_init(mb + 3, F::NC);
+    for (int i = 0; i < F::NBUF; ++i) {
+      mbar_init(mb + i, F::NP);
+      mbar_init(mb + F::NBUF + i, F::NC);
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
