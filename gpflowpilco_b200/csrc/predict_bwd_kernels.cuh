@@ -98,7 +98,8 @@ __device__ void contract_grad_item(double* __restrict__ smem, const int tid, con
   } else {
     const double wgt = grad_ld<PERSIST>(omega + ((size_t)n * L + a) * L + b) + grad_ld<PERSIST>(omega + ((size_t)n * L + b) * L + a);
     if (wgt == 0.0) return;
-    if (PERSIST) grad_sync<PERSIST>();         // the previous item's readers of this scratch are done
+    // (persistent caller: every thread passed the ticket barrier of persist_bwd_contract after it finished the previous item, so the
+    //  previous item's readers of this scratch are done)
     for (int t = tid; t < PP::SIZE; t += kGradThreads) pk[t] = grad_ld<PERSIST>(packs + ((size_t)n * L * L + p) * PP::SIZE + t);
   }
   if (fill_table)
