@@ -61,6 +61,13 @@ def _slice(k: SquaredExponential, mu, cov, Z=None):
   return mu[..., idx], cov[..., idx, :][..., :, idx], (None if Z is None else Z[..., idx])
 
 
+def _on_separate_dims(k1: SquaredExponential, k2: SquaredExponential) -> bool:
+  """gpflow.kernels.Kernel.on_separate_dims: both kernels name their active dimensions and share none"""
+  if k1.active_dims is None or k2.active_dims is None:
+    return False
+  return not (set(k1.active_dims) & set(k2.active_dims))
+
+
 def _Z(z):
   return z.Z if isinstance(z, InducingPoints) else z
 
@@ -72,6 +79,13 @@ def _single(p, k1, z1, k2=None, z2=None):
   if k2 is None:
     m, S, Z = _slice(k1, mu, cov, _Z(z1))
     return ops.ekxz(m, S, Z, k1.ell(m.shape[-1]).to(m.device), float(k1.variance))
+  if _on_separate_dims(k1, k2):
+    # upstream :85-94: no joint expectation is required when the two kernels read disjoint state dimensions AND those dimensions
+    # are independent under p (DiagonalGaussian): E[k1(Z1,x) k2(x,Z2)] = E[k1(Z1,x)] E[k2(x,Z2)]
+    if isinstance(p, DiagonalGaussian):
+      return _single(p, k1, z1)[:, :, None] * _single(p, k2, z2)[:, None, :]
+    raise NotImplementedError("The expectation over two kernels only has an analytical implementation if both kernels "
+                              "have the same active features.")
   if (k1.active_dims or None) != (k2.active_dims or None):
     raise NotImplementedError("The expectation over two kernels only has an analytical implementation if both kernels "
                               "have the same active features.")            # upstream :91-94

@@ -107,6 +107,40 @@ def test_kernel_expectation_signatures():
   scaled_close(kernel_expectation(p, (mk, mz), (mk, mz)), ps.eKuffu_list(mu, cov, ks, Zs), 1e-11, "eKuffu list")
 
 
+def test_kernel_expectation_separate_dims_shortcut():
+  """upstream _E (kernel_expectation.py:85-94): kernels on disjoint active dims under a DiagonalGaussian factorise into two Psi1
+  blocks; under a full Gaussian the case is refused.  Checked against the oracle's Psi1 outer product and, independently, against
+  the JOINT Psi2 kernel with the inactive dimensions switched off by lengthscales of 1e8."""
+  from gpflowpilco_b200 import models as M
+  from gpflowpilco_b200.utils.kernel_expectation import DiagonalGaussian, Gaussian, kernel_expectation
+  g = torch.Generator().manual_seed(7)
+  D, N, M1, M2 = 4, 3, 9, 7
+  A, B = (0, 1), (2, 3)
+  mu = torch.randn(N, D, dtype=DTYPE, generator=g)
+  var = log_uniform([N, D], 0.05, 0.5, g)
+  ka, kb = ps.SEKernel(0.7, log_uniform([2], 0.5, 2.0, g)), ps.SEKernel(1.3, log_uniform([2], 0.5, 2.0, g))
+  Z1, Z2 = torch.randn(M1, D, dtype=DTYPE, generator=g), torch.randn(M2, D, dtype=DTYPE, generator=g)
+  fa = M.SquaredExponential(_dev(ka.variance), _dev(ka.lengthscales), active_dims=A)
+  fb = M.SquaredExponential(_dev(kb.variance), _dev(kb.lengthscales), active_dims=B)
+  p = DiagonalGaussian(_dev(mu), _dev(var))
+  got = kernel_expectation(p, (fa, M.InducingPoints(_dev(Z1))), (fb, M.InducingPoints(_dev(Z2))))
+  assert got.shape == (N, M1, M2)
+  cov = torch.diag_embed(var)
+  ia, ib = list(A), list(B)
+  e1 = ps.eKxz(mu[:, ia], cov[:, ia][:, :, ia], ka, Z1[:, ia])
+  e2 = ps.eKxz(mu[:, ib], cov[:, ib][:, :, ib], kb, Z2[:, ib])
+  scaled_close(got, e1[:, :, None] * e2[:, None, :], 1e-12, "separate dims vs oracle Psi1 x Psi1")
+  big = torch.full([2], 1e8, dtype=DTYPE)
+  ka_full = ps.SEKernel(ka.variance, torch.cat([ka.lengthscales, big]))
+  kb_full = ps.SEKernel(kb.variance, torch.cat([big, kb.lengthscales]))
+  joint = kernel_expectation(Gaussian(_dev(mu), _dev(cov)),
+                             (M.SquaredExponential(_dev(ka_full.variance), _dev(ka_full.lengthscales)), M.InducingPoints(_dev(Z1))),
+                             (M.SquaredExponential(_dev(kb_full.variance), _dev(kb_full.lengthscales)), M.InducingPoints(_dev(Z2))))
+  scaled_close(got, joint.cpu(), 1e-10, "separate dims vs the joint Psi2 kernel")
+  with pytest.raises(NotImplementedError):
+    kernel_expectation(Gaussian(_dev(mu), _dev(cov)), (fa, M.InducingPoints(_dev(Z1))), (fb, M.InducingPoints(_dev(Z2))))
+
+
 def test_mm_closure_fused_equals_rule_by_rule_and_oracle():
   from gpflowpilco_b200.components import GaussianObjective, TrigonometricEncoder
   from gpflowpilco_b200.loops import EpisodeSpec, GaussianStateDistribution, MomentMatchingPILCO

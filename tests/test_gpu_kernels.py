@@ -129,6 +129,27 @@ def test_mm_gp_predict_vs_reference_form(L, M, D, N, whiten, unc, P):
   assert float(off.abs().max()) == 0.0
 
 
+def test_mm_gp_predict_elementwise_worst_case():
+  """`scaled_close` measures against the LARGEST entry of a tensor.  Once, element by element, at the cart-pole shape (L=4, M=256,
+  D=6): every entry must agree with the oracle to 1e-6 of its OWN magnitude unless it is itself below 1e-9 of the tensor's scale
+  (entries of Sff that are differences of O(1) terms carry the absolute rounding of those terms)."""
+  params = synthetic.random_svgp(L=4, M=256, D=6, seed=5, whiten=True)
+  mu, cov, _ = _inputs(16, 6, 905)
+  ref = gm.mm_svgp_mo(mo.GaussianMoments(mu, cov, True), oracle_svgp(params), model_uncertainty=True, jitter=1e-8)
+  f1, Sff, cross = cuda_handle(params, True).predict(_dev(mu), _dev(cov), jitter=1e-8)
+  for name, got, want in (("f1", f1, ref.y.mean()), ("Sff", Sff, ref.y.covariance()), ("cross", cross, ref.cross[0])):
+    got = got.cpu()
+    scale = float(want.abs().max())
+    big = want.abs() > 1e-9 * scale
+    rel = ((got - want).abs() / want.abs().clamp_min(1e-300))[big]
+    small_abs = (got - want).abs()[~big]
+    worst_small = float(small_abs.max()) / scale if small_abs.numel() else 0.0
+    print(f"[elementwise] {name}: worst element-wise rel err {float(rel.max()):.2e} over {int(big.sum())} entries "
+          f"(smallest |entry| / scale {float(want.abs()[big].min()) / scale:.1e}); {int((~big).sum())} tiny entries, abs err / scale {worst_small:.1e}")
+    assert float(rel.max()) <= 1e-6, name
+    assert worst_small <= 1e-12, name
+
+
 def test_mm_gp_predict_gpr():
   """Exact GPR (upstream moment_matching/models.py:44-111, tests/test_moment_matching.py:87-136 sizes)."""
   from gpflowpilco_b200 import ops
