@@ -27,6 +27,7 @@ SIGNATURES = {
     "gpp_mm_encoder": (c_int, [c_int, c_int, c_int, POINTER(c_int), _P, _P, _P, _P, _P, _P]),
     "gpp_mm_squash": (c_int, [c_int, _P, _P, c_double, c_double, _P, _P, _P, _P]),
     "gpp_mm_squash_nd": (c_int, [c_int, c_int, _P, _P, c_double, c_double, _P, _P, _P, _P]),
+    "gpp_mm_squash_nd_bwd": (c_int, [c_int, c_int, _P, _P, c_double, c_double, _P, _P, _P, _P, _P, _P]),
     "gpp_cost_gaussian": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "gpp_cost_samples": (c_int, [c_int, c_int, _P, _P, _P, _P, _P]),
     "gpp_owens_t": (c_int, [c_int, _P, _P, _P, _P]),

@@ -66,6 +66,53 @@ __global__ void k_mm_squash_nd(int N, int A, const double* __restrict__ mf, cons
   }
 }
 
+// Reverse mode of k_mm_squash_nd, one thread per state.  No bivariate probability is needed: with Phi2 the BVN distribution function
+//   d Phi2(h, k; r) / dh = phi(h) Phi((k - r h) / sqrt(1 - r^2)),     d Phi2 / dr = phi2(h, k; r)  (the bivariate density),
+// applied to the four corners of the box [-9, h_i] x [-9, h_j] the forward integrates over.
+__device__ __forceinline__ double bvn_pdf(double h, double k, double r) {
+  const double om = (1.0 - r) * (1.0 + r);
+  return 0.15915494309189533577 * rsqrt(om) * exp(-0.5 * (h * h - 2.0 * r * h * k + k * k) / om);
+}
+__device__ __forceinline__ double box_dh(double h, double kl, double ku, double r) {   // d/dh P(. < h, kl < . < ku)
+  const double is = rsqrt((1.0 - r) * (1.0 + r));
+  return 0.39894228040143267794 * exp(-0.5 * h * h) * (bvn_ndtr((ku - r * h) * is) - bvn_ndtr((kl - r * h) * is));
+}
+__global__ void k_mm_squash_nd_bwd(int N, int A, const double* __restrict__ mf, const double* __restrict__ Sf, double scale, double shift,
+                                   const double* __restrict__ mu_bar, const double* __restrict__ Su_bar,
+                                   const double* __restrict__ gain_bar, double* __restrict__ mf_bar, double* __restrict__ Sf_bar) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const double* S = Sf + (size_t)n * A * A;
+  double q[GPP_SMALL_MAX], h[GPP_SMALL_MAX], y1[GPP_SMALL_MAX], ph[GPP_SMALL_MAX], hb[GPP_SMALL_MAX], qb[GPP_SMALL_MAX];
+  for (int i = 0; i < A; ++i) {
+    q[i] = rsqrt(S[i * A + i] + 1.0);
+    h[i] = mf[(size_t)n * A + i] * q[i];
+    y1[i] = bvn_ndtr(h[i]);
+    ph[i] = 0.39894228040143267794 * exp(-0.5 * h[i] * h[i]);
+    const double mb = mu_bar ? mu_bar[(size_t)n * A + i] : 0.0, gb = gain_bar ? gain_bar[(size_t)n * A + i] : 0.0;
+    hb[i] = scale * ph[i] * (mb - gb * q[i] * h[i]);       // mu = scale (Phi(h) + shift), gain = scale q phi(h)
+    qb[i] = gb * scale * ph[i];
+  }
+  double* Sb = Sf_bar + (size_t)n * A * A;
+  const double s2 = scale * scale;
+  for (int i = 0; i < A; ++i)
+    for (int j = 0; j < A; ++j) {
+      const double g = Su_bar ? s2 * Su_bar[((size_t)n * A + i) * A + j] : 0.0;      // Su_ij = scale^2 (y2 - y1_i y1_j)
+      const double r = S[i * A + j] * q[i] * q[j];
+      hb[i] += g * (box_dh(h[i], -9.0, h[j], r) - y1[j] * ph[i]);
+      hb[j] += g * (box_dh(h[j], -9.0, h[i], r) - y1[i] * ph[j]);
+      const double rb = g * (bvn_pdf(h[i], h[j], r) - bvn_pdf(h[i], -9.0, r) - bvn_pdf(-9.0, h[j], r) + bvn_pdf(-9.0, -9.0, r));
+      Sb[i * A + j] = rb * q[i] * q[j];                    // rho = S_ij q_i q_j
+      qb[i] += rb * S[i * A + j] * q[j];
+      qb[j] += rb * S[i * A + j] * q[i];
+    }
+  for (int i = 0; i < A; ++i) {
+    mf_bar[(size_t)n * A + i] = hb[i] * q[i];             // h = m q
+    const double qbi = qb[i] + hb[i] * mf[(size_t)n * A + i];
+    Sb[i * A + i] += -0.5 * qbi * q[i] * q[i] * q[i];     // q = (1 + S_ii)^-1/2
+  }
+}
+
 __global__ void k_owens_t(int N, const double* h, const double* a, double* out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n < N) out[n] = owens_t<double>(h[n], a[n]);
@@ -113,6 +160,19 @@ int gpp_mm_squash_nd(int N, int A, const double* mf, const double* Sf, double sc
   if (N <= 0) return GPP_OK;
   const long long total = (long long)N * A * A;
   gpp::k_mm_squash_nd<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(N, A, mf, Sf, scale, shift, mu, Su, gain);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
+}
+
+int gpp_mm_squash_nd_bwd(int N, int A, const double* mf, const double* Sf, double scale, double shift, const double* mu_bar,
+                         const double* Su_bar, const double* gain_bar, double* mf_bar, double* Sf_bar, void* stream) {
+  GPP_NVTX_RANGE();
+  GPP_REQUIRE(mf && Sf && mf_bar && Sf_bar, GPP_ERR_NULL, "gpp_mm_squash_nd_bwd: null argument");
+  GPP_REQUIRE(A >= 1 && A <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE, "gpp_mm_squash_nd_bwd: A=%d", A);
+  if (N <= 0) return GPP_OK;
+  gpp::k_mm_squash_nd_bwd<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(N, A, mf, Sf, scale, shift, mu_bar, Su_bar, gain_bar, mf_bar,
+                                                                           Sf_bar);
   gpp::count_launch();
   GPP_CUDA_OK(cudaGetLastError());
   return GPP_OK;

@@ -113,6 +113,34 @@ def _mm_scale(x, bijector: Scale, **kwargs):
   return moment_matching(x, torch.mul, bijector.scale, **kwargs)
 
 
+class _SquashND(torch.autograd.Function):
+  """gpp_mm_squash_nd with its closed-form reverse mode (gpp_mm_squash_nd_bwd): upstream differentiates the multi-dimensional
+  NormalCDF rule through utils/bvn.py with the tape (optimizers.py:52-56)."""
+
+  @staticmethod
+  def forward(ctx, mf, Sf):
+    lib = _lib.load()
+    mf, Sf = _c(mf.detach()), _c(Sf.detach())
+    N, A = mf.shape
+    mu = torch.empty(N, A, dtype=F64, device=mf.device)
+    Su = torch.empty(N, A, A, dtype=F64, device=mf.device)
+    gain = torch.empty(N, A, dtype=F64, device=mf.device)
+    _lib.check(lib.gpp_mm_squash_nd(N, A, _ptr(mf), _ptr(Sf), 1.0, 0.0, _ptr(mu), _ptr(Su), _ptr(gain), _stream()))
+    ctx.save_for_backward(mf, Sf)
+    return mu, Su, gain
+
+  @staticmethod
+  def backward(ctx, mu_bar, Su_bar, gain_bar):
+    lib = _lib.load()
+    mf, Sf = ctx.saved_tensors
+    N, A = mf.shape
+    bars = [None if b is None else _c(b.to(F64)) for b in (mu_bar, Su_bar, gain_bar)]
+    mf_bar, Sf_bar = torch.empty_like(mf), torch.empty_like(Sf)
+    _lib.check(lib.gpp_mm_squash_nd_bwd(N, A, _ptr(mf), _ptr(Sf), 1.0, 0.0, *(None if b is None else _ptr(b) for b in bars),
+                                        _ptr(mf_bar), _ptr(Sf_bar), _stream()))
+    return mf_bar, Sf_bar
+
+
 @dispatcher.register(GaussianMoments, NormalCDF)
 def _mm_gauss_ndtr(x, _):
   """y = Phi(x): the 1-D owens_t branch (upstream bijectors.py:37-58) and the multi-dimensional branch with Genz's bivariate
@@ -128,11 +156,7 @@ def _mm_gauss_ndtr(x, _):
     return GaussianMatch(x=x, y=y, cross=(gain[:, None, None], True))
   mf, Sf = _c(x.mean()), _c(x.covariance())
   _dev_check(mf, Sf)
-  N, A = mf.shape
-  mu = torch.empty(N, A, dtype=F64, device=mf.device)
-  Su = torch.empty(N, A, A, dtype=F64, device=mf.device)
-  gain = torch.empty(N, A, dtype=F64, device=mf.device)
-  _lib.check(lib.gpp_mm_squash_nd(N, A, _ptr(mf), _ptr(Sf), 1.0, 0.0, _ptr(mu), _ptr(Su), _ptr(gain), _stream()))
+  mu, Su, gain = _SquashND.apply(mf, Sf)
   return GaussianMatch(x=x, y=GaussianMoments(moments=(mu, Su), centered=True), cross=(torch.diag_embed(gain), True))
 
 

@@ -114,6 +114,11 @@ int gpp_mm_squash(int N, const double* mf, const double* vf, double scale, doubl
                   void* stream);
 int gpp_mm_squash_nd(int N, int A, const double* mf, const double* Sf, double scale, double shift, double* mu, double* Su, double* gain,
                      void* stream);
+/* reverse mode of gpp_mm_squash_nd (upstream differentiates bijectors.py:59-63 through utils/bvn.py with the tape): adjoints of
+ * (mu, Su, gain) -> adjoints of (mf, Sf), every entry of Sf treated as an independent variable like the forward reads it; any of the
+ * three incoming adjoints may be NULL (= zero).  Closed form: Phi2's partial derivatives are phi * Phi and the bivariate density. */
+int gpp_mm_squash_nd_bwd(int N, int A, const double* mf, const double* Sf, double scale, double shift, const double* mu_bar,
+                         const double* Su_bar, const double* gain_bar, double* mf_bar, double* Sf_bar, void* stream);
 int gpp_cost_gaussian(int N, int De, const double* me, const double* See, const double* target, const double* W, double* out,
                       void* stream);
 int gpp_cost_samples(int N, int De, const double* e, const double* target, const double* W, double* out, void* stream);

@@ -259,3 +259,41 @@ def test_sharded_closures_single_process_and_chunk_invariance():
                                                                  _dev(cfg["target"]), _dev(cfg["W"]), cfg["squash_scale"], cfg["squash_shift"])
   assert losses.shape == (R,) and (start, count) == (0, R) and grads[0].shape == Z.shape and torch.isfinite(grads[0]).all()
   assert float((losses[1:] - losses[0]).abs().max()) > 0     # different restarts, different losses
+
+
+@pytest.mark.parametrize("A", [2, 3])
+def test_squash_nd_backward_against_finite_differences(A):
+  """Multi-dimensional NormalCDF rule (upstream bijectors.py:59-63 through utils/bvn.py): the closed-form reverse mode
+  (gpp_mm_squash_nd_bwd: phi * Phi and the bivariate density, no bivariate probability) against Richardson-extrapolated central
+  differences of the device forward, every entry of the covariance perturbed on its own as the forward reads it."""
+  from gpflowpilco_b200 import models as M
+  from gpflowpilco_b200.moment_matching import GaussianMoments, moment_matching
+  g = torch.Generator().manual_seed(40 + A)
+  N = 4
+  mf = 0.8 * torch.randn(N, A, dtype=DTYPE, generator=g)
+  Sf = generate_covariance(A, [N], 0.6, g)
+  w_mu, w_S, w_g = (torch.randn(*s, dtype=DTYPE, generator=g) for s in ((N, A), (N, A, A), (N, A)))
+
+  def value(m, S):
+    match = moment_matching(GaussianMoments(moments=(m, S), centered=True), M.NormalCDF())
+    gain = torch.diagonal(match.cross[0], dim1=-2, dim2=-1)
+    return (match.y.mean() * _dev(w_mu)).sum() + (match.y.covariance() * _dev(w_S)).sum() + (gain * _dev(w_g)).sum()
+
+  m_d, S_d = _dev(mf).requires_grad_(True), _dev(Sf).requires_grad_(True)
+  gm_, gS_ = torch.autograd.grad(value(m_d, S_d), (m_d, S_d))
+
+  def fd(which, index, h):
+    out = []
+    for sgn in (+1, -1):
+      m, S = mf.clone(), Sf.clone()
+      (m if which == 0 else S)[index] += sgn * h
+      out.append(float(value(_dev(m), _dev(S))))
+    return (out[0] - out[1]) / (2 * h)
+
+  def richardson(which, index):
+    return (4 * fd(which, index, 5e-4) - fd(which, index, 1e-3)) / 3
+
+  fm = torch.tensor([[richardson(0, (n, i)) for i in range(A)] for n in range(N)], dtype=DTYPE)
+  fS = torch.tensor([[[richardson(1, (n, i, j)) for j in range(A)] for i in range(A)] for n in range(N)], dtype=DTYPE)
+  scaled_close(gm_, fm, 1e-7, "d/d mean")
+  scaled_close(gS_, fS, 1e-7, "d/d covariance")
