@@ -246,6 +246,23 @@ def pathwise_section(dev, lib, pk, world):
     if it:
       times.append(ms.value)
   pw_clocks = sampler.stop()
+  # mixed-precision variant (FP32 Fourier weights + FP32 cosine polynomial, gpp_rollout_pathwise_fwd_mixed): reported beside the
+  # FP64 figure, never instead of it
+  mx_times = []
+  paths.weights_f32()
+  sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+  sampler.start()
+  for it in range(3):
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    loss_mx, _, _ = rollout_pathwise(paths, policy, x0, H, cfg["active_dims"], target, W, beta=beta, mixed_precision=True)
+    ms = ctypes.c_float()
+    lib.gpp_profile_last_ms(ctypes.byref(ms))
+    if it:
+      mx_times.append(ms.value)
+  mx_clocks = sampler.stop()
+  mx_diff = float((loss_mx.mean() - loss.mean()).abs() / loss.mean().abs())
   lib.gpp_profile_enable(0)
   # gradient mode: forward with per-step Jacobians + reverse sweep (policy gradient), events around the pair
   from gpflowpilco_b200.autograd import rollout_pathwise_loss
@@ -306,12 +323,13 @@ def pathwise_section(dev, lib, pk, world):
         full["efficiency_note"] = "T(one rank's share of the particles, run alone on rank 0) / T(sharded job incl. all-reduce); 1-GPU job time = world x share"
     else:
       full["efficiency_vs_n1"] = 1.0
-  t = torch.tensor([float(np.mean(times)), float(np.mean(gtimes))], dtype=torch.float64, device=dev)
+  t = torch.tensor([float(np.mean(times)), float(np.mean(gtimes)), float(np.mean(mx_times))], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  sec, gsec = float(t[0]) * 1e-3, float(t[1]) * 1e-3
+  sec, gsec, msec = float(t[0]) * 1e-3, float(t[1]) * 1e-3, float(t[2]) * 1e-3
   L, M, D = 4, d["Z"].shape[1], 6
   bytes_per_pstep = 8 * L * (F + M) + 2 * 8 * 4
+  bytes_per_pstep_mx = 4 * L * F + 8 * L * M + 2 * 8 * 4
   flop_per_pstep = L * F * (2 * D + 2 + 20) + L * M * (2 * D + 2 + 20) + 30 * (2 * 5 + 22)
   psteps = S * H
   return {
@@ -323,9 +341,18 @@ def pathwise_section(dev, lib, pk, world):
       "full_config4": full,
       "with_policy_gradient": {"value": world * psteps / gsec, "unit": "particle_steps/s (gradient-mode forward + reverse sweep)",
                                "ms": 1e3 * gsec, "hbm_frac": bytes_per_pstep * psteps / gsec / 1e9 / pk.get("hbm_gbs")},
+      "mixed_precision": {
+          "value": world * psteps / msec, "unit": "particle_steps/s", "ms_per_launch": 1e3 * msec, "speedup_vs_fp64": sec / msec,
+          "what": "gpp_rollout_pathwise_fwd_mixed: FP32 Fourier weights and cosine polynomial; phases (DMMA), quarter-turn reduction, "
+                  "canonical-basis part, policy, cost and state update FP64; FP32 partial sums folded into FP64 every 32 feature tiles",
+          "tolerance": "one-step drift within 5e-6 of the FP64 kernel (tests/test_gpu_pathwise.py); NOT the headline dtype",
+          "mean_loss_rel_diff_vs_fp64": mx_diff, "clocks": mx_clocks,
+          "roofline": {"bound": "hbm", "achieved": bytes_per_pstep_mx * psteps / msec / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                       "frac": bytes_per_pstep_mx * psteps / msec / 1e9 / pk.get("hbm_gbs"),
+                       "algorithmic": f"{bytes_per_pstep_mx} B per particle-step (FP32 Fourier weights)"}},
       "roofline": {"bound": "hbm", "achieved": bytes_per_pstep * psteps / sec / 1e9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
-                   "frac": bytes_per_pstep * psteps / sec / 1e9 / pk.get("hbm_gbs"), "traffic": 0.99998 * bytes_per_pstep * psteps,
-                   "traffic_source": "ncu --set full at H=10 (profiles/r1b_pathwise_full.txt): dram read 105.575 GB vs 105.577 GB algorithmic; scaled to this launch",
+                   "frac": bytes_per_pstep * psteps / sec / 1e9 / pk.get("hbm_gbs"), "traffic": 1.0001 * bytes_per_pstep * psteps,
+                   "traffic_source": "ncu --set full at H=4 (profiles/r2f_pathwise_dmma_full.txt): dram read 42.236 GB vs 42.232 GB algorithmic; scaled to this launch",
                    "kernel": "k_pathwise_rollout",
                    "algorithmic": f"{bytes_per_pstep} B and {flop_per_pstep} flop per particle-step",
                    "fp64_achieved_tflops": flop_per_pstep * psteps / sec / 1e12},

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_ulonglong, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpp_b200.so")
@@ -50,6 +50,10 @@ SIGNATURES = {
     "gpp_rollout_pathwise_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
                                          _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
                                          _P, _P, _P, _P, _P]),
+    "gpp_rollout_pathwise_fwd_mixed": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
+                                               _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
+                                               _P, _P, _P, _P, _P]),
+    "gpp_pathwise_weights_f32": (c_int, [c_longlong, _P, _P, _P]),
     "gpp_rollout_pathwise_fwd_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
                                               _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
                                               _P, _P, _P, _P, _P, _P]),

@@ -16,6 +16,8 @@
 //     round-to-nearest (no Cody-Waite), then a degree-6 polynomial in r^2 with sin/cos coefficients selected by quadrant.
 #include <cublas_v2.h>
 
+#include <algorithm>
+
 #include "mm_small.cuh"
 #include "mma_exp.cuh"
 #include "model.cuh"
@@ -62,6 +64,31 @@ __device__ __forceinline__ void cos_quarter_turns(double (&q)[K]) {
   }
 }
 
+// Mixed-precision variant (gpp_rollout_pathwise_fwd_mixed).  ONE FP64 add reduces the phase: q + 1.5 * 2^22 has an ulp of 2^-30, so the low
+// 32 bits of its mantissa are round(q * 2^30) mod 2^32 — the phase modulo 4 quarter turns (one full turn) as a 32-bit fixed-point
+// number, the wrap-around of integer arithmetic doing the modulo (|q| < 2^21; resolution 1e-9 quarter turns).  Quadrant folding is
+// integer work (r = phase - 2 round(phase / 2) in [-1, 1), sign = parity of the rounding), then an int -> float conversion and an
+// FP32 polynomial on the FMA pipe: degree 4 in z = r^2, least-squares Chebyshev fit of sqrt(2) cos(pi/4 sqrt z) on [0, 1] (fit
+// error 7e-11), and the same double-angle step as the FP64 kernel; abs. error of the cosine <= 3.3e-7.  (A double -> float
+// conversion of an FP64-reduced r instead costs a quarter-rate F2F per value: measured 0.54 of the halved HBM stream.)
+template <int K>
+__device__ __forceinline__ void cos_quarter_turns_f32(const double (&q)[K], float (&c)[K]) {
+  const double MAGIC30 = 6291456.0;            // 1.5 * 2^22
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const unsigned u = (unsigned)lo_int(q[k] + MAGIC30) + 0x40000000u;        // bit 31: parity of round(phase / 2)
+    const int rfix = (int)(u & 0x7fffffffu) - 0x40000000;                     // r * 2^30, r in [-1, 1)
+    const float r = (float)rfix * 9.313225746154785e-10f;
+    const float z = r * r;
+    float p = fmaf(z, 4.991897185391281e-06f, -0.0004609467869158834f);
+    p = fmaf(p, z, 0.022421400994062424f);
+    p = fmaf(p, z, -0.4361790120601654f);
+    p = fmaf(p, z, 1.4142135381698608f);
+    const float v = fmaf(p, p, -1.0f);
+    c[k] = __int_as_float(__float_as_int(v) ^ (int)(u & 0x80000000u));
+  }
+}
+
 // cos and sin of pi/2 * q in lock-step (gradient mode): sin(pi/2 r) = 2 sin(pi/4 r) cos(pi/4 r) = P(z) * (r * Qs(z)),
 // Qs(z) = sqrt(2) sin(pi/4 sqrt z) / sqrt z  (degree 6; abs. error <= 5e-16).  19 FP64 ops for the pair.
 static __constant__ double kSinH[8] = {0x1.1c5831add62e4p+0, -0x1.d3ba5c1c5f465p-4, 0x1.cda106381dcb8p-9, -0x1.b1e9f34807cbep-15,
@@ -105,6 +132,7 @@ struct PathwiseParams {
   const double* basis;    // [L][F][BS]     4 omega/(2 pi ell) [D], 4 b/(2 pi)
   const double* zbasis;   // [L][Mpad][BS]  z/ell [D]
   const double* w;        // [L][F][ldS]
+  const float* w32;       // mixed-precision variant: the same weights in FP32 (w is not read then)
   const double* v;        // [L][Mpad][ldS]
   const double* amp;      // [L] sqrt(2 var/F)
   const double* var;      // [L]
@@ -128,6 +156,10 @@ struct PathwiseCfg {
   // weight rows are padded by 2 doubles: in the tensor-core form of the phase (below) the lanes of a quad read 4 different feature rows
   // at the same particle; a row stride of 2 (mod 8) doubles spreads a half-warp's 64-bit loads over all 32 banks
   static constexpr int PS = P + 2;
+  // mixed-precision variant: FP32 weight rows, padded by 4 floats (row stride = 4 mod 16 words: the 32 lanes (r, c) of a warp read
+  // rows 2c (+1) at particles r and hit 32 different banks); 16-byte multiples for the bulk copies
+  static constexpr int PS32 = P + 4;
+  static_assert((PS32 * 4) % 16 == 0 && PS32 * 4 <= PS * 8, "FP32 rows fit in, and are aligned like, the FP64 rows' space");
   static constexpr int STAGE_DOUBLES = TF * BS + TF * PS;
   static constexpr int NWARPS = P / 32 + 1;
   static_assert((NS & (NS - 1)) == 0, "the 32-bit tile counter may wrap: stage = it % NS and parity = (it / NS) & 1 need a power-of-two NS");
@@ -138,8 +170,9 @@ struct PathwiseCfg {
                                  sizeof(double) * (64 * (GPP_SMALL_MAX + 1) + 8 * GPP_SMALL_MAX * GPP_SMALL_MAX) + sizeof(double) * DSTAGE;
 };
 
-template <int D, int P, int TF, int NS, bool GRAD>
+template <int D, int P, int TF, int NS, bool GRAD, bool W32 = false>
 __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p) {
+  static_assert(!W32 || (!GRAD && PathwiseCfg<D, P, TF, NS>::MMA_PHASE), "FP32 weights: forward only, tensor-core phase form");
   using CF = PathwiseCfg<D, P, TF, NS>;
   constexpr int BS = CF::BS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -185,28 +218,40 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
   const double* c_mean = c_amp + 16;
 
   if (warp == P / 32) {
-    // ------------------------------------------------------------------ producer warp (one elected lane)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ producer warp: lane 0 = basis tile, lanes 1..TF = weight rows
+    // (one elected lane issuing all TF + 1 bulk copies of a tile needs ~150 cycles per copy; that bounded the mixed-precision variant,
+    //  whose consumers are done with a tile sooner than 9 serial copies can be issued)
+    if (lane <= TF) {
       const int pcount = min(P, p.ldS - s0);        // particles this CTA really has columns for (last CTA of a launch)
       constexpr int PS = CF::PS;
-      const unsigned bytes = (unsigned)(sizeof(double) * (TF * BS + TF * pcount));
+      constexpr unsigned kIssuers = (1u << (TF + 1)) - 1u;
+      const unsigned bytes64 = (unsigned)(sizeof(double) * (TF * BS + TF * pcount));
+      const unsigned bytes32 = (unsigned)(sizeof(double) * TF * BS + sizeof(float) * TF * pcount);
+      const int f = lane - 1;                       // this lane's weight row of the tile
       unsigned it = 0;
       for (int t = 0; t < p.H; ++t)
         for (int l = 0; l < p.L; ++l)
           for (int tile = 0; tile < tiles_f + tiles_m; ++tile, ++it) {
             const int st = (int)(it % NS);
             const unsigned ph = (unsigned)((it / NS) & 1);
-            mbar_wait(&empty[st], ph ^ 1u);
+            mbar_wait(&empty[st], ph ^ 1u);         // every issuing lane sees the stage released itself
             double* sb = stages + st * CF::STAGE_DOUBLES;
-            mbar_expect_tx(&full[st], bytes);
             const bool rff = tile < tiles_f;
             const int row0 = (rff ? tile : tile - tiles_f) * TF;
-            const double* bsrc = rff ? p.basis + ((size_t)l * p.F + row0) * BS : p.zbasis + ((size_t)l * p.Mpad + row0) * BS;
-            const double* wsrc = rff ? p.w + ((size_t)l * p.F + row0) * p.ldS + s0 : p.v + ((size_t)l * p.Mpad + row0) * p.ldS + s0;
-            bulk_g2s(sb, bsrc, (unsigned)(sizeof(double) * TF * BS), &full[st]);
-#pragma unroll 1
-            for (int f = 0; f < TF; ++f)
-              bulk_g2s(sb + TF * BS + f * PS, wsrc + (size_t)f * p.ldS, (unsigned)(sizeof(double) * pcount), &full[st]);
+            if (lane == 0) {
+              mbar_expect_tx(&full[st], (W32 && rff) ? bytes32 : bytes64);
+              const double* bsrc = rff ? p.basis + ((size_t)l * p.F + row0) * BS : p.zbasis + ((size_t)l * p.Mpad + row0) * BS;
+              bulk_g2s(sb, bsrc, (unsigned)(sizeof(double) * TF * BS), &full[st]);
+            }
+            __syncwarp(kIssuers);                   // the expected byte count is registered before any row can complete
+            if (lane == 0) continue;
+            if (W32 && rff) {
+              const float* wsrc32 = p.w32 + ((size_t)l * p.F + row0 + f) * p.ldS + s0;
+              bulk_g2s(reinterpret_cast<float*>(sb + TF * BS) + f * CF::PS32, wsrc32, (unsigned)(sizeof(float) * pcount), &full[st]);
+            } else {
+              const double* wsrc = rff ? p.w + ((size_t)l * p.F + row0 + f) * p.ldS + s0 : p.v + ((size_t)l * p.Mpad + row0 + f) * p.ldS + s0;
+              bulk_g2s(sb + TF * BS + f * PS, wsrc, (unsigned)(sizeof(double) * pcount), &full[st]);
+            }
           }
     }
     return;
@@ -275,28 +320,58 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) afr[g][ks] = dstage[(size_t)(warp * 32 + 8 * g + r) * 8 + c + 4 * ks];
         double acc[4][2];
+        float accf[W32 ? 4 : 1][2];              // mixed precision: FP32 partial sums, folded into `acc` every 32 tiles
 #pragma unroll
         for (int g = 0; g < 4; ++g) acc[g][0] = acc[g][1] = 0.0;
-        for (int tile = 0; tile < tiles_f; ++tile, ++it) {
-          const int st = (int)(it % NS);
-          mbar_wait(&full[st], (unsigned)((it / NS) & 1));
+#pragma unroll
+        for (int g = 0; g < (W32 ? 4 : 1); ++g) accf[g][0] = accf[g][1] = 0.0f;
+        // phases of the 8 (particle, feature) pairs of this lane in tile `it_` (waits for the tile's stage)
+        auto phases = [&](unsigned it_, double (&qq)[8]) {
+          const int st = (int)(it_ % NS);
+          mbar_wait(&full[st], (unsigned)((it_ / NS) & 1));
           const double* bs = stages + st * CF::STAGE_DOUBLES;
-          const double* ws = bs + TF * BS + warp * 32 + r;
           // B fragment: lane (n, k) = (lane >> 2, lane & 3) holds entry k + 4 ks of feature n's basis row (rows are BS wide, zero padded)
           const double b0 = bs[r * BS + c];
           const double b1 = (c + 4 < BS) ? bs[r * BS + c + 4] : 0.0;
-          double q[8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            q[2 * g] = 0.0; q[2 * g + 1] = 0.0;
-            dmma_m8n8k4(q[2 * g], q[2 * g + 1], afr[g][0], b0);
-            dmma_m8n8k4(q[2 * g], q[2 * g + 1], afr[g][1], b1);
+            qq[2 * g] = 0.0; qq[2 * g + 1] = 0.0;
+            dmma_m8n8k4(qq[2 * g], qq[2 * g + 1], afr[g][0], b0);
+            dmma_m8n8k4(qq[2 * g], qq[2 * g + 1], afr[g][1], b1);
           }
-          cos_quarter_turns<8>(q);
+        };
+        // (Issuing the next tile's DMMAs ahead of this tile's FP32 work — software pipelining by one tile inside the warp — was
+        //  measured SLOWER for the mixed variant, 7.96 vs 5.90 ms at H = 4: the second set of phases costs 16 registers at the
+        //  96-register cap of a 544-thread CTA.)
+        for (int tile = 0; tile < tiles_f; ++tile, ++it) {
+          const int st = (int)(it % NS);
+          double q[8];
+          phases(it, q);
+          if constexpr (W32) {
+            const float* wsf = reinterpret_cast<const float*>(stages + st * CF::STAGE_DOUBLES + TF * BS) + warp * 32 + r;
+            float cf[8];
+            cos_quarter_turns_f32<8>(q, cf);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            acc[g][0] = fma(ws[(2 * c) * PS + 8 * g], q[2 * g], acc[g][0]);
-            acc[g][1] = fma(ws[(2 * c + 1) * PS + 8 * g], q[2 * g + 1], acc[g][1]);
+            for (int g = 0; g < 4; ++g) {
+              accf[g][0] = fmaf(wsf[(2 * c) * CF::PS32 + 8 * g], cf[2 * g], accf[g][0]);
+              accf[g][1] = fmaf(wsf[(2 * c + 1) * CF::PS32 + 8 * g], cf[2 * g + 1], accf[g][1]);
+            }
+            if ((tile & 31) == 31 || tile + 1 == tiles_f) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                acc[g][0] += (double)accf[g][0];
+                acc[g][1] += (double)accf[g][1];
+                accf[g][0] = accf[g][1] = 0.0f;
+              }
+            }
+          } else {
+            const double* ws = stages + st * CF::STAGE_DOUBLES + TF * BS + warp * 32 + r;
+            cos_quarter_turns<8>(q);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              acc[g][0] = fma(ws[(2 * c) * PS + 8 * g], q[2 * g], acc[g][0]);
+              acc[g][1] = fma(ws[(2 * c + 1) * PS + 8 * g], q[2 * g + 1], acc[g][1]);
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[st]);
@@ -446,7 +521,12 @@ __global__ void k_pack_basis(int L, int F, int M, int Mpad, int D, int BS, const
   }
 }
 
-template <int D, bool GRAD>
+// FP64 -> FP32 copy of the Fourier weights for the mixed-precision rollout (round to nearest even, grid-stride)
+__global__ void k_weights_f32(long long count, const double* __restrict__ w, float* __restrict__ w32) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) w32[i] = (float)w[i];
+}
+
+template <int D, bool GRAD, bool W32 = false>
 static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
   // gradient mode carries 2 D more accumulators per thread: 256-particle CTAs (8 consumer warps + the producer, one CTA per SM)
   // keep them in registers without spills (168 registers); measured faster than 2 spilling CTAs per SM or 480-particle CTAs
@@ -454,12 +534,12 @@ static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
   using CF = PathwiseCfg<D, P, TF, NS>;
   static bool configured = false;
   if (!configured) {
-    GPP_CUDA_OK(cudaFuncSetAttribute(k_pathwise_rollout<D, P, TF, NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+    GPP_CUDA_OK(cudaFuncSetAttribute(k_pathwise_rollout<D, P, TF, NS, GRAD, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
     configured = true;
   }
   int grid = (p.S + P - 1) / P;
   profile_begin(stream);
-  k_pathwise_rollout<D, P, TF, NS, GRAD><<<grid, P + 32, CF::SMEM, stream>>>(p);
+  k_pathwise_rollout<D, P, TF, NS, GRAD, W32><<<grid, P + 32, CF::SMEM, stream>>>(p);
   profile_end(stream);
   count_launch();
   GPP_CUDA_OK(cudaGetLastError());
@@ -473,9 +553,10 @@ static int pathwise_fwd_impl(int S, int ldS, int H, int L, int F, int Mpad, int 
                              const double* variance, const double* inv_lengthscales, const double* mean_const,
                              int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
                              double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
-                             const double* x0, double* loss, double* x_final, double* traj, double* jac, void* stream) {
+                             const double* x0, double* loss, double* x_final, double* traj, double* jac, void* stream,
+                             const float* w32 = nullptr) {
   using namespace gpp;
-  GPP_REQUIRE(basis && zbasis && w && v && amp && variance && inv_lengthscales && mean_const && policy_Zs && policy_inv_lengthscales &&
+  GPP_REQUIRE(basis && zbasis && (w || w32) && v && amp && variance && inv_lengthscales && mean_const && policy_Zs && policy_inv_lengthscales &&
                   policy_alpha && cost_target && cost_W && x0 && loss, GPP_ERR_NULL, "gpp_rollout_pathwise_fwd: null argument");
   GPP_REQUIRE(S >= 1 && H >= 0 && L >= 1 && L <= GPP_SMALL_MAX && Dx >= 1 && Dx <= GPP_SMALL_MAX, GPP_ERR_BAD_SHAPE,
               "gpp_rollout_pathwise_fwd: bad sizes S=%d H=%d L=%d Dx=%d", S, H, L, Dx);
@@ -490,9 +571,18 @@ static int pathwise_fwd_impl(int S, int ldS, int H, int L, int F, int Mpad, int 
   for (int k = 0; k < num_active; ++k) p.enc.active[k] = active_dims[k];
   p.enc.finish();
   p.S = S; p.ldS = ldS; p.H = H; p.L = L; p.F = F; p.Mpad = Mpad; p.Dx = Dx; p.De = Dx + num_active; p.Mp = Mp;
-  p.basis = basis; p.zbasis = zbasis; p.w = w; p.v = v; p.amp = amp; p.var = variance; p.inv_ell = inv_lengthscales; p.mean = mean_const;
+  p.basis = basis; p.zbasis = zbasis; p.w = w; p.w32 = w32; p.v = v; p.amp = amp; p.var = variance; p.inv_ell = inv_lengthscales; p.mean = mean_const;
   p.pZs = policy_Zs; p.pInvEll = policy_inv_lengthscales; p.pAlpha = policy_alpha; p.scale = squash_scale; p.shift = squash_shift;
   p.target = cost_target; p.W = cost_W; p.x0 = x0; p.loss = loss; p.x_final = x_final; p.traj = traj; p.jac = jac;
+  if (w32) {
+    GPP_REQUIRE(!jac, GPP_ERR_UNSUPPORTED, "gpp_rollout_pathwise_fwd_mixed: no gradient mode");
+    switch (D) {
+#define GPP_CASE(d) case d: return launch_pathwise<d, false, true>(p, (cudaStream_t)stream);
+      GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7)
+#undef GPP_CASE
+      default: set_error("gpp_rollout_pathwise_fwd_mixed: unsupported D=%d (2..7)", D); return GPP_ERR_UNSUPPORTED;
+    }
+  }
   switch (D) {
 #define GPP_CASE(d) case d: return jac ? launch_pathwise<d, true>(p, (cudaStream_t)stream) : launch_pathwise<d, false>(p, (cudaStream_t)stream);
     GPP_CASE(2) GPP_CASE(3) GPP_CASE(4) GPP_CASE(5) GPP_CASE(6) GPP_CASE(7) GPP_CASE(8)
@@ -530,6 +620,31 @@ int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int 
   return pathwise_fwd_impl(S, ldS, H, L, F, Mpad, D, Dx, num_active, active_dims, basis, zbasis, w, v, amp, variance, inv_lengthscales,
                            mean_const, Mp, policy_Zs, policy_inv_lengthscales, policy_alpha, squash_scale, squash_shift, cost_target,
                            cost_W, x0, loss, x_final, traj, nullptr, stream);
+}
+
+int gpp_rollout_pathwise_fwd_mixed(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
+                                   const double* basis, const double* zbasis, const float* w32, const double* v, const double* amp,
+                                   const double* variance, const double* inv_lengthscales, const double* mean_const,
+                                   int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                                   double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                                   const double* x0, double* loss, double* x_final, double* traj, void* stream) {
+  GPP_NVTX_RANGE();
+  GPP_REQUIRE(w32, GPP_ERR_NULL, "gpp_rollout_pathwise_fwd_mixed: null FP32 weights");
+  return pathwise_fwd_impl(S, ldS, H, L, F, Mpad, D, Dx, num_active, active_dims, basis, zbasis, nullptr, v, amp, variance,
+                           inv_lengthscales, mean_const, Mp, policy_Zs, policy_inv_lengthscales, policy_alpha, squash_scale,
+                           squash_shift, cost_target, cost_W, x0, loss, x_final, traj, nullptr, stream, w32);
+}
+
+int gpp_pathwise_weights_f32(long long count, const double* w, float* w32, void* stream) {
+  GPP_NVTX_RANGE();
+  GPP_REQUIRE(count >= 0 && (count == 0 || (w && w32)), GPP_ERR_NULL, "gpp_pathwise_weights_f32: null argument");
+  if (count == 0) return GPP_OK;
+  const int threads = 256;
+  const long long blocks = std::min<long long>((count + threads - 1) / threads, 148LL * 16);
+  gpp::k_weights_f32<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(count, w, w32);
+  gpp::count_launch();
+  GPP_CUDA_OK(cudaGetLastError());
+  return GPP_OK;
 }
 
 int gpp_rollout_pathwise_fwd_grad(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,

@@ -34,6 +34,15 @@ class PackedPaths:
   mean_const: torch.Tensor  # [L]
   num_particles: int
   D: int
+  w32: Optional[torch.Tensor] = None     # FP32 copy of w for the mixed-precision rollout (made on first use)
+
+  def weights_f32(self) -> torch.Tensor:
+    """FP32 copy of the Fourier weights (gpp_pathwise_weights_f32), cached: half the bytes the rollout streams."""
+    if self.w32 is None:
+      out = torch.empty(self.w.shape, dtype=torch.float32, device=self.w.device)
+      _lib.check(_lib.load().gpp_pathwise_weights_f32(self.w.numel(), _ptr(self.w), _ptr(out), _stream()))
+      self.w32 = out
+    return self.w32
 
   @staticmethod
   def layout(S: int, F: int, M: int):
@@ -119,9 +128,11 @@ def generate_paths(handle, num_samples: int, num_bases: int, seed: int, first_pa
 
 def rollout_pathwise(paths: PackedPaths, policy: PolicyParams, x0: torch.Tensor, horizon: int, active_dims: Sequence[int],
                      cost_target: torch.Tensor, cost_W: torch.Tensor, return_trajectory: bool = False,
-                     beta: Optional[torch.Tensor] = None, save_for_backward: bool = False):
+                     beta: Optional[torch.Tensor] = None, save_for_backward: bool = False, mixed_precision: bool = False):
   """loss [S] (and final states / trajectory) of S particles, particle s evaluated on function draw s.
-  With save_for_backward the gradient-mode kernel runs and the result is (loss, x_final, traj, jac)."""
+  With save_for_backward the gradient-mode kernel runs and the result is (loss, x_final, traj, jac).
+  `mixed_precision` selects gpp_rollout_pathwise_fwd_mixed (FP32 Fourier weights and cosine polynomial, everything else FP64;
+  tolerance stated in include/gpp_b200.h); the default is the all-FP64 kernel."""
   x0, cost_target, cost_W = map(_c, (x0, cost_target, cost_W))
   _dev_check(x0, cost_target, cost_W)
   S, Dx = x0.shape
@@ -153,6 +164,13 @@ def rollout_pathwise(paths: PackedPaths, policy: PolicyParams, x0: torch.Tensor,
         _ptr(alpha), float(policy.squash_scale), float(policy.squash_shift), _ptr(cost_target), _ptr(cost_W), _ptr(x0), _ptr(loss),
         _ptr(xf), _ptr(traj), _ptr(jac), _stream()))
     return loss, xf, traj, jac
+  if mixed_precision:
+    _lib.check(_lib.load().gpp_rollout_pathwise_fwd_mixed(
+        S, ldS, int(horizon), L, F, Mpad, paths.D, Dx, na, act, _ptr(paths.basis), _ptr(paths.zbasis), _ptr(paths.weights_f32()),
+        _ptr(paths.v), _ptr(paths.amp), _ptr(paths.variance), _ptr(paths.inv_lengthscales), _ptr(paths.mean_const), Mp, _ptr(pZs),
+        _ptr(pinv), _ptr(alpha), float(policy.squash_scale), float(policy.squash_shift), _ptr(cost_target), _ptr(cost_W), _ptr(x0),
+        _ptr(loss), _ptr(xf), _ptr(traj), _stream()))
+    return loss, xf, traj
   _lib.check(_lib.load().gpp_rollout_pathwise_fwd(
       S, ldS, int(horizon), L, F, Mpad, paths.D, Dx, na, act, _ptr(paths.basis), _ptr(paths.zbasis), _ptr(paths.w), _ptr(paths.v),
       _ptr(paths.amp), _ptr(paths.variance), _ptr(paths.inv_lengthscales), _ptr(paths.mean_const), Mp, _ptr(pZs), _ptr(pinv),

@@ -218,6 +218,21 @@ int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int 
 /* Gradient mode of gpp_rollout_pathwise_fwd: same rollout, and while the weights stream past it also reduces
  * jac [H, L*D, ldS] = d f_{s,l} / d d_b of every particle-step (the derivative of each particle's function draw w.r.t. its
  * input).  traj [H+1,S,Dx] and jac are required: they are what gpp_rollout_pathwise_bwd reads. */
+/* Mixed-precision variant of gpp_rollout_pathwise_fwd (north_star permits an FP32 / mixed path with a stated tolerance): the Fourier
+ * weights are streamed as FP32 (`w32`, same [L][F][ldS] layout; half the HBM traffic of the rollout) and the cosine polynomial and the
+ * weight products run in FP32; phases (FP64 tensor path), quarter-turn reduction, the canonical-basis part, the policy, the cost and
+ * the state update stay FP64, FP32 partial sums are folded into FP64 every 32 feature tiles.  Stated tolerance: per-step drift within
+ * 5e-6 of the FP64 kernel relative to the largest drift entry (measured 1.5e-6 at F = 1024; the cosine polynomial is good to 3.3e-7);
+ * over a rollout the states inherit the dynamics' own error growth (tests/test_gpu_pathwise.py: 10 cart-pole steps stay within 2e-5,
+ * the mean loss within 2e-6).  D = 2..7; no gradient mode.
+ *   gpp_pathwise_weights_f32 converts `count` weights (round to nearest). */
+int gpp_rollout_pathwise_fwd_mixed(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
+                                   const double* basis, const double* zbasis, const float* w32, const double* v, const double* amp,
+                                   const double* variance, const double* inv_lengthscales, const double* mean_const,
+                                   int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                                   double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                                   const double* x0, double* loss, double* x_final, double* traj, void* stream);
+int gpp_pathwise_weights_f32(long long count, const double* w, float* w32, void* stream);
 int gpp_rollout_pathwise_fwd_grad(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
                                   const double* basis, const double* zbasis, const double* w, const double* v, const double* amp,
                                   const double* variance, const double* inv_lengthscales, const double* mean_const,

@@ -91,3 +91,36 @@ def test_chunked_rollout_with_overlapped_generation_matches_serial():
     got = rollout_pathwise_chunked(handle, P, m0, S0, total, F, seed, *args, first_particle=first, particles_per_launch=per, overlap=overlap)
     torch.cuda.synchronize()
     assert torch.equal(got, ref), (overlap, float(got), float(ref))
+
+
+def test_mixed_precision_rollout_within_its_stated_tolerance():
+  """gpp_rollout_pathwise_fwd_mixed (FP32 Fourier weights + FP32 cosine polynomial; phases, reduction, canonical part, policy, cost
+  FP64) against the all-FP64 kernel on the same paths: one step's drift within 5e-6 of the largest drift entry (the tolerance the
+  header states), and a 10-step rollout's per-particle loss and final state within 2e-5 (the dynamics amplify the per-step
+  difference), mean loss within 2e-6."""
+  from gpflowpilco_b200.pathwise import draw_initial_states, generate_paths, rollout_pathwise
+  from gpflowpilco_b200.rollouts import PolicyParams
+  from tests.helpers import cuda_handle
+  cfg = synthetic.config1_cartpole(M=64, Mp=10)
+  p = cfg["policy"]
+  handle = cuda_handle(cfg["dynamics"])
+  P = PolicyParams(_dev(p["Z"]), _dev(p["lengthscales"]), _dev(p["variance"]), _dev(p["q_mu"][:, 0][None]), whiten=True,
+                   squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+  S, F = 700, 1024
+  paths = generate_paths(handle, S, F, seed=5, first_particle=0)
+  x0 = draw_initial_states(_dev(cfg["m0"][0]), _dev(cfg["S0"][0]), 5, 0, S)
+  args = (cfg["active_dims"], _dev(cfg["target"]), _dev(cfg["W"]))
+  _, x1_64, _ = rollout_pathwise(paths, P, x0, 1, *args)
+  _, x1_mx, _ = rollout_pathwise(paths, P, x0, 1, *args, mixed_precision=True)
+  assert paths.w32 is not None and paths.w32.dtype == torch.float32
+  d64, dmx = x1_64 - x0, x1_mx - x0
+  step_err = float((dmx - d64).abs().max() / d64.abs().max())
+  print(f"[mixed] one-step drift: max |diff| / max |drift| = {step_err:.2e}")
+  assert 0.0 < step_err <= 5e-6, step_err
+  l64, xf64, _ = rollout_pathwise(paths, P, x0, 10, *args)
+  lmx, xfmx, _ = rollout_pathwise(paths, P, x0, 10, *args, mixed_precision=True)
+  e_loss = float((lmx - l64).abs().max() / l64.abs().max())
+  e_x = float((xfmx - xf64).abs().max() / xf64.abs().max())
+  e_mean = float((lmx.mean() - l64.mean()).abs() / l64.mean().abs())
+  print(f"[mixed] H=10: per-particle loss {e_loss:.2e}, final state {e_x:.2e}, mean loss {e_mean:.2e}")
+  assert e_loss <= 2e-5 and e_x <= 2e-5 and e_mean <= 2e-6, (e_loss, e_x, e_mean)
