@@ -48,16 +48,33 @@ struct NvtxRange {
 void profile_begin(cudaStream_t stream);
 void profile_end(cudaStream_t stream);
 
-inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// Per-DEVICE caches: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to the device that is current when
+// they are set / read, and one process may drive several devices (a handle lives on whichever device its tensors are on).
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int d = current_device_slot();
+  if (!n[d]) {
+    cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+    if (n[d] <= 0) n[d] = 148;
+  }
+  return n[d];
+}
+// largest dynamic shared-memory size a kernel has been opted into, per device: `raise(bytes)` is true when the opt-in must be (re)done
+struct PerDeviceSmemOptIn {
+  size_t bytes[kMaxDevices] = {};
+  bool raise(size_t want) {
+    const int d = current_device_slot();
+    if (want <= bytes[d]) return false;
+    bytes[d] = want;
+    return true;
+  }
+};
 
 // ---- device-side helpers ------------------------------------------------------------------------------
 #if defined(__CUDACC__)

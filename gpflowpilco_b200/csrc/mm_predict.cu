@@ -84,10 +84,9 @@ template <int D, int T, int NP, int NC>
 static int launch_contract(const ContractParams& cp, cudaStream_t stream) {
   constexpr int NT = ContractCfg<D, T, NP, NC>::NT;
   size_t smem = sizeof(double) * ContractCfg<D, T, NP, NC>::TOTAL;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceSmemOptIn configured;
+  if (configured.raise(smem)) {
     GPP_CUDA_OK(cudaFuncSetAttribute(k_contract<D, T, NP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   int per_sm = 1;
   GPP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_contract<D, T, NP, NC>, NT, smem));

@@ -88,12 +88,10 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   profile_begin(stream);
   {
     const size_t smem = sizeof(double) * (GradCfg<D>::FIXED + (size_t)lo.nrb * kGradCols);   // nrb == number of column blocks
-    static size_t configured = 0;
-    if (smem > configured) {
-      GPP_REQUIRE(smem <= 227 * 1024, GPP_ERR_UNSUPPORTED, "gpp_mm_gp_predict_bwd: M=%d needs %zu bytes of shared memory", m->M, smem);
+    static PerDeviceSmemOptIn configured;
+    GPP_REQUIRE(smem <= 227 * 1024, GPP_ERR_UNSUPPORTED, "gpp_mm_gp_predict_bwd: M=%d needs %zu bytes of shared memory", m->M, smem);
+    if (configured.raise(smem))
       GPP_CUDA_OK(cudaFuncSetAttribute(k_contract_grad<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
     k_contract_grad<D><<<N * (L * (L + 1) / 2) * lo.nrb, kGradThreads, smem, stream>>>(m->Z, m->beta, m->C, packs, omega, stats, m->M,
                                                                                      L, lo.nrb);
   }
@@ -104,11 +102,9 @@ static int predict_bwd(const gpp_gp_model* m, const double* mu, const double* S,
   {
     const int npairs = L * (L + 1) / 2;
     const size_t smem = sizeof(double) * (size_t)npairs * FinalizeSmem<D>::PER_PAIR;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
+    static PerDeviceSmemOptIn configured;
+    if (smem > 48 * 1024 && configured.raise(smem))
       GPP_CUDA_OK(cudaFuncSetAttribute(k_bwd_finalize<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
     k_bwd_finalize<D><<<N, 128, smem, stream>>>(fp);
   }
   count_launch(3);

@@ -532,10 +532,9 @@ static int launch_pathwise(const PathwiseParams& p, cudaStream_t stream) {
   // keep them in registers without spills (168 registers); measured faster than 2 spilling CTAs per SM or 480-particle CTAs
   constexpr int P = GRAD ? kPathPGrad : kPathP, TF = kPathTF, NS = 4;
   using CF = PathwiseCfg<D, P, TF, NS>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceSmemOptIn configured;
+  if (configured.raise(CF::SMEM)) {
     GPP_CUDA_OK(cudaFuncSetAttribute(k_pathwise_rollout<D, P, TF, NS, GRAD, W32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
-    configured = true;
   }
   int grid = (p.S + P - 1) / P;
   profile_begin(stream);

@@ -281,10 +281,9 @@ static int run_ekzxkxz(const double* mu, const double* cov, int N, const double*
   k_psi2_cols<D><<<dim3(ncb, N), kPsi2Threads, 0, stream>>>(packs, Z2, M2, colext);
   count_launch();
   const size_t smem = sizeof(double) * Psi2Cfg<D>::TOTAL;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceSmemOptIn configured;
+  if (configured.raise(smem)) {
     GPP_CUDA_OK(cudaFuncSetAttribute(k_ekzxkxz<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   profile_begin(stream);
   k_ekzxkxz<D><<<grid, kPsi2Threads, smem, stream>>>(packs, Z1, M1, colext, M2, out);

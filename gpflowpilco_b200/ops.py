@@ -144,6 +144,12 @@ class GPModelHandle:
       self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
     return self._ws
 
+  def _same_device(self, *tensors):
+    """a handle's device arrays live on ONE device: inputs from another GPU of the process are refused, not dereferenced"""
+    for t in tensors:
+      if t is not None and t.device != self.device:
+        raise ValueError(f"tensor on {t.device}, model handle on {self.device}")
+
   def predict(self, m, S, full_output_cov: bool = True, jitter: float = 0.0, out=None, check: bool = True):
     """(f1 [N,P], Sff [N,P,P], cross [N,D,P] pre-inverted) — upstream moment_matching/models.py:44-299."""
     m, S = _c(m), _c(S)
@@ -159,9 +165,11 @@ class GPModelHandle:
       f1, Sff, cross = out
     ws = self.workspace(N)
     info = _new_info(self.device)
-    _lib.check(_lib.load().gpp_mm_gp_predict_fwd(self._h, _ptr(m), _ptr(S), N, _ptr(f1), _ptr(Sff), _ptr(cross),
-                                                 int(bool(full_output_cov)), float(jitter), _ptr(ws), ws.numel(), _ptr(info),
-                                                 _stream()))
+    self._same_device(m, S)
+    with torch.cuda.device(self.device):      # the library launches on the CURRENT device / its current stream
+      _lib.check(_lib.load().gpp_mm_gp_predict_fwd(self._h, _ptr(m), _ptr(S), N, _ptr(f1), _ptr(Sff), _ptr(cross),
+                                                   int(bool(full_output_cov)), float(jitter), _ptr(ws), ws.numel(), _ptr(info),
+                                                   _stream()))
     if check:
       raise_if_not_pd(info, "mm_gp_predict")
     return f1, Sff, cross
@@ -184,9 +192,11 @@ def _predict_bwd(self, m, S, f1_bar=None, Sff_bar=None, cross_bar=None, full_out
   m_bar = torch.empty(N, self.D, dtype=F64, device=self.device)
   S_bar = torch.empty(N, self.D, self.D, dtype=F64, device=self.device)
   info = _new_info(self.device)
-  _lib.check(lib.gpp_mm_gp_predict_bwd(self._h, _ptr(m), _ptr(S), N, _ptr(f1_bar), _ptr(Sff_bar), _ptr(cross_bar),
-                                       int(bool(full_output_cov)), _ptr(m_bar), _ptr(S_bar), _ptr(self._ws_bwd), self._ws_bwd.numel(),
-                                       _ptr(info), _stream()))
+  self._same_device(m, S, f1_bar, Sff_bar, cross_bar)
+  with torch.cuda.device(self.device):
+    _lib.check(lib.gpp_mm_gp_predict_bwd(self._h, _ptr(m), _ptr(S), N, _ptr(f1_bar), _ptr(Sff_bar), _ptr(cross_bar),
+                                         int(bool(full_output_cov)), _ptr(m_bar), _ptr(S_bar), _ptr(self._ws_bwd), self._ws_bwd.numel(),
+                                         _ptr(info), _stream()))
   if check:
     raise_if_not_pd(info, "mm_gp_predict_bwd")
   return m_bar, S_bar

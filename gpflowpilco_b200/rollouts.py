@@ -40,8 +40,9 @@ class PolicyParams:
     R, Mp, Dp = self.Z.shape
     out = torch.empty(R, Mp, dtype=F64, device=self.Z.device)
     info = _new_info(self.Z.device)
-    _lib.check(_lib.load().gpp_policy_prepare(R, Mp, Dp, _ptr(self.Z), _ptr(self.lengthscales), _ptr(self.variance), _ptr(self.q_mu),
-                                              int(self.whiten), float(self.jitter), _ptr(out), _ptr(info), _stream()))
+    with torch.cuda.device(self.Z.device):
+      _lib.check(_lib.load().gpp_policy_prepare(R, Mp, Dp, _ptr(self.Z), _ptr(self.lengthscales), _ptr(self.variance), _ptr(self.q_mu),
+                                                int(self.whiten), float(self.jitter), _ptr(out), _ptr(info), _stream()))
     if check and int(info.item()):
       raise _lib.GppError(-3, f"policy Kuu of parameter set {int(info.item()) - 1} is not positive definite")
     return out
@@ -56,9 +57,10 @@ def policy_beta_bwd(policy: PolicyParams, beta: torch.Tensor, beta_bar: torch.Te
     raise ValueError("policy_beta_bwd: gradient buffers must be contiguous (they are updated in place)")
   R, Mp, Dp = policy.shape
   q_bar = torch.empty(R, Mp, dtype=F64, device=beta.device)
-  _lib.check(_lib.load().gpp_policy_prepare_bwd(R, Mp, Dp, _ptr(policy.Z), _ptr(policy.lengthscales), _ptr(policy.variance), _ptr(beta),
-                                                _ptr(beta_bar), int(policy.whiten), float(policy.jitter), _ptr(Z_bar), _ptr(lengthscales_bar),
-                                                _ptr(q_bar), _stream()))
+  with torch.cuda.device(beta.device):
+    _lib.check(_lib.load().gpp_policy_prepare_bwd(R, Mp, Dp, _ptr(policy.Z), _ptr(policy.lengthscales), _ptr(policy.variance), _ptr(beta),
+                                                  _ptr(beta_bar), int(policy.whiten), float(policy.jitter), _ptr(Z_bar), _ptr(lengthscales_bar),
+                                                  _ptr(q_bar), _stream()))
   return q_bar
 
 
@@ -103,6 +105,7 @@ def rollout_mm(dynamics: GPModelHandle, policy: PolicyParams, m0: torch.Tensor, 
   if R not in (1, N):
     raise ValueError("rollout_mm: policy must have 1 or N parameter sets")
   dev = m0.device
+  dynamics._same_device(m0, S0, cost_target, cost_W, policy.Z)
   if beta is None:
     beta = policy.beta(check=check)
   lib = _lib.load()
@@ -118,17 +121,19 @@ def rollout_mm(dynamics: GPModelHandle, policy: PolicyParams, m0: torch.Tensor, 
   act = (ctypes.c_int * max(na, 1))(*active_dims)
   if save_for_backward:
     saved = torch.empty(lib.gpp_rollout_mm_saved_doubles(dynamics._h, N, Dx, int(horizon)), dtype=F64, device=dev)
-    _lib.check(lib.gpp_rollout_mm_fwd_save(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
-                                           _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
-                                           _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
-                                           _ptr(mf), _ptr(Sf), _ptr(saved), _ptr(ws), ws.numel(), _ptr(info), _stream()))
+    with torch.cuda.device(dev):      # the library launches on the current device and is given its current stream
+      _lib.check(lib.gpp_rollout_mm_fwd_save(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
+                                             _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
+                                             _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
+                                             _ptr(mf), _ptr(Sf), _ptr(saved), _ptr(ws), ws.numel(), _ptr(info), _stream()))
     if check:
       raise_if_not_pd(info, "rollout_mm")
     return MMRolloutResult(loss, mf, Sf, tm, tS, saved)
-  _lib.check(lib.gpp_rollout_mm_fwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
-                                    _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
-                                    _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
-                                    _ptr(mf), _ptr(Sf), _ptr(ws), ws.numel(), _ptr(info), _stream()))
+  with torch.cuda.device(dev):      # the library launches on the current device and is given its current stream
+    _lib.check(lib.gpp_rollout_mm_fwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
+                                      _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
+                                      _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
+                                      _ptr(mf), _ptr(Sf), _ptr(ws), ws.numel(), _ptr(info), _stream()))
   if check:
     raise_if_not_pd(info, "rollout_mm")
   return MMRolloutResult(loss, mf, Sf, tm, tS)
@@ -150,6 +155,7 @@ def rollout_mm_bwd(dynamics: GPModelHandle, policy: PolicyParams, beta: torch.Te
   if loss_bar is not None and loss_bar.shape != (N,):
     raise ValueError("rollout_mm_bwd: loss_bar must be [N]")
   dev = traj_m.device
+  dynamics._same_device(traj_m, traj_S, cost_target, cost_W, beta, policy.Z)
   lib = _lib.load()
   if saved is not None and (not saved.is_cuda or saved.numel() != lib.gpp_rollout_mm_saved_doubles(dynamics._h, N, Dx, H1 - 1)):
     raise ValueError("rollout_mm_bwd: `saved` does not match this rollout")
@@ -162,10 +168,11 @@ def rollout_mm_bwd(dynamics: GPModelHandle, policy: PolicyParams, beta: torch.Te
   S0b = torch.empty(N, Dx, Dx, dtype=F64, device=dev)
   info = _new_info(dev)
   act = (ctypes.c_int * max(na, 1))(*active_dims)
-  _lib.check(lib.gpp_rollout_mm_bwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
-                                    _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
-                                    _ptr(cost_target), _ptr(cost_W), H1 - 1, _ptr(traj_m), _ptr(traj_S), _ptr(saved), _ptr(loss_bar),
-                                    _ptr(Zb), _ptr(eb), _ptr(bb), _ptr(m0b), _ptr(S0b), _ptr(ws), ws.numel(), _ptr(info), _stream()))
+  with torch.cuda.device(dev):      # the library launches on the current device and is given its current stream
+    _lib.check(lib.gpp_rollout_mm_bwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
+                                      _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
+                                      _ptr(cost_target), _ptr(cost_W), H1 - 1, _ptr(traj_m), _ptr(traj_S), _ptr(saved), _ptr(loss_bar),
+                                      _ptr(Zb), _ptr(eb), _ptr(bb), _ptr(m0b), _ptr(S0b), _ptr(ws), ws.numel(), _ptr(info), _stream()))
   if check:
     raise_if_not_pd(info, "rollout_mm_bwd")
   return Zb, eb, bb, m0b, S0b

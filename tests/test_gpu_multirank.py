@@ -69,3 +69,29 @@ def test_two_ranks_match_one():
       assert float((a - b[start:start + count]).abs().max()) <= 1e-10 * float(b.abs().max())
   assert ret[0][0] == ret[1][0]
   assert sorted((ret[0][3], ret[1][3])) == [0, 3]                           # 5 restarts -> blocks [0,3) and [3,5)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+  """A model handle lives on the device of its tensors; the library's per-device state (shared-memory opt-ins, SM count) and the
+  host side's device context follow it even when another device is current.  Inputs from the wrong device are refused."""
+  from gpflowpilco_b200.rollouts import PolicyParams, rollout_mm, rollout_mm_bwd
+  out = []
+  rng = np.random.default_rng(0)
+  xin = rng.standard_normal((3, 6))
+  A = 0.2 * rng.standard_normal((3, 6, 6))
+  Sin = A @ A.transpose(0, 2, 1) + 0.05 * np.eye(6)
+  for dev in ("cuda:0", "cuda:1"):
+    cfg, T, handle, p = _problem(dev)
+    torch.cuda.set_device(0)                       # the handle on cuda:1 is used while cuda:0 is current
+    f1, Sff, cross = handle.predict(T(xin), T(Sin))
+    pol = PolicyParams(T(p["Z"]), T(p["lengthscales"]), T(p["variance"]), T(p["q_mu"][:, 0][None]), whiten=True,
+                       squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+    res = rollout_mm(handle, pol, T(cfg["m0"]), T(cfg["S0"]), 6, cfg["active_dims"], T(cfg["target"]), T(cfg["W"]), save_for_backward=True)
+    grads = rollout_mm_bwd(handle, pol, pol.beta(), res.traj_m, res.traj_S, cfg["active_dims"], T(cfg["target"]), T(cfg["W"]), saved=res.saved)
+    out.append([t.cpu() for t in (f1, Sff, cross, res.loss, *grads)])
+  for a, b in zip(*out):
+    assert torch.equal(a, b)
+  cfg, T, handle, p = _problem("cuda:1")
+  with pytest.raises(ValueError):
+    handle.predict(torch.as_tensor(xin, dtype=torch.float64, device="cuda:0"), torch.as_tensor(Sin, dtype=torch.float64, device="cuda:0"))
