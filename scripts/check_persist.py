@@ -94,3 +94,14 @@ def sweep():
 
 if len(sys.argv) > 1 and sys.argv[1] == "sweep":
   sweep()
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "fuzz":
+  # rollout counts around the thresholds of the forward hand-over (urgent / deferred partials at 16, continuous mode from 2), odd
+  # counts, one-step and longer horizons, one / several tiles per CTA
+  worst = 0.0
+  for R, H, M in ((2, 1, None), (3, 2, None), (15, 3, None), (16, 3, None), (17, 3, None), (31, 2, None), (33, 5, None), (100, 2, None),
+                  (17, 4, 100), (40, 3, 100), (5, 7, 40), (64, 1, None), (129, 2, None)):
+    worst = max(worst, compare(R, H, M))
+  print("WORST", worst)
+  sys.exit(0 if worst < 1e-7 else 1)

@@ -1,6 +1,8 @@
 """GPU parity: fused moment-matched rollout vs the oracle's step-by-step restatement of
 forward_sde + MomentMatchingEuler + GaussianObjective (upstream dynamics/forward_sde.py:95-137, dynamics/solvers.py:110-135,
 loops/pilco.py:199-217).  Tolerance 1e-6 relative (north star); observed errors are reported in the assertion text."""
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -150,3 +152,26 @@ def test_graphed_policy_gradient_replays_the_eager_result():
     assert torch.equal(gl, loss.detach())
     for a, b in zip(gg, ref):
       assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("R,H,M", [(2, 1, None), (3, 2, None), (15, 3, None), (16, 3, None), (17, 3, None), (33, 4, None), (17, 4, 100),
+                                   (5, 7, 40), (129, 2, None)])
+def test_persistent_sweeps_match_the_per_stage_path_around_their_thresholds(R, H, M):
+  """The persistent forward / backward kernels against the one-launch-per-stage path (same device functions, different
+  orchestration) at rollout counts around the switches of the forward hand-over (continuous item stream from 2 rollouts, deferred
+  partial reduction from 16), odd counts, one step, several tiles per CTA (M = 100, 40): every output and every gradient."""
+  import importlib.util
+  import os
+  spec = importlib.util.spec_from_file_location("check_persist", os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts", "check_persist.py"))
+  cp = importlib.util.module_from_spec(spec)
+  argv = sys.argv
+  sys.argv = ["check_persist.py", "none"]
+  try:
+    spec.loader.exec_module(cp)
+    from gpflowpilco_b200 import rollouts
+    try:
+      assert cp.compare(R, H, M) < 1e-7
+    finally:
+      rollouts.set_rollout_mode(rollouts.ROLLOUT_AUTO)
+  finally:
+    sys.argv = argv
