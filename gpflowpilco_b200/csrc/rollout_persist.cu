@@ -598,12 +598,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_rollout_bwd_persist(const Pe
   for (int i = threadIdx.x; i < 256 * CF::REP; i += kBwdThreads) etab[i] = kExp2Tab256[i / CF::REP];
   __syncthreads();
   // (reallocate, then synchronise the CTA before any warp can return: see k_rollout_fwd_persist)
+  // 192 / 72 registers: the contraction main loop is register-starved at 64 (measured 148 -> 145 us per step at 64 rollouts; 160 / 80
+  // loses it again in the scalar stages: 146.5, and one rollout goes from 86 to 89.5 us per step)
   if (threadIdx.x < kGroupThreads) {
-    warpgroup_reg_inc<224>();
+    warpgroup_reg_inc<192>();
     role_bar_sync<8, kBwdThreads>();
     persist_bwd_scalar<D>(P, smem + fsm_offset);
   } else {
-    warpgroup_reg_dec<64>();
+    warpgroup_reg_dec<72>();
     role_bar_sync<8, kBwdThreads>();
     persist_bwd_contract<D>(P, smem);
   }
