@@ -156,7 +156,9 @@ struct PersistFwdCfg {
   static_assert(NC == 8 || NC == 16, "one or two consumer warps per 8-row strip");
   static constexpr int HALVES = NC / 8, COLS = T / HALVES;             // columns of the tile a consumer warp covers
   static constexpr int THREADS = kGroupThreads + 32 * (NP + NC);
-  static constexpr int REGS_SCALAR = NC == 8 ? 224 : 112, REGS_CONTRACT = NC == 8 ? 96 : 72;
+  // 192 / 104 (NC = 8): 74.4 us per step at 64 rollouts against 76.3 with 224 / 96; 160 / 112 gains another 0.7 us there but costs
+  // 1.3 us per step at 1..16 rollouts, where the scalar stages are the critical path
+  static constexpr int REGS_SCALAR = NC == 8 ? 192 : 112, REGS_CONTRACT = NC == 8 ? 104 : 72;
   static constexpr int PT = 32 * NP, CT = 32 * NC, NTC = PT + CT;      // producer / consumer / contraction threads
   static constexpr int KS = ExtLayout<D>::KS, LDC = T + 8;
   static constexpr int REP = KS <= 2 ? 16 : 8;                          // replication of the exp table
