@@ -412,7 +412,7 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) a[ks] = ra[ks * T * 4];
       double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
       for (int cg = 0; cg < F::COLS / 8; cg += 2) {
         double tt[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
