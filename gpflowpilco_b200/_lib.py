@@ -54,6 +54,10 @@ SIGNATURES = {
                                                _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
                                                _P, _P, _P, _P, _P]),
     "gpp_pathwise_weights_f32": (c_int, [c_longlong, _P, _P, _P]),
+    "gpp_dtype_supported": (c_int, [c_char_p, c_int]),
+    "gpp_rollout_pathwise_fwd_typed": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
+                                               _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
+                                               _P, _P, _P, _P, _P]),
     "gpp_rollout_pathwise_fwd_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
                                               _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_double, c_double, _P, _P,
                                               _P, _P, _P, _P, _P, _P]),

@@ -17,6 +17,7 @@
 #include <cublas_v2.h>
 
 #include <algorithm>
+#include <cstring>
 
 #include "mm_small.cuh"
 #include "mma_exp.cuh"
@@ -632,6 +633,29 @@ int gpp_rollout_pathwise_fwd_mixed(int S, int ldS, int H, int L, int F, int Mpad
   return pathwise_fwd_impl(S, ldS, H, L, F, Mpad, D, Dx, num_active, active_dims, basis, zbasis, nullptr, v, amp, variance,
                            inv_lengthscales, mean_const, Mp, policy_Zs, policy_inv_lengthscales, policy_alpha, squash_scale,
                            squash_shift, cost_target, cost_W, x0, loss, x_final, traj, nullptr, stream, w32);
+}
+
+int gpp_dtype_supported(const char* entry_point, gpp_dtype dtype) {
+  if (dtype == GPP_F64) return 1;
+  if (dtype == GPP_MIXED_F32_WEIGHTS && entry_point)
+    return std::strcmp(entry_point, "gpp_rollout_pathwise_fwd") == 0 || std::strcmp(entry_point, "gpp_rollout_pathwise_fwd_typed") == 0;
+  return 0;
+}
+
+int gpp_rollout_pathwise_fwd_typed(gpp_dtype dtype, int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active,
+                                   const int* active_dims, const double* basis, const double* zbasis, const void* w, const double* v,
+                                   const double* amp, const double* variance, const double* inv_lengthscales, const double* mean_const,
+                                   int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                                   double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                                   const double* x0, double* loss, double* x_final, double* traj, void* stream) {
+  GPP_NVTX_RANGE();
+  GPP_REQUIRE(dtype == GPP_F64 || dtype == GPP_MIXED_F32_WEIGHTS, GPP_ERR_UNSUPPORTED, "gpp_rollout_pathwise_fwd_typed: unknown dtype %d",
+              (int)dtype);
+  const bool mixed = dtype == GPP_MIXED_F32_WEIGHTS;
+  return pathwise_fwd_impl(S, ldS, H, L, F, Mpad, D, Dx, num_active, active_dims, basis, zbasis,
+                           mixed ? nullptr : static_cast<const double*>(w), v, amp, variance, inv_lengthscales, mean_const, Mp, policy_Zs,
+                           policy_inv_lengthscales, policy_alpha, squash_scale, squash_shift, cost_target, cost_W, x0, loss, x_final,
+                           traj, nullptr, stream, mixed ? static_cast<const float*>(w) : nullptr);
 }
 
 int gpp_pathwise_weights_f32(long long count, const double* w, float* w32, void* stream) {

@@ -17,6 +17,9 @@ from gpflowpilco_b200.ops import F64, _c, _dev_check, _ptr, _stream
 from gpflowpilco_b200.rollouts import PolicyParams
 
 
+GPP_F64, GPP_MIXED_F32_WEIGHTS = 0, 1      # gpp_dtype (include/gpp_b200.h)
+
+
 def _round_up(x: int, m: int) -> int:
   return (x + m - 1) // m * m
 
@@ -165,8 +168,8 @@ def rollout_pathwise(paths: PackedPaths, policy: PolicyParams, x0: torch.Tensor,
         _ptr(xf), _ptr(traj), _ptr(jac), _stream()))
     return loss, xf, traj, jac
   if mixed_precision:
-    _lib.check(_lib.load().gpp_rollout_pathwise_fwd_mixed(
-        S, ldS, int(horizon), L, F, Mpad, paths.D, Dx, na, act, _ptr(paths.basis), _ptr(paths.zbasis), _ptr(paths.weights_f32()),
+    _lib.check(_lib.load().gpp_rollout_pathwise_fwd_typed(
+        GPP_MIXED_F32_WEIGHTS, S, ldS, int(horizon), L, F, Mpad, paths.D, Dx, na, act, _ptr(paths.basis), _ptr(paths.zbasis), _ptr(paths.weights_f32()),
         _ptr(paths.v), _ptr(paths.amp), _ptr(paths.variance), _ptr(paths.inv_lengthscales), _ptr(paths.mean_const), Mp, _ptr(pZs),
         _ptr(pinv), _ptr(alpha), float(policy.squash_scale), float(policy.squash_shift), _ptr(cost_target), _ptr(cost_W), _ptr(x0),
         _ptr(loss), _ptr(xf), _ptr(traj), _stream()))

@@ -218,6 +218,11 @@ int gpp_rollout_pathwise_fwd(int S, int ldS, int H, int L, int F, int Mpad, int 
 /* Gradient mode of gpp_rollout_pathwise_fwd: same rollout, and while the weights stream past it also reduces
  * jac [H, L*D, ldS] = d f_{s,l} / d d_b of every particle-step (the derivative of each particle's function draw w.r.t. its
  * input).  traj [H+1,S,Dx] and jac are required: they are what gpp_rollout_pathwise_bwd reads. */
+/* Arithmetic of an entry point.  Everything computes in GPP_F64 (the reference's default_float, upstream
+ * gpflow_pilco/moment_matching/models.py:145,216) unless the entry point takes a gpp_dtype; GPP_MIXED_F32_WEIGHTS is the opt-in
+ * variant described below (pathwise forward rollout only).  gpp_dtype_supported() lets a binding probe an operation by name. */
+typedef enum gpp_dtype { GPP_F64 = 0, GPP_MIXED_F32_WEIGHTS = 1 } gpp_dtype;
+int gpp_dtype_supported(const char* entry_point, gpp_dtype dtype);   /* 1 / 0 */
 /* Mixed-precision variant of gpp_rollout_pathwise_fwd (north_star permits an FP32 / mixed path with a stated tolerance): the Fourier
  * weights are streamed as FP32 (`w32`, same [L][F][ldS] layout; half the HBM traffic of the rollout) and the cosine polynomial and the
  * weight products run in FP32; phases (FP64 tensor path), quarter-turn reduction, the canonical-basis part, the policy, the cost and
@@ -233,6 +238,13 @@ int gpp_rollout_pathwise_fwd_mixed(int S, int ldS, int H, int L, int F, int Mpad
                                    double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
                                    const double* x0, double* loss, double* x_final, double* traj, void* stream);
 int gpp_pathwise_weights_f32(long long count, const double* w, float* w32, void* stream);
+/* gpp_rollout_pathwise_fwd / _mixed behind one signature: `w` points to double (GPP_F64) or float (GPP_MIXED_F32_WEIGHTS) weights */
+int gpp_rollout_pathwise_fwd_typed(gpp_dtype dtype, int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active,
+                                   const int* active_dims, const double* basis, const double* zbasis, const void* w, const double* v,
+                                   const double* amp, const double* variance, const double* inv_lengthscales, const double* mean_const,
+                                   int Mp, const double* policy_Zs, const double* policy_inv_lengthscales, const double* policy_alpha,
+                                   double squash_scale, double squash_shift, const double* cost_target, const double* cost_W,
+                                   const double* x0, double* loss, double* x_final, double* traj, void* stream);
 int gpp_rollout_pathwise_fwd_grad(int S, int ldS, int H, int L, int F, int Mpad, int D, int Dx, int num_active, const int* active_dims,
                                   const double* basis, const double* zbasis, const double* w, const double* v, const double* amp,
                                   const double* variance, const double* inv_lengthscales, const double* mean_const,

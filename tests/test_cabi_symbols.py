@@ -75,3 +75,14 @@ def test_graphed_policy_gradient_refuses_cpu_tensors():
                             torch.zeros(1, 4, dtype=torch.float64), torch.zeros(1, 4, dtype=torch.float64),
                             torch.eye(4, dtype=torch.float64)[None], 3, (1,), torch.zeros(5, dtype=torch.float64),
                             torch.eye(5, dtype=torch.float64))
+
+
+def test_dtype_probe_is_a_host_function():
+  """gpp_dtype_supported answers without touching a device: FP64 everywhere, the mixed variant only for the pathwise forward rollout"""
+  from gpflowpilco_b200 import _lib
+  lib = _lib.load()
+  assert lib.gpp_dtype_supported(b"gpp_mm_gp_predict_fwd", 0) == 1
+  assert lib.gpp_dtype_supported(b"gpp_mm_gp_predict_fwd", 1) == 0
+  assert lib.gpp_dtype_supported(b"gpp_rollout_pathwise_fwd", 1) == 1
+  assert lib.gpp_dtype_supported(b"gpp_rollout_pathwise_fwd_typed", 1) == 1
+  assert lib.gpp_dtype_supported(b"gpp_rollout_pathwise_fwd", 7) == 0
