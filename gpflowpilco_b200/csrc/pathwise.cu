@@ -344,6 +344,10 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
         // (Issuing the next tile's DMMAs ahead of this tile's FP32 work — software pipelining by one tile inside the warp — was
         //  measured SLOWER for the mixed variant, 7.96 vs 5.90 ms at H = 4: the second set of phases costs 16 registers at the
         //  96-register cap of a 544-thread CTA.)
+        // unrolled by 4 tiles: at the 96-register cap ptxas re-materialises the lane-derived shared-memory offsets and re-loads the
+        // polynomial constants at the top of every iteration (~33 non-FP64 instructions per tile, each ~0.8 issue cycles beside the
+        // FP64 pipe); once per four tiles instead: 8.10 -> 7.52 ms at H = 4 (0.80 -> 0.86 of the HBM peak), by 8: no further gain
+#pragma unroll 4
         for (int tile = 0; tile < tiles_f; ++tile, ++it) {
           const int st = (int)(it % NS);
           double q[8];
