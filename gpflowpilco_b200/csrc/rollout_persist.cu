@@ -280,7 +280,6 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
     issue(next_n(0), 1);                     // (an item index past the segment only fetches an existing pack a second time)
     int cn = 0, ct = t0, cs = 0;             // item j:      rollout, step, landing slot
     int rn = 0, rt = t0;                     // item j - NBUF:  rollout, step
-    int b = 0;                               // j % NBUF
     int in2 = next_n(next_n(0));             // item j + 2:  rollout (its landing slot is (cs + 2) % 3)
     // With many rollouts in flight the partial of item j - 2 is not urgent (its reader is the scalar stage of the NEXT step, N items
     // away): its reduction stays off the path EMPTY -> pack -> vectors -> FULL that the consumers wait for, and the two COLUMN warps
@@ -301,7 +300,10 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
         if (!(P.debug & 2)) hint_add(P.part_hint + rn);
       }
     };
+    static_assert(F::NBUF == 2, "b = j & 1 below");
+#pragma unroll 2
     for (int j = 0; j < segs.seg_items + F::NBUF; ++j) {
+      const int b = j & 1;                   // (unrolled by two: a compile-time constant in each copy)
       if (j >= F::NBUF) {                    // consumers are done with item j-NBUF: its vector buffers are free, its partial is complete
         mbar_wait_bounded(&empty[b], (pe >> b) & 1u);
         pe ^= 1u << b;
@@ -367,7 +369,6 @@ __device__ void persist_fwd_producer(const PersistFwdParams& P, double* smem) {
         rn = next_n(rn);
         if (rn == 0) ++rt;
       }
-      b = b + 1 == F::NBUF ? 0 : b + 1;
     }
   }
 }
@@ -401,8 +402,11 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
       if (diag) persist_load_tile<D, NC>(P, sl, Ct, F::PT + ctid);
       resident = slot;
     }
-    int b = 0;                               // j % NBUF
+    static_assert(F::NBUF == 2, "b = j & 1 below");
+    // unrolled by two items: the buffer index becomes a compile-time constant in each copy (shared-memory addresses fold)
+#pragma unroll 2
     for (int j = 0; j < segs.seg_items; ++j) {
+      const int b = j & 1;
       mbar_wait_bounded(&full[b], (pf >> b) & 1u);
       pf ^= 1u << b;
       const double* ra = rowA + b * F::FBUF + strip * 32 + lane;
@@ -433,7 +437,6 @@ __device__ void persist_fwd_consumer(const PersistFwdParams& P, double* smem) {
       red[(j & (F::NRED - 1)) * F::DBUF + cwarp * 32 + lane] = total;
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[b]);
-      b = b + 1 == F::NBUF ? 0 : b + 1;
     }
   }
 }
