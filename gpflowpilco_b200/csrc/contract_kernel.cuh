@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
       double pv[NPV];
 #pragma unroll
       for (int q = 0; q < NPV; ++q) pv[q] = tid + q * PT < PP::SIZE ? pk0[tid + q * PT] : 0.0;
+#pragma unroll 2
       for (int k = 0; k < it.K + 2; ++k) {
         const int b = k & 1;
         if (k >= 2) {                        // consumers are done with input k-2 (buffer b): reduce its lane partials
@@ -240,8 +241,9 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
   const unsigned etab_lane = (unsigned)__cvta_generic_to_shared(etab + (lane & (CF::REP - 1)));
   while (contract_next_item<D, T, NP, NC>(p, Ct, &s_item, it)) {
     const bool diag = it.diag;
+#pragma unroll 2
     for (int k = 0; k < it.K; ++k) {
-      const int b = k & 1;
+      const int b = k & 1;                    // (unrolled by two: a compile-time constant in each copy)
       named_bar_sync<BAR_FULL>(b, NT);
       const double* ra = rowA + b * FBUF + strip * 32 + lane;
       const double* cb = colB + b * FBUF + lane;
