@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s0 = blockIdx.x * P;
   const int tiles_f = p.F / TF, tiles_m = p.Mpad / TF;
-  const int tiles_per_step = p.L * (tiles_f + tiles_m);
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -432,6 +431,10 @@ __global__ void __launch_bounds__(P + 32, 1) k_pathwise_rollout(PathwiseParams p
       double ds[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) ds[d] = dd[d] * c_inv_ell[l * D + d];
+      // (two tiles per iteration in the forward-only kernels, like the Fourier part; the gradient-mode kernel is at its register
+      //  limit and spills when unrolled)
+      constexpr int kUnrollM = GRAD ? 1 : 2;
+#pragma unroll kUnrollM
       for (int tile = 0; tile < tiles_m; ++tile, ++it) {
         const int st = (int)(it % NS);
         mbar_wait(&full[st], (unsigned)((it / NS) & 1));
