@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(32 * (NP + NC)) k_contract(ContractParams p) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) a[ks] = ra[ks * T * 4];
       double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
       for (int cg = 0; cg < T / 8; cg += 2) {
         double t[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
