@@ -68,9 +68,10 @@ def rollout_mm_loss(dynamics: GPModelHandle, Z: torch.Tensor, lengthscales: torc
                     jitter: float = 1e-6, check: bool = True) -> torch.Tensor:
   """loss[N] of the moment-matched rollout (upstream MomentMatchingPILCO closure, loops/pilco.py:192-220), differentiable
   w.r.t. the policy parameters Z [R,Mp,De], lengthscales [R,De], q_mu [R,Mp] and the initial moments (m0, S0).
-  `check=False` skips the synchronising reads of the not-positive-definite flags (timed loops, CUDA-graph capture)."""
+  `check=False` skips the synchronising reads of the not-positive-definite flags (timed loops, CUDA-graph capture);
+  `check="defer"` queues them for one `rollouts.raise_deferred()` after the backward pass (no synchronisation in between)."""
   return _RolloutMM.apply(Z, lengthscales, q_mu, m0, S0, dynamics, variance, bool(whiten), float(jitter), float(squash_scale),
-                          float(squash_shift), int(horizon), tuple(active_dims), cost_target, cost_W, bool(check))
+                          float(squash_shift), int(horizon), tuple(active_dims), cost_target, cost_W, check if isinstance(check, str) else bool(check))
 
 
 class _RolloutPathwise(torch.autograd.Function):

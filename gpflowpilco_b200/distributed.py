@@ -122,6 +122,7 @@ def mm_restart_losses_and_grads(dynamics, Z: torch.Tensor, lengthscales: torch.T
   state distribution (m0 [1,Dx], S0 [1,Dx,Dx]), sharded over ranks; forward + backward of the moment-matched rollout.
   Returns (loss [R] on every rank, (start, count) of this rank's block, its gradients [count, ...] for Z, lengthscales, q_mu)."""
   from gpflowpilco_b200.autograd import rollout_mm_loss
+  from gpflowpilco_b200.rollouts import raise_deferred
   R = Z.shape[0]
 
   def local(start: int, count: int):
@@ -129,8 +130,9 @@ def mm_restart_losses_and_grads(dynamics, Z: torch.Tensor, lengthscales: torch.T
     params = [t[sl].detach().clone().requires_grad_(True) for t in (Z, lengthscales, q_mu)]
     loss = rollout_mm_loss(dynamics, params[0], params[1], variance[sl].contiguous(), params[2], m0.expand(count, -1).contiguous(),
                            S0.expand(count, -1, -1).contiguous(), horizon, active_dims, cost_target, cost_W,
-                           squash_scale=squash_scale, squash_shift=squash_shift, whiten=whiten)
+                           squash_scale=squash_scale, squash_shift=squash_shift, whiten=whiten, check="defer")
     loss.sum().backward()
+    raise_deferred()      # the not-positive-definite flags of policy weights, forward and reverse sweep: one synchronisation
     return loss.detach(), [p.grad for p in params]
 
   return sharded_restarts(R, local, group)

@@ -11,6 +11,35 @@ from gpflowpilco_b200 import _lib
 from gpflowpilco_b200.ops import F64, GPModelHandle, _c, _dev_check, _new_info, _ptr, _stream, raise_if_not_pd
 
 
+# ---- not-positive-definite flags --------------------------------------------------------------------------
+# Every entry point reports a failed factorisation through an asynchronous device flag.  check=True reads it right away (one device
+# synchronisation per call); check="defer" queues it, and raise_deferred() reads all queued flags with ONE synchronisation — a
+# policy-optimisation step then enqueues policy weights, forward sweep, reverse sweep and policy adjoint back to back instead of
+# draining the GPU three times; check=False drops the flag (CUDA-graph capture, timed kernels).
+_DEFERRED: list = []
+
+
+def _finish_check(info: torch.Tensor, what: str, check) -> None:
+  if isinstance(check, str):
+    if check != "defer":
+      raise ValueError("check must be True, False or 'defer'")
+    _DEFERRED.append((info, what))
+  elif check:
+    raise_if_not_pd(info, what)
+
+
+def raise_deferred() -> None:
+  """Read every flag queued by check='defer' (one device synchronisation) and raise for the first failure."""
+  global _DEFERRED
+  pending, _DEFERRED = _DEFERRED, []
+  if not pending:
+    return
+  values = torch.stack([info.reshape(-1)[0] for info, _ in pending]).tolist()
+  for v, (_, what) in zip(values, pending):
+    if v:
+      raise _lib.GppError(-3, f"{what}: a covariance of batch element / parameter set {int(v) - 1} is not positive definite")
+
+
 @dataclass
 class PolicyParams:
   """R sets of SE-ARD kernel-regressor parameters with a scalar output (the upstream RBF policy):
@@ -43,8 +72,7 @@ class PolicyParams:
     with torch.cuda.device(self.Z.device):
       _lib.check(_lib.load().gpp_policy_prepare(R, Mp, Dp, _ptr(self.Z), _ptr(self.lengthscales), _ptr(self.variance), _ptr(self.q_mu),
                                                 int(self.whiten), float(self.jitter), _ptr(out), _ptr(info), _stream()))
-    if check and int(info.item()):
-      raise _lib.GppError(-3, f"policy Kuu of parameter set {int(info.item()) - 1} is not positive definite")
+    _finish_check(info, "policy Kuu (gpp_policy_prepare)", check)
     return out
 
 
@@ -126,16 +154,14 @@ def rollout_mm(dynamics: GPModelHandle, policy: PolicyParams, m0: torch.Tensor, 
                                              _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
                                              _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
                                              _ptr(mf), _ptr(Sf), _ptr(saved), _ptr(ws), ws.numel(), _ptr(info), _stream()))
-    if check:
-      raise_if_not_pd(info, "rollout_mm")
+    _finish_check(info, "rollout_mm", check)
     return MMRolloutResult(loss, mf, Sf, tm, tS, saved)
   with torch.cuda.device(dev):      # the library launches on the current device and is given its current stream
     _lib.check(lib.gpp_rollout_mm_fwd(dynamics._h, N, Dx, na, act, R, Mp, _ptr(policy.Z), _ptr(policy.lengthscales),
                                       _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
                                       _ptr(cost_target), _ptr(cost_W), int(horizon), _ptr(m0), _ptr(S0), _ptr(loss), _ptr(tm), _ptr(tS),
                                       _ptr(mf), _ptr(Sf), _ptr(ws), ws.numel(), _ptr(info), _stream()))
-  if check:
-    raise_if_not_pd(info, "rollout_mm")
+  _finish_check(info, "rollout_mm", check)
   return MMRolloutResult(loss, mf, Sf, tm, tS)
 
 
@@ -173,6 +199,5 @@ def rollout_mm_bwd(dynamics: GPModelHandle, policy: PolicyParams, beta: torch.Te
                                       _ptr(policy.variance), _ptr(beta), float(policy.squash_scale), float(policy.squash_shift),
                                       _ptr(cost_target), _ptr(cost_W), H1 - 1, _ptr(traj_m), _ptr(traj_S), _ptr(saved), _ptr(loss_bar),
                                       _ptr(Zb), _ptr(eb), _ptr(bb), _ptr(m0b), _ptr(S0b), _ptr(ws), ws.numel(), _ptr(info), _stream()))
-  if check:
-    raise_if_not_pd(info, "rollout_mm_bwd")
+  _finish_check(info, "rollout_mm_bwd", check)
   return Zb, eb, bb, m0b, S0b

@@ -175,3 +175,32 @@ def test_persistent_sweeps_match_the_per_stage_path_around_their_thresholds(R, H
       rollouts.set_rollout_mode(rollouts.ROLLOUT_AUTO)
   finally:
     sys.argv = argv
+
+
+def test_deferred_not_positive_definite_check():
+  """check='defer' queues the asynchronous flags of policy weights / forward sweep / reverse sweep; raise_deferred() reads them with
+  one synchronisation: silent for a healthy rollout, GppError for a covariance that is not positive definite."""
+  from gpflowpilco_b200 import _lib, rollouts
+  from gpflowpilco_b200.autograd import rollout_mm_loss
+  from tests.helpers import cuda_handle
+  cfg = synthetic.config1_cartpole(M=32, Mp=8)
+  p = cfg["policy"]
+  handle = cuda_handle(cfg["dynamics"])
+  T = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda")
+  Z, ell, q = (T(p["Z"]).clone().requires_grad_(True), T(p["lengthscales"]).clone().requires_grad_(True),
+               T(p["q_mu"][:, 0][None]).clone().requires_grad_(True))
+  args = (3, cfg["active_dims"], T(cfg["target"]), T(cfg["W"]))
+  kw = dict(squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"], check="defer")
+  loss = rollout_mm_loss(handle, Z, ell, T(p["variance"]), q, T(cfg["m0"]), T(cfg["S0"]), *args, **kw)
+  loss.sum().backward()
+  assert len(rollouts._DEFERRED) == 3
+  rollouts.raise_deferred()
+  assert not rollouts._DEFERRED
+  ref = rollout_mm_loss(handle, Z, ell, T(p["variance"]), q, T(cfg["m0"]), T(cfg["S0"]), *args, squash_scale=cfg["squash_scale"],
+                        squash_shift=cfg["squash_shift"])
+  assert torch.equal(ref, loss)
+  bad = -10.0 * torch.eye(T(cfg["S0"]).shape[-1], dtype=torch.float64, device="cuda")[None]
+  rollout_mm_loss(handle, Z, ell, T(p["variance"]), q, T(cfg["m0"]), bad, *args, **kw)        # no error here: nothing has been read yet
+  with pytest.raises(_lib.GppError):
+    rollouts.raise_deferred()
+  assert not rollouts._DEFERRED
