@@ -466,6 +466,7 @@ def policy_opt_section(dev, lib, world, fp64_peak):
   sec = float(t[0]) * 1e-3
   # BASELINE config #1 (the reference's own CPU-runnable case): one cart-pole rollout, N = 1, H = 30, forward and forward+backward
   from gpflowpilco_b200.autograd import rollout_mm_loss
+  from gpflowpilco_b200 import rollouts as gp_rollouts
   H1 = cfg["horizon"]
   Z1 = T(p["Z"]).clone().requires_grad_(True)
   q1 = T(p["q_mu"][:, 0][None]).clone().requires_grad_(True)
@@ -477,10 +478,11 @@ def policy_opt_section(dev, lib, world, fp64_peak):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
     l1 = rollout_mm_loss(handle, Z1, e1_, T(p["variance"]), q1, T(cfg["m0"]), T(cfg["S0"]), H1, cfg["active_dims"], T(cfg["target"]), T(cfg["W"]),
-                         squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"])
+                         squash_scale=cfg["squash_scale"], squash_shift=cfg["squash_shift"], check="defer")
     ev[1].record()
     l1.sum().backward()
     ev[2].record()
+    gp_rollouts.raise_deferred()          # the three not-positive-definite flags, one synchronisation (rollouts.py)
     torch.cuda.synchronize()
     launches1 = lib.gpp_launch_count() - l0_
     if it:
