@@ -336,7 +336,9 @@ def pathwise_section(dev, lib, pk, world):
       "metric": "pathwise_particle_steps_per_s", "value": world * psteps / sec, "unit": "particle_steps/s",
       "config": {"workload": "config#4 pathwise cart-pole rollouts", "particles_per_gpu_per_launch": S, "bases": F, "horizon": H,
                  "latents": L, "inducing": M, "weights": "streamed from HBM (generated on device beforehand, Philox by global particle index)",
-                 "note": "1M particles = ceil(2^20 / particles_per_launch) identical launches per GPU"},
+                 "note": "1M particles = ceil(2^20 / particles_per_launch) identical launches per GPU",
+                 "parity": "UNPINNED: gpflow_sampling (upstream's path sampler) is not in the reference tree; the kernels are checked "
+                           "against oracle/pathwise.py, a restatement of the published algorithm (DESIGN section 2)"},
       "ms_per_launch": 1e3 * sec, "generation_s": gen_s, "mean_loss": float(loss.mean()), "clocks": pw_clocks,
       "full_config4": full,
       "with_policy_gradient": {"value": world * psteps / gsec, "unit": "particle_steps/s (gradient-mode forward + reverse sweep)",
