@@ -61,7 +61,8 @@ __device__ __forceinline__ void cos_quarter_turns(double (&q)[K]) {
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double val = fma(p[k], p[k], -1.0);
-    q[k] = make_double(hi_int(val) ^ (lo_int(t[k]) << 31), lo_int(val));   // (-1)^k through the sign bit
+    // (-1)^n through the sign bit: adding n * 2^31 to the high word toggles bit 31 for odd n (one IMAD instead of shift + xor)
+    q[k] = make_double((int)((unsigned)hi_int(val) + (unsigned)lo_int(t[k]) * 0x80000000u), lo_int(val));
   }
 }
 
@@ -115,11 +116,11 @@ __device__ __forceinline__ void sincos_quarter_turns(double (&q)[K], double (&sn
     for (int k = 0; k < K; ++k) { p[k] = fma(p[k], z[k], kCosH[j]); s[k] = fma(s[k], z[k], kSinH[j]); }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const int sign = lo_int(t[k]) << 31;
+    const unsigned nlo = (unsigned)lo_int(t[k]);
     double c = fma(p[k], p[k], -1.0);
     double sv = p[k] * (r[k] * s[k]);
-    q[k] = make_double(hi_int(c) ^ sign, lo_int(c));
-    sn[k] = make_double(hi_int(sv) ^ sign, lo_int(sv));
+    q[k] = make_double((int)((unsigned)hi_int(c) + nlo * 0x80000000u), lo_int(c));
+    sn[k] = make_double((int)((unsigned)hi_int(sv) + nlo * 0x80000000u), lo_int(sv));
   }
 }
 
