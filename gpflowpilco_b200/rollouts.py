@@ -34,7 +34,8 @@ def raise_deferred() -> None:
   pending, _DEFERRED = _DEFERRED, []
   if not pending:
     return
-  values = torch.stack([info.reshape(-1)[0] for info, _ in pending]).tolist()
+  dev0 = pending[0][0].device                  # (flags queued from several devices of one process are gathered on the first)
+  values = torch.stack([info.reshape(-1)[0].to(dev0) for info, _ in pending]).tolist()
   for v, (_, what) in zip(values, pending):
     if v:
       raise _lib.GppError(-3, f"{what}: a covariance of batch element / parameter set {int(v) - 1} is not positive definite")
