@@ -736,8 +736,8 @@ def run_b200(args):
         "config": {"workload": "config#2 batched exact MM GP predict (M=1000, D=6, E=4, full 4x4 cov + cross)",
                    "inputs_per_gpu": N, "l2": "flushed between timed steps (256 MB write)", "timing": "CUDA events per step, max over ranks"},
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                     "traffic": 95.27e6 if N == 8192 else None,
-                     "traffic_source": "ncu --set full of this command at N=8192 (profiles/r1e_contract_final_bench_full.txt): dram read 77.36 MB + write 17.91 MB per launch",
+                     "traffic": 96.25e6 if N == 8192 else None,
+                     "traffic_source": "ncu --set full of this command at N=8192 (profiles/r2m_contract_final_bench_full.txt): dram read 78.41 MB + write 17.84 MB per launch",
                      "kernel": "k_contract", "kernel_ms": 1e3 * kern_s,
                      "kernel_share_of_step": kern_s / (total_s / args.steps),
                      "algorithmic": f"{FLOP_PER_ENTRY} flop/entry x {ENTRIES_PER_INPUT} entries/input x {N} inputs",
